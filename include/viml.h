@@ -1,0 +1,224 @@
+/*
+ * viml.h — C-ABI of the B200-native sliding-window linearisation hot path of TC-VIML.
+ *
+ * This is the drop-in boundary.  Every entry point is `extern "C"`, takes plain
+ * pointers and sizes, and replaces one reference interface on the hot path (paths are relative to
+ * the reference tree, /root/reference):
+ *
+ *   viml_linearize_batch   <- ProjectionFactor::Evaluate        vins_estimator/src/factor/projection_factor.cpp:21-124
+ *                             LineProjectionFactor::Evaluate    vins_estimator/src/factor/line_projection_factor.cpp:19-120
+ *                             ResidualBlockInfo::Evaluate       vins_estimator/src/factor/marginalization_factor.cpp:3-69
+ *                             ThreadsConstructA (J^T J, J^T r)  vins_estimator/src/factor/marginalization_factor.cpp:141-172
+ *                             landmark part of MarginalizationInfo::marginalize  marginalization_factor.cpp:267-282
+ *   viml_marginalize_batch <- MarginalizationInfo::marginalize  marginalization_factor.cpp:174-299 (dense prior part)
+ *   viml_line_associate    <- Estimator::UpdateLinesInFoV       vins_estimator/src/estimator.cpp:385-447
+ *                             Estimator::LineCorrespondenceInFrame  estimator.cpp:671-885
+ *                             (+ CalAngleDist :601-613, CalEulerDist :615-669, Line2D fm.cpp:4-15,:46-71)
+ *   viml_set_map           <- lines3d_map ingest                vins_estimator/src/parameters.cpp:50-59, estimator.cpp:54-58
+ *   viml_config            <- the fields Estimator::setParameters reads for this path, estimator.cpp:54-124
+ *
+ * Conventions
+ *   - parameter-block layout is the reference's (estimator.cpp:1492-1532): pose = [px,py,pz,qx,qy,qz,qw],
+ *     feature = inverse depth, extrinsic pose like pose.  All arithmetic is IEEE binary64 unless noted.
+ *   - every function returns VIML_OK (0) or a negative error code; viml_last_error() gives the text.
+ *     No exception crosses the ABI.  Buffers are caller-owned.
+ *   - a context belongs to one CUDA device and one calling host thread; all device work of a context is
+ *     ordered on its own stream.  There is NO CPU fallback: without a usable CUDA device viml_create fails.
+ *   - pointers in the in/out structs are HOST pointers (pinned preferred, see viml_host_alloc) unless
+ *     VIML_PTRS_DEVICE is set, in which case they are device pointers on the context's device, the call only
+ *     enqueues work on the context stream, and the caller synchronises with viml_sync().
+ */
+#ifndef VIML_H_
+#define VIML_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIML_ABI_VERSION 1
+
+/* ---- error codes ---------------------------------------------------------------------------- */
+#define VIML_OK 0
+#define VIML_ERR_INVALID (-1)  /* bad argument / inconsistent sizes                               */
+#define VIML_ERR_CUDA (-2)     /* CUDA runtime error (text in viml_last_error)                    */
+#define VIML_ERR_NO_DEVICE (-3)/* no usable sm_100 device: there is deliberately no CPU fallback  */
+#define VIML_ERR_NOMAP (-4)    /* viml_line_associate before viml_set_map                         */
+#define VIML_ERR_UNSUPPORTED (-5)
+
+/* ---- flags ---------------------------------------------------------------------------------- */
+#define VIML_OUT_RESIDUAL_JACOBIAN 0x01u /* mode A: per-factor r and J blocks (Ceres Evaluate layouts) */
+#define VIML_OUT_HB 0x02u                /* mode B: per-window block-structured H = J^T J, b = +J^T r  */
+#define VIML_OUT_SCHUR 0x04u             /* landmark-eliminated S, g per window                        */
+#define VIML_LOSS_CAUCHY 0x10u           /* apply the ResidualBlockInfo::Evaluate loss correction      */
+#define VIML_PTRS_DEVICE 0x100u          /* in/out pointers are device pointers; call is asynchronous  */
+
+typedef struct viml_ctx viml_ctx;
+
+/* Fields of Estimator::setParameters (estimator.cpp:54-124) that the hot path reads. */
+typedef struct viml_config {
+  double fx, fy, cx, cy;      /* pixel intrinsics K (estimator.cpp:66-71)                          */
+  int32_t width, height;      /* image size (estimator.cpp:78-79)                                  */
+  double Rbw[9];              /* map -> VIO-world rotation, row-major (estimator.cpp:91-100)       */
+  double Tbw[3];              /* map -> VIO-world translation                                      */
+  double overlap_th;          /* estimator.cpp:116                                                 */
+  double dist_th;             /* estimator.cpp:117                                                 */
+  double angle_th;            /* estimator.cpp:119                                                 */
+  double sqrt_info;           /* ProjectionFactor::sqrt_info = s*I2, s = FOCAL_LENGTH/1.5 (:85)    */
+  double cauchy_a;            /* ceres::CauchyLoss(a), a = 1.0 (estimator.cpp:1682)                */
+} viml_config;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+int viml_abi_version(void);
+int viml_create(viml_ctx** out, const viml_config* cfg, int device);
+void viml_destroy(viml_ctx* ctx);
+const char* viml_last_error(const viml_ctx* ctx);
+int viml_sync(viml_ctx* ctx);                 /* cudaStreamSynchronize on the context stream        */
+void* viml_stream(viml_ctx* ctx);             /* the context's cudaStream_t (for event timing)      */
+int viml_host_alloc(void** p, size_t bytes);  /* pinned host memory (cudaHostAlloc)                 */
+int viml_host_free(void* p);
+int viml_device_alloc(viml_ctx* ctx, void** p, size_t bytes);
+int viml_device_free(viml_ctx* ctx, void* p);
+int viml_memcpy_h2d(viml_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
+int viml_memcpy_d2h(viml_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
+int64_t viml_kernel_launches(const viml_ctx* ctx); /* kernels launched by this context so far       */
+
+/* ---- prior line map -------------------------------------------------------------------------- */
+/* lines_xyzxyz: N rows of [sx sy sz ex ey ez] exactly as line_3d.txt (parameters.cpp:50-59).
+ * Always a HOST pointer.  The map is packed once into six SoA planes in HBM.                    */
+int viml_set_map(viml_ctx* ctx, const double* lines_xyzxyz, int64_t n_lines);
+
+/* ---- linearisation ---------------------------------------------------------------------------
+ * A batch of W independent sliding windows.  Factors are grouped by window (CSR offsets); inside a
+ * window the order is free (it only fixes floating-point summation order).
+ *
+ * Point factor k (ProjectionFactor, projection_factor.h:10-21) couples pose i, pose j, the extrinsic
+ * and feature `feat` of its window:   pf_idx[k] = i | (j << 8) | (feat << 16).
+ * pf_obs[k] = {pts_i.x, pts_i.y, pts_j.x, pts_j.y}; pts_i.z = pf_pts_i_z[k] or 1.0 when that is NULL
+ * (the tracker always publishes z = 1, feature_tracker_node.cpp:121-189; pts_j.z is never read).
+ *
+ * Line factor k (LineProjectionFactor, line_projection_factor.h:13-34) couples pose lf_frame[k] only.
+ * lf_geom is SoA, nine planes of n_line_factors doubles: P_start.xyz, P_end.xyz (already in VIO world,
+ * estimator.cpp:1832-1833), then the detected line's A, B, C (raw-pixel, un-normalised, fm.cpp:11-13).
+ * Its K is viml_config's; its b_c_R/b_c_T are the window's extrinsic, rotation normalised
+ * (estimator.cpp:1777-1781).                                                                      */
+typedef struct viml_window_batch {
+  int32_t n_windows;         /* W                                                               */
+  int32_t poses_per_window;  /* P  (WINDOW_SIZE+1 = 11; up to 255)                              */
+  int32_t feats_per_window;  /* F  stride of inv_depth (<= 65535)                               */
+  int32_t reserved0;
+  const double* poses;       /* [W][P][7]                                                       */
+  const double* ex_pose;     /* [W][7]                                                          */
+  const double* inv_depth;   /* [W][F]                                                          */
+  int64_t n_point_factors;   /* NP                                                              */
+  const int32_t* pf_window_offset; /* [W+1], pf_window_offset[W] == NP                          */
+  const uint32_t* pf_idx;    /* [NP]                                                            */
+  const double* pf_obs;      /* [NP][4]                                                         */
+  const double* pf_pts_i_z;  /* [NP] or NULL                                                    */
+  int64_t n_line_factors;    /* NL                                                              */
+  const int32_t* lf_window_offset; /* [W+1]                                                     */
+  const int32_t* lf_frame;   /* [NL]                                                            */
+  const double* lf_geom;     /* [9][NL]                                                         */
+} viml_window_batch;
+
+/* Any pointer may be NULL (= not wanted).  D = 6*(P+1): pose blocks 0..P-1 then the extrinsic.
+ * Jacobians are row-major 2x7 with column 6 zero, exactly what Evaluate writes
+ * (projection_factor.cpp:77-119, line_projection_factor.cpp:102-114).
+ * H blocks: H_pp [W][D][D] row-major, full symmetric; H_lp [W][F][D] (row l = landmark l against
+ * all pose columns); H_ll [W][F]; b_p [W][D]; b_l [W][F];  b = +J^T r (marginalization_factor.cpp:168).
+ * Schur: S = H_pp - sum_l H_lp[l]^T H_lp[l] / H_ll[l],  g = b_p - sum_l H_lp[l]^T b_l[l] / H_ll[l],
+ * landmarks with H_ll <= 1e-8 (MarginalizationInfo::eps) are skipped like the reference's pseudo-inverse. */
+typedef struct viml_linearize_out {
+  double* pf_residual;   /* [NP][2]  */
+  double* pf_jac_pose_i; /* [NP][14] */
+  double* pf_jac_pose_j; /* [NP][14] */
+  double* pf_jac_ex;     /* [NP][14] */
+  double* pf_jac_feat;   /* [NP][2]  */
+  double* lf_residual;   /* [NL][2]  */
+  double* lf_jac_pose;   /* [NL][14] */
+  double* H_pp;          /* [W][D][D] */
+  double* H_lp;          /* [W][F][D] */
+  double* H_ll;          /* [W][F]    */
+  double* b_p;           /* [W][D]    */
+  double* b_l;           /* [W][F]    */
+  double* S;             /* [W][D][D] */
+  double* g;             /* [W][D]    */
+} viml_linearize_out;
+
+int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_linearize_out* out,
+                         uint32_t flags);
+
+/* ---- dense marginalisation (marginalization_factor.cpp:264-293) --------------------------------
+ * Per problem k: A [pos][pos] row-major, b [pos], marginalised block = leading m rows, kept n = pos-m.
+ *   Amm <- (Amm+Amm^T)/2;  Amm^+ by symmetric eigen-decomposition, eigenvalues <= eps dropped;
+ *   Ar = Arr - Arm Amm^+ Amr;  br = brr - Arm Amm^+ bmm;  second eigen-decomposition of Ar gives
+ *   linearized_jacobians = sqrt(S) V^T  [n][n]  and  linearized_residuals = sqrt(S^+) V^T br  [n].
+ * Outputs A_schur [n][n], b_schur [n] are always written when non-NULL.                           */
+typedef struct viml_marg_batch {
+  int32_t n_problems;
+  int32_t pos;   /* m + n, <= 256 */
+  int32_t m;
+  int32_t reserved0;
+  double eps;    /* 1e-8 */
+  const double* A; /* [K][pos][pos] */
+  const double* b; /* [K][pos]      */
+} viml_marg_batch;
+
+typedef struct viml_marg_out {
+  double* A_schur;              /* [K][n][n] */
+  double* b_schur;              /* [K][n]    */
+  double* linearized_jacobians; /* [K][n][n] */
+  double* linearized_residuals; /* [K][n]    */
+} viml_marg_out;
+
+int viml_marginalize_batch(viml_ctx* ctx, const viml_marg_batch* in, const viml_marg_out* out,
+                           uint32_t flags);
+
+/* ---- 2D-3D line association --------------------------------------------------------------------
+ * For every pose p: (1) FoV cull of the whole map with cull_poses[p] (UpdateLinesInFoV; the reference
+ * caches this list at frame entry, estimator.cpp:342), (2) for each of the L detected 2D lines the
+ * arg-min candidate under match_poses[p] (LineCorrespondenceInFrame).  match_poses == NULL means the
+ * cull pose is used for both.  lines2d are raw-pixel endpoints [sx sy ex ey] as doubles (they arrive as
+ * float32 ROS channels, estimator_node.cpp:406-410).  n_lines2d[p] (optional) gives ragged counts <= L. */
+typedef struct viml_assoc_query {
+  int32_t n_poses;           /* Pq                                  */
+  int32_t lines_per_pose;    /* L (stride)                          */
+  const double* cull_poses;  /* [Pq][7]                             */
+  const double* match_poses; /* [Pq][7] or NULL                     */
+  const double* ex_pose;     /* [Pq][7]                             */
+  const double* lines2d;     /* [Pq][L][4]                          */
+  const int32_t* n_lines2d;  /* [Pq] or NULL (= L everywhere)       */
+} viml_assoc_query;
+
+/* match_index: MAP index of the chosen 3D line, -1 = none (est.cpp:869-878 / :703-713).
+ * err: {errA, errD, overlap} as the reference's Vector3f (-1,-1,-1 when unmatched).
+ * projected: the chosen candidate's projected 2D segment (xx,yy,xx_,yy_ / clipped endpoint), untouched
+ *            when unmatched.
+ * fov_count [Pq]; fov_index [Pq][fov_capacity] = map indices in map order (the WorldLinesInFOV list);
+ * a list longer than fov_capacity is truncated in the output only (fov_count still exact, matching
+ * still uses the full list).  fov_mask: [Pq][ceil(N/32)] bitset, bit j of word j/32.              */
+typedef struct viml_assoc_out {
+  int32_t* match_index; /* [Pq][L]    */
+  float* err;           /* [Pq][L][3] */
+  double* projected;    /* [Pq][L][4] */
+  int32_t* fov_count;   /* [Pq]       */
+  int32_t* fov_index;   /* [Pq][fov_capacity] */
+  int32_t fov_capacity;
+  int32_t reserved0;
+  uint32_t* fov_mask;   /* [Pq][ceil(N/32)] */
+} viml_assoc_out;
+
+int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_assoc_out* out,
+                        uint32_t flags);
+
+/* Sum partial [S | g] (or H/b) buffers of the single-huge-window case across ranks.  `comm` is an
+ * ncclComm_t; buf is a device pointer of `count` doubles; in-place ncclAllReduce(sum) on the context
+ * stream.  Returns VIML_ERR_UNSUPPORTED when libnccl cannot be loaded.                            */
+int viml_allreduce_hb(viml_ctx* ctx, void* nccl_comm, double* buf, int64_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIML_H_ */

@@ -1,0 +1,216 @@
+"""tc-viml_b200 — B200-native linearisation hot path of TC-VIML.
+
+The product is the C-ABI library csrc/ -> libviml_b200.so (hand-written sm_100a CUDA) plus the C++ host
+shim under host/ that keeps the reference's class interfaces.  This Python module is only a thin ctypes
+binding of the C-ABI for tests and bench.py.  There is no CPU fallback: if the library is missing or no
+CUDA device is usable, construction fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi, build, synth  # noqa: F401
+from ._abi import (LOSS_CAUCHY, OUT_HB, OUT_RESIDUAL_JACOBIAN, OUT_SCHUR, PTRS_DEVICE, Batch,  # noqa: F401
+                   make_config)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libviml_b200.so")
+_LIB = None
+
+# every symbol include/viml.h declares
+ABI_SYMBOLS = (
+    "viml_abi_version", "viml_create", "viml_destroy", "viml_last_error", "viml_sync", "viml_stream",
+    "viml_host_alloc", "viml_host_free", "viml_device_alloc", "viml_device_free", "viml_memcpy_h2d",
+    "viml_memcpy_d2h", "viml_kernel_launches", "viml_set_map", "viml_linearize_batch",
+    "viml_marginalize_batch", "viml_line_associate", "viml_allreduce_hb",
+)
+
+
+class VimlError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen libviml_b200.so and check every ABI symbol.  Works without a GPU (no device call)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise VimlError(f"{LIB_PATH} is missing: run `python __graft_entry__.py` (build()) first; "
+                        "there is no CPU fallback for the hot path")
+    lib = C.CDLL(LIB_PATH)
+    for s in ABI_SYMBOLS:
+        if not hasattr(lib, s):
+            raise VimlError(f"libviml_b200.so does not export {s}")
+    lib.viml_last_error.restype = C.c_char_p
+    lib.viml_last_error.argtypes = [C.c_void_p]
+    lib.viml_stream.restype = C.c_void_p
+    lib.viml_stream.argtypes = [C.c_void_p]
+    lib.viml_kernel_launches.restype = C.c_int64
+    lib.viml_kernel_launches.argtypes = [C.c_void_p]
+    lib.viml_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_abi.Config), C.c_int]
+    lib.viml_destroy.argtypes = [C.c_void_p]
+    lib.viml_sync.argtypes = [C.c_void_p]
+    lib.viml_set_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    lib.viml_linearize_batch.argtypes = [C.c_void_p, C.POINTER(_abi.WindowBatch), C.POINTER(_abi.LinearizeOut), C.c_uint32]
+    lib.viml_marginalize_batch.argtypes = [C.c_void_p, C.POINTER(_abi.MargBatch), C.POINTER(_abi.MargOut), C.c_uint32]
+    lib.viml_line_associate.argtypes = [C.c_void_p, C.POINTER(_abi.AssocQuery), C.POINTER(_abi.AssocOut), C.c_uint32]
+    lib.viml_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    lib.viml_host_free.argtypes = [C.c_void_p]
+    lib.viml_device_alloc.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t]
+    lib.viml_device_free.argtypes = [C.c_void_p, C.c_void_p]
+    lib.viml_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.viml_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.viml_allreduce_hb.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    _LIB = lib
+    return lib
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc'ed memory (viml_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        lib = load_library()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        rc = lib.viml_host_alloc(C.byref(p), max(self.nbytes, 1))
+        if rc != 0:
+            raise VimlError(f"viml_host_alloc failed ({rc})")
+        self._p = p
+        buf = (C.c_byte * max(self.nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            load_library().viml_host_free(self._p)
+            self._p = None
+
+
+def pinned_like(a):
+    pa = PinnedArray(a.shape, a.dtype)
+    pa.array[...] = a
+    return pa
+
+
+class Context:
+    """One viml_ctx (one CUDA device, one stream).  Mirrors the C-ABI one to one."""
+
+    def __init__(self, cfg, device=0):
+        self.lib = load_library()
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = self.lib.viml_create(C.byref(h), C.byref(cfg), int(device))
+        if rc != 0:
+            raise VimlError(f"viml_create failed with {rc}: no usable CUDA device and no CPU fallback")
+        self.h = h
+        self.n_map = 0
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.viml_destroy(self.h)
+            self.h = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise VimlError(f"viml error {rc}: {self.lib.viml_last_error(self.h).decode()}")
+
+    def sync(self):
+        self._check(self.lib.viml_sync(self.h))
+
+    def stream(self):
+        return self.lib.viml_stream(self.h)
+
+    def kernel_launches(self):
+        return int(self.lib.viml_kernel_launches(self.h))
+
+    # -- device memory helpers (for the resident-input benchmark path) --
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self.lib.viml_device_alloc(self.h, C.byref(p), max(int(nbytes), 1)))
+        return p.value
+
+    def device_free(self, p):
+        self._check(self.lib.viml_device_free(self.h, p))
+
+    def h2d(self, dptr, arr):
+        self._check(self.lib.viml_memcpy_h2d(self.h, dptr, _abi.ptr(arr), arr.nbytes))
+
+    def d2h(self, arr, dptr):
+        self._check(self.lib.viml_memcpy_d2h(self.h, _abi.ptr(arr), dptr, arr.nbytes))
+
+    def to_device(self, arr):
+        d = self.device_alloc(arr.nbytes)
+        self.h2d(d, arr)
+        return d
+
+    # -- ABI calls --
+    def set_map(self, lines_xyzxyz):
+        lines = np.ascontiguousarray(lines_xyzxyz, dtype=np.float64).reshape(-1, 6)
+        self._check(self.lib.viml_set_map(self.h, _abi.ptr(lines), len(lines)))
+        self.n_map = len(lines)
+
+    def linearize(self, batch, flags, out=None):
+        """viml_linearize_batch with host buffers; returns dict of numpy outputs."""
+        bufs = batch.alloc_out(flags) if out is None else out
+        s = batch.struct()
+        o = _abi.out_struct(bufs)
+        self._check(self.lib.viml_linearize_batch(self.h, C.byref(s), C.byref(o), flags & ~PTRS_DEVICE))
+        return bufs
+
+    def linearize_raw(self, batch_struct, out_struct, flags):
+        self._check(self.lib.viml_linearize_batch(self.h, C.byref(batch_struct), C.byref(out_struct), flags))
+
+    def marginalize(self, A, b, m, eps=1e-8, want_lin=True):
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        if A.ndim == 2:
+            A, b = A[None], b[None]
+        K, pos = A.shape[0], A.shape[1]
+        n = pos - m
+        res = {"A_schur": np.full((K, n, n), np.nan), "b_schur": np.full((K, n), np.nan)}
+        if want_lin:
+            res["linearized_jacobians"] = np.full((K, n, n), np.nan)
+            res["linearized_residuals"] = np.full((K, n), np.nan)
+        i = _abi.MargBatch()
+        i.n_problems, i.pos, i.m, i.eps, i.A, i.b = K, pos, m, eps, _abi.ptr(A), _abi.ptr(b)
+        o = _abi.MargOut()
+        o.A_schur, o.b_schur = _abi.ptr(res["A_schur"]), _abi.ptr(res["b_schur"])
+        o.linearized_jacobians = _abi.ptr(res.get("linearized_jacobians"))
+        o.linearized_residuals = _abi.ptr(res.get("linearized_residuals"))
+        self._check(self.lib.viml_marginalize_batch(self.h, C.byref(i), C.byref(o), 0))
+        return res
+
+    def associate(self, cull_poses, match_poses, ex_pose, lines2d, n_lines2d=None, fov_capacity=0,
+                  want_mask=False):
+        """viml_line_associate with host buffers; returns dict of numpy outputs."""
+        keep = [None if x is None else np.ascontiguousarray(x, dtype=np.float64)
+                for x in (cull_poses, match_poses, ex_pose, lines2d)]
+        Pq, L = keep[3].shape[0], keep[3].shape[1]
+        q = _abi.AssocQuery()
+        q.n_poses, q.lines_per_pose = Pq, L
+        q.cull_poses, q.match_poses, q.ex_pose, q.lines2d = [_abi.ptr(k) for k in keep]
+        nl = None if n_lines2d is None else np.ascontiguousarray(n_lines2d, dtype=np.int32)
+        q.n_lines2d = _abi.ptr(nl)
+        res = {"match_index": np.full((Pq, L), -2, dtype=np.int32),
+               "err": np.full((Pq, L, 3), np.nan, dtype=np.float32),
+               "projected": np.full((Pq, L, 4), np.nan), "fov_count": np.zeros(Pq, dtype=np.int32)}
+        if fov_capacity:
+            res["fov_index"] = np.full((Pq, fov_capacity), -1, dtype=np.int32)
+        if want_mask:
+            res["fov_mask"] = np.zeros((Pq, (self.n_map + 31) // 32), dtype=np.uint32)
+        o = _abi.AssocOut()
+        o.match_index, o.err, o.projected, o.fov_count = [_abi.ptr(res[k]) for k in ("match_index", "err", "projected", "fov_count")]
+        o.fov_index, o.fov_capacity, o.fov_mask = _abi.ptr(res.get("fov_index")), fov_capacity, _abi.ptr(res.get("fov_mask"))
+        self._check(self.lib.viml_line_associate(self.h, C.byref(q), C.byref(o), 0))
+        return res
+
+    def associate_raw(self, q, o, flags):
+        self._check(self.lib.viml_line_associate(self.h, C.byref(q), C.byref(o), flags))

@@ -1,0 +1,194 @@
+"""ctypes mirror of include/viml.h (struct layouts, flags, error codes).
+
+Shared by the product binding (this package) and by the test-only oracle binding (oracle/oracle.py), so
+that both sides of a parity test are driven with the very same structs.
+"""
+import ctypes as C
+
+import numpy as np
+
+VIML_OK = 0
+VIML_ERR_INVALID = -1
+VIML_ERR_CUDA = -2
+VIML_ERR_NO_DEVICE = -3
+VIML_ERR_NOMAP = -4
+VIML_ERR_UNSUPPORTED = -5
+
+OUT_RESIDUAL_JACOBIAN = 0x01
+OUT_HB = 0x02
+OUT_SCHUR = 0x04
+LOSS_CAUCHY = 0x10
+PTRS_DEVICE = 0x100
+
+c_double_p = C.POINTER(C.c_double)
+c_float_p = C.POINTER(C.c_float)
+c_int32_p = C.POINTER(C.c_int32)
+c_uint32_p = C.POINTER(C.c_uint32)
+
+
+class Config(C.Structure):
+    """viml_config — estimator.cpp:54-124 fields read by the hot path."""
+
+    _fields_ = [
+        ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("Rbw", C.c_double * 9), ("Tbw", C.c_double * 3),
+        ("overlap_th", C.c_double), ("dist_th", C.c_double), ("angle_th", C.c_double),
+        ("sqrt_info", C.c_double), ("cauchy_a", C.c_double),
+    ]
+
+
+class WindowBatch(C.Structure):
+    _fields_ = [
+        ("n_windows", C.c_int32), ("poses_per_window", C.c_int32),
+        ("feats_per_window", C.c_int32), ("reserved0", C.c_int32),
+        ("poses", C.c_void_p), ("ex_pose", C.c_void_p), ("inv_depth", C.c_void_p),
+        ("n_point_factors", C.c_int64),
+        ("pf_window_offset", C.c_void_p), ("pf_idx", C.c_void_p), ("pf_obs", C.c_void_p),
+        ("pf_pts_i_z", C.c_void_p),
+        ("n_line_factors", C.c_int64),
+        ("lf_window_offset", C.c_void_p), ("lf_frame", C.c_void_p), ("lf_geom", C.c_void_p),
+    ]
+
+
+LIN_OUT_FIELDS = ("pf_residual", "pf_jac_pose_i", "pf_jac_pose_j", "pf_jac_ex", "pf_jac_feat",
+                  "lf_residual", "lf_jac_pose", "H_pp", "H_lp", "H_ll", "b_p", "b_l", "S", "g")
+
+
+class LinearizeOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in LIN_OUT_FIELDS]
+
+
+class MargBatch(C.Structure):
+    _fields_ = [("n_problems", C.c_int32), ("pos", C.c_int32), ("m", C.c_int32),
+                ("reserved0", C.c_int32), ("eps", C.c_double), ("A", C.c_void_p), ("b", C.c_void_p)]
+
+
+class MargOut(C.Structure):
+    _fields_ = [("A_schur", C.c_void_p), ("b_schur", C.c_void_p),
+                ("linearized_jacobians", C.c_void_p), ("linearized_residuals", C.c_void_p)]
+
+
+class AssocQuery(C.Structure):
+    _fields_ = [("n_poses", C.c_int32), ("lines_per_pose", C.c_int32),
+                ("cull_poses", C.c_void_p), ("match_poses", C.c_void_p), ("ex_pose", C.c_void_p),
+                ("lines2d", C.c_void_p), ("n_lines2d", C.c_void_p)]
+
+
+class AssocOut(C.Structure):
+    _fields_ = [("match_index", C.c_void_p), ("err", C.c_void_p), ("projected", C.c_void_p),
+                ("fov_count", C.c_void_p), ("fov_index", C.c_void_p),
+                ("fov_capacity", C.c_int32), ("reserved0", C.c_int32), ("fov_mask", C.c_void_p)]
+
+
+def ptr(a):
+    """Address of a numpy array (host) or an int device pointer; None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return int(a)
+    if hasattr(a, "data_ptr"):  # torch tensor (host pinned or device)
+        return int(a.data_ptr())
+    assert a.flags["C_CONTIGUOUS"], "ABI buffers must be C-contiguous"
+    return a.ctypes.data
+
+
+def make_config(fx=461.6, fy=460.3, cx=363.0, cy=248.1, width=752, height=480, Rbw=None, Tbw=None,
+                overlap_th=0.45, dist_th=50.0, angle_th=0.1745, sqrt_info=460.0 / 1.5, cauchy_a=1.0):
+    """Defaults are EuRoC cam0 and the thresholds of benchmark_publisher/config/V1_01_easy/sensor.yaml."""
+    cfg = Config()
+    cfg.fx, cfg.fy, cfg.cx, cfg.cy = fx, fy, cx, cy
+    cfg.width, cfg.height = width, height
+    R = np.eye(3) if Rbw is None else np.asarray(Rbw, dtype=np.float64).reshape(3, 3)
+    T = np.zeros(3) if Tbw is None else np.asarray(Tbw, dtype=np.float64).reshape(3)
+    for k in range(9):
+        cfg.Rbw[k] = float(R.reshape(-1)[k])
+    for k in range(3):
+        cfg.Tbw[k] = float(T[k])
+    cfg.overlap_th, cfg.dist_th, cfg.angle_th = overlap_th, dist_th, angle_th
+    cfg.sqrt_info, cfg.cauchy_a = sqrt_info, cauchy_a
+    return cfg
+
+
+class Batch:
+    """Host-side container of one viml_window_batch (numpy arrays, SoA as in viml.h)."""
+
+    def __init__(self, poses, ex_pose, inv_depth, pf_window_offset, pf_idx, pf_obs,
+                 lf_window_offset=None, lf_frame=None, lf_geom=None, pf_pts_i_z=None):
+        self.poses = np.ascontiguousarray(poses, dtype=np.float64)
+        self.ex_pose = np.ascontiguousarray(ex_pose, dtype=np.float64)
+        self.inv_depth = np.ascontiguousarray(inv_depth, dtype=np.float64)
+        self.pf_window_offset = np.ascontiguousarray(pf_window_offset, dtype=np.int32)
+        self.pf_idx = np.ascontiguousarray(pf_idx, dtype=np.uint32)
+        self.pf_obs = np.ascontiguousarray(pf_obs, dtype=np.float64).reshape(-1, 4)
+        self.pf_pts_i_z = None if pf_pts_i_z is None else np.ascontiguousarray(pf_pts_i_z, dtype=np.float64)
+        W = self.poses.shape[0]
+        if lf_window_offset is None:
+            lf_window_offset = np.zeros(W + 1, dtype=np.int32)
+            lf_frame = np.zeros(0, dtype=np.int32)
+            lf_geom = np.zeros((9, 0), dtype=np.float64)
+        self.lf_window_offset = np.ascontiguousarray(lf_window_offset, dtype=np.int32)
+        self.lf_frame = np.ascontiguousarray(lf_frame, dtype=np.int32)
+        self.lf_geom = np.ascontiguousarray(lf_geom, dtype=np.float64).reshape(9, -1)
+        assert self.poses.ndim == 3 and self.poses.shape[2] == 7
+        assert self.ex_pose.shape == (W, 7) and self.inv_depth.shape[0] == W
+        assert self.pf_window_offset.shape == (W + 1,) and self.lf_window_offset.shape == (W + 1,)
+
+    W = property(lambda s: s.poses.shape[0])
+    P = property(lambda s: s.poses.shape[1])
+    F = property(lambda s: s.inv_depth.shape[1])
+    D = property(lambda s: 6 * (s.poses.shape[1] + 1))
+    NP = property(lambda s: int(s.pf_idx.shape[0]))
+    NL = property(lambda s: int(s.lf_frame.shape[0]))
+
+    def arrays(self):
+        return {k: getattr(self, k) for k in ("poses", "ex_pose", "inv_depth", "pf_window_offset", "pf_idx",
+                                              "pf_obs", "pf_pts_i_z", "lf_window_offset", "lf_frame", "lf_geom")}
+
+    def struct(self, arrays=None):
+        a = self.arrays() if arrays is None else arrays
+        s = WindowBatch()
+        s.n_windows, s.poses_per_window, s.feats_per_window = self.W, self.P, self.F
+        s.poses, s.ex_pose, s.inv_depth = ptr(a["poses"]), ptr(a["ex_pose"]), ptr(a["inv_depth"])
+        s.n_point_factors = self.NP
+        s.pf_window_offset, s.pf_idx, s.pf_obs = ptr(a["pf_window_offset"]), ptr(a["pf_idx"]), ptr(a["pf_obs"])
+        s.pf_pts_i_z = ptr(a.get("pf_pts_i_z"))
+        s.n_line_factors = self.NL
+        s.lf_window_offset, s.lf_frame, s.lf_geom = ptr(a["lf_window_offset"]), ptr(a["lf_frame"]), ptr(a["lf_geom"])
+        return s
+
+    def out_shapes(self):
+        W, F, D, NP, NL = self.W, self.F, self.D, self.NP, self.NL
+        return {"pf_residual": (NP, 2), "pf_jac_pose_i": (NP, 14), "pf_jac_pose_j": (NP, 14),
+                "pf_jac_ex": (NP, 14), "pf_jac_feat": (NP, 2), "lf_residual": (NL, 2), "lf_jac_pose": (NL, 14),
+                "H_pp": (W, D, D), "H_lp": (W, F, D), "H_ll": (W, F), "b_p": (W, D), "b_l": (W, F),
+                "S": (W, D, D), "g": (W, D)}
+
+    def alloc_out(self, flags, fill=np.nan):
+        """numpy output buffers for the requested modes, NaN-filled so unwritten entries are caught."""
+        sh = self.out_shapes()
+        names = []
+        if flags & OUT_RESIDUAL_JACOBIAN:
+            names += ["pf_residual", "pf_jac_pose_i", "pf_jac_pose_j", "pf_jac_ex", "pf_jac_feat",
+                      "lf_residual", "lf_jac_pose"]
+        if flags & OUT_HB:
+            names += ["H_pp", "H_lp", "H_ll", "b_p", "b_l"]
+        if flags & OUT_SCHUR:
+            names += ["S", "g"]
+        return {n: np.full(sh[n], fill, dtype=np.float64) for n in names}
+
+    def slice_windows(self, lo, hi):
+        """Sub-batch of windows [lo, hi) (used to shard windows over ranks)."""
+        p0, p1 = int(self.pf_window_offset[lo]), int(self.pf_window_offset[hi])
+        l0, l1 = int(self.lf_window_offset[lo]), int(self.lf_window_offset[hi])
+        return Batch(self.poses[lo:hi], self.ex_pose[lo:hi], self.inv_depth[lo:hi],
+                     self.pf_window_offset[lo:hi + 1] - p0, self.pf_idx[p0:p1], self.pf_obs[p0:p1],
+                     self.lf_window_offset[lo:hi + 1] - l0, self.lf_frame[l0:l1], self.lf_geom[:, l0:l1],
+                     None if self.pf_pts_i_z is None else self.pf_pts_i_z[p0:p1])
+
+
+def out_struct(bufs):
+    o = LinearizeOut()
+    for n in LIN_OUT_FIELDS:
+        setattr(o, n, ptr(bufs.get(n)))
+    return o
