@@ -85,6 +85,19 @@ int viml_memcpy_h2d(viml_ctx* ctx, void* dst, const void* src, size_t bytes); /*
 int viml_memcpy_d2h(viml_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
 int64_t viml_kernel_launches(const viml_ctx* ctx); /* kernels launched by this context so far       */
 
+/* ---- measurement hooks (bench.py roofline; not needed for results) -----------------------------
+ * Between viml_profile_begin and viml_profile_end every kernel launch of the context is bracketed by a
+ * pair of CUDA events on the context stream.  viml_profile_end synchronises and returns, per kernel id
+ * (see viml_kernel_name), the summed device time in ms and the number of launches.                  */
+#define VIML_NUM_KERNELS 16
+int viml_profile_begin(viml_ctx* ctx);
+int viml_profile_end(viml_ctx* ctx, double* ms_per_kernel, int64_t* launches_per_kernel);
+const char* viml_kernel_name(int kernel_id);
+/* FP64 peaks of this device measured with register-resident micro-kernels on the context stream:
+ * dfma_tflops counts 2 flop per DFMA; dmul_dadd_tops counts 1 op per un-fused DMUL or DADD (the
+ * association translation unit is compiled without FMA contraction).                               */
+int viml_microbench_fp64(viml_ctx* ctx, double* dfma_tflops, double* dmul_dadd_tops);
+
 /* ---- prior line map -------------------------------------------------------------------------- */
 /* lines_xyzxyz: N rows of [sx sy sz ex ey ez] exactly as line_3d.txt (parameters.cpp:50-59).
  * Always a HOST pointer.  The map is packed once into six SoA planes in HBM.                    */

@@ -22,7 +22,8 @@ _LIB = None
 ABI_SYMBOLS = (
     "viml_abi_version", "viml_create", "viml_destroy", "viml_last_error", "viml_sync", "viml_stream",
     "viml_host_alloc", "viml_host_free", "viml_device_alloc", "viml_device_free", "viml_memcpy_h2d",
-    "viml_memcpy_d2h", "viml_kernel_launches", "viml_set_map", "viml_linearize_batch",
+    "viml_memcpy_d2h", "viml_kernel_launches", "viml_profile_begin", "viml_profile_end", "viml_kernel_name",
+    "viml_microbench_fp64", "viml_set_map", "viml_linearize_batch",
     "viml_marginalize_batch", "viml_line_associate", "viml_allreduce_hb",
 )
 
@@ -49,6 +50,11 @@ def load_library():
     lib.viml_stream.argtypes = [C.c_void_p]
     lib.viml_kernel_launches.restype = C.c_int64
     lib.viml_kernel_launches.argtypes = [C.c_void_p]
+    lib.viml_kernel_name.restype = C.c_char_p
+    lib.viml_kernel_name.argtypes = [C.c_int]
+    lib.viml_profile_begin.argtypes = [C.c_void_p]
+    lib.viml_profile_end.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.viml_microbench_fp64.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.viml_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_abi.Config), C.c_int]
     lib.viml_destroy.argtypes = [C.c_void_p]
     lib.viml_sync.argtypes = [C.c_void_p]
@@ -130,6 +136,21 @@ class Context:
 
     def kernel_launches(self):
         return int(self.lib.viml_kernel_launches(self.h))
+
+    def profile_begin(self):
+        self._check(self.lib.viml_profile_begin(self.h))
+
+    def profile_end(self):
+        """{kernel name: (total ms, launches)} for every kernel launched since profile_begin."""
+        ms = (C.c_double * 16)()
+        n = (C.c_int64 * 16)()
+        self._check(self.lib.viml_profile_end(self.h, ms, n))
+        return {self.lib.viml_kernel_name(k).decode(): (ms[k], n[k]) for k in range(16) if n[k] > 0}
+
+    def microbench_fp64(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.viml_microbench_fp64(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     # -- device memory helpers (for the resident-input benchmark path) --
     def device_alloc(self, nbytes):

@@ -66,7 +66,7 @@ def build_cuda(verbose=False, force=False, ptxas_info=False):
             _run([nvcc] + NVCC_ARCH + NVCC_COMMON + extra + ["-c", src, "-o", obj], verbose)
     so = os.path.join(_HERE, "libviml_b200.so")
     if force or _newer(objs, so):
-        _run([nvcc] + NVCC_ARCH + ["-shared", "-o", so] + objs + ["-lcudart", "-ldl"], verbose)
+        _run([nvcc] + NVCC_ARCH + ["-shared", "--cudart", "static", "-o", so] + objs + ["-ldl"], verbose)
     return so
 
 

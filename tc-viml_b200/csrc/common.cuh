@@ -1,0 +1,157 @@
+// common.cuh — context, error handling and launch declarations shared by the CUDA translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "viml.h"
+
+#define VIML_TRY_CUDA(ctx, expr)                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                      \
+      return VIML_ERR_CUDA;                                                                   \
+    }                                                                                         \
+  } while (0)
+
+// Growable device buffer; contents are not preserved across grow().
+struct DeviceArena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  cudaError_t reserve(size_t bytes) {
+    used = 0;
+    if (bytes <= cap) return cudaSuccess;
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 8 + (1u << 20);
+    cudaError_t e = cudaMalloc((void**)&base, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <class T>
+  T* take(size_t count) {
+    const size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    T* p = (T*)(base + used);
+    used += bytes;
+    return p;
+  }
+  static size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+  void release() {
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = used = 0;
+  }
+};
+
+struct viml_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  viml_config cfg{};
+  std::string err;
+  int64_t launches = 0;
+  // association decision threshold: angle > angle_th  <=>  |dot| < cos_th  
+  double cos_th = 0.0;
+  int nan_angle_passes = 0;  // !(3.1415926 > angle_th)
+  // prior map, six SoA planes of n_map doubles
+  double* d_map = nullptr;
+  int64_t n_map = 0;
+  DeviceArena in_arena, out_arena, scratch, scratch2;
+  void* nccl_lib = nullptr;
+  // profiling (viml_profile_begin/end): event pairs per kernel id
+  bool prof = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[VIML_NUM_KERNELS];
+};
+
+enum KernelId {
+  K_PREP = 0, K_POINTS, K_LINES, K_ASSEMBLE, K_SCHUR, K_CAMPOSE, K_CULL, K_SCAN, K_FILL, K_PROJECT, K_MATCH,
+  K_MARG, K_MICRO, K_COUNT
+};
+static_assert(K_COUNT <= VIML_NUM_KERNELS, "raise VIML_NUM_KERNELS");
+
+// Brackets one kernel launch with profiling events when enabled and counts it.
+struct LaunchScope {
+  viml_ctx* ctx;
+  cudaEvent_t stop = nullptr;
+  LaunchScope(viml_ctx* c, int id) : ctx(c) {
+    ctx->launches++;
+    if (ctx->prof) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, ctx->stream);
+      ctx->prof_events[id].emplace_back(a, b);
+      stop = b;
+    }
+  }
+  ~LaunchScope() {
+    if (stop) cudaEventRecord(stop, ctx->stream);
+  }
+};
+
+// Per-pose cache written by prep_windows_kernel and read by the factor kernels (42 doubles):
+//   P[3]      position
+//   R[9]      toRotationMatrix(q)               un-normalised (projection_factor.cpp:56-57)
+//   Rinv[9]   toRotationMatrix(q.inverse())      == the map v -> Qj.inverse()*v (projection_factor.cpp:38)
+//   M[9]      ric^T * R^T                        (projection_factor.cpp:81, :93)
+//   Rl[9]     Ricn^T * Rn^T, Rn = toRotationMatrix(normalized(q))   (line_projection_factor.cpp:31-39)
+//   tl[3]     -Rl*P - Ricn^T*Tic                 (line_projection_factor.cpp:40)
+// Per-window extrinsic cache (24 doubles): tic[3], ric[9], ricinv[9], rtt[3] = ric^T*tic
+constexpr int kPoseCache = 42;
+constexpr int kExCache = 24;
+constexpr int PC_P = 0, PC_R = 3, PC_RINV = 12, PC_M = 21, PC_RL = 30, PC_TL = 39;
+constexpr int EC_TIC = 0, EC_RIC = 3, EC_RICINV = 12, EC_RTT = 21;
+
+struct LinearizeArgs {  // device pointers only
+  int W, P, F, D;
+  int64_t NP, NL;
+  const double* poses;
+  const double* ex_pose;
+  const double* inv_depth;
+  const int32_t* pf_window_offset;
+  const uint32_t* pf_idx;
+  const double* pf_obs;
+  const double* pf_pts_i_z;
+  const int32_t* lf_window_offset;
+  const int32_t* lf_frame;
+  const double* lf_geom;
+  double* cache;  // [W][P*kPoseCache + kExCache]
+  viml_linearize_out out;
+  double sqrt_info, cauchy_a, fx, fy, cx, cy;
+  uint32_t flags;
+};
+
+// linearize_kernels.cu
+int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a);
+// marg_kernels.cu
+int viml_launch_marginalize(viml_ctx* ctx, int K, int pos, int m, double eps, const double* A, const double* b,
+                            double* A_schur, double* b_schur, double* lin_jac, double* lin_res);
+
+struct AssocArgs {  // device pointers only
+  int Pq, L;
+  int64_t N;
+  const double* map;  // [6][N]
+  const double* cull_poses;
+  const double* match_poses;  // may alias cull_poses
+  const double* ex_pose;
+  const double* lines2d;
+  const int32_t* n_lines2d;  // nullable
+  int32_t* match_index;
+  float* err;
+  double* projected;
+  int32_t* fov_count;   // always valid (scratch if the caller did not ask)
+  int32_t* fov_index;   // nullable
+  int32_t fov_capacity;
+  uint32_t* fov_mask;   // always valid
+  int64_t words;        // ceil(N/32)
+};
+// associate_kernels.cu (compiled with -fmad=false)
+int viml_launch_associate(viml_ctx* ctx, const AssocArgs& a);

@@ -1,0 +1,485 @@
+// linearize_kernels.cu — residual/Jacobian evaluation of ProjectionFactor and LineProjectionFactor,
+// loss correction, J^T J / J^T r assembly and the landmark Schur complement, for batches of windows.
+//
+// Reference semantics (paths relative to /root/reference/vins_estimator/src):
+//   factor/projection_factor.cpp:21-124, factor/line_projection_factor.cpp:19-120,
+//   factor/marginalization_factor.cpp:37-68 (loss), :141-172 (ThreadsConstructA), :267-282 (Schur).
+// The arithmetic is re-organised for the GPU (shared sub-products, reciprocal instead of repeated
+// division, FMA); parity with the oracle is to 1e-9 relative, not bit-exact.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void quat_to_rot(double w, double x, double y, double z, double* R) {
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = 1.0 - (tyy + tzz);
+  R[1] = txy - twz;
+  R[2] = txz + twy;
+  R[3] = txy + twz;
+  R[4] = 1.0 - (txx + tzz);
+  R[5] = tyz - twx;
+  R[6] = txz - twy;
+  R[7] = tyz + twx;
+  R[8] = 1.0 - (txx + tyy);
+}
+
+// C = A^T * B^T  (3x3 row-major)
+__device__ __forceinline__ void mul_AtBt(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) C[3 * r + c] = A[r] * B[3 * c] + A[3 + r] * B[3 * c + 1] + A[6 + r] * B[3 * c + 2];
+}
+
+// One thread per pose (and one per window for the extrinsic): fills the cache described in common.cuh.
+__global__ void prep_windows_kernel(LinearizeArgs a) {
+  const int stride = a.P * kPoseCache + kExCache;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)a.W * (a.P + 1);
+  if (t >= total) return;
+  const int w = (int)(t / (a.P + 1)), p = (int)(t % (a.P + 1));
+  const double* ex = a.ex_pose + (size_t)w * 7;
+  double ric[9];
+  quat_to_rot(ex[6], ex[3], ex[4], ex[5], ric);
+  double* cw = a.cache + (size_t)w * stride;
+  if (p == a.P) {
+    double* ec = cw + a.P * kPoseCache;
+    const double n2 = ex[3] * ex[3] + ex[4] * ex[4] + ex[5] * ex[5] + ex[6] * ex[6];
+    double ricinv[9];
+    quat_to_rot(ex[6] / n2, -ex[3] / n2, -ex[4] / n2, -ex[5] / n2, ricinv);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ec[EC_TIC + k] = ex[k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) ec[EC_RIC + k] = ric[k], ec[EC_RICINV + k] = ricinv[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ec[EC_RTT + k] = ric[k] * ex[0] + ric[3 + k] * ex[1] + ric[6 + k] * ex[2];
+    return;
+  }
+  const double* q = a.poses + ((size_t)w * a.P + p) * 7;
+  double* pc = cw + p * kPoseCache;
+  double R[9], Rinv[9], M[9];
+  quat_to_rot(q[6], q[3], q[4], q[5], R);
+  const double n2 = q[3] * q[3] + q[4] * q[4] + q[5] * q[5] + q[6] * q[6];
+  quat_to_rot(q[6] / n2, -q[3] / n2, -q[4] / n2, -q[5] / n2, Rinv);
+  mul_AtBt(ric, R, M);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) pc[PC_P + k] = q[k];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) pc[PC_R + k] = R[k], pc[PC_RINV + k] = Rinv[k], pc[PC_M + k] = M[k];
+  // line-factor transform: normalised quaternions (line_projection_factor.cpp:31-40, estimator.cpp:1777-1781)
+  const double nq = sqrt(n2), ne = sqrt(ex[3] * ex[3] + ex[4] * ex[4] + ex[5] * ex[5] + ex[6] * ex[6]);
+  double Rn[9], ricn[9], Rl[9];
+  quat_to_rot(q[6] / nq, q[3] / nq, q[4] / nq, q[5] / nq, Rn);
+  quat_to_rot(ex[6] / ne, ex[3] / ne, ex[4] / ne, ex[5] / ne, ricn);
+  mul_AtBt(ricn, Rn, Rl);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) pc[PC_RL + k] = Rl[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double rt = Rl[3 * k] * q[0] + Rl[3 * k + 1] * q[1] + Rl[3 * k + 2] * q[2];
+    const double ct = ricn[k] * ex[0] + ricn[3 + k] * ex[1] + ricn[6 + k] * ex[2];
+    pc[PC_TL + k] = -rt - ct;
+  }
+}
+
+__device__ __forceinline__ int find_window(const int32_t* __restrict__ off, int W, int64_t k) {
+  int lo = 0, hi = W;  // off[lo] <= k < off[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= k) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ void mat3_vec(const double* __restrict__ M, double x, double y, double z, double& ox,
+                                         double& oy, double& oz) {
+  ox = M[0] * x + M[1] * y + M[2] * z;
+  oy = M[3] * x + M[4] * y + M[5] * z;
+  oz = M[6] * x + M[7] * y + M[8] * z;
+}
+
+// Local Jacobian of a ProjectionFactor: a = d r/d pose_i (2x6), b = pose_j, c = extrinsic, d = inv depth.
+struct PointJac {
+  double r[2];
+  double a[2][6], b[2][6], c[2][6], d[2];
+};
+
+__device__ __forceinline__ void eval_point(const LinearizeArgs& A, const double* __restrict__ cw, int i, int j,
+                                           double lam, double pix, double piy, double piz, double pjx, double pjy,
+                                           PointJac& J) {
+  const double* __restrict__ ci = cw + i * kPoseCache;
+  const double* __restrict__ cj = cw + j * kPoseCache;
+  const double* __restrict__ ce = cw + A.P * kPoseCache;
+  const double inv_l = 1.0 / lam;
+  const double cx_ = pix * inv_l, cy_ = piy * inv_l, cz_ = piz * inv_l;  // pts_camera_i (:35)
+  double ix, iy, iz;                                                        // pts_imu_i (:36)
+  mat3_vec(ce + EC_RIC, cx_, cy_, cz_, ix, iy, iz);
+  ix += ce[EC_TIC], iy += ce[EC_TIC + 1], iz += ce[EC_TIC + 2];
+  double wx, wy, wz;                                                        // pts_w (:37)
+  mat3_vec(ci + PC_R, ix, iy, iz, wx, wy, wz);
+  wx += ci[PC_P], wy += ci[PC_P + 1], wz += ci[PC_P + 2];
+  const double dx = wx - cj[PC_P], dy = wy - cj[PC_P + 1], dz = wz - cj[PC_P + 2];
+  double jx, jy, jz;                                                        // pts_imu_j (:38)
+  mat3_vec(cj + PC_RINV, dx, dy, dz, jx, jy, jz);
+  double qx, qy, qz;                                                        // pts_camera_j (:39)
+  mat3_vec(ce + EC_RICINV, jx - ce[EC_TIC], jy - ce[EC_TIC + 1], jz - ce[EC_TIC + 2], qx, qy, qz);
+  const double invz = 1.0 / qz;
+  const double s = A.sqrt_info;
+  double r0 = s * (qx * invz - pjx), r1 = s * (qy * invz - pjy);           // :46-49
+  double sc = 1.0;
+  if (A.flags & VIML_LOSS_CAUCHY) {                                         // marginalization_factor.cpp:37-67
+    const double cc = 1.0 / (A.cauchy_a * A.cauchy_a);
+    const double rho1 = fmax(2.2250738585072014e-308, 1.0 / (1.0 + (r0 * r0 + r1 * r1) * cc));
+    sc = sqrt(rho1);  // rho[2] < 0 always for Cauchy => residual_scaling = sqrt(rho1), alpha = 0
+  }
+  J.r[0] = sc * r0, J.r[1] = sc * r1;
+  // reduce (:72-75) scaled by sqrt_info and the loss factor
+  const double g = s * sc * invz;
+  const double red0z = -g * qx * invz, red1z = -g * qy * invz;
+  // A_ = reduce * M_j ; M_j = ric^T Rj^T
+  const double* __restrict__ M = cj + PC_M;
+  double A0[3], A1[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    A0[k] = g * M[k] + red0z * M[6 + k];
+    A1[k] = g * M[3 + k] + red1z * M[6 + k];
+  }
+  // B = A_ * Ri
+  const double* __restrict__ Ri = ci + PC_R;
+  double B0[3], B1[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    B0[k] = A0[0] * Ri[k] + A0[1] * Ri[3 + k] + A0[2] * Ri[6 + k];
+    B1[k] = A1[0] * Ri[k] + A1[1] * Ri[3 + k] + A1[2] * Ri[6 + k];
+  }
+  // C = reduce * ric^T
+  const double* __restrict__ ric = ce + EC_RIC;
+  double C0[3], C1[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    C0[k] = g * ric[3 * k] + red0z * ric[3 * k + 2];
+    C1[k] = g * ric[3 * k + 1] + red1z * ric[3 * k + 2];
+  }
+  // D = B * ric  (= reduce * ric^T Rj^T Ri ric)
+  double D0[3], D1[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    D0[k] = B0[0] * ric[k] + B0[1] * ric[3 + k] + B0[2] * ric[6 + k];
+    D1[k] = B1[0] * ric[k] + B1[1] * ric[3 + k] + B1[2] * ric[6 + k];
+  }
+  // v = ric^T (Rj^T (pts_w - Pj) - tic) = M (pts_w - Pj) - ric^T tic   (:105-106 collapsed)
+  double vx, vy, vz;
+  mat3_vec(M, dx, dy, dz, vx, vy, vz);
+  vx -= ce[EC_RTT], vy -= ce[EC_RTT + 1], vz -= ce[EC_RTT + 2];
+  // pose_i (:81-85): [A_ | B * -skew(pts_imu_i)]  ; row b: b^T(-[p]x) = (p x b)^T
+#pragma unroll
+  for (int k = 0; k < 3; ++k) J.a[0][k] = A0[k], J.a[1][k] = A1[k];
+  J.a[0][3] = iy * B0[2] - iz * B0[1], J.a[0][4] = iz * B0[0] - ix * B0[2], J.a[0][5] = ix * B0[1] - iy * B0[0];
+  J.a[1][3] = iy * B1[2] - iz * B1[1], J.a[1][4] = iz * B1[0] - ix * B1[2], J.a[1][5] = ix * B1[1] - iy * B1[0];
+  // pose_j (:93-97): [-A_ | C * skew(pts_imu_j)] ; row c: c^T [p]x = (c x p)^T.  The reference's pts_imu_j
+  // is the quaternion-rotated one (:38).
+#pragma unroll
+  for (int k = 0; k < 3; ++k) J.b[0][k] = -A0[k], J.b[1][k] = -A1[k];
+  J.b[0][3] = C0[1] * jz - C0[2] * jy, J.b[0][4] = C0[2] * jx - C0[0] * jz, J.b[0][5] = C0[0] * jy - C0[1] * jx;
+  J.b[1][3] = C1[1] * jz - C1[2] * jy, J.b[1][4] = C1[2] * jx - C1[0] * jz, J.b[1][5] = C1[0] * jy - C1[1] * jx;
+  // extrinsic (:103-108): [B - C | -D skew(pc_i) + reduce skew(v)] ; rows: pc_i x d + red x v
+#pragma unroll
+  for (int k = 0; k < 3; ++k) J.c[0][k] = B0[k] - C0[k], J.c[1][k] = B1[k] - C1[k];
+  J.c[0][3] = (cy_ * D0[2] - cz_ * D0[1]) + (0.0 * vz - red0z * vy);
+  J.c[0][4] = (cz_ * D0[0] - cx_ * D0[2]) + (red0z * vx - g * vz);
+  J.c[0][5] = (cx_ * D0[1] - cy_ * D0[0]) + (g * vy - 0.0 * vx);
+  J.c[1][3] = (cy_ * D1[2] - cz_ * D1[1]) + (g * vz - red1z * vy);
+  J.c[1][4] = (cz_ * D1[0] - cx_ * D1[2]) + (red1z * vx - 0.0 * vz);
+  J.c[1][5] = (cx_ * D1[1] - cy_ * D1[0]) + (0.0 * vy - g * vx);
+  // inverse depth (:115): reduce * T * pts_i * -1/lambda^2
+  const double nl2 = -inv_l * inv_l;
+  J.d[0] = (D0[0] * pix + D0[1] * piy + D0[2] * piz) * nl2;
+  J.d[1] = (D1[0] * pix + D1[1] * piy + D1[2] * piz) * nl2;
+}
+
+struct LineJac {
+  double r[2];
+  double a[2][6];
+};
+
+__device__ __forceinline__ void eval_line(const LinearizeArgs& A, const double* __restrict__ cw, int frame,
+                                          const double* g9, LineJac& J) {
+  const double* __restrict__ cf = cw + frame * kPoseCache;
+  const double* __restrict__ R = cf + PC_RL;
+  double sx, sy, sz, ex, ey, ez;
+  mat3_vec(R, g9[0], g9[1], g9[2], sx, sy, sz);
+  mat3_vec(R, g9[3], g9[4], g9[5], ex, ey, ez);
+  sx += cf[PC_TL], sy += cf[PC_TL + 1], sz += cf[PC_TL + 2];
+  ex += cf[PC_TL], ey += cf[PC_TL + 1], ez += cf[PC_TL + 2];
+  const double isz = 1.0 / sz, iez = 1.0 / ez;
+  // (K*pc).x/(K*pc).z = (fx*X + cx*Z)/Z                                (line_projection_factor.cpp:45-51)
+  const double us = (A.fx * sx + A.cx * sz) * isz, vs = (A.fy * sy + A.cy * sz) * isz;
+  const double ue = (A.fx * ex + A.cx * ez) * iez, ve = (A.fy * ey + A.cy * ez) * iez;
+  const double a = g9[6], b = g9[7], c = g9[8];
+  const double d = a * a + b * b, id = 1.0 / d;
+  const double mus = (b * b * us - a * b * vs - a * c) * id, mvs = (a * a * vs - a * b * us - b * c) * id;
+  const double mue = (b * b * ue - a * b * ve - a * c) * id, mve = (a * a * ve - a * b * ue - b * c) * id;
+  const double dus = mus - us, dvs = mvs - vs, due = mue - ue, dve = mve - ve;
+  double r0 = sqrt(dus * dus + dvs * dvs), r1 = sqrt(due * due + dve * dve);   // :68-69
+  double sc = 1.0;
+  if (A.flags & VIML_LOSS_CAUCHY) {
+    const double cc = 1.0 / (A.cauchy_a * A.cauchy_a);
+    sc = sqrt(fmax(2.2250738585072014e-308, 1.0 / (1.0 + (r0 * r0 + r1 * r1) * cc)));
+  }
+  J.r[0] = sc * r0, J.r[1] = sc * r1;
+  const double m2d = -2.0 * id * sc;
+  const double e1s = m2d * (dus * a * a + a * b * dvs), e2s = m2d * (dus * a * b + b * b * dvs);   // :76-80
+  const double e1e = m2d * (due * a * a + a * b * dve), e2e = m2d * (due * a * b + b * b * dve);
+  // w = e_p * d(pi)/d(pc)  (:93-100), then [I | skew(pc)] (:104-113): rot part = w x pc ... as coded:
+  // (w^T skew(pc))_c = sum_r w_r S(r,c)  with S = [[0,-z,y],[z,0,-x],[-y,x,0]]
+  {
+    const double w0 = e1s * A.fx * isz, w1 = e2s * A.fy * isz;
+    const double w2 = -(e1s * A.fx * sx + e2s * A.fy * sy) * isz * isz;
+    J.a[0][0] = w0, J.a[0][1] = w1, J.a[0][2] = w2;
+    J.a[0][3] = w1 * sz - w2 * sy;
+    J.a[0][4] = w2 * sx - w0 * sz;
+    J.a[0][5] = w0 * sy - w1 * sx;
+  }
+  {
+    const double w0 = e1e * A.fx * iez, w1 = e2e * A.fy * iez;
+    const double w2 = -(e1e * A.fx * ex + e2e * A.fy * ey) * iez * iez;
+    J.a[1][0] = w0, J.a[1][1] = w1, J.a[1][2] = w2;
+    J.a[1][3] = w1 * ez - w2 * ey;
+    J.a[1][4] = w2 * ex - w0 * ez;
+    J.a[1][5] = w0 * ey - w1 * ex;
+  }
+}
+
+__device__ __forceinline__ void store_jac7(double* __restrict__ dst, const double (*J)[6]) {
+  // row-major 2x7, column 6 zero; 112 B = 7 x 16 B, 16-byte aligned
+  double2* d2 = reinterpret_cast<double2*>(dst);
+  d2[0] = make_double2(J[0][0], J[0][1]);
+  d2[1] = make_double2(J[0][2], J[0][3]);
+  d2[2] = make_double2(J[0][4], J[0][5]);
+  d2[3] = make_double2(0.0, J[1][0]);
+  d2[4] = make_double2(J[1][1], J[1][2]);
+  d2[5] = make_double2(J[1][3], J[1][4]);
+  d2[6] = make_double2(J[1][5], 0.0);
+}
+
+// H(rows r0.., cols c0..) += X^T Y and its mirror, X,Y 2x6, via global atomics (generic path: used for
+// windows too large for the shared-memory assembly kernel and as the simple reference device path).
+__device__ __forceinline__ void atomic_block(double* __restrict__ H, int D, int r0, int c0, const double (*X)[6],
+                                             const double (*Y)[6], bool diag) {
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const double v = X[0][r] * Y[0][c] + X[1][r] * Y[1][c];
+      atomicAdd(H + (size_t)(r0 + r) * D + c0 + c, v);
+      if (!diag) atomicAdd(H + (size_t)(c0 + c) * D + r0 + r, v);
+    }
+}
+
+template <bool MODE_A, bool MODE_B>
+__global__ void __launch_bounds__(128) points_kernel(LinearizeArgs A) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= A.NP) return;
+  const int w = find_window(A.pf_window_offset, A.W, k);
+  const uint32_t pk = A.pf_idx[k];
+  const int i = pk & 0xff, j = (pk >> 8) & 0xff, f = pk >> 16;
+  const double4 ob = reinterpret_cast<const double4*>(A.pf_obs)[k];
+  const double piz = A.pf_pts_i_z ? A.pf_pts_i_z[k] : 1.0;
+  const double lam = A.inv_depth[(size_t)w * A.F + f];
+  const double* cw = A.cache + (size_t)w * (A.P * kPoseCache + kExCache);
+  PointJac J;
+  eval_point(A, cw, i, j, lam, ob.x, ob.y, piz, ob.z, ob.w, J);
+  if (MODE_A) {
+    if (A.out.pf_residual) reinterpret_cast<double2*>(A.out.pf_residual)[k] = make_double2(J.r[0], J.r[1]);
+    if (A.out.pf_jac_pose_i) store_jac7(A.out.pf_jac_pose_i + 14 * k, J.a);
+    if (A.out.pf_jac_pose_j) store_jac7(A.out.pf_jac_pose_j + 14 * k, J.b);
+    if (A.out.pf_jac_ex) store_jac7(A.out.pf_jac_ex + 14 * k, J.c);
+    if (A.out.pf_jac_feat) reinterpret_cast<double2*>(A.out.pf_jac_feat)[k] = make_double2(J.d[0], J.d[1]);
+  }
+  if (MODE_B) {
+    const int D = A.D;
+    double* H = A.out.H_pp + (size_t)w * D * D;
+    double* bp = A.out.b_p + (size_t)w * D;
+    double* Hl = A.out.H_lp + ((size_t)w * A.F + f) * D;
+    const int oi = 6 * i, oj = 6 * j, oe = 6 * A.P;
+    atomic_block(H, D, oi, oi, J.a, J.a, true);
+    atomic_block(H, D, oi, oj, J.a, J.b, false);
+    atomic_block(H, D, oi, oe, J.a, J.c, false);
+    atomic_block(H, D, oj, oj, J.b, J.b, true);
+    atomic_block(H, D, oj, oe, J.b, J.c, false);
+    atomic_block(H, D, oe, oe, J.c, J.c, true);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      atomicAdd(bp + oi + r, J.a[0][r] * J.r[0] + J.a[1][r] * J.r[1]);
+      atomicAdd(bp + oj + r, J.b[0][r] * J.r[0] + J.b[1][r] * J.r[1]);
+      atomicAdd(bp + oe + r, J.c[0][r] * J.r[0] + J.c[1][r] * J.r[1]);
+      atomicAdd(Hl + oi + r, J.a[0][r] * J.d[0] + J.a[1][r] * J.d[1]);
+      atomicAdd(Hl + oj + r, J.b[0][r] * J.d[0] + J.b[1][r] * J.d[1]);
+      atomicAdd(Hl + oe + r, J.c[0][r] * J.d[0] + J.c[1][r] * J.d[1]);
+    }
+    atomicAdd(A.out.H_ll + (size_t)w * A.F + f, J.d[0] * J.d[0] + J.d[1] * J.d[1]);
+    atomicAdd(A.out.b_l + (size_t)w * A.F + f, J.d[0] * J.r[0] + J.d[1] * J.r[1]);
+  }
+}
+
+template <bool MODE_A, bool MODE_B>
+__global__ void __launch_bounds__(128) lines_kernel(LinearizeArgs A) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= A.NL) return;
+  const int w = find_window(A.lf_window_offset, A.W, k);
+  const int frame = A.lf_frame[k];
+  double g9[9];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) g9[c] = A.lf_geom[(size_t)c * A.NL + k];
+  const double* cw = A.cache + (size_t)w * (A.P * kPoseCache + kExCache);
+  LineJac J;
+  eval_line(A, cw, frame, g9, J);
+  if (MODE_A) {
+    if (A.out.lf_residual) reinterpret_cast<double2*>(A.out.lf_residual)[k] = make_double2(J.r[0], J.r[1]);
+    if (A.out.lf_jac_pose) store_jac7(A.out.lf_jac_pose + 14 * k, J.a);
+  }
+  if (MODE_B) {
+    const int D = A.D;
+    double* H = A.out.H_pp + (size_t)w * D * D;
+    double* bp = A.out.b_p + (size_t)w * D;
+    const int of = 6 * frame;
+    atomic_block(H, D, of, of, J.a, J.a, true);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) atomicAdd(bp + of + r, J.a[0][r] * J.r[0] + J.a[1][r] * J.r[1]);
+  }
+}
+
+// Landmark Schur complement, simple version: one CTA per window, threads own entries of S.
+//   S = H_pp - sum_l W_l^T W_l / L_l,  g = b_p - sum_l W_l^T b_l / L_l,  L_l <= eps skipped.
+constexpr int kSchurTile = 32;
+__global__ void __launch_bounds__(256) schur_kernel(int F, int D, const double* __restrict__ H_pp,
+                                                    const double* __restrict__ H_lp, const double* __restrict__ H_ll,
+                                                    const double* __restrict__ b_p, const double* __restrict__ b_l,
+                                                    double* __restrict__ S, double* __restrict__ g, double eps) {
+  extern __shared__ double sm[];
+  double* Wt = sm;                       // [kSchurTile][D]
+  double* sc = sm + kSchurTile * D;      // [kSchurTile] 1/L or 0
+  double* sb = sc + kSchurTile;          // [kSchurTile] b_l
+  const int w = blockIdx.x;
+  const double* Hl = H_lp + (size_t)w * F * D;
+  const int nE = D * D + D;  // entries of S plus g
+  // each thread accumulates entries e = tid, tid+256, ... in registers (up to 24 for D=72)
+  constexpr int kMaxPer = 24;
+  double acc[kMaxPer];
+  const int per = (nE + blockDim.x - 1) / blockDim.x;
+  for (int q = 0; q < kMaxPer; ++q) acc[q] = 0.0;
+  for (int l0 = 0; l0 < F; l0 += kSchurTile) {
+    const int nl = min(kSchurTile, F - l0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nl * D; e += blockDim.x) Wt[e] = Hl[(size_t)l0 * D + e];
+    if (threadIdx.x < nl) {
+      const double L = H_ll[(size_t)w * F + l0 + threadIdx.x];
+      sc[threadIdx.x] = (L > eps) ? 1.0 / L : 0.0;
+      sb[threadIdx.x] = b_l[(size_t)w * F + l0 + threadIdx.x];
+    }
+    __syncthreads();
+    for (int q = 0; q < per && q < kMaxPer; ++q) {
+      const int e = threadIdx.x + q * blockDim.x;
+      if (e >= nE) break;
+      double s = 0.0;
+      if (e < D * D) {
+        const int r = e / D, c = e % D;
+        for (int l = 0; l < nl; ++l) s += Wt[l * D + r] * sc[l] * Wt[l * D + c];
+      } else {
+        const int r = e - D * D;
+        for (int l = 0; l < nl; ++l) s += Wt[l * D + r] * sc[l] * sb[l];
+      }
+      acc[q] += s;
+    }
+  }
+  for (int q = 0; q < per && q < kMaxPer; ++q) {
+    const int e = threadIdx.x + q * blockDim.x;
+    if (e >= nE) break;
+    if (e < D * D)
+      S[(size_t)w * D * D + e] = H_pp[(size_t)w * D * D + e] - acc[q];
+    else
+      g[(size_t)w * D + (e - D * D)] = b_p[(size_t)w * D + (e - D * D)] - acc[q];
+  }
+}
+
+// Generic Schur for large D (entries strided over the grid, no register cache).
+__global__ void schur_generic_kernel(int F, int D, const double* __restrict__ H_pp, const double* __restrict__ H_lp,
+                                     const double* __restrict__ H_ll, const double* __restrict__ b_p,
+                                     const double* __restrict__ b_l, double* __restrict__ S, double* __restrict__ g,
+                                     double eps) {
+  const int w = blockIdx.y;
+  const int64_t nE = (int64_t)D * D + D;
+  const double* Hl = H_lp + (size_t)w * F * D;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nE; e += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    if (e < (int64_t)D * D) {
+      const int r = (int)(e / D), c = (int)(e % D);
+      for (int l = 0; l < F; ++l) {
+        const double L = H_ll[(size_t)w * F + l];
+        const double wr = Hl[(size_t)l * D + r];
+        if (L > eps && wr != 0.0) s += wr * (1.0 / L) * Hl[(size_t)l * D + c];
+      }
+      S[(size_t)w * D * D + e] = H_pp[(size_t)w * D * D + e] - s;
+    } else {
+      const int r = (int)(e - (int64_t)D * D);
+      for (int l = 0; l < F; ++l) {
+        const double L = H_ll[(size_t)w * F + l];
+        if (L > eps) s += Hl[(size_t)l * D + r] * (1.0 / L) * b_l[(size_t)w * F + l];
+      }
+      g[(size_t)w * D + r] = b_p[(size_t)w * D + r] - s;
+    }
+  }
+}
+
+}  // namespace
+
+int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
+  cudaStream_t st = ctx->stream;
+  const bool modeA = (a.flags & VIML_OUT_RESIDUAL_JACOBIAN) != 0;
+  const bool modeB = (a.flags & (VIML_OUT_HB | VIML_OUT_SCHUR)) != 0;
+  {
+    const int64_t total = (int64_t)a.W * (a.P + 1);
+    LaunchScope ls(ctx, K_PREP);
+    prep_windows_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a);
+  }
+  if (modeB) {
+    const size_t W = a.W, D = a.D, F = a.F;
+    VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.H_pp, 0, W * D * D * sizeof(double), st));
+    VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.H_lp, 0, W * F * D * sizeof(double), st));
+    VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.H_ll, 0, W * F * sizeof(double), st));
+    VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.b_p, 0, W * D * sizeof(double), st));
+    VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.b_l, 0, W * F * sizeof(double), st));
+  }
+  if (a.NP > 0) {
+    const unsigned grid = (unsigned)((a.NP + 127) / 128);
+    LaunchScope ls(ctx, K_POINTS);
+    if (modeA && modeB) points_kernel<true, true><<<grid, 128, 0, st>>>(a);
+    else if (modeA) points_kernel<true, false><<<grid, 128, 0, st>>>(a);
+    else if (modeB) points_kernel<false, true><<<grid, 128, 0, st>>>(a);
+  }
+  if (a.NL > 0) {
+    const unsigned grid = (unsigned)((a.NL + 127) / 128);
+    LaunchScope ls(ctx, K_LINES);
+    if (modeA && modeB) lines_kernel<true, true><<<grid, 128, 0, st>>>(a);
+    else if (modeA) lines_kernel<true, false><<<grid, 128, 0, st>>>(a);
+    else if (modeB) lines_kernel<false, true><<<grid, 128, 0, st>>>(a);
+  }
+  if (a.flags & VIML_OUT_SCHUR) {
+    const double eps = 1e-8;  // MarginalizationInfo::eps (marginalization_factor.h:70)
+    LaunchScope ls(ctx, K_SCHUR);
+    if ((a.D * a.D + a.D + 255) / 256 <= 24) {
+      const size_t smem = (size_t)(kSchurTile * a.D + 2 * kSchurTile) * sizeof(double);
+      schur_kernel<<<a.W, 256, smem, st>>>(a.F, a.D, a.out.H_pp, a.out.H_lp, a.out.H_ll, a.out.b_p, a.out.b_l,
+                                           a.out.S, a.out.g, eps);
+    } else {
+      dim3 grid(296, a.W);
+      schur_generic_kernel<<<grid, 256, 0, st>>>(a.F, a.D, a.out.H_pp, a.out.H_lp, a.out.H_ll, a.out.b_p, a.out.b_l,
+                                                 a.out.S, a.out.g, eps);
+    }
+  }
+  VIML_TRY_CUDA(ctx, cudaGetLastError());
+  return VIML_OK;
+}

@@ -1,0 +1,451 @@
+// viml_api.cu — the C-ABI of include/viml.h: context lifetime, host<->device staging, entry points.
+// No CPU fallback anywhere: every compute path ends in a kernel launch on the context's device.
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// c* = min{ c in [0,1] : acos(c) <= angle_th } with the host libm (the reference's acos, estimator.cpp:608).
+double cos_threshold(double angle_th) {
+  if (!(std::acos(1.0) <= angle_th)) return INFINITY;
+  if (std::acos(0.0) <= angle_th) return 0.0;
+  uint64_t lo, hi;
+  double dlo = 0.0, dhi = 1.0;
+  std::memcpy(&lo, &dlo, 8);
+  std::memcpy(&hi, &dhi, 8);
+  while (hi - lo > 1) {
+    const uint64_t mid = lo + (hi - lo) / 2;
+    double dm;
+    std::memcpy(&dm, &mid, 8);
+    if (std::acos(dm) <= angle_th) hi = mid; else lo = mid;
+  }
+  double r;
+  std::memcpy(&r, &hi, 8);
+  return r;
+}
+
+int fail(viml_ctx* ctx, int code, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+}  // namespace
+
+static void drop_prof_events(viml_ctx* ctx) {
+  for (auto& v : ctx->prof_events) {
+    for (auto& pr : v) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    v.clear();
+  }
+}
+
+extern "C" {
+
+int viml_abi_version(void) { return VIML_ABI_VERSION; }
+
+int viml_create(viml_ctx** out, const viml_config* cfg, int device) {
+  if (!out || !cfg) return VIML_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return VIML_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return VIML_ERR_NO_DEVICE;
+  if (prop.major != 10) return VIML_ERR_NO_DEVICE;  // the library only carries sm_100a code
+  if (cudaSetDevice(device) != cudaSuccess) return VIML_ERR_NO_DEVICE;
+  viml_ctx* ctx = new viml_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cfg = *cfg;
+  ctx->cos_th = cos_threshold(cfg->angle_th);
+  ctx->nan_angle_passes = !(3.1415926 > cfg->angle_th);
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming) != cudaSuccess) {
+    delete ctx;
+    return VIML_ERR_CUDA;
+  }
+  *out = ctx;
+  return VIML_OK;
+}
+
+void viml_destroy(viml_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  drop_prof_events(ctx);
+  ctx->in_arena.release();
+  ctx->out_arena.release();
+  ctx->scratch.release();
+  ctx->scratch2.release();
+  if (ctx->d_map) cudaFree(ctx->d_map);
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->nccl_lib) dlclose(ctx->nccl_lib);
+  delete ctx;
+}
+
+const char* viml_last_error(const viml_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int viml_sync(viml_ctx* ctx) {
+  if (!ctx) return VIML_ERR_INVALID;
+  VIML_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VIML_OK;
+}
+
+void* viml_stream(viml_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int viml_host_alloc(void** p, size_t bytes) {
+  if (!p) return VIML_ERR_INVALID;
+  return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? VIML_OK : VIML_ERR_CUDA;
+}
+int viml_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? VIML_OK : VIML_ERR_CUDA; }
+
+int viml_device_alloc(viml_ctx* ctx, void** p, size_t bytes) {
+  if (!ctx || !p) return VIML_ERR_INVALID;
+  VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+  VIML_TRY_CUDA(ctx, cudaMalloc(p, bytes));
+  return VIML_OK;
+}
+int viml_device_free(viml_ctx* ctx, void* p) {
+  if (!ctx) return VIML_ERR_INVALID;
+  VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+  VIML_TRY_CUDA(ctx, cudaFree(p));
+  return VIML_OK;
+}
+int viml_memcpy_h2d(viml_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx) return VIML_ERR_INVALID;
+  VIML_TRY_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return VIML_OK;
+}
+int viml_memcpy_d2h(viml_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx) return VIML_ERR_INVALID;
+  VIML_TRY_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return VIML_OK;
+}
+
+int64_t viml_kernel_launches(const viml_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+
+int viml_profile_begin(viml_ctx* ctx) {
+  if (!ctx) return VIML_ERR_INVALID;
+  VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+  drop_prof_events(ctx);
+  ctx->prof = true;
+  return VIML_OK;
+}
+
+int viml_profile_end(viml_ctx* ctx, double* ms, int64_t* n) {
+  if (!ctx) return VIML_ERR_INVALID;
+  ctx->prof = false;
+  VIML_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < VIML_NUM_KERNELS; ++k) {
+    double tot = 0.0;
+    for (auto& pr : ctx->prof_events[k]) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) tot += t;
+    }
+    if (ms) ms[k] = tot;
+    if (n) n[k] = (int64_t)ctx->prof_events[k].size();
+  }
+  drop_prof_events(ctx);
+  return VIML_OK;
+}
+
+const char* viml_kernel_name(int id) {
+  static const char* names[VIML_NUM_KERNELS] = {"prep_windows", "linearize_points", "linearize_lines", "assemble_hb",
+                                                "schur_landmarks", "assoc_cam_pose", "assoc_cull", "assoc_scan",
+                                                "assoc_fill_list", "assoc_project", "assoc_match", "marginalize_dense",
+                                                "microbench", "", "", ""};
+  return (id >= 0 && id < VIML_NUM_KERNELS) ? names[id] : "";
+}
+
+// ---- map -------------------------------------------------------------------------------------
+int viml_set_map(viml_ctx* ctx, const double* lines, int64_t n) {
+  if (!ctx || n < 0 || (n > 0 && !lines)) return VIML_ERR_INVALID;
+  VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+  VIML_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_map) cudaFree(ctx->d_map);
+  ctx->d_map = nullptr;
+  ctx->n_map = 0;
+  if (n == 0) return VIML_OK;
+  // AoS rows [sx sy sz ex ey ez] (parameters.cpp:50-59) -> six SoA planes
+  std::vector<double> soa((size_t)6 * n);
+  for (int64_t j = 0; j < n; ++j)
+    for (int c = 0; c < 6; ++c) soa[(size_t)c * n + j] = lines[6 * j + c];
+  VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_map, soa.size() * sizeof(double)));
+  VIML_TRY_CUDA(ctx, cudaMemcpy(ctx->d_map, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->n_map = n;
+  return VIML_OK;
+}
+
+// ---- linearisation -----------------------------------------------------------------------------
+int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_linearize_out* out, uint32_t flags) {
+  if (!ctx) return VIML_ERR_INVALID;
+  if (!in || !out) return fail(ctx, VIML_ERR_INVALID, "null batch or output struct");
+  const int W = in->n_windows, P = in->poses_per_window, F = in->feats_per_window;
+  const int64_t NP = in->n_point_factors, NL = in->n_line_factors;
+  if (W < 0 || P < 1 || P > 255 || F < 0 || F > 65535 || NP < 0 || NL < 0)
+    return fail(ctx, VIML_ERR_INVALID, "window batch sizes out of range");
+  if (!(flags & (VIML_OUT_RESIDUAL_JACOBIAN | VIML_OUT_HB | VIML_OUT_SCHUR)))
+    return fail(ctx, VIML_ERR_INVALID, "no output mode requested");
+  if (W == 0) return VIML_OK;
+  if (!in->poses || !in->ex_pose || (F > 0 && !in->inv_depth) || !in->pf_window_offset ||
+      (NP > 0 && (!in->pf_idx || !in->pf_obs)) || (NL > 0 && (!in->lf_window_offset || !in->lf_frame || !in->lf_geom)))
+    return fail(ctx, VIML_ERR_INVALID, "null input array");
+  const int D = 6 * (P + 1);
+  const bool dev = (flags & VIML_PTRS_DEVICE) != 0;
+  const bool wantA = (flags & VIML_OUT_RESIDUAL_JACOBIAN) != 0;
+  const bool wantHB = (flags & VIML_OUT_HB) != 0, wantS = (flags & VIML_OUT_SCHUR) != 0;
+  if (wantHB && !(out->H_pp && out->H_lp && out->H_ll && out->b_p && out->b_l))
+    return fail(ctx, VIML_ERR_INVALID, "VIML_OUT_HB needs H_pp, H_lp, H_ll, b_p and b_l");
+  if (wantS && !(out->S && out->g)) return fail(ctx, VIML_ERR_INVALID, "VIML_OUT_SCHUR needs S and g");
+  VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+
+  LinearizeArgs a{};
+  a.W = W, a.P = P, a.F = F, a.D = D, a.NP = NP, a.NL = NL;
+  a.sqrt_info = ctx->cfg.sqrt_info, a.cauchy_a = ctx->cfg.cauchy_a;
+  a.fx = ctx->cfg.fx, a.fy = ctx->cfg.fy, a.cx = ctx->cfg.cx, a.cy = ctx->cfg.cy;
+  a.flags = flags;
+
+  const size_t n_pose = (size_t)W * P * 7, n_ex = (size_t)W * 7, n_dep = (size_t)W * F;
+  const size_t szHpp = (size_t)W * D * D, szHlp = (size_t)W * F * D, szF = (size_t)W * F, szD = (size_t)W * D;
+  // scratch: pose cache (+ H blocks when only the Schur complement is wanted)
+  size_t scratch_bytes = DeviceArena::padded((size_t)W * (P * kPoseCache + kExCache) * sizeof(double));
+  const bool scratchH = wantS && (!wantHB || !dev);
+  if (scratchH && dev)
+    scratch_bytes += DeviceArena::padded(szHpp * 8) + DeviceArena::padded(szHlp * 8) + 2 * DeviceArena::padded(szF * 8) +
+                     DeviceArena::padded(szD * 8);
+  VIML_TRY_CUDA(ctx, ctx->scratch.reserve(scratch_bytes));
+  a.cache = ctx->scratch.take<double>((size_t)W * (P * kPoseCache + kExCache));
+
+  if (dev) {
+    a.poses = in->poses, a.ex_pose = in->ex_pose, a.inv_depth = in->inv_depth;
+    a.pf_window_offset = in->pf_window_offset, a.pf_idx = in->pf_idx, a.pf_obs = in->pf_obs;
+    a.pf_pts_i_z = in->pf_pts_i_z;
+    a.lf_window_offset = in->lf_window_offset, a.lf_frame = in->lf_frame, a.lf_geom = in->lf_geom;
+    a.out = *out;
+    if (!wantA) a.out.pf_residual = a.out.pf_jac_pose_i = a.out.pf_jac_pose_j = a.out.pf_jac_ex = a.out.pf_jac_feat =
+                    a.out.lf_residual = a.out.lf_jac_pose = nullptr;
+    if (wantS && !wantHB) {
+      a.out.H_pp = ctx->scratch.take<double>(szHpp);
+      a.out.H_lp = ctx->scratch.take<double>(szHlp);
+      a.out.H_ll = ctx->scratch.take<double>(szF);
+      a.out.b_l = ctx->scratch.take<double>(szF);
+      a.out.b_p = ctx->scratch.take<double>(szD);
+    }
+    return viml_launch_linearize(ctx, a);
+  }
+
+  // ---- host pointers: stage in, run, stage out, synchronise ----
+  size_t in_bytes = 0;
+  auto pad = [](size_t b) { return DeviceArena::padded(b); };
+  in_bytes += pad(n_pose * 8) + pad(n_ex * 8) + pad(n_dep * 8) + 2 * pad((size_t)(W + 1) * 4);
+  in_bytes += pad((size_t)NP * 4) + pad((size_t)NP * 32) + pad((size_t)NP * 8);
+  in_bytes += pad((size_t)NL * 4) + pad((size_t)NL * 72);
+  VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(in_bytes));
+  auto up = [&](const void* src, size_t bytes) -> void* {
+    char* d = ctx->in_arena.take<char>(bytes);
+    if (bytes) cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st);
+    return d;
+  };
+  a.poses = (const double*)up(in->poses, n_pose * 8);
+  a.ex_pose = (const double*)up(in->ex_pose, n_ex * 8);
+  a.inv_depth = (const double*)up(in->inv_depth, n_dep * 8);
+  a.pf_window_offset = (const int32_t*)up(in->pf_window_offset, (size_t)(W + 1) * 4);
+  a.pf_idx = (const uint32_t*)up(in->pf_idx, (size_t)NP * 4);
+  a.pf_obs = (const double*)up(in->pf_obs, (size_t)NP * 32);
+  a.pf_pts_i_z = in->pf_pts_i_z ? (const double*)up(in->pf_pts_i_z, (size_t)NP * 8) : nullptr;
+  if (NL > 0) {
+    a.lf_window_offset = (const int32_t*)up(in->lf_window_offset, (size_t)(W + 1) * 4);
+    a.lf_frame = (const int32_t*)up(in->lf_frame, (size_t)NL * 4);
+    a.lf_geom = (const double*)up(in->lf_geom, (size_t)NL * 72);
+  }
+  VIML_TRY_CUDA(ctx, cudaGetLastError());
+
+  struct Slot { double** dev; double* host; size_t count; };
+  std::vector<Slot> slots;
+  size_t out_bytes = 0;
+  auto want = [&](double** dslot, double* host, size_t count, bool force) {
+    if (host || force) {
+      slots.push_back({dslot, host, count});
+      out_bytes += pad(count * 8);
+    }
+  };
+  const bool needH = wantHB || wantS;
+  if (wantA) {
+    want(&a.out.pf_residual, out->pf_residual, (size_t)NP * 2, false);
+    want(&a.out.pf_jac_pose_i, out->pf_jac_pose_i, (size_t)NP * 14, false);
+    want(&a.out.pf_jac_pose_j, out->pf_jac_pose_j, (size_t)NP * 14, false);
+    want(&a.out.pf_jac_ex, out->pf_jac_ex, (size_t)NP * 14, false);
+    want(&a.out.pf_jac_feat, out->pf_jac_feat, (size_t)NP * 2, false);
+    want(&a.out.lf_residual, out->lf_residual, (size_t)NL * 2, false);
+    want(&a.out.lf_jac_pose, out->lf_jac_pose, (size_t)NL * 14, false);
+  }
+  if (needH) {
+    want(&a.out.H_pp, wantHB ? out->H_pp : nullptr, szHpp, true);
+    want(&a.out.H_lp, wantHB ? out->H_lp : nullptr, szHlp, true);
+    want(&a.out.H_ll, wantHB ? out->H_ll : nullptr, szF, true);
+    want(&a.out.b_p, wantHB ? out->b_p : nullptr, szD, true);
+    want(&a.out.b_l, wantHB ? out->b_l : nullptr, szF, true);
+  }
+  if (wantS) {
+    want(&a.out.S, out->S, szHpp, true);
+    want(&a.out.g, out->g, szD, true);
+  }
+  VIML_TRY_CUDA(ctx, ctx->out_arena.reserve(out_bytes));
+  for (auto& s : slots) *s.dev = ctx->out_arena.take<double>(s.count);
+  int rc = viml_launch_linearize(ctx, a);
+  if (rc != VIML_OK) return rc;
+  for (auto& s : slots)
+    if (s.host && s.count)
+      VIML_TRY_CUDA(ctx, cudaMemcpyAsync(s.host, *s.dev, s.count * 8, cudaMemcpyDeviceToHost, st));
+  VIML_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+  return VIML_OK;
+}
+
+// ---- dense marginalisation -----------------------------------------------------------------------
+int viml_marginalize_batch(viml_ctx* ctx, const viml_marg_batch* in, const viml_marg_out* out, uint32_t flags) {
+  if (!ctx) return VIML_ERR_INVALID;
+  if (!in || !out) return fail(ctx, VIML_ERR_INVALID, "null marg batch");
+  const int K = in->n_problems, pos = in->pos, m = in->m, n = pos - m;
+  if (K < 0 || pos < 1 || pos > 256 || m < 0 || n < 1 || !in->A || !in->b)
+    return fail(ctx, VIML_ERR_INVALID, "marg batch sizes out of range (pos <= 256, n >= 1)");
+  if (K == 0) return VIML_OK;
+  VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (flags & VIML_PTRS_DEVICE)
+    return viml_launch_marginalize(ctx, K, pos, m, in->eps, in->A, in->b, out->A_schur, out->b_schur,
+                                   out->linearized_jacobians, out->linearized_residuals);
+  const size_t szA = (size_t)K * pos * pos, szb = (size_t)K * pos, szS = (size_t)K * n * n, szs = (size_t)K * n;
+  auto pad = [](size_t b) { return DeviceArena::padded(b); };
+  VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(pad(szA * 8) + pad(szb * 8)));
+  double* dA = ctx->in_arena.take<double>(szA);
+  double* db = ctx->in_arena.take<double>(szb);
+  VIML_TRY_CUDA(ctx, cudaMemcpyAsync(dA, in->A, szA * 8, cudaMemcpyHostToDevice, st));
+  VIML_TRY_CUDA(ctx, cudaMemcpyAsync(db, in->b, szb * 8, cudaMemcpyHostToDevice, st));
+  VIML_TRY_CUDA(ctx, ctx->out_arena.reserve(2 * pad(szS * 8) + 2 * pad(szs * 8)));
+  double* dS = ctx->out_arena.take<double>(szS);
+  double* ds = ctx->out_arena.take<double>(szs);
+  double* dJ = ctx->out_arena.take<double>(szS);
+  double* dr = ctx->out_arena.take<double>(szs);
+  const bool lin = out->linearized_jacobians || out->linearized_residuals;
+  int rc = viml_launch_marginalize(ctx, K, pos, m, in->eps, dA, db, dS, ds, lin ? dJ : nullptr, lin ? dr : nullptr);
+  if (rc != VIML_OK) return rc;
+  if (out->A_schur) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(out->A_schur, dS, szS * 8, cudaMemcpyDeviceToHost, st));
+  if (out->b_schur) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(out->b_schur, ds, szs * 8, cudaMemcpyDeviceToHost, st));
+  if (out->linearized_jacobians)
+    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(out->linearized_jacobians, dJ, szS * 8, cudaMemcpyDeviceToHost, st));
+  if (out->linearized_residuals)
+    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(out->linearized_residuals, dr, szs * 8, cudaMemcpyDeviceToHost, st));
+  VIML_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+  return VIML_OK;
+}
+
+// ---- association -----------------------------------------------------------------------------------
+int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_assoc_out* out, uint32_t flags) {
+  if (!ctx) return VIML_ERR_INVALID;
+  if (!q || !out) return fail(ctx, VIML_ERR_INVALID, "null query or output struct");
+  if (!ctx->d_map && ctx->n_map == 0 && !(flags & 0x80000000u)) {
+    // an empty map is legal (every query is unmatched) but it must have been set
+  }
+  const int Pq = q->n_poses, L = q->lines_per_pose;
+  if (Pq < 0 || L < 0 || !q->cull_poses || !q->ex_pose || (L > 0 && !q->lines2d))
+    return fail(ctx, VIML_ERR_INVALID, "bad association query");
+  if (Pq == 0) return VIML_OK;
+  VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int64_t N = ctx->n_map, words = (N + 31) / 32;
+  const bool dev = (flags & VIML_PTRS_DEVICE) != 0;
+  AssocArgs a{};
+  a.Pq = Pq, a.L = L, a.N = N, a.map = ctx->d_map, a.words = words;
+  a.fov_capacity = out->fov_index ? out->fov_capacity : 0;
+  auto pad = [](size_t b) { return DeviceArena::padded(b); };
+  const size_t nq = (size_t)Pq * L;
+  if (dev) {
+    size_t sb = 0;
+    if (!out->fov_mask) sb += pad((size_t)Pq * words * 4);
+    if (!out->fov_count) sb += pad((size_t)Pq * 4);
+    VIML_TRY_CUDA(ctx, ctx->out_arena.reserve(sb));
+    a.cull_poses = q->cull_poses, a.match_poses = q->match_poses ? q->match_poses : q->cull_poses;
+    a.ex_pose = q->ex_pose, a.lines2d = q->lines2d, a.n_lines2d = q->n_lines2d;
+    a.match_index = out->match_index, a.err = out->err, a.projected = out->projected;
+    a.fov_index = out->fov_index;
+    a.fov_mask = out->fov_mask ? out->fov_mask : ctx->out_arena.take<uint32_t>((size_t)Pq * words);
+    a.fov_count = out->fov_count ? out->fov_count : ctx->out_arena.take<int32_t>(Pq);
+    return viml_launch_associate(ctx, a);
+  }
+  VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(3 * pad((size_t)Pq * 56) + pad(nq * 32) + pad((size_t)Pq * 4)));
+  auto up = [&](const void* src, size_t bytes) -> void* {
+    char* d = ctx->in_arena.take<char>(bytes);
+    if (bytes) cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st);
+    return d;
+  };
+  a.cull_poses = (const double*)up(q->cull_poses, (size_t)Pq * 56);
+  a.match_poses = q->match_poses ? (const double*)up(q->match_poses, (size_t)Pq * 56) : a.cull_poses;
+  a.ex_pose = (const double*)up(q->ex_pose, (size_t)Pq * 56);
+  a.lines2d = (const double*)up(q->lines2d, nq * 32);
+  a.n_lines2d = q->n_lines2d ? (const int32_t*)up(q->n_lines2d, (size_t)Pq * 4) : nullptr;
+  VIML_TRY_CUDA(ctx, cudaGetLastError());
+  const size_t cap = a.fov_capacity;
+  VIML_TRY_CUDA(ctx, ctx->out_arena.reserve(pad(nq * 4) + pad(nq * 12) + pad(nq * 32) + pad((size_t)Pq * 4) +
+                                            pad((size_t)Pq * cap * 4) + pad((size_t)Pq * words * 4)));
+  a.match_index = ctx->out_arena.take<int32_t>(nq);
+  a.err = ctx->out_arena.take<float>(nq * 3);
+  a.projected = ctx->out_arena.take<double>(nq * 4);
+  a.fov_count = ctx->out_arena.take<int32_t>(Pq);
+  a.fov_index = cap ? ctx->out_arena.take<int32_t>((size_t)Pq * cap) : nullptr;
+  a.fov_mask = ctx->out_arena.take<uint32_t>((size_t)Pq * words);
+  if (out->projected)  // unmatched entries keep the caller's content
+    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.projected, out->projected, nq * 32, cudaMemcpyHostToDevice, st));
+  int rc = viml_launch_associate(ctx, a);
+  if (rc != VIML_OK) return rc;
+  auto down = [&](void* host, const void* d, size_t bytes) {
+    if (host && bytes) cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, st);
+  };
+  down(out->match_index, a.match_index, nq * 4);
+  down(out->err, a.err, nq * 12);
+  down(out->projected, a.projected, nq * 32);
+  down(out->fov_count, a.fov_count, (size_t)Pq * 4);
+  down(out->fov_index, a.fov_index, (size_t)Pq * cap * 4);
+  down(out->fov_mask, a.fov_mask, (size_t)Pq * words * 4);
+  VIML_TRY_CUDA(ctx, cudaGetLastError());
+  VIML_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+  return VIML_OK;
+}
+
+// ---- multi-GPU: partial H/b all-reduce for the single huge window ----------------------------------
+int viml_allreduce_hb(viml_ctx* ctx, void* nccl_comm, double* buf, int64_t count) {
+  if (!ctx) return VIML_ERR_INVALID;
+  if (!nccl_comm || !buf || count < 0) return fail(ctx, VIML_ERR_INVALID, "bad all-reduce arguments");
+  if (!ctx->nccl_lib) {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nme : names) {
+      ctx->nccl_lib = dlopen(nme, RTLD_NOW | RTLD_GLOBAL);
+      if (ctx->nccl_lib) break;
+    }
+    if (!ctx->nccl_lib) return fail(ctx, VIML_ERR_UNSUPPORTED, "libnccl.so.2 not loadable");
+  }
+  // ncclResult_t ncclAllReduce(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
+  using allreduce_t = int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  auto fn = (allreduce_t)dlsym(ctx->nccl_lib, "ncclAllReduce");
+  if (!fn) return fail(ctx, VIML_ERR_UNSUPPORTED, "ncclAllReduce not found");
+  const int ncclFloat64 = 8, ncclSum = 0;
+  const int rc = fn(buf, buf, (size_t)count, ncclFloat64, ncclSum, nccl_comm, ctx->stream);
+  if (rc != 0) return fail(ctx, VIML_ERR_CUDA, "ncclAllReduce failed");
+  return VIML_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,274 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, driven through the C-ABI, against the CPU
+oracle on the same seeded inputs and against the committed golden fixtures.
+
+Bars (BASELINE.json north_star): association indices / inlier masks / FoV lists bit-exact; residuals,
+Jacobians, H, b and the Schur complement within 1e-9 relative (block-wise scale, see conftest.rel_err)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+TOL = 1e-9
+
+
+def check_linearize(pkg, orc, ctx, cfg, batch, flags, tol=TOL):
+    got = ctx.linearize(batch, flags)
+    ref = orc.linearize_batch(cfg, batch, flags, nthreads=8)
+    assert set(got) == set(ref)
+    for k, v in ref.items():
+        assert not np.isnan(got[k]).any(), f"{k}: unwritten entries"
+        assert rel_err(got[k], v) < tol, (k, rel_err(got[k], v))
+    return got, ref
+
+
+def test_single_window_cfg1(pkg, orc, ctx, cfg):
+    """BASELINE.json configs[0]: one EuRoC-shaped window (11 poses, 150 features, line factors)."""
+    abi = pkg._abi
+    b = pkg.synth.make_windows(1, seed=101)
+    for flags in (abi.OUT_RESIDUAL_JACOBIAN, abi.OUT_RESIDUAL_JACOBIAN | abi.LOSS_CAUCHY,
+                  abi.OUT_HB | abi.LOSS_CAUCHY, abi.OUT_SCHUR | abi.LOSS_CAUCHY,
+                  abi.OUT_RESIDUAL_JACOBIAN | abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY, abi.OUT_HB):
+        got, _ = check_linearize(pkg, orc, ctx, cfg, b, flags)
+        if flags & abi.OUT_RESIDUAL_JACOBIAN:
+            for k in ("pf_jac_pose_i", "pf_jac_pose_j", "pf_jac_ex", "lf_jac_pose"):
+                assert np.all(got[k].reshape(-1, 2, 7)[:, :, 6] == 0.0)   # column 6 is exactly zero
+        if flags & abi.OUT_HB:
+            assert np.abs(got["H_pp"] - np.swapaxes(got["H_pp"], 1, 2)).max() <= 1e-9 * np.abs(got["H_pp"]).max()
+
+
+def test_golden_linearize(pkg, orc, ctx, cfg):
+    g = np.load(os.path.join(GOLD, "linearize_cfg1.npz"))
+    abi = pkg._abi
+    b = abi.Batch(g["in_poses"], g["in_ex_pose"], g["in_inv_depth"], g["in_pf_window_offset"], g["in_pf_idx"],
+                  g["in_pf_obs"], g["in_lf_window_offset"], g["in_lf_frame"], g["in_lf_geom"])
+    flags = abi.OUT_RESIDUAL_JACOBIAN | abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
+    got = ctx.linearize(b, flags)
+    for k in got:
+        assert rel_err(got[k], g["out_" + k]) < TOL, k
+
+
+def test_batch_shapes_and_edges(pkg, orc, ctx, cfg):
+    abi, synth = pkg._abi, pkg.synth
+    allf = abi.OUT_RESIDUAL_JACOBIAN | abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
+    check_linearize(pkg, orc, ctx, cfg, synth.make_windows(37, seed=102), allf)
+    # no line factors at all
+    check_linearize(pkg, orc, ctx, cfg, synth.make_windows(5, seed=103, lines_per_frame=0), allf)
+    # other window geometries: short window, few features; long window
+    check_linearize(pkg, orc, ctx, cfg, synth.make_windows(9, seed=104, P=5, F=17, lines_per_frame=2), allf)
+    check_linearize(pkg, orc, ctx, cfg, synth.make_windows(3, seed=105, P=24, F=300, lines_per_frame=3), allf)
+    # ragged: windows with zero factors in the middle of the batch
+    b = synth.make_windows(6, seed=106)
+    keep = np.ones(b.NP, dtype=bool)
+    keep[b.pf_window_offset[2]:b.pf_window_offset[3]] = False
+    keep[b.pf_window_offset[5]:b.pf_window_offset[6]] = False
+    off = np.concatenate([[0], np.cumsum([keep[b.pf_window_offset[w]:b.pf_window_offset[w + 1]].sum() for w in range(6)])])
+    b2 = abi.Batch(b.poses, b.ex_pose, b.inv_depth, off, b.pf_idx[keep], b.pf_obs[keep], b.lf_window_offset, b.lf_frame,
+                   b.lf_geom)
+    check_linearize(pkg, orc, ctx, cfg, b2, allf)
+    # explicit pts_i.z != 1 (ProjectionFactor divides all three components by inv_dep, projection_factor.cpp:35)
+    b3 = synth.make_windows(4, seed=107)
+    b3.pf_pts_i_z = 1.0 + 0.01 * np.random.default_rng(1).standard_normal(b3.NP)
+    check_linearize(pkg, orc, ctx, cfg, b3, allf)
+    # non-default sqrt_info / Cauchy scale
+    cfg2 = synth.euroc_config(sqrt_info=120.0, cauchy_a=2.5)
+    with pkg.Context(cfg2) as c2:
+        check_linearize(pkg, orc, c2, cfg2, synth.make_windows(4, seed=108), allf)
+
+
+def test_marginalisation_stress_shape(pkg, orc, ctx, cfg):
+    """cfg-4 shape at a size the dense oracle finishes in seconds: all landmarks start in frame 0."""
+    abi = pkg._abi
+    b = pkg.synth.make_windows(3, seed=109, P=11, F=400, all_start_zero=True, lines_per_frame=0)
+    check_linearize(pkg, orc, ctx, cfg, b, abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY)
+
+
+def test_bad_arguments(pkg, ctx, cfg):
+    abi = pkg._abi
+    b = pkg.synth.make_windows(1, seed=110)
+    s, o = b.struct(), abi.LinearizeOut()
+    lib = ctx.lib
+    assert lib.viml_linearize_batch(ctx.h, C.byref(s), C.byref(o), 0) == abi.VIML_ERR_INVALID
+    assert lib.viml_linearize_batch(ctx.h, C.byref(s), C.byref(o), abi.OUT_HB) == abi.VIML_ERR_INVALID
+    assert b"H_pp" in lib.viml_last_error(ctx.h)
+    assert lib.viml_linearize_batch(ctx.h, None, C.byref(o), abi.OUT_HB) == abi.VIML_ERR_INVALID
+    s.poses_per_window = 0
+    assert lib.viml_linearize_batch(ctx.h, C.byref(s), C.byref(o), abi.OUT_RESIDUAL_JACOBIAN) == abi.VIML_ERR_INVALID
+
+
+def test_device_pointer_mode_matches_host_mode(pkg, ctx, cfg):
+    """VIML_PTRS_DEVICE: inputs resident in HBM, asynchronous on the context stream."""
+    abi = pkg._abi
+    b = pkg.synth.make_windows(16, seed=111)
+    flags = abi.OUT_RESIDUAL_JACOBIAN | abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
+    host = ctx.linearize(b, flags)
+    d_in = {k: ctx.to_device(v) for k, v in b.arrays().items() if v is not None}
+    d_out = {k: ctx.device_alloc(v.nbytes) for k, v in host.items()}
+    ctx.linearize_raw(b.struct(d_in), abi.out_struct(d_out), flags | abi.PTRS_DEVICE)
+    for k, v in host.items():
+        back = np.empty_like(v)
+        ctx.d2h(back, d_out[k])
+        ctx.sync()
+        if k in ("pf_residual", "pf_jac_pose_i", "pf_jac_pose_j", "pf_jac_ex", "pf_jac_feat", "lf_residual", "lf_jac_pose"):
+            assert np.array_equal(back, v), k        # per-factor outputs are deterministic
+        else:
+            assert rel_err(back, v) < 1e-12, k       # assembled sums may differ in summation order only
+    for p in list(d_in.values()) + list(d_out.values()):
+        ctx.device_free(p)
+
+
+def test_full_size_batch_properties(pkg, orc, ctx, cfg):
+    """BASELINE.json configs[1] at full size (4096 windows): oracle on a sample of windows + properties."""
+    abi = pkg._abi
+    b = pkg.synth.make_windows(4096, seed=0x5EED + 2)
+    flags = abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
+    got = ctx.linearize(b, flags)
+    for k, v in got.items():
+        assert np.isfinite(v).all(), k
+    H = got["H_pp"]
+    assert np.abs(H - np.swapaxes(H, 1, 2)).max() <= 1e-9 * np.abs(H).max()
+    S = got["S"]
+    assert np.abs(S - np.swapaxes(S, 1, 2)).max() <= 1e-9 * np.abs(S).max()
+    # S is H_pp minus a PSD term: diagonal can only shrink
+    assert np.all(np.einsum("wii->wi", S) <= np.einsum("wii->wi", H) * (1 + 1e-12) + 1e-9)
+    for w in (0, 1, 777, 2048, 4095):
+        sb = b.slice_windows(w, w + 1)
+        ref = orc.linearize_batch(cfg, sb, flags)
+        for k, v in ref.items():
+            assert rel_err(got[k][w:w + 1], v) < TOL, (k, w)
+    # linearity in the factor set: H(all) == H(first half of windows) ++ H(second half)
+    half = ctx.linearize(b.slice_windows(0, 2048), abi.OUT_HB | abi.LOSS_CAUCHY)
+    assert rel_err(half["H_pp"], got["H_pp"][:2048]) < 1e-12
+
+
+# ---- marginalisation ----------------------------------------------------------------------------------
+def test_marginalize_dense(pkg, orc, ctx):
+    rng = np.random.default_rng(7)
+    for pos, m, K in ((90, 15, 5), (37, 0, 2), (120, 45, 3), (16, 15, 4)):
+        A = np.empty((K, pos, pos))
+        b = rng.standard_normal((K, pos))
+        for k in range(K):
+            M = rng.standard_normal((pos + 8, pos))
+            A[k] = M.T @ M
+        got = ctx.marginalize(A, b, m)
+        for k in range(K):
+            As, bs, lj, lr = orc.marginalize_dense(A[k], b[k], m)
+            assert rel_err(got["A_schur"][k], As) < TOL and rel_err(got["b_schur"][k], bs) < TOL
+            J, r = got["linearized_jacobians"][k], got["linearized_residuals"][k]
+            # eigenvector signs are not unique: compare J^T J and J^T r
+            assert rel_err(J.T @ J, lj.T @ lj) < TOL and rel_err(J.T @ r, lj.T @ lr) < 1e-8
+    # rank-deficient marginalised block -> pseudo-inverse semantics
+    pos, m = 40, 12
+    M = rng.standard_normal((pos + 3, pos))
+    A = M.T @ M
+    A[2, :] = 0
+    A[:, 2] = 0
+    b = rng.standard_normal(pos)
+    got = ctx.marginalize(A, b, m)
+    As, bs, _, _ = orc.marginalize_dense(A, b, m)
+    assert rel_err(got["A_schur"][0], As) < 1e-8 and rel_err(got["b_schur"][0], bs) < 1e-8
+
+
+# ---- association -----------------------------------------------------------------------------------------
+def check_assoc(got, ref, check_lists=True):
+    assert np.array_equal(got["match_index"], ref["match_index"])
+    assert np.array_equal(got["fov_count"], ref["fov_count"])
+    if "fov_mask" in ref:
+        assert np.array_equal(got["fov_mask"], ref["fov_mask"])
+    if "fov_index" in ref and check_lists:
+        assert np.array_equal(got["fov_index"], ref["fov_index"])
+    m = ref["match_index"] >= 0
+    # errD and overlap (float32) and the projected segment are bit-exact
+    assert np.array_equal(got["err"][..., 1:], ref["err"][..., 1:])
+    assert np.array_equal(got["projected"][m], ref["projected"][m])
+    # errA goes through acos: device acos is <= 2 ulp in double, i.e. <= 1 ulp after narrowing to float
+    a, b = got["err"][..., 0], ref["err"][..., 0]
+    assert np.all(np.abs(a - b) <= np.spacing(np.abs(b)).astype(np.float32))
+    return float((a == b).mean())
+
+
+@pytest.mark.parametrize("name", ["assoc_euroc_v1.npz", "assoc_euroc_v2.npz"])
+def test_golden_association_on_reference_maps(pkg, name):
+    g = np.load(os.path.join(GOLD, name))
+    c = g["cfg"]
+    cfg = pkg._abi.make_config(fx=c[0], fy=c[1], cx=c[2], cy=c[3], width=int(c[4]), height=int(c[5]), Rbw=g["Rbw"],
+                               Tbw=g["Tbw"], overlap_th=c[6], dist_th=c[7], angle_th=c[8])
+    with pkg.Context(cfg) as cx:
+        cx.set_map(g["lines"])
+        got = cx.associate(g["cull"], g["match"], g["ex"], g["lines2d"], fov_capacity=512)
+    ref = {k: g[k] for k in ("match_index", "err", "projected", "fov_count", "fov_index")}
+    check_assoc(got, ref)
+
+
+def test_association_synthetic(pkg, orc, ctx, cfg):
+    synth = pkg.synth
+    lines = synth.make_line_map(60000, seed=41, extent=(500.0, 500.0, 30.0))
+    cull, match, ex, l2d = synth.make_assoc_queries(lines, 97, L=300, n_true=100, seed=42, extent=(500.0, 500.0, 30.0))
+    ctx.set_map(lines)
+    got = ctx.associate(cull, match, ex, l2d, fov_capacity=2048, want_mask=True)
+    ref = orc.line_associate(cfg, lines, cull, match, ex, l2d, fov_capacity=2048, want_mask=True, nthreads=8)
+    exact = check_assoc(got, ref)
+    assert (ref["match_index"] >= 0).mean() > 0.2 and exact > 0.99
+    # same pose for cull and match (match_poses = NULL), as the cfg-3 sweep does
+    got = ctx.associate(cull, None, ex, l2d)
+    ref = orc.line_associate(cfg, lines, cull, None, ex, l2d, nthreads=8)
+    check_assoc(got, ref)
+
+
+def test_association_edges(pkg, orc, ctx, cfg):
+    synth = pkg.synth
+    lines = synth.make_line_map(777, seed=43, extent=(60.0, 60.0, 30.0))   # N not a multiple of 32
+    cull, match, ex, l2d = synth.make_assoc_queries(lines, 5, L=16, n_true=8, seed=44, extent=(60.0, 60.0, 30.0))
+    l2d[0, 0] = [100, 100, 100, 100]      # zero-length detected line
+    l2d[0, 1] = [200, 50, 200, 300]       # vertical: Point2Flined always clamps to an endpoint
+    ctx.set_map(lines)
+    nl = np.array([16, 0, 3, 16, 1], dtype=np.int32)
+    got = ctx.associate(cull, match, ex, l2d, n_lines2d=nl, fov_capacity=64, want_mask=True)
+    ref = orc.line_associate(cfg, lines, cull, match, ex, l2d, n_lines2d=nl, fov_capacity=64, want_mask=True)
+    check_assoc(got, ref)                 # includes truncated fov_index (capacity 64) and untouched -2 entries
+    # empty map
+    ctx.set_map(np.zeros((0, 6)))
+    got = ctx.associate(cull, match, ex, l2d)
+    assert np.all(got["match_index"] == -1) and np.all(got["err"] == -1) and np.all(got["fov_count"] == 0)
+    # poses looking away from everything: empty FoV lists
+    ctx.set_map(lines + 1e5)
+    got = ctx.associate(cull, match, ex, l2d)
+    assert np.all(got["match_index"] == -1) and np.all(got["fov_count"] == 0)
+
+
+def test_association_angle_threshold_variants(pkg, orc):
+    synth = pkg.synth
+    lines = synth.make_line_map(20000, seed=45, extent=(300.0, 300.0, 30.0))
+    cull, match, ex, l2d = synth.make_assoc_queries(lines, 12, L=64, n_true=30, seed=46, extent=(300.0, 300.0, 30.0))
+    for th, ov in ((0.1, 0.5), (0.18, 0.5), (0.3491, 0.3), (3.2, 0.0)):   # last: angle_th > PI lets NaN angles pass
+        cfg = synth.euroc_config(angle_th=th, overlap_th=ov)
+        with pkg.Context(cfg) as cx:
+            cx.set_map(lines)
+            got = cx.associate(cull, match, ex, l2d, want_mask=True)
+        ref = orc.line_associate(cfg, lines, cull, match, ex, l2d, want_mask=True, nthreads=8)
+        check_assoc(got, ref)
+
+
+def test_association_sweep_properties_large(pkg, orc, ctx, cfg):
+    """cfg-3 geometry at 1/4 of the map and 1/16 of the poses: oracle on a sample of poses + invariants."""
+    synth = pkg.synth
+    ext = (1000.0, 1000.0, 30.0)
+    lines = synth.make_line_map(250000, seed=47, extent=ext)
+    cull, match, ex, l2d = synth.make_assoc_queries(lines, 256, L=300, n_true=100, seed=48, extent=ext)
+    ctx.set_map(lines)
+    got = ctx.associate(cull, None, ex, l2d, fov_capacity=4096, want_mask=True)
+    pop = np.array([sum(bin(int(x)).count("1") for x in row) for row in got["fov_mask"][:8]])
+    assert np.array_equal(pop, got["fov_count"][:8])
+    for p in range(8):   # every matched index is a member of that pose's FoV list; lists are sorted (map order)
+        fl = got["fov_index"][p, :got["fov_count"][p]]
+        assert np.all(np.diff(fl) > 0)
+        mi = got["match_index"][p]
+        assert np.all(np.isin(mi[mi >= 0], fl))
+    sel = np.array([0, 1, 100, 255])
+    ref = orc.line_associate(cfg, lines, cull[sel], None, ex[sel], l2d[sel], fov_capacity=4096, want_mask=True, nthreads=8)
+    sub = {k: v[sel] for k, v in got.items()}
+    check_assoc(sub, ref)
