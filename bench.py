@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the sliding-window linearisation hot path on N B200s (one process per GPU).
+
+  python bench.py --gpus 1 --steps 20 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...      the reference's CPU algorithm (oracle port) on the host cores
+
+One JSON line on rank 0.  A step = one pass of the hot path over one batch:
+  BASELINE.json configs[1]: 4096 independent EuRoC-shaped windows per GPU, every ProjectionFactor and
+  LineProjectionFactor evaluated with the Cauchy loss correction and assembled into the block-structured
+  H = J^T J, b = J^T r of its window (viml_linearize_batch, VIML_OUT_HB | VIML_LOSS_CAUCHY).
+`value` times it with inputs resident in HBM (CUDA events on the context stream); `e2e` is the same call with
+pinned HOST buffers (H2D of all inputs and D2H of all H/b blocks inside the timed region).  The `assoc`
+object reports the second BASELINE metric (2D-3D line associations/s, configs[2]) the same way, `schur`
+the landmark Schur complement (configs[3] shape), `mode_a` the per-factor r/J output mode.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+# SURVEY.md §8(d) algorithmic bytes
+B_POINT_A, B_LINE_A = 412, 204            # mode A: inputs + r/J outputs per factor
+B_POINT_IN, B_LINE_IN = 44, 76            # mode B inputs per factor
+
+
+def window_bytes(P, F):
+    D = 6 * (P + 1)
+    shared_in = (P * 7 + 7 + F) * 8        # poses + extrinsic + inverse depths, once per window
+    out = (D * D + D * F + F + D + F) * 8  # H_pp + strips + diag + b
+    return shared_in, out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def cpu_linearize_rate(orc, cfg, batch, flags, nthreads, target_s=12.0):
+    """Oracle (= the reference's CPU algorithm) on a bounded sample of the same workload."""
+    probe = batch.slice_windows(0, min(batch.W, 2 * nthreads))
+    t0 = time.perf_counter()
+    orc.linearize_batch(cfg, probe, flags, nthreads=nthreads)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    nwin = int(min(batch.W, max(2 * nthreads, probe.W * target_s / dt)))
+    sample = batch.slice_windows(0, nwin)
+    t0 = time.perf_counter()
+    orc.linearize_batch(cfg, sample, flags, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return (sample.NP + sample.NL) / dt, nwin, dt
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    pkg, orc = ge.load_package(), ge.load_oracle()
+    abi, synth = pkg._abi, pkg.synth
+    cfg = synth.euroc_config()
+    nthreads = orc.hardware_threads()
+    flags = abi.OUT_HB | abi.LOSS_CAUCHY
+    nwin = max(2 * nthreads, 64)
+    batch = synth.make_windows(nwin, seed=0x5EED + 2)
+    # size the per-step sample so the whole run stays within a few minutes
+    t0 = time.perf_counter()
+    orc.linearize_batch(cfg, batch, flags, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    budget = 120.0 / max(args.steps + args.warmup, 1)
+    scale = int(max(1, min(16, budget / max(dt, 1e-6))))
+    if scale > 1:
+        batch = synth.make_windows(nwin * scale, seed=0x5EED + 2)
+    for _ in range(args.warmup):
+        orc.linearize_batch(cfg, batch, flags, nthreads=nthreads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.linearize_batch(cfg, batch, flags, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    factors = batch.NP + batch.NL
+    val = factors * args.steps / dt
+    sample = f"{batch.W} of 4096 windows per step ({factors} factors), Evaluate + Cauchy correction + ThreadsConstructA-rule dense A/b"
+    print(json.dumps({
+        "impl": "reference", "metric": "linearized_factors_per_s", "value": val, "unit": "factors/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2: 4096 EuRoC-shaped windows/GPU (11 poses, 150 features, ~560 ProjectionFactors + 110 "
+                               "LineProjectionFactors each): Evaluate + loss correction + H/b assembly", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "factors/s", "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "factors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference needs Eigen/Ceres/ROS and cannot be built here; this is the dependency-free oracle port of its "
+                "CPU algorithm, std::thread over windows on all host threads",
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--windows", type=int, default=4096, help="windows per GPU")
+    ap.add_argument("--map-lines", type=int, default=1000000)
+    ap.add_argument("--assoc-poses", type=int, default=4096, help="poses per GPU")
+    ap.add_argument("--skip-assoc", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="only the headline linearise metric")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    pkg = ge.load_package()
+    abi, synth = pkg._abi, pkg.synth
+    cfg = synth.euroc_config()
+    ctx = pkg.Context(cfg, device=local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    hbm_peak, peak_src = peaks()
+    K, Wm = args.steps, args.warmup
+
+    def timed_device(fn, steps, warm):
+        """K launches of fn on the context stream between two CUDA events, barrier+sync on both sides,
+        per-kernel times from the library's own event pairs.  Returns (max-over-ranks ms total, profile)."""
+        for _ in range(warm):
+            fn()
+        ctx.sync()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.profile_begin()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        prof = ctx.profile_end()
+        e1.synchronize()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), prof
+
+    # ------------------------------------------------------------------ linearise (headline)
+    batch = synth.make_windows(args.windows, seed=0x5EED + 2 + rank)
+    factors = batch.NP + batch.NL
+    flags = abi.OUT_HB | abi.LOSS_CAUCHY
+    d_in = {k: ctx.to_device(v) for k, v in batch.arrays().items() if v is not None}
+    shapes = batch.out_shapes()
+    d_out = {k: ctx.device_alloc(int(np.prod(shapes[k])) * 8) for k in ("H_pp", "H_lp", "H_ll", "b_p", "b_l")}
+    s_in, s_out = batch.struct(d_in), abi.out_struct(d_out)
+    ctx.sync()
+    launches0 = ctx.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_total, prof = timed_device(lambda: ctx.linearize_raw(s_in, s_out, flags | abi.PTRS_DEVICE), K, Wm)
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches() - launches0
+    gpu_launches = int(round(launches * K / (K + Wm)))
+    ms_step = ms_total / K
+    total_factors = sum_over_ranks(float(factors))
+    value = total_factors / (ms_step * 1e-3)
+    shared_in, out_b = window_bytes(batch.P, batch.F)
+    step_bytes = batch.NP * B_POINT_IN + batch.NL * B_LINE_IN + batch.W * (shared_in + out_b)
+    dom = max(prof.items(), key=lambda kv: kv[1][0])
+    dom_name, (dom_ms, dom_n) = dom
+    # the dominant kernel's own algorithmic bytes per launch
+    kb = {"linearize_points": batch.NP * B_POINT_IN + batch.W * (shared_in + out_b),
+          "assemble_hb": step_bytes, "linearize_lines": batch.NL * B_LINE_IN, "prep_windows": batch.W * shared_in}
+    dom_bytes = kb.get(dom_name, step_bytes)
+    achieved = dom_bytes / (dom_ms / dom_n * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms / dom_n,
+                "step_algorithmic_bytes": step_bytes, "step_frac": step_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                "kernel_ms_per_step": {k: v[0] / K for k, v in prof.items()}}
+    ncu_traffic = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(ncu_traffic):
+        roofline["traffic"] = json.load(open(ncu_traffic)).get(dom_name)
+
+    # ------------------------------------------------------------------ e2e: same call, pinned host buffers
+    pins = {k: pkg.pinned_like(v) for k, v in batch.arrays().items() if v is not None}
+    pouts = {k: pkg.PinnedArray(shapes[k], np.float64) for k in d_out}
+    hb = abi.Batch(**{k: p.array for k, p in pins.items()})
+    ho = {k: p.array for k, p in pouts.items()}
+    h2d = sum(p.nbytes for p in pins.values())
+    d2h = sum(p.nbytes for p in pouts.values())
+    for _ in range(2):
+        ctx.linearize(hb, flags, out=ho)
+    barrier()
+    e_steps = max(3, min(K, 10))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        ctx.linearize(hb, flags, out=ho)
+    e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e_steps
+    barrier()
+    e2e = {"value": total_factors / (e_ms * 1e-3), "unit": "factors/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": e_ms, "steps": e_steps,
+           "api": "viml_linearize_batch(host pointers, VIML_OUT_HB|VIML_LOSS_CAUCHY)"}
+    # spot check against the device-resident run so the e2e path is the same computation
+    chk = np.empty(shapes["b_p"])
+    ctx.d2h(chk, d_out["b_p"])
+    ctx.sync()
+    assert np.allclose(chk, ho["b_p"], rtol=1e-9, atol=1e-6 * np.abs(chk).max()), "e2e and device-resident results differ"
+    for p in list(pins.values()) + list(pouts.values()):
+        p.free()
+
+    out = {"metric": "linearized_factors_per_s", "value": value, "unit": "factors/s", "n_gpus": world, "steps": K,
+           "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "cfg2: 4096 EuRoC-shaped windows/GPU (11 poses, 150 features, ~560 ProjectionFactors + 110 "
+                                  "LineProjectionFactors each): Evaluate + loss correction + H/b assembly",
+                      "windows_per_gpu": batch.W, "point_factors_per_gpu": batch.NP, "line_factors_per_gpu": batch.NL,
+                      "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (step_bytes / 1e6),
+                      "parallelism": f"{world} GPU(s), windows sharded, no data-path collective"},
+           "roofline": roofline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks}
+
+    if not args.skip_extras:
+        # ---------------- mode A (per-factor r/J for the Ceres shim)
+        flagsA = abi.OUT_RESIDUAL_JACOBIAN | abi.LOSS_CAUCHY
+        namesA = ("pf_residual", "pf_jac_pose_i", "pf_jac_pose_j", "pf_jac_ex", "pf_jac_feat", "lf_residual", "lf_jac_pose")
+        dA = {k: ctx.device_alloc(int(np.prod(shapes[k])) * 8) for k in namesA}
+        sA = abi.out_struct(dA)
+        msA, profA = timed_device(lambda: ctx.linearize_raw(s_in, sA, flagsA | abi.PTRS_DEVICE), K, Wm)
+        bytesA = batch.NP * B_POINT_A + batch.NL * B_LINE_A + batch.W * shared_in
+        pa = profA.get("linearize_points", (msA, K))
+        out["mode_a"] = {"value": total_factors / (msA / K * 1e-3), "unit": "factors/s", "ms_per_step": msA / K,
+                         "roofline": {"bound": "hbm", "kernel": "linearize_points",
+                                      "achieved": (batch.NP * B_POINT_A) / (pa[0] / pa[1] * 1e-3) / 1e9, "peak": hbm_peak,
+                                      "unit": "GB/s", "frac": (batch.NP * B_POINT_A) / (pa[0] / pa[1] * 1e-3) / 1e9 / hbm_peak,
+                                      "step_frac": bytesA / (msA / K * 1e-3) / 1e9 / hbm_peak}}
+        for p in dA.values():
+            ctx.device_free(p)
+        # ---------------- landmark Schur (cfg-4 shape, windows scaled to fit the step budget)
+        flagsS = abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
+        dS = {k: ctx.device_alloc(int(np.prod(shapes[k])) * 8) for k in ("S", "g")}
+        sS = abi.out_struct({**d_out, **dS})
+        msS, profS = timed_device(lambda: ctx.linearize_raw(s_in, sS, flagsS | abi.PTRS_DEVICE), K, Wm)
+        ps = profS.get("schur_landmarks", (msS, K))
+        D, F = batch.D, batch.F
+        fl = (2.0 * D * D * F + 2.0 * D * F) * batch.W
+        out["schur"] = {"windows_per_s": sum_over_ranks(float(batch.W)) / (ps[0] / ps[1] * 1e-3), "ms_per_launch": ps[0] / ps[1],
+                        "gflops": fl / (ps[0] / ps[1] * 1e-3) / 1e9, "shape": f"{batch.W} windows x (D={D}, {F} landmarks)",
+                        "step_ms_with_linearize": msS / K}
+        for p in dS.values():
+            ctx.device_free(p)
+        out["fp64_peaks"] = dict(zip(("dfma_tflops", "dmul_dadd_tops"), ctx.microbench_fp64()))
+    for p in list(d_in.values()) + list(d_out.values()):
+        ctx.device_free(p)
+
+    # ------------------------------------------------------------------ association (second metric)
+    if not args.skip_assoc and not args.skip_extras:
+        ext = (2000.0, 2000.0, 30.0)
+        lines = synth.make_line_map(args.map_lines, seed=0x5EED + 3, extent=ext)
+        Pq, L = args.assoc_poses, 300
+        cull, match, ex, l2d = synth.make_assoc_queries(lines, Pq, L=L, n_true=100, seed=0x5EED + 33 + rank, extent=ext,
+                                                       pose_drift=False)
+        ctx.set_map(lines)
+        N, words = len(lines), (len(lines) + 31) // 32
+        q = abi.AssocQuery()
+        q.n_poses, q.lines_per_pose = Pq, L
+        dq = {k: ctx.to_device(v) for k, v in (("cull", cull), ("ex", ex), ("l2d", l2d))}
+        q.cull_poses, q.match_poses, q.ex_pose, q.lines2d, q.n_lines2d = dq["cull"], None, dq["ex"], dq["l2d"], None
+        o = abi.AssocOut()
+        do = {"match_index": ctx.device_alloc(Pq * L * 4), "err": ctx.device_alloc(Pq * L * 12),
+              "projected": ctx.device_alloc(Pq * L * 32), "fov_count": ctx.device_alloc(Pq * 4),
+              "fov_mask": ctx.device_alloc(Pq * words * 4)}
+        o.match_index, o.err, o.projected, o.fov_count, o.fov_mask = (do[k] for k in ("match_index", "err", "projected", "fov_count", "fov_mask"))
+        o.fov_index, o.fov_capacity = None, 0
+        a_steps = max(3, min(K, 5))
+        msQ, profQ = timed_device(lambda: ctx.associate_raw(q, o, abi.PTRS_DEVICE), a_steps, 3)
+        msQ /= a_steps
+        cnt = np.empty(Pq, dtype=np.int32)
+        mi = np.empty((Pq, L), dtype=np.int32)
+        ctx.d2h(cnt, do["fov_count"])
+        ctx.d2h(mi, do["match_index"])
+        ctx.sync()
+        n_assoc = sum_over_ranks(float(Pq * L))
+        fp = out.get("fp64_peaks", {})
+        pc = profQ.get("assoc_cull", (msQ, 1))
+        cull_ms = pc[0] / pc[1]
+        pairs = float(N) * Pq
+        cull_tops = 54.0 * pairs / (cull_ms * 1e-3) / 1e12
+        t0 = time.perf_counter()
+        for _ in range(2):
+            res = ctx.associate(cull, None, ex, l2d)
+        e_ms_a = max_over_ranks((time.perf_counter() - t0) * 1e3) / 2
+        out["assoc"] = {"metric": "line_associations_per_s", "value": n_assoc / (msQ * 1e-3), "unit": "assoc/s",
+                        "ms_per_step": msQ, "steps": a_steps,
+                        "config": {"workload": f"cfg3: {N} map lines x {Pq} poses/GPU x {L} 2D lines/pose, cull pose == match pose",
+                                   "fov_list_median": int(np.median(cnt)), "matched_fraction": float((mi >= 0).mean())},
+                        "cull_pairs_per_s": sum_over_ranks(pairs) / (cull_ms * 1e-3),
+                        "roofline": {"bound": "fp64 (un-fused DMUL/DADD, bit-exact contract)", "kernel": "assoc_cull",
+                                     "achieved": cull_tops, "peak": fp.get("dmul_dadd_tops"), "unit": "Top/s",
+                                     "frac": (cull_tops / fp["dmul_dadd_tops"]) if fp.get("dmul_dadd_tops") else None,
+                                     "algorithmic_ops_per_pair": 54, "avg_launch_ms": cull_ms,
+                                     "peak_source": "viml_microbench_fp64 on this device, same run"},
+                        "kernel_ms_per_step": {k: v[0] / a_steps for k, v in profQ.items()},
+                        "e2e": {"value": n_assoc / (e_ms_a * 1e-3), "unit": "assoc/s", "ms_per_step": e_ms_a,
+                                "h2d_bytes_per_step": int(cull.nbytes + ex.nbytes + l2d.nbytes),
+                                "d2h_bytes_per_step": int(res["match_index"].nbytes + res["err"].nbytes + res["projected"].nbytes + res["fov_count"].nbytes)}}
+        out["gpu_launches_assoc_per_step"] = 6
+        if rank == 0 and not args.skip_cpu:
+            orc = ge.load_oracle()
+            nt = orc.hardware_threads()
+            npose = max(nt, 16)
+            t0 = time.perf_counter()
+            orc.line_associate(cfg, lines, cull[:npose], None, ex[:npose], l2d[:npose], nthreads=nt)
+            dt = time.perf_counter() - t0
+            out["assoc"]["cpu_baseline"] = {"value": npose * L / dt, "unit": "assoc/s", "cores": nt, "kind": "port",
+                                            "sample": f"{npose} of {Pq} poses against the full {N}-line map ({dt:.1f} s)"}
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        orc = ge.load_oracle()
+        nt = orc.hardware_threads()
+        rate, nwin, dt = cpu_linearize_rate(orc, cfg, batch, flags, nt)
+        out["cpu_baseline"] = {"value": rate, "unit": "factors/s", "cores": nt, "kind": "port",
+                               "sample": f"{nwin} of {batch.W} windows, all {nt} host threads, {dt:.1f} s; oracle port of the reference's "
+                                         "Evaluate + loss correction + ThreadsConstructA dense A/b"}
+        r1, n1, d1 = cpu_linearize_rate(orc, cfg, batch, flags, 1, target_s=4.0)
+        out["cpu_baseline"]["single_thread_factors_per_s"] = r1
+    elif rank == 0:
+        out["cpu_baseline"] = None
+
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
