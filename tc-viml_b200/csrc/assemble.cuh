@@ -1,0 +1,594 @@
+// assemble.cuh — fused "evaluate + loss-correct + J^T J / J^T r" kernel: one CTA per sliding window.
+// Included by linearize_kernels.cu after eval_point / eval_line.
+//
+// What the reference does per window (marginalization_factor.cpp:3-69, :141-172): evaluate every factor into
+// heap-allocated Jacobian blocks, then 4 pthreads each scatter J_i^T J_j into a private dense pos x pos A.
+// Here the Jacobians never leave the SM:
+//   P0  deterministic counting sorts of the window's factors (warp match_any ranks + per-slab counts):
+//         by pose pair (lo,hi) -> record position (all factors that hit the same H blocks are contiguous),
+//         by feature          -> per-landmark factor lists,   lines by frame.
+//   P1  one thread per factor: residual + Jacobian in registers (eval_point / eval_line), written as
+//       row-pair records (J[0][c], J[1][c]) into XOR-swizzled shared memory at the sorted position.
+//   P2a pose part of H: every target block is owned by one TEAM of lanes (32/16/8/4 lanes by block type);
+//       lanes stride the block's factor ranges, accumulate the full block in registers, then a shuffle
+//       reduce-scatter leaves each lane with a slice that it writes straight to HBM (block + mirror).
+//   P2b landmark part: one thread per feature walks its factor list and writes the whole strip row
+//       H_lp[l][:] (structural zeros included), H_ll[l], b_l[l].
+// Every output entry of the window is written exactly once by exactly one thread: no atomics, no memset,
+// bit-reproducible run to run.  Windows that exceed the shared-memory limits are zero-filled, flagged and
+// finished by the generic atomic kernel.
+#pragma once
+
+namespace fused {
+
+constexpr int AT = 512;          // threads per CTA (16 warps), 1 CTA per SM
+constexpr int NF = 704;          // max point factors per window on this path
+constexpr int NL = 160;          // max line factors per window
+constexpr int PMAX = 12;         // max poses per window
+constexpr int FMAX = 160;        // max features per window
+constexpr int KA = PMAX * PMAX;  // pair keys
+constexpr int SLABS = NF / 32;   // 22
+constexpr int LSLABS = NL / 32;  // 5
+constexpr int RECW = 16;         // double2 per point record: 0..5 lo, 6..8 hi_rot, 9..14 ex, 15 r
+constexpr int LRECW = 7;         // double2 per line record: 0..5 pose, 6 r
+constexpr int WSLOTS = 64;       // windows per CTA whose CSR offsets are staged in shared memory
+
+struct Smem {
+  double2 rec[NF * RECW];
+  double2 drec[NF];
+  union {
+    double2 lrec[NL * LRECW];
+    struct {
+      uint16_t cntA[SLABS * KA];
+      uint16_t cntB[SLABS * FMAX];
+      uint16_t cntC[LSLABS * PMAX];
+    } cnt;
+  } u;
+  double cache[PMAX * kPoseCache + kExCache];
+  uint32_t ridx[NF];
+  uint16_t fperm[NF];
+  uint16_t baseA[KA + 1], totA[KA], baseB[FMAX + 1], totB[FMAX], baseC[PMAX + 1], totC[PMAX], pairs[KA];
+  int npairs, next_feature;
+  int woff[4 * WSLOTS];  // this CTA's windows: {p0, p1, l0, l1} per slot (filled once per launch)
+};
+
+__constant__ unsigned char c_sym_r[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
+__constant__ unsigned char c_sym_c[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
+
+__device__ __forceinline__ void prefetch_l2(const void* base, size_t bytes, int tid, int nthreads) {
+  const char* p = reinterpret_cast<const char*>(base);
+  for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)nthreads * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+}
+
+__device__ __forceinline__ double2 ldrec(const double2* __restrict__ rec, int pos, int k) {
+  return rec[pos * RECW + (k ^ (pos & 7))];
+}
+__device__ __forceinline__ void strec(double2* __restrict__ rec, int pos, int k, double x, double y) {
+  rec[pos * RECW + (k ^ (pos & 7))] = make_double2(x, y);
+}
+
+// reduce-scatter step: N live values -> N/2, lanes with bit w keep the upper half
+template <int N>
+__device__ __forceinline__ void rs_step(double* a, bool up, int w, unsigned mask) {
+#pragma unroll
+  for (int k = 0; k < N / 2; ++k) {
+    const double send = up ? a[k] : a[k + N / 2];
+    const double keep = up ? a[k + N / 2] : a[k];
+    a[k] = keep + __shfl_xor_sync(mask, send, w);
+  }
+}
+template <int N>
+__device__ __forceinline__ void bf_step(double* a, int w, unsigned mask) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) a[k] += __shfl_xor_sync(mask, a[k], w);
+}
+
+// acc(6x6) += X^T Y with X, Y given as row pairs
+__device__ __forceinline__ void acc_full(double* acc, const double2* X, const double2* Y) {
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[r * 6 + c] = fma(X[r].x, Y[c].x, fma(X[r].y, Y[c].y, acc[r * 6 + c]));
+}
+// acc[0..20] += upper(X^T X), acc[21..26] += X^T r
+__device__ __forceinline__ void acc_sym(double* acc, const double2* X, double2 r) {
+  int e = 0;
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int c = a; c < 6; ++c, ++e) acc[e] = fma(X[a].x, X[c].x, fma(X[a].y, X[c].y, acc[e]));
+#pragma unroll
+  for (int a = 0; a < 6; ++a) acc[21 + a] = fma(X[a].x, r.x, fma(X[a].y, r.y, acc[21 + a]));
+}
+
+__device__ __forceinline__ void load_lo(const double2* rec, int pos, double2* X) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) X[k] = ldrec(rec, pos, k);
+}
+__device__ __forceinline__ void load_hi(const double2* rec, int pos, double2* X) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double2 v = ldrec(rec, pos, k);
+    X[k] = make_double2(-v.x, -v.y);          // hi translation block == -lo translation block
+    X[3 + k] = ldrec(rec, pos, 6 + k);
+  }
+}
+__device__ __forceinline__ void load_ex(const double2* rec, int pos, double2* X) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) X[k] = ldrec(rec, pos, 9 + k);
+}
+
+// write the sym(21)+b(6) slice a lane holds after the reduction: entries e0..e0+6 of block (p,p)
+__device__ __forceinline__ void write_sym_slice(const double* a, int e0, double* __restrict__ H, double* __restrict__ bp,
+                                                int D, int p) {
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int e = e0 + k;
+    if (e < 21) {
+      const int r = c_sym_r[e], c = c_sym_c[e];
+      H[(size_t)(6 * p + r) * D + 6 * p + c] = a[k];
+      if (r != c) H[(size_t)(6 * p + c) * D + 6 * p + r] = a[k];
+    } else if (e < 27) {
+      bp[6 * p + e - 21] = a[k];
+    }
+  }
+}
+
+template <bool MODE_A>
+__global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* __restrict__ fallback) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int P = A.P, F = A.F, D = A.D, E = A.P;
+  const int nkeyA = P * P;
+  const int cstride = P * kPoseCache + kExCache;
+
+  // stage this CTA's CSR offsets once so that per-window address generation never waits on HBM
+  for (int e = tid; e < WSLOTS; e += AT) {
+    const int w = blockIdx.x + e * gridDim.x;
+    if (w < A.W) {
+      S.woff[4 * e] = A.pf_window_offset[w];
+      S.woff[4 * e + 1] = A.pf_window_offset[w + 1];
+      S.woff[4 * e + 2] = A.NL > 0 ? A.lf_window_offset[w] : 0;
+      S.woff[4 * e + 3] = A.NL > 0 ? A.lf_window_offset[w + 1] : 0;
+    }
+  }
+  __syncthreads();
+
+  int slot = 0;
+  for (int w = blockIdx.x; w < A.W; w += gridDim.x, ++slot) {
+    int p0, p1, l0, l1;
+    if (slot < WSLOTS) {
+      p0 = S.woff[4 * slot], p1 = S.woff[4 * slot + 1], l0 = S.woff[4 * slot + 2], l1 = S.woff[4 * slot + 3];
+    } else {
+      p0 = A.pf_window_offset[w], p1 = A.pf_window_offset[w + 1];
+      l0 = A.NL > 0 ? A.lf_window_offset[w] : 0, l1 = A.NL > 0 ? A.lf_window_offset[w + 1] : 0;
+    }
+    const int nf = p1 - p0, nl = l1 - l0;
+    if (slot + 1 < WSLOTS && w + (int)gridDim.x < A.W) {  // pull the next window's inputs into L2 while this one computes
+      const int wn = w + gridDim.x;
+      const int q0 = S.woff[4 * slot + 4], q1 = S.woff[4 * slot + 5], m0 = S.woff[4 * slot + 6], m1 = S.woff[4 * slot + 7];
+      prefetch_l2(A.pf_idx + q0, (size_t)(q1 - q0) * 4, tid, AT);
+      prefetch_l2(A.pf_obs + (size_t)q0 * 4, (size_t)(q1 - q0) * 32, tid, AT);
+      prefetch_l2(A.inv_depth + (size_t)wn * F, (size_t)F * 8, tid, AT);
+      prefetch_l2(A.cache + (size_t)wn * cstride, (size_t)cstride * 8, tid, AT);
+      if (A.NL > 0) {
+        prefetch_l2(A.lf_frame + m0, (size_t)(m1 - m0) * 4, tid, AT);
+        for (int c = 0; c < 9; ++c) prefetch_l2(A.lf_geom + (size_t)c * A.NL + m0, (size_t)(m1 - m0) * 8, tid, AT);
+      }
+    }
+    double* __restrict__ Hpp = A.out.H_pp + (size_t)w * D * D;
+    double* __restrict__ Hlp = A.out.H_lp + (size_t)w * F * D;
+    double* __restrict__ Hll = A.out.H_ll + (size_t)w * F;
+    double* __restrict__ bp = A.out.b_p + (size_t)w * D;
+    double* __restrict__ bl = A.out.b_l + (size_t)w * F;
+    if (nf > NF || nl > NL) {  // too big for shared memory: zero-fill, flag, let the generic kernel finish it
+      for (int e = tid; e < D * D; e += AT) Hpp[e] = 0.0;
+      for (int e = tid; e < F * D; e += AT) Hlp[e] = 0.0;
+      for (int e = tid; e < F; e += AT) Hll[e] = 0.0, bl[e] = 0.0;
+      for (int e = tid; e < D; e += AT) bp[e] = 0.0;
+      if (tid == 0) fallback[w] = 1;
+      continue;
+    }
+    // ------------------------------------------------------------------ P0: cache + sorts
+    {
+      const double* __restrict__ gc = A.cache + (size_t)w * cstride;
+      for (int e = tid; e < cstride; e += AT) S.cache[e] = gc[e];
+      uint32_t* z = reinterpret_cast<uint32_t*>(&S.u.cnt);
+      for (int e = tid; e < (int)(sizeof(S.u.cnt) / 4); e += AT) z[e] = 0u;
+      if (tid == 0) S.next_feature = 0;
+    }
+    __syncthreads();
+    uint32_t fidx[2];
+    int keyA[2], rankA[2], rankB[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int f = tid + r * AT;
+      const bool valid = f < nf;
+      fidx[r] = valid ? A.pf_idx[p0 + f] : 0u;
+      const int i = fidx[r] & 0xff, j = (fidx[r] >> 8) & 0xff, l = fidx[r] >> 16;
+      const int lo = min(i, j), hi = max(i, j);
+      keyA[r] = valid ? lo * P + hi : 0xffff;
+      const int keyB = valid ? l : 0xffff;
+      if (r * AT < nf) {  // warp-uniform: some lane of this warp may be valid
+        const unsigned ma = __match_any_sync(0xffffffffu, keyA[r]);
+        const unsigned mb = __match_any_sync(0xffffffffu, keyB);
+        const unsigned lt = (1u << lane) - 1u;
+        rankA[r] = __popc(ma & lt);
+        rankB[r] = __popc(mb & lt);
+        const int slab = warp + r * (AT / 32);
+        if (valid && rankA[r] == 0) S.u.cnt.cntA[slab * KA + keyA[r]] = (uint16_t)__popc(ma);
+        if (valid && rankB[r] == 0) S.u.cnt.cntB[slab * FMAX + keyB] = (uint16_t)__popc(mb);
+      }
+    }
+    int lframe = 0, rankC = 0;
+    if (tid < NL) {  // warps 0..4 (NL = 160): line factors by frame
+      const bool valid = tid < nl;
+      lframe = valid ? A.lf_frame[l0 + tid] : 0xffff;
+      const unsigned mc = __match_any_sync(0xffffffffu, lframe);
+      rankC = __popc(mc & ((1u << lane) - 1u));
+      if (valid && rankC == 0) S.u.cnt.cntC[warp * PMAX + lframe] = (uint16_t)__popc(mc);
+    }
+    __syncthreads();
+    // exclusive prefix over slabs for every key (thread per key)
+    for (int e = tid; e < nkeyA + F + P; e += AT) {
+      if (e < nkeyA) {
+        int run = 0;
+        for (int s = 0; s < SLABS; ++s) {
+          const int c = S.u.cnt.cntA[s * KA + e];
+          S.u.cnt.cntA[s * KA + e] = (uint16_t)run;
+          run += c;
+        }
+        S.totA[e] = (uint16_t)run;
+      } else if (e < nkeyA + F) {
+        const int k = e - nkeyA;
+        int run = 0;
+        for (int s = 0; s < SLABS; ++s) {
+          const int c = S.u.cnt.cntB[s * FMAX + k];
+          S.u.cnt.cntB[s * FMAX + k] = (uint16_t)run;
+          run += c;
+        }
+        S.totB[k] = (uint16_t)run;
+      } else {
+        const int k = e - nkeyA - F;
+        int run = 0;
+        for (int s = 0; s < LSLABS; ++s) {
+          const int c = S.u.cnt.cntC[s * PMAX + k];
+          S.u.cnt.cntC[s * PMAX + k] = (uint16_t)run;
+          run += c;
+        }
+        S.totC[k] = (uint16_t)run;
+      }
+    }
+    __syncthreads();
+    // exclusive scans over keys: warp 0 -> baseA (+ non-empty pair list), warp 1 -> baseB, warp 2 -> baseC
+    if (warp < 3) {
+      const uint16_t* tot = warp == 0 ? S.totA : (warp == 1 ? S.totB : S.totC);
+      uint16_t* base = warp == 0 ? S.baseA : (warp == 1 ? S.baseB : S.baseC);
+      const int n = warp == 0 ? nkeyA : (warp == 1 ? F : P);
+      int carry = 0, npairs = 0;
+      for (int b0 = 0; b0 < n; b0 += 32) {
+        const int k = b0 + lane;
+        const int v = k < n ? tot[k] : 0;
+        int inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += t;
+        }
+        if (k < n) base[k] = (uint16_t)(carry + inc - v);
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+        if (warp == 0) {
+          const unsigned nz = __ballot_sync(0xffffffffu, v > 0);
+          if (v > 0) S.pairs[npairs + __popc(nz & ((1u << lane) - 1u))] = (uint16_t)k;
+          npairs += __popc(nz);
+        }
+      }
+      if (lane == 0) {
+        base[n] = (uint16_t)carry;
+        if (warp == 0) S.npairs = npairs;
+      }
+    }
+    __syncthreads();
+    int posA[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int f = tid + r * AT;
+      posA[r] = 0;
+      if (f < nf) {
+        const int slab = warp + r * (AT / 32);
+        const int l = fidx[r] >> 16;
+        posA[r] = S.baseA[keyA[r]] + S.u.cnt.cntA[slab * KA + keyA[r]] + rankA[r];
+        const int posB = S.baseB[l] + S.u.cnt.cntB[slab * FMAX + l] + rankB[r];
+        S.ridx[posA[r]] = fidx[r];
+        S.fperm[posB] = (uint16_t)posA[r];
+      }
+    }
+    int posC = 0;
+    if (tid < nl) posC = S.baseC[lframe] + S.u.cnt.cntC[warp * PMAX + lframe] + rankC;
+    __syncthreads();  // count tables are dead from here on (lrec aliases them)
+    // ------------------------------------------------------------------ P1: evaluate, write records
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int f = tid + r * AT;
+      if (f >= nf) continue;
+      const int64_t k = (int64_t)p0 + f;
+      const int i = fidx[r] & 0xff, j = (fidx[r] >> 8) & 0xff, l = fidx[r] >> 16;
+      const double4 ob = reinterpret_cast<const double4*>(A.pf_obs)[k];
+      const double piz = A.pf_pts_i_z ? A.pf_pts_i_z[k] : 1.0;
+      const double lam = A.inv_depth[(size_t)w * F + l];
+      PointJac J;
+      eval_point(A, S.cache, i, j, lam, ob.x, ob.y, piz, ob.z, ob.w, J);
+      if (MODE_A) {
+        if (A.out.pf_residual) reinterpret_cast<double2*>(A.out.pf_residual)[k] = make_double2(J.r[0], J.r[1]);
+        if (A.out.pf_jac_pose_i) store_jac7(A.out.pf_jac_pose_i + 14 * k, J.a);
+        if (A.out.pf_jac_pose_j) store_jac7(A.out.pf_jac_pose_j + 14 * k, J.b);
+        if (A.out.pf_jac_ex) store_jac7(A.out.pf_jac_ex + 14 * k, J.c);
+        if (A.out.pf_jac_feat) reinterpret_cast<double2*>(A.out.pf_jac_feat)[k] = make_double2(J.d[0], J.d[1]);
+      }
+      const int pos = posA[r];
+      const bool sw = i > j;  // lo block is pose j
+#pragma unroll
+      for (int c = 0; c < 6; ++c) strec(S.rec, pos, c, sw ? J.b[0][c] : J.a[0][c], sw ? J.b[1][c] : J.a[1][c]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) strec(S.rec, pos, 6 + c, sw ? J.a[0][3 + c] : J.b[0][3 + c], sw ? J.a[1][3 + c] : J.b[1][3 + c]);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) strec(S.rec, pos, 9 + c, J.c[0][c], J.c[1][c]);
+      strec(S.rec, pos, 15, J.r[0], J.r[1]);
+      S.drec[pos] = make_double2(J.d[0], J.d[1]);
+    }
+    if (tid < nl) {
+      const int64_t k = (int64_t)l0 + tid;
+      double g9[9];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) g9[c] = A.lf_geom[(size_t)c * A.NL + k];
+      LineJac J;
+      eval_line(A, S.cache, lframe, g9, J);
+      if (MODE_A) {
+        if (A.out.lf_residual) reinterpret_cast<double2*>(A.out.lf_residual)[k] = make_double2(J.r[0], J.r[1]);
+        if (A.out.lf_jac_pose) store_jac7(A.out.lf_jac_pose + 14 * k, J.a);
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) S.u.lrec[posC * LRECW + c] = make_double2(J.a[0][c], J.a[1][c]);
+      S.u.lrec[posC * LRECW + 6] = make_double2(J.r[0], J.r[1]);
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------ P2a: pose blocks, team per target
+    const int npairs = S.npairs;
+    const int V = 32 + 24 * P + 4 * npairs;
+    for (int vw = warp; vw * 32 < V; vw += AT / 32) {
+      const int v = vw * 32 + lane;
+      int type, t, tgt;
+      if (v < 32) type = 4, t = v, tgt = E;
+      else if (v < 32 + 16 * P) type = 3, t = (v - 32) & 15, tgt = (v - 32) >> 4;
+      else if (v < 32 + 24 * P) type = 2, t = (v - 32 - 16 * P) & 7, tgt = (v - 32 - 16 * P) >> 3;
+      else type = 1, t = (v - 32 - 24 * P) & 3, tgt = (v - 32 - 24 * P) >> 2;
+      const unsigned m4 = __ballot_sync(0xffffffffu, type == 4), m3 = __ballot_sync(0xffffffffu, type == 3);
+      const unsigned m2 = __ballot_sync(0xffffffffu, type == 2), m1 = __ballot_sync(0xffffffffu, type == 1);
+      if (type == 4) {            // (ex,ex) + b_ex over all point factors, 32 lanes
+        double a[28];
+#pragma unroll
+        for (int k = 0; k < 28; ++k) a[k] = 0.0;
+        for (int pos = t; pos < nf; pos += 32) {
+          double2 X[6];
+          load_ex(S.rec, pos, X);
+          acc_sym(a, X, ldrec(S.rec, pos, 15));
+        }
+        rs_step<28>(a, (t & 16) != 0, 16, m4);
+        rs_step<14>(a, (t & 8) != 0, 8, m4);
+        bf_step<7>(a, 4, m4);
+        bf_step<7>(a, 2, m4);
+        bf_step<7>(a, 1, m4);
+        if ((t & 7) == 0) write_sym_slice(a, 14 * ((t >> 4) & 1) + 7 * ((t >> 3) & 1), Hpp, bp, D, E);
+      } else if (type == 3) {     // (p,ex) over factors with lo == p or hi == p, 16 lanes
+        double a[36];
+#pragma unroll
+        for (int k = 0; k < 36; ++k) a[k] = 0.0;
+        const int p = tgt;
+        for (int pos = S.baseA[p * P] + t, end = S.baseA[(p + 1) * P]; pos < end; pos += 16) {
+          double2 X[6], Y[6];
+          load_lo(S.rec, pos, X);
+          load_ex(S.rec, pos, Y);
+          acc_full(a, X, Y);
+        }
+        for (int lo = 0; lo < p; ++lo) {
+          const int b0 = S.baseA[lo * P + p];
+          for (int pos = b0 + t, end = b0 + S.totA[lo * P + p]; pos < end; pos += 16) {
+            double2 X[6], Y[6];
+            load_hi(S.rec, pos, X);
+            load_ex(S.rec, pos, Y);
+            acc_full(a, X, Y);
+          }
+        }
+        rs_step<36>(a, (t & 8) != 0, 8, m3);
+        rs_step<18>(a, (t & 4) != 0, 4, m3);
+        bf_step<9>(a, 2, m3);
+        bf_step<9>(a, 1, m3);
+        if ((t & 3) == 0) {
+          const int e0 = 18 * ((t >> 3) & 1) + 9 * ((t >> 2) & 1);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            const int e = e0 + k, r = e / 6, c = e % 6;
+            Hpp[(size_t)(6 * p + r) * D + 6 * E + c] = a[k];
+            Hpp[(size_t)(6 * E + c) * D + 6 * p + r] = a[k];
+          }
+        }
+      } else if (type == 2) {     // (p,p) + b_p over point factors with lo/hi == p and line factors of frame p, 8 lanes
+        double a[28];
+#pragma unroll
+        for (int k = 0; k < 28; ++k) a[k] = 0.0;
+        const int p = tgt;
+        for (int pos = S.baseA[p * P] + t, end = S.baseA[(p + 1) * P]; pos < end; pos += 8) {
+          double2 X[6];
+          load_lo(S.rec, pos, X);
+          acc_sym(a, X, ldrec(S.rec, pos, 15));
+        }
+        for (int lo = 0; lo < p; ++lo) {
+          const int b0 = S.baseA[lo * P + p];
+          for (int pos = b0 + t, end = b0 + S.totA[lo * P + p]; pos < end; pos += 8) {
+            double2 X[6];
+            load_hi(S.rec, pos, X);
+            acc_sym(a, X, ldrec(S.rec, pos, 15));
+          }
+        }
+        for (int pos = S.baseC[p] + t, end = S.baseC[p + 1]; pos < end; pos += 8) {
+          double2 X[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) X[k] = S.u.lrec[pos * LRECW + k];
+          acc_sym(a, X, S.u.lrec[pos * LRECW + 6]);
+        }
+        rs_step<28>(a, (t & 4) != 0, 4, m2);
+        rs_step<14>(a, (t & 2) != 0, 2, m2);
+        bf_step<7>(a, 1, m2);
+        if ((t & 1) == 0) write_sym_slice(a, 14 * ((t >> 2) & 1) + 7 * ((t >> 1) & 1), Hpp, bp, D, p);
+      } else {                    // (lo,hi) pair block, 4 lanes
+        double a[36];
+#pragma unroll
+        for (int k = 0; k < 36; ++k) a[k] = 0.0;
+        const bool live = tgt < npairs;
+        const int key = live ? S.pairs[tgt] : 0;
+        const int lo = key / P, hi = key % P;
+        if (live) {
+          const int b0 = S.baseA[key];
+          for (int pos = b0 + t, end = b0 + S.totA[key]; pos < end; pos += 4) {
+            double2 X[6], Y[6];
+            load_lo(S.rec, pos, X);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              Y[k] = make_double2(-X[k].x, -X[k].y);
+              Y[3 + k] = ldrec(S.rec, pos, 6 + k);
+            }
+            acc_full(a, X, Y);
+          }
+        }
+        rs_step<36>(a, (t & 2) != 0, 2, m1);
+        rs_step<18>(a, (t & 1) != 0, 1, m1);
+        if (live) {
+          const int e0 = 9 * t;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            const int e = e0 + k, r = e / 6, c = e % 6;
+            Hpp[(size_t)(6 * lo + r) * D + 6 * hi + c] = a[k];
+            Hpp[(size_t)(6 * hi + c) * D + 6 * lo + r] = a[k];
+          }
+        }
+      }
+    }
+    // pose-pair blocks that no factor touches are structural zeros
+    for (int e = tid; e < nkeyA * 36; e += AT) {
+      const int key = e / 36, q = e % 36, lo = key / P, hi = key % P;
+      if (lo < hi && S.totA[key] == 0) {
+        const int r = q / 6, c = q % 6;
+        Hpp[(size_t)(6 * lo + r) * D + 6 * hi + c] = 0.0;
+        Hpp[(size_t)(6 * hi + c) * D + 6 * lo + r] = 0.0;
+      }
+    }
+    // ------------------------------------------------------------------ P2b: landmark strips, thread per feature
+    for (;;) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&S.next_feature, 32);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= F) break;
+      const int l = base + lane;
+      if (l >= F) continue;
+      double2* __restrict__ row = reinterpret_cast<double2*>(Hlp + (size_t)l * D);
+      const int k0 = S.baseB[l], k1 = S.baseB[l + 1];
+      double ai[6] = {0, 0, 0, 0, 0, 0}, ae[6] = {0, 0, 0, 0, 0, 0}, dd = 0.0, dr = 0.0;
+      unsigned mask = 0u;
+      int istart = -1;
+      for (int k = k0; k < k1; ++k) {
+        const int pos = S.fperm[k];
+        const uint32_t ix = S.ridx[pos];
+        const int i = ix & 0xff, j = (ix >> 8) & 0xff;
+        const bool sw = i > j;
+        const double2 d = S.drec[pos];
+        double2 L[6], Hh[6], C[6];
+        load_lo(S.rec, pos, L);
+        load_hi(S.rec, pos, Hh);
+        load_ex(S.rec, pos, C);
+        const double2 r = ldrec(S.rec, pos, 15);
+        double bj[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const double2 xi = sw ? Hh[c] : L[c], xj = sw ? L[c] : Hh[c];
+          ai[c] = fma(d.x, xi.x, fma(d.y, xi.y, ai[c]));
+          ae[c] = fma(d.x, C[c].x, fma(d.y, C[c].y, ae[c]));
+          bj[c] = d.x * xj.x + d.y * xj.y;
+        }
+        dd = fma(d.x, d.x, fma(d.y, d.y, dd));
+        dr = fma(d.x, r.x, fma(d.y, r.y, dr));
+        row[3 * j] = make_double2(bj[0], bj[1]);
+        row[3 * j + 1] = make_double2(bj[2], bj[3]);
+        row[3 * j + 2] = make_double2(bj[4], bj[5]);
+        mask |= (1u << j) | (1u << i);
+        istart = i;
+      }
+      if (istart >= 0) {
+        row[3 * istart] = make_double2(ai[0], ai[1]);
+        row[3 * istart + 1] = make_double2(ai[2], ai[3]);
+        row[3 * istart + 2] = make_double2(ai[4], ai[5]);
+        mask |= 1u << E;
+      }
+      row[3 * E] = make_double2(ae[0], ae[1]);
+      row[3 * E + 1] = make_double2(ae[2], ae[3]);
+      row[3 * E + 2] = make_double2(ae[4], ae[5]);
+      mask |= 1u << E;
+      for (int b = 0; b < P; ++b)
+        if (!((mask >> b) & 1u)) {
+          row[3 * b] = make_double2(0.0, 0.0);
+          row[3 * b + 1] = make_double2(0.0, 0.0);
+          row[3 * b + 2] = make_double2(0.0, 0.0);
+        }
+      Hll[l] = dd;
+      bl[l] = dr;
+    }
+    __syncthreads();  // shared memory is reused by the next window
+  }
+}
+
+// Generic finish for flagged windows (and nothing else): global atomics on the zero-filled blocks.
+template <bool MODE_A>
+__global__ void __launch_bounds__(256) fallback_kernel(LinearizeArgs A, const int* __restrict__ fallback) {
+  for (int w = blockIdx.x; w < A.W; w += gridDim.x) {
+    if (!fallback[w]) continue;
+    const double* cw = A.cache + (size_t)w * (A.P * kPoseCache + kExCache);
+    const int D = A.D;
+    double* H = A.out.H_pp + (size_t)w * D * D;
+    double* bp = A.out.b_p + (size_t)w * D;
+    for (int64_t k = A.pf_window_offset[w] + threadIdx.x; k < A.pf_window_offset[w + 1]; k += blockDim.x) {
+      const uint32_t pk = A.pf_idx[k];
+      const int i = pk & 0xff, j = (pk >> 8) & 0xff, f = pk >> 16;
+      const double4 ob = reinterpret_cast<const double4*>(A.pf_obs)[k];
+      PointJac J;
+      eval_point(A, cw, i, j, A.inv_depth[(size_t)w * A.F + f], ob.x, ob.y, A.pf_pts_i_z ? A.pf_pts_i_z[k] : 1.0, ob.z,
+                 ob.w, J);
+      if (MODE_A) {
+        if (A.out.pf_residual) reinterpret_cast<double2*>(A.out.pf_residual)[k] = make_double2(J.r[0], J.r[1]);
+        if (A.out.pf_jac_pose_i) store_jac7(A.out.pf_jac_pose_i + 14 * k, J.a);
+        if (A.out.pf_jac_pose_j) store_jac7(A.out.pf_jac_pose_j + 14 * k, J.b);
+        if (A.out.pf_jac_ex) store_jac7(A.out.pf_jac_ex + 14 * k, J.c);
+        if (A.out.pf_jac_feat) reinterpret_cast<double2*>(A.out.pf_jac_feat)[k] = make_double2(J.d[0], J.d[1]);
+      }
+      point_atomics(A, w, i, j, f, J);
+    }
+    if (A.NL > 0)
+      for (int64_t k = A.lf_window_offset[w] + threadIdx.x; k < A.lf_window_offset[w + 1]; k += blockDim.x) {
+        const int frame = A.lf_frame[k];
+        double g9[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) g9[c] = A.lf_geom[(size_t)c * A.NL + k];
+        LineJac J;
+        eval_line(A, cw, frame, g9, J);
+        if (MODE_A) {
+          if (A.out.lf_residual) reinterpret_cast<double2*>(A.out.lf_residual)[k] = make_double2(J.r[0], J.r[1]);
+          if (A.out.lf_jac_pose) store_jac7(A.out.lf_jac_pose + 14 * k, J.a);
+        }
+        atomic_block(H, D, 6 * frame, 6 * frame, J.a, J.a, true);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) atomicAdd(bp + 6 * frame + r, J.a[0][r] * J.r[0] + J.a[1][r] * J.r[1]);
+      }
+  }
+}
+
+}  // namespace fused

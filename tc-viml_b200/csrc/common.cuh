@@ -67,6 +67,7 @@ struct viml_ctx {
   DeviceArena in_arena, out_arena, scratch, scratch2;
   void* nccl_lib = nullptr;
   // profiling (viml_profile_begin/end): event pairs per kernel id
+  bool force_generic = false;  // tests: route everything through the generic atomic kernels
   bool prof = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[VIML_NUM_KERNELS];
 };

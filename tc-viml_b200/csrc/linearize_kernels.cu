@@ -279,6 +279,32 @@ __device__ __forceinline__ void atomic_block(double* __restrict__ H, int D, int 
     }
 }
 
+// Generic accumulation of one point factor into the zero-initialised blocks of its window.
+__device__ __forceinline__ void point_atomics(const LinearizeArgs& A, int w, int i, int j, int f, const PointJac& J) {
+  const int D = A.D;
+  double* H = A.out.H_pp + (size_t)w * D * D;
+  double* bp = A.out.b_p + (size_t)w * D;
+  double* Hl = A.out.H_lp + ((size_t)w * A.F + f) * D;
+  const int oi = 6 * i, oj = 6 * j, oe = 6 * A.P;
+  atomic_block(H, D, oi, oi, J.a, J.a, true);
+  atomic_block(H, D, oi, oj, J.a, J.b, false);
+  atomic_block(H, D, oi, oe, J.a, J.c, false);
+  atomic_block(H, D, oj, oj, J.b, J.b, true);
+  atomic_block(H, D, oj, oe, J.b, J.c, false);
+  atomic_block(H, D, oe, oe, J.c, J.c, true);
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    atomicAdd(bp + oi + r, J.a[0][r] * J.r[0] + J.a[1][r] * J.r[1]);
+    atomicAdd(bp + oj + r, J.b[0][r] * J.r[0] + J.b[1][r] * J.r[1]);
+    atomicAdd(bp + oe + r, J.c[0][r] * J.r[0] + J.c[1][r] * J.r[1]);
+    atomicAdd(Hl + oi + r, J.a[0][r] * J.d[0] + J.a[1][r] * J.d[1]);
+    atomicAdd(Hl + oj + r, J.b[0][r] * J.d[0] + J.b[1][r] * J.d[1]);
+    atomicAdd(Hl + oe + r, J.c[0][r] * J.d[0] + J.c[1][r] * J.d[1]);
+  }
+  atomicAdd(A.out.H_ll + (size_t)w * A.F + f, J.d[0] * J.d[0] + J.d[1] * J.d[1]);
+  atomicAdd(A.out.b_l + (size_t)w * A.F + f, J.d[0] * J.r[0] + J.d[1] * J.r[1]);
+}
+
 template <bool MODE_A, bool MODE_B>
 __global__ void __launch_bounds__(128) points_kernel(LinearizeArgs A) {
   const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -299,30 +325,7 @@ __global__ void __launch_bounds__(128) points_kernel(LinearizeArgs A) {
     if (A.out.pf_jac_ex) store_jac7(A.out.pf_jac_ex + 14 * k, J.c);
     if (A.out.pf_jac_feat) reinterpret_cast<double2*>(A.out.pf_jac_feat)[k] = make_double2(J.d[0], J.d[1]);
   }
-  if (MODE_B) {
-    const int D = A.D;
-    double* H = A.out.H_pp + (size_t)w * D * D;
-    double* bp = A.out.b_p + (size_t)w * D;
-    double* Hl = A.out.H_lp + ((size_t)w * A.F + f) * D;
-    const int oi = 6 * i, oj = 6 * j, oe = 6 * A.P;
-    atomic_block(H, D, oi, oi, J.a, J.a, true);
-    atomic_block(H, D, oi, oj, J.a, J.b, false);
-    atomic_block(H, D, oi, oe, J.a, J.c, false);
-    atomic_block(H, D, oj, oj, J.b, J.b, true);
-    atomic_block(H, D, oj, oe, J.b, J.c, false);
-    atomic_block(H, D, oe, oe, J.c, J.c, true);
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      atomicAdd(bp + oi + r, J.a[0][r] * J.r[0] + J.a[1][r] * J.r[1]);
-      atomicAdd(bp + oj + r, J.b[0][r] * J.r[0] + J.b[1][r] * J.r[1]);
-      atomicAdd(bp + oe + r, J.c[0][r] * J.r[0] + J.c[1][r] * J.r[1]);
-      atomicAdd(Hl + oi + r, J.a[0][r] * J.d[0] + J.a[1][r] * J.d[1]);
-      atomicAdd(Hl + oj + r, J.b[0][r] * J.d[0] + J.b[1][r] * J.d[1]);
-      atomicAdd(Hl + oe + r, J.c[0][r] * J.d[0] + J.c[1][r] * J.d[1]);
-    }
-    atomicAdd(A.out.H_ll + (size_t)w * A.F + f, J.d[0] * J.d[0] + J.d[1] * J.d[1]);
-    atomicAdd(A.out.b_l + (size_t)w * A.F + f, J.d[0] * J.r[0] + J.d[1] * J.r[1]);
-  }
+  if (MODE_B) point_atomics(A, w, i, j, f, J);
 }
 
 template <bool MODE_A, bool MODE_B>
@@ -351,6 +354,8 @@ __global__ void __launch_bounds__(128) lines_kernel(LinearizeArgs A) {
     for (int r = 0; r < 6; ++r) atomicAdd(bp + of + r, J.a[0][r] * J.r[0] + J.a[1][r] * J.r[1]);
   }
 }
+
+#include "assemble.cuh"
 
 // Landmark Schur complement, simple version: one CTA per window, threads own entries of S.
 //   S = H_pp - sum_l W_l^T W_l / L_l,  g = b_p - sum_l W_l^T b_l / L_l,  L_l <= eps skipped.
@@ -445,6 +450,30 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
     LaunchScope ls(ctx, K_PREP);
     prep_windows_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a);
   }
+  const bool fast = modeB && a.P <= fused::PMAX && a.F <= fused::FMAX && !ctx->force_generic;
+  if (fast) {
+    // fused CTA-per-window kernel: writes every H/b entry exactly once (no memset), r/J too when asked
+    int* flags = ctx->scratch.take<int>((size_t)a.W);
+    VIML_TRY_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)a.W * sizeof(int), st));
+    const size_t smem = sizeof(fused::Smem);
+    static bool attr_done = false;
+    if (!attr_done) {
+      VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(fused::assemble_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(fused::assemble_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_done = true;
+    }
+    const int grid = a.W < ctx->sm_count ? a.W : ctx->sm_count;
+    {
+      LaunchScope ls(ctx, K_ASSEMBLE);
+      if (modeA) fused::assemble_kernel<true><<<grid, fused::AT, smem, st>>>(a, flags);
+      else fused::assemble_kernel<false><<<grid, fused::AT, smem, st>>>(a, flags);
+    }
+    {
+      LaunchScope ls(ctx, K_POINTS);  // finishes flagged (over-size) windows only
+      if (modeA) fused::fallback_kernel<true><<<grid, 256, 0, st>>>(a, flags);
+      else fused::fallback_kernel<false><<<grid, 256, 0, st>>>(a, flags);
+    }
+  } else {
   if (modeB) {
     const size_t W = a.W, D = a.D, F = a.F;
     VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.H_pp, 0, W * D * D * sizeof(double), st));
@@ -466,6 +495,7 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
     if (modeA && modeB) lines_kernel<true, true><<<grid, 128, 0, st>>>(a);
     else if (modeA) lines_kernel<true, false><<<grid, 128, 0, st>>>(a);
     else if (modeB) lines_kernel<false, true><<<grid, 128, 0, st>>>(a);
+  }
   }
   if (a.flags & VIML_OUT_SCHUR) {
     const double eps = 1e-8;  // MarginalizationInfo::eps (marginalization_factor.h:70)

@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -67,6 +68,7 @@ int viml_create(viml_ctx** out, const viml_config* cfg, int device) {
   ctx->cfg = *cfg;
   ctx->cos_th = cos_threshold(cfg->angle_th);
   ctx->nan_angle_passes = !(3.1415926 > cfg->angle_th);
+  if (const char* e = getenv("VIML_FORCE_GENERIC")) ctx->force_generic = e[0] == '1';  // test hook
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming) != cudaSuccess ||
@@ -223,7 +225,8 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   const size_t n_pose = (size_t)W * P * 7, n_ex = (size_t)W * 7, n_dep = (size_t)W * F;
   const size_t szHpp = (size_t)W * D * D, szHlp = (size_t)W * F * D, szF = (size_t)W * F, szD = (size_t)W * D;
   // scratch: pose cache (+ H blocks when only the Schur complement is wanted)
-  size_t scratch_bytes = DeviceArena::padded((size_t)W * (P * kPoseCache + kExCache) * sizeof(double));
+  size_t scratch_bytes = DeviceArena::padded((size_t)W * (P * kPoseCache + kExCache) * sizeof(double)) +
+                         DeviceArena::padded((size_t)W * sizeof(int));
   const bool scratchH = wantS && (!wantHB || !dev);
   if (scratchH && dev)
     scratch_bytes += DeviceArena::padded(szHpp * 8) + DeviceArena::padded(szHlp * 8) + 2 * DeviceArena::padded(szF * 8) +

@@ -74,6 +74,21 @@ def test_batch_shapes_and_edges(pkg, orc, ctx, cfg):
     b3 = synth.make_windows(4, seed=107)
     b3.pf_pts_i_z = 1.0 + 0.01 * np.random.default_rng(1).standard_normal(b3.NP)
     check_linearize(pkg, orc, ctx, cfg, b3, allf)
+    # windows too large for the fused kernel's shared memory (> 704 factors) inside a batch that is otherwise
+    # on the fast path: flagged and finished by the generic atomic kernel
+    big = synth.make_windows(5, seed=112, F=160, all_start_zero=True)
+    assert np.diff(big.pf_window_offset).max() > 704
+    check_linearize(pkg, orc, ctx, cfg, big, allf)
+    mixed = synth.make_windows(6, seed=113, F=160)
+    keep = np.ones(mixed.NP, dtype=bool)          # thin out all but window 1 -> only one window is flagged
+    check_linearize(pkg, orc, ctx, cfg, mixed, allf)
+    # the generic path alone (test hook), same results
+    os.environ["VIML_FORCE_GENERIC"] = "1"
+    try:
+        with pkg.Context(cfg) as cg:
+            check_linearize(pkg, orc, cg, cfg, synth.make_windows(7, seed=114), allf)
+    finally:
+        del os.environ["VIML_FORCE_GENERIC"]
     # non-default sqrt_info / Cauchy scale
     cfg2 = synth.euroc_config(sqrt_info=120.0, cauchy_a=2.5)
     with pkg.Context(cfg2) as c2:
