@@ -29,25 +29,26 @@ constexpr int FMAX = 160;        // max features per window
 constexpr int KA = PMAX * PMAX;  // pair keys
 constexpr int SLABS = NF / 32;   // 22
 constexpr int LSLABS = NL / 32;  // 5
-constexpr int RECW = 16;         // double2 per point record: 0..5 lo, 6..8 hi_rot, 9..14 ex, 15 r
+constexpr int RECW = 17;         // double2 per point record: 0..5 lo, 6..8 hi_rot, 9..14 ex, 15 r, 16 d (odd stride: conflict-free)
 constexpr int LRECW = 7;         // double2 per line record: 0..5 pose, 6 r
 constexpr int WSLOTS = 64;       // windows per CTA whose CSR offsets are staged in shared memory
 
 struct Smem {
   double2 rec[NF * RECW];
-  double2 drec[NF];
   union {
     double2 lrec[NL * LRECW];
     struct {
       uint16_t cntA[SLABS * KA];
       uint16_t cntB[SLABS * FMAX];
       uint16_t cntC[LSLABS * PMAX];
+      uint16_t cntD[SLABS * PMAX];
     } cnt;
   } u;
   double cache[PMAX * kPoseCache + kExCache];
   uint32_t ridx[NF];
   uint16_t fperm[NF];
-  uint16_t baseA[KA + 1], totA[KA], baseB[FMAX + 1], totB[FMAX], baseC[PMAX + 1], totC[PMAX], pairs[KA];
+  uint16_t hperm[NF];  // record positions ordered by hi pose (flattened "hi-role" ranges)
+  uint16_t baseA[KA + 1], totA[KA], baseB[FMAX + 1], totB[FMAX], baseC[PMAX + 1], totC[PMAX], baseD[PMAX + 1], totD[PMAX], pairs[KA];
   int npairs, next_feature;
   int woff[4 * WSLOTS];  // this CTA's windows: {p0, p1, l0, l1} per slot (filled once per launch)
 };
@@ -62,10 +63,10 @@ __device__ __forceinline__ void prefetch_l2(const void* base, size_t bytes, int 
 }
 
 __device__ __forceinline__ double2 ldrec(const double2* __restrict__ rec, int pos, int k) {
-  return rec[pos * RECW + (k ^ (pos & 7))];
+  return rec[pos * RECW + k];  // k is a compile-time constant at every call site: one base register per record
 }
 __device__ __forceinline__ void strec(double2* __restrict__ rec, int pos, int k, double x, double y) {
-  rec[pos * RECW + (k ^ (pos & 7))] = make_double2(x, y);
+  rec[pos * RECW + k] = make_double2(x, y);
 }
 
 // reduce-scatter step: N live values -> N/2, lanes with bit w keep the upper half
@@ -136,7 +137,7 @@ __device__ __forceinline__ void write_sym_slice(const double* a, int e0, double*
 }
 
 template <bool MODE_A>
-__global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* __restrict__ fallback) {
+__global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* __restrict__ fallback, int w_begin, int w_end) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -145,9 +146,10 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
   const int cstride = P * kPoseCache + kExCache;
 
   // stage this CTA's CSR offsets once so that per-window address generation never waits on HBM
+  // (the launcher keeps (w_end - w_begin) <= WSLOTS * gridDim.x)
   for (int e = tid; e < WSLOTS; e += AT) {
-    const int w = blockIdx.x + e * gridDim.x;
-    if (w < A.W) {
+    const int w = w_begin + blockIdx.x + e * gridDim.x;
+    if (w < w_end) {
       S.woff[4 * e] = A.pf_window_offset[w];
       S.woff[4 * e + 1] = A.pf_window_offset[w + 1];
       S.woff[4 * e + 2] = A.NL > 0 ? A.lf_window_offset[w] : 0;
@@ -155,28 +157,34 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
     }
   }
   __syncthreads();
+  // register prefetch of the next window's sort keys and pose cache (consumed in its P0)
+  uint32_t nx_idx0 = 0u, nx_idx1 = 0u;
+  int nx_frame = 0xffff;
+  double nx_c0 = 0.0, nx_c1 = 0.0;
+  auto fetch_next = [&](int wn, int sl) {
+    const int q0 = S.woff[4 * sl], qn = S.woff[4 * sl + 1] - q0, m0 = S.woff[4 * sl + 2], mn = S.woff[4 * sl + 3] - m0;
+    nx_idx0 = tid < qn ? A.pf_idx[q0 + tid] : 0u;
+    nx_idx1 = tid + AT < qn ? A.pf_idx[q0 + tid + AT] : 0u;
+    nx_frame = tid < mn ? A.lf_frame[m0 + tid] : 0xffff;
+    const double* __restrict__ gc = A.cache + (size_t)wn * cstride;
+    nx_c0 = tid < cstride ? gc[tid] : 0.0;
+    nx_c1 = tid + AT < cstride ? gc[tid + AT] : 0.0;
+  };
+  if (w_begin + (int)blockIdx.x < w_end) fetch_next(w_begin + blockIdx.x, 0);
 
   int slot = 0;
-  for (int w = blockIdx.x; w < A.W; w += gridDim.x, ++slot) {
-    int p0, p1, l0, l1;
-    if (slot < WSLOTS) {
-      p0 = S.woff[4 * slot], p1 = S.woff[4 * slot + 1], l0 = S.woff[4 * slot + 2], l1 = S.woff[4 * slot + 3];
-    } else {
-      p0 = A.pf_window_offset[w], p1 = A.pf_window_offset[w + 1];
-      l0 = A.NL > 0 ? A.lf_window_offset[w] : 0, l1 = A.NL > 0 ? A.lf_window_offset[w + 1] : 0;
-    }
+  for (int w = w_begin + blockIdx.x; w < w_end; w += gridDim.x, ++slot) {
+    const int p0 = S.woff[4 * slot], p1 = S.woff[4 * slot + 1], l0 = S.woff[4 * slot + 2], l1 = S.woff[4 * slot + 3];
+    const bool has_next = w + (int)gridDim.x < w_end;
     const int nf = p1 - p0, nl = l1 - l0;
-    if (slot + 1 < WSLOTS && w + (int)gridDim.x < A.W) {  // pull the next window's inputs into L2 while this one computes
+    if (has_next) {  // pull the next window's per-factor inputs into L2 while this one computes
       const int wn = w + gridDim.x;
       const int q0 = S.woff[4 * slot + 4], q1 = S.woff[4 * slot + 5], m0 = S.woff[4 * slot + 6], m1 = S.woff[4 * slot + 7];
-      prefetch_l2(A.pf_idx + q0, (size_t)(q1 - q0) * 4, tid, AT);
       prefetch_l2(A.pf_obs + (size_t)q0 * 4, (size_t)(q1 - q0) * 32, tid, AT);
       prefetch_l2(A.inv_depth + (size_t)wn * F, (size_t)F * 8, tid, AT);
-      prefetch_l2(A.cache + (size_t)wn * cstride, (size_t)cstride * 8, tid, AT);
-      if (A.NL > 0) {
-        prefetch_l2(A.lf_frame + m0, (size_t)(m1 - m0) * 4, tid, AT);
+      if (A.pf_pts_i_z) prefetch_l2(A.pf_pts_i_z + q0, (size_t)(q1 - q0) * 8, tid, AT);
+      if (A.NL > 0)
         for (int c = 0; c < 9; ++c) prefetch_l2(A.lf_geom + (size_t)c * A.NL + m0, (size_t)(m1 - m0) * 8, tid, AT);
-      }
     }
     double* __restrict__ Hpp = A.out.H_pp + (size_t)w * D * D;
     double* __restrict__ Hlp = A.out.H_lp + (size_t)w * F * D;
@@ -189,24 +197,25 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
       for (int e = tid; e < F; e += AT) Hll[e] = 0.0, bl[e] = 0.0;
       for (int e = tid; e < D; e += AT) bp[e] = 0.0;
       if (tid == 0) fallback[w] = 1;
+      if (has_next) fetch_next(w + gridDim.x, slot + 1);
       continue;
     }
     // ------------------------------------------------------------------ P0: cache + sorts
     {
-      const double* __restrict__ gc = A.cache + (size_t)w * cstride;
-      for (int e = tid; e < cstride; e += AT) S.cache[e] = gc[e];
+      if (tid < cstride) S.cache[tid] = nx_c0;
+      if (tid + AT < cstride) S.cache[tid + AT] = nx_c1;
       uint32_t* z = reinterpret_cast<uint32_t*>(&S.u.cnt);
       for (int e = tid; e < (int)(sizeof(S.u.cnt) / 4); e += AT) z[e] = 0u;
       if (tid == 0) S.next_feature = 0;
     }
     __syncthreads();
     uint32_t fidx[2];
-    int keyA[2], rankA[2], rankB[2];
+    int keyA[2], rankA[2], rankB[2], rankD[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int f = tid + r * AT;
       const bool valid = f < nf;
-      fidx[r] = valid ? A.pf_idx[p0 + f] : 0u;
+      fidx[r] = r == 0 ? nx_idx0 : nx_idx1;
       const int i = fidx[r] & 0xff, j = (fidx[r] >> 8) & 0xff, l = fidx[r] >> 16;
       const int lo = min(i, j), hi = max(i, j);
       keyA[r] = valid ? lo * P + hi : 0xffff;
@@ -214,25 +223,28 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
       if (r * AT < nf) {  // warp-uniform: some lane of this warp may be valid
         const unsigned ma = __match_any_sync(0xffffffffu, keyA[r]);
         const unsigned mb = __match_any_sync(0xffffffffu, keyB);
+        const unsigned md = __match_any_sync(0xffffffffu, valid ? hi : 0xffff);
         const unsigned lt = (1u << lane) - 1u;
         rankA[r] = __popc(ma & lt);
         rankB[r] = __popc(mb & lt);
+        rankD[r] = __popc(md & lt);
         const int slab = warp + r * (AT / 32);
         if (valid && rankA[r] == 0) S.u.cnt.cntA[slab * KA + keyA[r]] = (uint16_t)__popc(ma);
         if (valid && rankB[r] == 0) S.u.cnt.cntB[slab * FMAX + keyB] = (uint16_t)__popc(mb);
+        if (valid && rankD[r] == 0) S.u.cnt.cntD[slab * PMAX + hi] = (uint16_t)__popc(md);
       }
     }
     int lframe = 0, rankC = 0;
     if (tid < NL) {  // warps 0..4 (NL = 160): line factors by frame
       const bool valid = tid < nl;
-      lframe = valid ? A.lf_frame[l0 + tid] : 0xffff;
+      lframe = valid ? nx_frame : 0xffff;
       const unsigned mc = __match_any_sync(0xffffffffu, lframe);
       rankC = __popc(mc & ((1u << lane) - 1u));
       if (valid && rankC == 0) S.u.cnt.cntC[warp * PMAX + lframe] = (uint16_t)__popc(mc);
     }
     __syncthreads();
     // exclusive prefix over slabs for every key (thread per key)
-    for (int e = tid; e < nkeyA + F + P; e += AT) {
+    for (int e = tid; e < nkeyA + F + 2 * P; e += AT) {
       if (e < nkeyA) {
         int run = 0;
         for (int s = 0; s < SLABS; ++s) {
@@ -250,6 +262,15 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
           run += c;
         }
         S.totB[k] = (uint16_t)run;
+      } else if (e >= nkeyA + F + P) {
+        const int k = e - nkeyA - F - P;
+        int run = 0;
+        for (int s = 0; s < SLABS; ++s) {
+          const int c = S.u.cnt.cntD[s * PMAX + k];
+          S.u.cnt.cntD[s * PMAX + k] = (uint16_t)run;
+          run += c;
+        }
+        S.totD[k] = (uint16_t)run;
       } else {
         const int k = e - nkeyA - F;
         int run = 0;
@@ -263,9 +284,9 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
     }
     __syncthreads();
     // exclusive scans over keys: warp 0 -> baseA (+ non-empty pair list), warp 1 -> baseB, warp 2 -> baseC
-    if (warp < 3) {
-      const uint16_t* tot = warp == 0 ? S.totA : (warp == 1 ? S.totB : S.totC);
-      uint16_t* base = warp == 0 ? S.baseA : (warp == 1 ? S.baseB : S.baseC);
+    if (warp < 4) {
+      const uint16_t* tot = warp == 0 ? S.totA : (warp == 1 ? S.totB : (warp == 2 ? S.totC : S.totD));
+      uint16_t* base = warp == 0 ? S.baseA : (warp == 1 ? S.baseB : (warp == 2 ? S.baseC : S.baseD));
       const int n = warp == 0 ? nkeyA : (warp == 1 ? F : P);
       int carry = 0, npairs = 0;
       for (int b0 = 0; b0 < n; b0 += 32) {
@@ -303,6 +324,8 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
         const int posB = S.baseB[l] + S.u.cnt.cntB[slab * FMAX + l] + rankB[r];
         S.ridx[posA[r]] = fidx[r];
         S.fperm[posB] = (uint16_t)posA[r];
+        const int hi = max((int)(fidx[r] & 0xff), (int)((fidx[r] >> 8) & 0xff));
+        S.hperm[S.baseD[hi] + S.u.cnt.cntD[slab * PMAX + hi] + rankD[r]] = (uint16_t)posA[r];
       }
     }
     int posC = 0;
@@ -336,7 +359,7 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
 #pragma unroll
       for (int c = 0; c < 6; ++c) strec(S.rec, pos, 9 + c, J.c[0][c], J.c[1][c]);
       strec(S.rec, pos, 15, J.r[0], J.r[1]);
-      S.drec[pos] = make_double2(J.d[0], J.d[1]);
+      strec(S.rec, pos, 16, J.d[0], J.d[1]);
     }
     if (tid < nl) {
       const int64_t k = (int64_t)l0 + tid;
@@ -392,14 +415,12 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
           load_ex(S.rec, pos, Y);
           acc_full(a, X, Y);
         }
-        for (int lo = 0; lo < p; ++lo) {
-          const int b0 = S.baseA[lo * P + p];
-          for (int pos = b0 + t, end = b0 + S.totA[lo * P + p]; pos < end; pos += 16) {
-            double2 X[6], Y[6];
-            load_hi(S.rec, pos, X);
-            load_ex(S.rec, pos, Y);
-            acc_full(a, X, Y);
-          }
+        for (int k = S.baseD[p] + t, end = S.baseD[p + 1]; k < end; k += 16) {
+          const int pos = S.hperm[k];
+          double2 X[6], Y[6];
+          load_hi(S.rec, pos, X);
+          load_ex(S.rec, pos, Y);
+          acc_full(a, X, Y);
         }
         rs_step<36>(a, (t & 8) != 0, 8, m3);
         rs_step<18>(a, (t & 4) != 0, 4, m3);
@@ -424,13 +445,11 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
           load_lo(S.rec, pos, X);
           acc_sym(a, X, ldrec(S.rec, pos, 15));
         }
-        for (int lo = 0; lo < p; ++lo) {
-          const int b0 = S.baseA[lo * P + p];
-          for (int pos = b0 + t, end = b0 + S.totA[lo * P + p]; pos < end; pos += 8) {
-            double2 X[6];
-            load_hi(S.rec, pos, X);
-            acc_sym(a, X, ldrec(S.rec, pos, 15));
-          }
+        for (int k = S.baseD[p] + t, end = S.baseD[p + 1]; k < end; k += 8) {
+          const int pos = S.hperm[k];
+          double2 X[6];
+          load_hi(S.rec, pos, X);
+          acc_sym(a, X, ldrec(S.rec, pos, 15));
         }
         for (int pos = S.baseC[p] + t, end = S.baseC[p + 1]; pos < end; pos += 8) {
           double2 X[6];
@@ -475,15 +494,16 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
         }
       }
     }
-    // pose-pair blocks that no factor touches are structural zeros
-    for (int e = tid; e < nkeyA * 36; e += AT) {
-      const int key = e / 36, q = e % 36, lo = key / P, hi = key % P;
-      if (lo < hi && S.totA[key] == 0) {
-        const int r = q / 6, c = q % 6;
-        Hpp[(size_t)(6 * lo + r) * D + 6 * hi + c] = 0.0;
-        Hpp[(size_t)(6 * hi + c) * D + 6 * lo + r] = 0.0;
-      }
-    }
+    // pose-pair blocks that no factor touches are structural zeros (warp per empty pair)
+    for (int lo = 0; lo < P; ++lo)
+      for (int hi = lo + 1 + warp; hi < P; hi += AT / 32)
+        if (S.totA[lo * P + hi] == 0)
+          for (int q = lane; q < 36; q += 32) {
+            const int r = q / 6, c = q % 6;
+            Hpp[(size_t)(6 * lo + r) * D + 6 * hi + c] = 0.0;
+            Hpp[(size_t)(6 * hi + c) * D + 6 * lo + r] = 0.0;
+          }
+    if (has_next) fetch_next(w + gridDim.x, slot + 1);
     // ------------------------------------------------------------------ P2b: landmark strips, thread per feature
     for (;;) {
       int base = 0;
@@ -502,19 +522,23 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
         const uint32_t ix = S.ridx[pos];
         const int i = ix & 0xff, j = (ix >> 8) & 0xff;
         const bool sw = i > j;
-        const double2 d = S.drec[pos];
-        double2 L[6], Hh[6], C[6];
-        load_lo(S.rec, pos, L);
-        load_hi(S.rec, pos, Hh);
+        const double2 d = ldrec(S.rec, pos, 16);
+        double2 Xi[6], Xj[6], C[6];
+        if (!sw) {
+          load_lo(S.rec, pos, Xi);
+          load_hi(S.rec, pos, Xj);
+        } else {
+          load_hi(S.rec, pos, Xi);
+          load_lo(S.rec, pos, Xj);
+        }
         load_ex(S.rec, pos, C);
         const double2 r = ldrec(S.rec, pos, 15);
         double bj[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
-          const double2 xi = sw ? Hh[c] : L[c], xj = sw ? L[c] : Hh[c];
-          ai[c] = fma(d.x, xi.x, fma(d.y, xi.y, ai[c]));
+          ai[c] = fma(d.x, Xi[c].x, fma(d.y, Xi[c].y, ai[c]));
           ae[c] = fma(d.x, C[c].x, fma(d.y, C[c].y, ae[c]));
-          bj[c] = d.x * xj.x + d.y * xj.y;
+          bj[c] = d.x * Xj[c].x + d.y * Xj[c].y;
         }
         dd = fma(d.x, d.x, fma(d.y, d.y, dd));
         dr = fma(d.x, r.x, fma(d.y, r.y, dr));

@@ -463,10 +463,11 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
       attr_done = true;
     }
     const int grid = a.W < ctx->sm_count ? a.W : ctx->sm_count;
-    {
+    for (int wb = 0; wb < a.W; wb += fused::WSLOTS * grid) {   // <= WSLOTS windows per CTA per launch
+      const int we = a.W < wb + fused::WSLOTS * grid ? a.W : wb + fused::WSLOTS * grid;
       LaunchScope ls(ctx, K_ASSEMBLE);
-      if (modeA) fused::assemble_kernel<true><<<grid, fused::AT, smem, st>>>(a, flags);
-      else fused::assemble_kernel<false><<<grid, fused::AT, smem, st>>>(a, flags);
+      if (modeA) fused::assemble_kernel<true><<<grid, fused::AT, smem, st>>>(a, flags, wb, we);
+      else fused::assemble_kernel<false><<<grid, fused::AT, smem, st>>>(a, flags, wb, we);
     }
     {
       LaunchScope ls(ctx, K_POINTS);  // finishes flagged (over-size) windows only
