@@ -203,6 +203,8 @@ typedef struct viml_assoc_query {
   const double* ex_pose;     /* [Pq][7]                             */
   const double* lines2d;     /* [Pq][L][4]                          */
   const int32_t* n_lines2d;  /* [Pq] or NULL (= L everywhere)       */
+  const double* cull_ex_pose;/* [Pq][7] or NULL: extrinsic at frame entry (UpdateLinesInFoV's _Ric/_Tic
+                                argument, estimator.cpp:385); NULL = ex_pose for both                    */
 } viml_assoc_query;
 
 /* match_index: MAP index of the chosen 3D line, -1 = none (est.cpp:869-878 / :703-713).

@@ -993,7 +993,8 @@ extern "C" int orc_line_associate(const viml_config* cfg, const double* map, int
   parallel_for(q->n_poses, nthreads, [&](int p) {
     std::vector<int32_t> fov(n);
     const double* ex = q->ex_pose + (size_t)p * 7;
-    const CamPose cull = camera_pose(cfg, q->cull_poses + (size_t)p * 7, ex);
+    const double* cex = q->cull_ex_pose ? q->cull_ex_pose + (size_t)p * 7 : ex;
+    const CamPose cull = camera_pose(cfg, q->cull_poses + (size_t)p * 7, cex);
     uint32_t* mask = out->fov_mask ? out->fov_mask + (size_t)p * words : nullptr;
     if (mask) std::fill(mask, mask + words, 0u);
     const int cnt = fov_cull(cfg, cull, map, n, fov.data(), mask);
@@ -1001,7 +1002,9 @@ extern "C" int orc_line_associate(const viml_config* cfg, const double* map, int
     if (out->fov_index)
       for (int k = 0; k < std::min(cnt, out->fov_capacity); ++k)
         out->fov_index[(size_t)p * out->fov_capacity + k] = fov[k];
-    const CamPose mp = q->match_poses ? camera_pose(cfg, q->match_poses + (size_t)p * 7, ex) : cull;
+    const CamPose mp = (q->match_poses || q->cull_ex_pose)
+                           ? camera_pose(cfg, (q->match_poses ? q->match_poses : q->cull_poses) + (size_t)p * 7, ex)
+                           : cull;
     const int nl = q->n_lines2d ? q->n_lines2d[p] : L;
     for (int l = 0; l < nl; ++l) {
       float err[3];

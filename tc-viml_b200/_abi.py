@@ -72,7 +72,7 @@ class MargOut(C.Structure):
 class AssocQuery(C.Structure):
     _fields_ = [("n_poses", C.c_int32), ("lines_per_pose", C.c_int32),
                 ("cull_poses", C.c_void_p), ("match_poses", C.c_void_p), ("ex_pose", C.c_void_p),
-                ("lines2d", C.c_void_p), ("n_lines2d", C.c_void_p)]
+                ("lines2d", C.c_void_p), ("n_lines2d", C.c_void_p), ("cull_ex_pose", C.c_void_p)]
 
 
 class AssocOut(C.Structure):

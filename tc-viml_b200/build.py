@@ -95,6 +95,9 @@ def build_host(verbose=False, force=False):
 
 def build_all(verbose=False, force=False):
     so = build_cuda(verbose=verbose, force=force)
+    # the selftest links the oracle as its checker: make sure it exists (building it is not using it)
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], stdout=subprocess.DEVNULL)
+    build_host(verbose=verbose, force=force)
     return so
 
 

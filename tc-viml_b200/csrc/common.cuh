@@ -143,6 +143,7 @@ struct AssocArgs {  // device pointers only
   const double* cull_poses;
   const double* match_poses;  // may alias cull_poses
   const double* ex_pose;
+  const double* cull_ex_pose;  // may alias ex_pose
   const double* lines2d;
   const int32_t* n_lines2d;  // nullable
   int32_t* match_index;

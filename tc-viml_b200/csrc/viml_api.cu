@@ -384,13 +384,14 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
     VIML_TRY_CUDA(ctx, ctx->out_arena.reserve(sb));
     a.cull_poses = q->cull_poses, a.match_poses = q->match_poses ? q->match_poses : q->cull_poses;
     a.ex_pose = q->ex_pose, a.lines2d = q->lines2d, a.n_lines2d = q->n_lines2d;
+    a.cull_ex_pose = q->cull_ex_pose ? q->cull_ex_pose : q->ex_pose;
     a.match_index = out->match_index, a.err = out->err, a.projected = out->projected;
     a.fov_index = out->fov_index;
     a.fov_mask = out->fov_mask ? out->fov_mask : ctx->out_arena.take<uint32_t>((size_t)Pq * words);
     a.fov_count = out->fov_count ? out->fov_count : ctx->out_arena.take<int32_t>(Pq);
     return viml_launch_associate(ctx, a);
   }
-  VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(3 * pad((size_t)Pq * 56) + pad(nq * 32) + pad((size_t)Pq * 4)));
+  VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(4 * pad((size_t)Pq * 56) + pad(nq * 32) + pad((size_t)Pq * 4)));
   auto up = [&](const void* src, size_t bytes) -> void* {
     char* d = ctx->in_arena.take<char>(bytes);
     if (bytes) cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st);
@@ -399,6 +400,7 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
   a.cull_poses = (const double*)up(q->cull_poses, (size_t)Pq * 56);
   a.match_poses = q->match_poses ? (const double*)up(q->match_poses, (size_t)Pq * 56) : a.cull_poses;
   a.ex_pose = (const double*)up(q->ex_pose, (size_t)Pq * 56);
+  a.cull_ex_pose = q->cull_ex_pose ? (const double*)up(q->cull_ex_pose, (size_t)Pq * 56) : a.ex_pose;
   a.lines2d = (const double*)up(q->lines2d, nq * 32);
   a.n_lines2d = q->n_lines2d ? (const int32_t*)up(q->n_lines2d, (size_t)Pq * 4) : nullptr;
   VIML_TRY_CUDA(ctx, cudaGetLastError());
