@@ -388,6 +388,35 @@ def main():
             out["assoc"]["cpu_baseline"] = {"value": npose * L / dt, "unit": "assoc/s", "cores": nt, "kind": "port",
                                             "sample": f"{npose} of {Pq} poses against the full {N}-line map ({dt:.1f} s)"}
 
+    # ------------------------------------------------------------------ one huge window (cfg 5b): partial [S|g] + all-reduce
+    if not args.skip_extras:
+        shard = pkg.shard
+        huge = synth.make_windows(1, seed=0x5EED + 5, P=201, F=3000, lines_per_frame=2, max_len=25)
+        part = shard.split_huge_window(huge, rank, world)
+        Dh = huge.D
+        dh_in = {k: ctx.to_device(v) for k, v in part.arrays().items() if v is not None}
+        sg = torch.zeros(Dh * Dh + Dh, dtype=torch.float64, device="cuda")
+        so = abi.LinearizeOut()
+        so.S, so.g = sg.data_ptr(), sg.data_ptr() + Dh * Dh * 8
+        sh = part.struct(dh_in)
+        fl = abi.OUT_SCHUR | abi.LOSS_CAUCHY | abi.PTRS_DEVICE
+
+        def huge_step():
+            ctx.linearize_raw(sh, so, fl)
+            if world > 1:
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(sg)
+
+        h_steps = max(3, min(K, 5))
+        msH, profH = timed_device(huge_step, h_steps, 3)
+        out["huge_window"] = {"factors_per_s": (huge.NP + huge.NL) / (msH / h_steps * 1e-3), "ms_per_step": msH / h_steps,
+                              "shape": f"1 window, {huge.P} poses, {huge.F} landmarks, {huge.NP}+{huge.NL} factors, split by landmark over {world} GPU(s)",
+                              "allreduce_doubles": int(Dh * Dh + Dh) if world > 1 else 0,
+                              "collective": "NCCL all-reduce(sum, f64) of [S|g] via torch.distributed" if world > 1 else "none (1 GPU)",
+                              "kernel_ms_per_step": {k: v[0] / h_steps for k, v in profH.items()}}
+        for p in dh_in.values():
+            ctx.device_free(p)
+
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
     if rank == 0 and world == 1 and not args.skip_cpu:
         orc = ge.load_oracle()

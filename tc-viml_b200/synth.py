@@ -77,7 +77,7 @@ def pose7(p, R, rng=None, norm_jitter=1e-12):
 
 # ---- sliding windows (cfg 1, 2, 4, 5) ---------------------------------------------------------------
 def make_windows(W, seed=0x5EED, P=11, F=150, lines_per_frame=10, start_max=None, min_len=2,
-                 all_start_zero=False, noise_px=0.5, z_plane=False):
+                 all_start_zero=False, noise_px=0.5, z_plane=False, max_len=None):
     """W independent EuRoC-shaped windows.
 
     P poses on a smooth random trajectory, F landmarks 2.5-8 m ahead of their start frame with
@@ -112,6 +112,8 @@ def make_windows(W, seed=0x5EED, P=11, F=150, lines_per_frame=10, start_max=None
     else:
         start = rng.integers(0, start_max + 1, (W, F))
     length = rng.integers(min_len, P - start + 1)  # frames observed incl. start
+    if max_len is not None:
+        length = np.minimum(length, max_len)
     u = rng.uniform(20, WIDTH - 20, (W, F))
     v = rng.uniform(20, HEIGHT - 20, (W, F))
     depth = rng.uniform(2.5, 8.0, (W, F))

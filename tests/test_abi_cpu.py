@@ -50,9 +50,16 @@ def test_no_cpu_fallback(pkg, cfg):
 
 
 def test_product_never_imports_oracle():
+    """Product sources never reference the oracle; the only mention is build.py linking the C++ SELF-TEST
+    (host/tests/, test infrastructure) against it.  The shipped libraries must not depend on it either."""
+    import subprocess
     pkgdir = os.path.join(ROOT, "tc-viml_b200")
     for dp, _, files in os.walk(pkgdir):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) and "tests" not in dp:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) and "tests" not in dp and f != "build.py":
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 assert "liboracle" not in src and "viml_oracle" not in src and "import oracle" not in src, f
+    for lib in ("libviml_b200.so", "libviml_host.so"):
+        path = os.path.join(pkgdir, lib)
+        if os.path.exists(path):
+            assert "oracle" not in subprocess.run(["ldd", path], capture_output=True, text=True).stdout

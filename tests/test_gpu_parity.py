@@ -160,6 +160,24 @@ def test_full_size_batch_properties(pkg, orc, ctx, cfg):
     assert rel_err(half["H_pp"], got["H_pp"][:2048]) < 1e-12
 
 
+def test_huge_window_partition_sums_to_full(pkg, orc, ctx, cfg):
+    """cfg-5b shape (one long window) at a size the dense oracle handles: the per-rank partial [S | g] of the
+    landmark partition (shard.split_huge_window) sum to the single-GPU result (what the NCCL all-reduce does)."""
+    abi, synth, shard = pkg._abi, pkg.synth, pkg.shard
+    huge = synth.make_windows(1, seed=121, P=40, F=300, lines_per_frame=2, max_len=12)
+    flags = abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
+    got, ref = check_linearize(pkg, orc, ctx, cfg, huge, flags)
+    acc = np.zeros(huge.D * huge.D + huge.D)
+    owned = 0
+    for r in range(4):
+        part = shard.split_huge_window(huge, r, 4)
+        owned += part.NP + part.NL
+        o = ctx.linearize(part, abi.OUT_SCHUR | abi.LOSS_CAUCHY)
+        acc += shard.pack_sg(o["S"][0], o["g"][0])
+    assert owned == huge.NP + huge.NL
+    assert rel_err(acc, shard.pack_sg(ref["S"][0], ref["g"][0])) < TOL
+
+
 # ---- marginalisation ----------------------------------------------------------------------------------
 def test_marginalize_dense(pkg, orc, ctx):
     rng = np.random.default_rng(7)
