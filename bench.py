@@ -151,6 +151,9 @@ def run_reference(args):
 
 
 def main():
+    # keep stdout for the single JSON line (NCCL / libraries may print banners): everything else goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -165,6 +168,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         return run_reference(args)
 
     import torch
@@ -322,7 +327,7 @@ def main():
                         "step_ms_with_linearize": msS / K}
         for p in dS.values():
             ctx.device_free(p)
-        out["fp64_peaks"] = dict(zip(("dfma_tflops", "dmul_dadd_tops"), ctx.microbench_fp64()))
+        out["fp64_peaks"] = dict(zip(("dfma_tflops", "dmul_dadd_tops", "dmma_tflops"), ctx.microbench_fp64()))
     for p in list(d_in.values()) + list(d_out.values()):
         ctx.device_free(p)
 
@@ -435,7 +440,8 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
 
 
 if __name__ == "__main__":

@@ -97,6 +97,8 @@ const char* viml_kernel_name(int kernel_id);
  * dfma_tflops counts 2 flop per DFMA; dmul_dadd_tops counts 1 op per un-fused DMUL or DADD (the
  * association translation unit is compiled without FMA contraction).                               */
 int viml_microbench_fp64(viml_ctx* ctx, double* dfma_tflops, double* dmul_dadd_tops);
+/* FP64 tensor-core peak: mma.sync m8n8k4.f64 (DMMA), 512 flop per warp instruction.                 */
+int viml_microbench_dmma(viml_ctx* ctx, double* dmma_tflops);
 
 /* ---- prior line map -------------------------------------------------------------------------- */
 /* lines_xyzxyz: N rows of [sx sy sz ex ey ez] exactly as line_3d.txt (parameters.cpp:50-59).

@@ -23,7 +23,7 @@ ABI_SYMBOLS = (
     "viml_abi_version", "viml_create", "viml_destroy", "viml_last_error", "viml_sync", "viml_stream",
     "viml_host_alloc", "viml_host_free", "viml_device_alloc", "viml_device_free", "viml_memcpy_h2d",
     "viml_memcpy_d2h", "viml_kernel_launches", "viml_profile_begin", "viml_profile_end", "viml_kernel_name",
-    "viml_microbench_fp64", "viml_set_map", "viml_linearize_batch",
+    "viml_microbench_fp64", "viml_microbench_dmma", "viml_set_map", "viml_linearize_batch",
     "viml_marginalize_batch", "viml_line_associate", "viml_allreduce_hb",
 )
 
@@ -55,6 +55,7 @@ def load_library():
     lib.viml_profile_begin.argtypes = [C.c_void_p]
     lib.viml_profile_end.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.viml_microbench_fp64.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.viml_microbench_dmma.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.viml_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_abi.Config), C.c_int]
     lib.viml_destroy.argtypes = [C.c_void_p]
     lib.viml_sync.argtypes = [C.c_void_p]
@@ -148,9 +149,10 @@ class Context:
         return {self.lib.viml_kernel_name(k).decode(): (ms[k], n[k]) for k in range(16) if n[k] > 0}
 
     def microbench_fp64(self):
-        a, b = C.c_double(), C.c_double()
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
         self._check(self.lib.viml_microbench_fp64(self.h, C.byref(a), C.byref(b)))
-        return a.value, b.value
+        self._check(self.lib.viml_microbench_dmma(self.h, C.byref(c)))
+        return a.value, b.value, c.value
 
     # -- device memory helpers (for the resident-input benchmark path) --
     def device_alloc(self, nbytes):

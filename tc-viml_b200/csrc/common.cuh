@@ -132,6 +132,10 @@ struct LinearizeArgs {  // device pointers only
 
 // linearize_kernels.cu
 int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a);
+// schur_kernels.cu
+int viml_launch_schur(viml_ctx* ctx, int W, int F, int D, const double* H_pp, const double* H_lp, const double* H_ll,
+                      const double* b_p, const double* b_l, double* S, double* g, double eps);
+double viml_dmma_peak_tflops(viml_ctx* ctx);
 // marg_kernels.cu
 int viml_launch_marginalize(viml_ctx* ctx, int K, int pos, int m, double eps, const double* A, const double* b,
                             double* A_schur, double* b_schur, double* lin_jac, double* lin_res);

@@ -357,88 +357,6 @@ __global__ void __launch_bounds__(128) lines_kernel(LinearizeArgs A) {
 
 #include "assemble.cuh"
 
-// Landmark Schur complement, simple version: one CTA per window, threads own entries of S.
-//   S = H_pp - sum_l W_l^T W_l / L_l,  g = b_p - sum_l W_l^T b_l / L_l,  L_l <= eps skipped.
-constexpr int kSchurTile = 32;
-__global__ void __launch_bounds__(256) schur_kernel(int F, int D, const double* __restrict__ H_pp,
-                                                    const double* __restrict__ H_lp, const double* __restrict__ H_ll,
-                                                    const double* __restrict__ b_p, const double* __restrict__ b_l,
-                                                    double* __restrict__ S, double* __restrict__ g, double eps) {
-  extern __shared__ double sm[];
-  double* Wt = sm;                       // [kSchurTile][D]
-  double* sc = sm + kSchurTile * D;      // [kSchurTile] 1/L or 0
-  double* sb = sc + kSchurTile;          // [kSchurTile] b_l
-  const int w = blockIdx.x;
-  const double* Hl = H_lp + (size_t)w * F * D;
-  const int nE = D * D + D;  // entries of S plus g
-  // each thread accumulates entries e = tid, tid+256, ... in registers (up to 24 for D=72)
-  constexpr int kMaxPer = 24;
-  double acc[kMaxPer];
-  const int per = (nE + blockDim.x - 1) / blockDim.x;
-  for (int q = 0; q < kMaxPer; ++q) acc[q] = 0.0;
-  for (int l0 = 0; l0 < F; l0 += kSchurTile) {
-    const int nl = min(kSchurTile, F - l0);
-    __syncthreads();
-    for (int e = threadIdx.x; e < nl * D; e += blockDim.x) Wt[e] = Hl[(size_t)l0 * D + e];
-    if (threadIdx.x < nl) {
-      const double L = H_ll[(size_t)w * F + l0 + threadIdx.x];
-      sc[threadIdx.x] = (L > eps) ? 1.0 / L : 0.0;
-      sb[threadIdx.x] = b_l[(size_t)w * F + l0 + threadIdx.x];
-    }
-    __syncthreads();
-    for (int q = 0; q < per && q < kMaxPer; ++q) {
-      const int e = threadIdx.x + q * blockDim.x;
-      if (e >= nE) break;
-      double s = 0.0;
-      if (e < D * D) {
-        const int r = e / D, c = e % D;
-        for (int l = 0; l < nl; ++l) s += Wt[l * D + r] * sc[l] * Wt[l * D + c];
-      } else {
-        const int r = e - D * D;
-        for (int l = 0; l < nl; ++l) s += Wt[l * D + r] * sc[l] * sb[l];
-      }
-      acc[q] += s;
-    }
-  }
-  for (int q = 0; q < per && q < kMaxPer; ++q) {
-    const int e = threadIdx.x + q * blockDim.x;
-    if (e >= nE) break;
-    if (e < D * D)
-      S[(size_t)w * D * D + e] = H_pp[(size_t)w * D * D + e] - acc[q];
-    else
-      g[(size_t)w * D + (e - D * D)] = b_p[(size_t)w * D + (e - D * D)] - acc[q];
-  }
-}
-
-// Generic Schur for large D (entries strided over the grid, no register cache).
-__global__ void schur_generic_kernel(int F, int D, const double* __restrict__ H_pp, const double* __restrict__ H_lp,
-                                     const double* __restrict__ H_ll, const double* __restrict__ b_p,
-                                     const double* __restrict__ b_l, double* __restrict__ S, double* __restrict__ g,
-                                     double eps) {
-  const int w = blockIdx.y;
-  const int64_t nE = (int64_t)D * D + D;
-  const double* Hl = H_lp + (size_t)w * F * D;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nE; e += (int64_t)gridDim.x * blockDim.x) {
-    double s = 0.0;
-    if (e < (int64_t)D * D) {
-      const int r = (int)(e / D), c = (int)(e % D);
-      for (int l = 0; l < F; ++l) {
-        const double L = H_ll[(size_t)w * F + l];
-        const double wr = Hl[(size_t)l * D + r];
-        if (L > eps && wr != 0.0) s += wr * (1.0 / L) * Hl[(size_t)l * D + c];
-      }
-      S[(size_t)w * D * D + e] = H_pp[(size_t)w * D * D + e] - s;
-    } else {
-      const int r = (int)(e - (int64_t)D * D);
-      for (int l = 0; l < F; ++l) {
-        const double L = H_ll[(size_t)w * F + l];
-        if (L > eps) s += Hl[(size_t)l * D + r] * (1.0 / L) * b_l[(size_t)w * F + l];
-      }
-      g[(size_t)w * D + r] = b_p[(size_t)w * D + r] - s;
-    }
-  }
-}
-
 }  // namespace
 
 int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
@@ -500,16 +418,7 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
   }
   if (a.flags & VIML_OUT_SCHUR) {
     const double eps = 1e-8;  // MarginalizationInfo::eps (marginalization_factor.h:70)
-    LaunchScope ls(ctx, K_SCHUR);
-    if ((a.D * a.D + a.D + 255) / 256 <= 24) {
-      const size_t smem = (size_t)(kSchurTile * a.D + 2 * kSchurTile) * sizeof(double);
-      schur_kernel<<<a.W, 256, smem, st>>>(a.F, a.D, a.out.H_pp, a.out.H_lp, a.out.H_ll, a.out.b_p, a.out.b_l,
-                                           a.out.S, a.out.g, eps);
-    } else {
-      dim3 grid(296, a.W);
-      schur_generic_kernel<<<grid, 256, 0, st>>>(a.F, a.D, a.out.H_pp, a.out.H_lp, a.out.H_ll, a.out.b_p, a.out.b_l,
-                                                 a.out.S, a.out.g, eps);
-    }
+    viml_launch_schur(ctx, a.W, a.F, a.D, a.out.H_pp, a.out.H_lp, a.out.H_ll, a.out.b_p, a.out.b_l, a.out.S, a.out.g, eps);
   }
   VIML_TRY_CUDA(ctx, cudaGetLastError());
   return VIML_OK;

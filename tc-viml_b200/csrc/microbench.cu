@@ -62,3 +62,10 @@ extern "C" int viml_microbench_fp64(viml_ctx* ctx, double* dfma_tflops, double* 
   if (dmul_dadd_tops) *dmul_dadd_tops = best[1];
   return VIML_OK;
 }
+
+extern "C" int viml_microbench_dmma(viml_ctx* ctx, double* dmma_tflops) {
+  if (!ctx || !dmma_tflops) return VIML_ERR_INVALID;
+  VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+  *dmma_tflops = viml_dmma_peak_tflops(ctx);
+  return VIML_OK;
+}

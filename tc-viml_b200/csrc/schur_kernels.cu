@@ -1,0 +1,166 @@
+// schur_kernels.cu — landmark Schur complement with FP64 tensor-core tiles (DMMA, mma.sync m8n8k4.f64).
+//
+//   S = H_pp - sum_l W_l^T W_l / L_l ,   g = b_p - sum_l W_l^T b_l / L_l ,   W_l = H_lp[l][:],  L_l = H_ll[l]
+//   landmarks with L_l <= eps are dropped (MarginalizationInfo::eps, marginalization_factor.h:70; the reference
+//   inverts Amm through an eigen pseudo-inverse, marginalization_factor.cpp:267-282, which for the diagonal
+//   landmark block is exactly this).
+//
+// It is a SYRK: D x D output, contraction over the F landmarks — the one GEMM-shaped piece of the hot path
+// (2 D^2 F flop over D F 8 bytes, ~18 flop/B at D = 72), so it goes to the FP64 tensor pipe.  tcgen05 has no
+// FP64 kind; on sm_100a the FP64 MMA is still mma.sync (DMMA in SASS).
+// One CTA per (72 x 72 output tile, window); 8 warps share the 81 8x8 sub-tiles (45 when the tile is on the
+// diagonal: only the upper triangle is computed and mirrored).  W is staged through shared memory in chunks
+// of 32 landmarks with a row stride of 76 doubles (conflict-free fragment loads).
+#include "common.cuh"
+
+namespace {
+
+constexpr int TS = 72;        // CTA tile edge (9 sub-tiles of 8)
+constexpr int KC = 32;        // landmarks per staged chunk
+constexpr int LDW = 76;       // padded row stride in doubles
+constexpr int SWARPS = 8;
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(SWARPS * 32) schur_dmma_kernel(int F, int D, const double* __restrict__ H_pp,
+                                                                 const double* __restrict__ H_lp,
+                                                                 const double* __restrict__ H_ll,
+                                                                 const double* __restrict__ b_p,
+                                                                 const double* __restrict__ b_l, double* __restrict__ S,
+                                                                 double* __restrict__ g, double eps, int ntile) {
+  __shared__ double sR[KC * LDW];   // W[l][row-tile columns]
+  __shared__ double sC[KC * LDW];   // W[l][col-tile columns]
+  __shared__ double sInv[KC], sB[KC];
+  // upper-triangular tile index -> (ty, tx), ty <= tx
+  int t = blockIdx.x, ty = 0;
+  while (t >= ntile - ty) t -= ntile - ty, ++ty;
+  const int tx = ty + t;
+  const bool diag = tx == ty;
+  const int w = blockIdx.y;
+  const int r0 = ty * TS, c0 = tx * TS;
+  const int nr = min(TS, D - r0), nc = min(TS, D - c0);
+  const double* __restrict__ Hl = H_lp + (size_t)w * F * D;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kq = lane & 3, mq = lane >> 2;
+  // this warp's sub-tiles
+  constexpr int MAXT = 11;
+  int nt = 0;
+  unsigned char str[MAXT], stc[MAXT];
+  for (int s = 0, k = 0; s < 81; ++s) {
+    const int a = s / 9, b = s % 9;
+    if (diag && a > b) continue;
+    if (8 * a >= nr || 8 * b >= nc) continue;
+    if ((k++ % SWARPS) == warp && nt < MAXT) str[nt] = (unsigned char)a, stc[nt] = (unsigned char)b, ++nt;
+  }
+  double acc[MAXT][2];
+#pragma unroll
+  for (int i = 0; i < MAXT; ++i) acc[i][0] = acc[i][1] = 0.0;
+  double gacc = 0.0;  // threads 0..71 of a diagonal tile own g[r0 + tid]
+  for (int l0 = 0; l0 < F; l0 += KC) {
+    const int nl = min(KC, F - l0);
+    __syncthreads();
+    for (int e = tid; e < KC * TS; e += SWARPS * 32) {
+      const int l = e / TS, c = e % TS;
+      sR[l * LDW + c] = (l < nl && c < nr) ? Hl[(size_t)(l0 + l) * D + r0 + c] : 0.0;
+      if (!diag) sC[l * LDW + c] = (l < nl && c < nc) ? Hl[(size_t)(l0 + l) * D + c0 + c] : 0.0;
+    }
+    if (tid < KC) {
+      const double L = tid < nl ? H_ll[(size_t)w * F + l0 + tid] : 0.0;
+      sInv[tid] = (L > eps) ? 1.0 / L : 0.0;
+      sB[tid] = tid < nl ? b_l[(size_t)w * F + l0 + tid] : 0.0;
+    }
+    __syncthreads();
+    const double* cs = diag ? sR : sC;
+#pragma unroll 2
+    for (int kk = 0; kk < KC; kk += 4) {
+      const double inv = sInv[kk + kq];
+#pragma unroll
+      for (int i = 0; i < MAXT; ++i)
+        if (i < nt) {
+          const double a = sR[(kk + kq) * LDW + 8 * str[i] + mq] * inv;
+          const double b = cs[(kk + kq) * LDW + 8 * stc[i] + mq];
+          dmma(acc[i][0], acc[i][1], a, b);
+        }
+    }
+    if (diag && tid < nr) {
+      double s = 0.0;
+      for (int l = 0; l < KC; ++l) s = fma(sR[l * LDW + tid] * sInv[l], sB[l], s);
+      gacc += s;
+    }
+  }
+  const double* __restrict__ Hp = H_pp + (size_t)w * D * D;
+  double* __restrict__ So = S + (size_t)w * D * D;
+#pragma unroll
+  for (int i = 0; i < MAXT; ++i)
+    if (i < nt) {
+      const int r = r0 + 8 * str[i] + mq;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = c0 + 8 * stc[i] + 2 * kq + h;
+        if (r < D && c < D) {
+          const double v = Hp[(size_t)r * D + c] - acc[i][h];
+          So[(size_t)r * D + c] = v;
+          // mirror: lower triangle of a diagonal tile's off-diagonal sub-tiles, and the transposed tile
+          if (!diag || str[i] != stc[i]) So[(size_t)c * D + r] = Hp[(size_t)c * D + r] - acc[i][h];
+        }
+      }
+    }
+  if (diag && tid < nr) g[(size_t)w * D + r0 + tid] = b_p[(size_t)w * D + r0 + tid] - gacc;
+}
+
+// ---- DMMA peak (for the roofline denominator of this kernel) ----
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, double a, double b, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i][0] = threadIdx.x, c[i][1] = i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma(c[i][0], c[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace
+
+int viml_launch_schur(viml_ctx* ctx, int W, int F, int D, const double* H_pp, const double* H_lp, const double* H_ll,
+                      const double* b_p, const double* b_l, double* S, double* g, double eps) {
+  const int ntile = (D + TS - 1) / TS;
+  dim3 grid((unsigned)(ntile * (ntile + 1) / 2), (unsigned)W);
+  LaunchScope ls(ctx, K_SCHUR);
+  schur_dmma_kernel<<<grid, SWARPS * 32, 0, ctx->stream>>>(F, D, H_pp, H_lp, H_ll, b_p, b_l, S, g, eps, ntile);
+  return VIML_OK;
+}
+
+double viml_dmma_peak_tflops(viml_ctx* ctx) {
+  const int blocks = ctx->sm_count * 8, threads = 256, iters = 2048;
+  if (ctx->scratch.reserve((size_t)blocks * threads * sizeof(double)) != cudaSuccess) return 0.0;
+  double* out = ctx->scratch.take<double>((size_t)blocks * threads);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, ctx->stream);
+    {
+      LaunchScope ls(ctx, K_MICRO);
+      dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(out, 1.0000001, 0.9999999, iters);
+    }
+    cudaEventRecord(e1, ctx->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = (double)blocks * (threads / 32) * iters * 8 * 512.0;  // m8n8k4 = 256 FMA
+    const double r = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && r > best) best = r;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return best;
+}

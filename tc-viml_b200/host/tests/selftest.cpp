@@ -155,6 +155,9 @@ static void make_window(Window& w) {
     std::memcpy(w.para_Pose[i], base, 56);
     for (int k = 0; k < 3; ++k) w.para_Pose[i][k] += 0.05 * i + 0.02 * nrand();
     for (int k = 3; k < 7; ++k) w.para_Pose[i][k] += 0.01 * nrand();
+    double qn = 0.0;
+    for (int k = 3; k < 7; ++k) qn += w.para_Pose[i][k] * w.para_Pose[i][k];
+    for (int k = 3; k < 7; ++k) w.para_Pose[i][k] *= (1.0 + 1e-12 * nrand()) / std::sqrt(qn);  // unit up to 1e-12
     for (int k = 0; k < 9; ++k) w.para_SpeedBias[i][k] = 0.1 * nrand();
   }
   const double ric[7] = {-0.0216, -0.0647, 0.0098, 0.0077, -0.0105, 0.7018, 0.7123};
