@@ -107,7 +107,7 @@ double ProjectionFactor::check(double** parameters) {
   double* jp[4] = {J[0], J[1], J[2], J[3]};
   Evaluate(parameters, r0, jp);
   const double eps = 1e-6;
-  double worst = 0.0;
+  double worst = 0.0, scale = 1e-300;
   for (int k = 0; k < 19; ++k) {
     double P[3][7], lam = parameters[3][0];
     for (int b = 0; b < 3; ++b) std::memcpy(P[b], parameters[b], 56);
@@ -135,9 +135,10 @@ double ProjectionFactor::check(double** parameters) {
       const double num = (r1[row] - r0[row]) / eps;
       const double ana = a < 3 ? J[a][7 * row + bb] : J[3][row];
       worst = std::max(worst, std::fabs(num - ana));
+      scale = std::max(scale, std::fabs(ana));
     }
   }
-  return worst;
+  return worst / scale;
 }
 
 LineProjectionFactor::LineProjectionFactor(const viml::Vector3d& _pts_start, const viml::Vector3d& _pts_end,

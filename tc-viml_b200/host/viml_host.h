@@ -119,7 +119,7 @@ class ProjectionFactor : public ceres::SizedCostFunction<2, 7, 7, 7, 1> {
  public:
   ProjectionFactor(const viml::Vector3d& _pts_i, const viml::Vector3d& _pts_j);
   virtual bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const;
-  // projection_factor.cpp:126-228: forward-difference check; returns the largest |analytic - numeric| entry.
+  // projection_factor.cpp:126-228: forward-difference check; returns max |analytic - numeric| / max |analytic|.
   double check(double** parameters);
 
   viml::Vector3d pts_i, pts_j;
