@@ -14,21 +14,25 @@
 //       reduce-scatter leaves each lane with a slice that it writes straight to HBM (block + mirror).
 //   P2b landmark part: one thread per feature walks its factor list and writes the whole strip row
 //       H_lp[l][:] (structural zeros included), H_ll[l], b_l[l].
-// Every output entry of the window is written exactly once by exactly one thread: no atomics, no memset,
-// bit-reproducible run to run.  Windows that exceed the shared-memory limits are zero-filled, flagged and
-// finished by the generic atomic kernel.
+// A window is processed in PARTS of <= NF point / NL line factors (any split of the factor list is valid: J^T J is
+// a sum over factors).  Part 0 writes every output entry of the window ("=", structural zeros included), later
+// parts accumulate ("+=" as one RED per entry, same CTA, ordered by __syncthreads), so any window size is handled
+// by the same kernel; an EuRoC-shaped window (~560 + 110 factors) is a single part.  Every entry is produced by
+// exactly one thread per part: no contended atomics, no memset, bit-reproducible run to run.
+// (Measured, round 1: 336-factor parts with two 256-thread CTAs per SM were 1.5x SLOWER than one 512-thread CTA per
+// SM: +32 % instructions for the per-part sorts/reductions and instruction-cache misses outweighed the overlap.)
 #pragma once
 
 namespace fused {
 
 constexpr int AT = 512;          // threads per CTA (16 warps), 1 CTA per SM
-constexpr int NF = 704;          // max point factors per window on this path
-constexpr int NL = 160;          // max line factors per window
+constexpr int NF = 704;          // point factors per PART (a window is processed in ceil(nf/NF) accumulating parts)
+constexpr int NL = 160;          // line factors per part
 constexpr int PMAX = 12;         // max poses per window
 constexpr int FMAX = 160;        // max features per window
 constexpr int KA = PMAX * PMAX;  // pair keys
-constexpr int SLABS = NF / 32;   // 22
-constexpr int LSLABS = NL / 32;  // 5
+constexpr int SLABS = (NF + 31) / 32;
+constexpr int LSLABS = (NL + 31) / 32;
 constexpr int RECW = 17;         // double2 per point record: 0..5 lo, 6..8 hi_rot, 9..14 ex, 15 r, 16 d (odd stride: conflict-free)
 constexpr int LRECW = 7;         // double2 per line record: 0..5 pose, 6 r
 constexpr int WSLOTS = 64;       // windows per CTA whose CSR offsets are staged in shared memory
@@ -41,14 +45,13 @@ struct Smem {
       uint16_t cntA[SLABS * KA];
       uint16_t cntB[SLABS * FMAX];
       uint16_t cntC[LSLABS * PMAX];
-      uint16_t cntD[SLABS * PMAX];
     } cnt;
   } u;
   double cache[PMAX * kPoseCache + kExCache];
   uint32_t ridx[NF];
   uint16_t fperm[NF];
   uint16_t hperm[NF];  // record positions ordered by hi pose (flattened "hi-role" ranges)
-  uint16_t baseA[KA + 1], totA[KA], baseB[FMAX + 1], totB[FMAX], baseC[PMAX + 1], totC[PMAX], baseD[PMAX + 1], totD[PMAX], pairs[KA];
+  uint16_t baseA[KA + 1], totA[KA], baseB[FMAX + 1], totB[FMAX], baseC[PMAX + 1], totC[PMAX], baseD[PMAX + 1], offD[KA], pairs[KA];
   int npairs, next_feature;
   int woff[4 * WSLOTS];  // this CTA's windows: {p0, p1, l0, l1} per slot (filled once per launch)
 };
@@ -120,24 +123,40 @@ __device__ __forceinline__ void load_ex(const double2* rec, int pos, double2* X)
   for (int k = 0; k < 6; ++k) X[k] = ldrec(rec, pos, 9 + k);
 }
 
+// "=" for the first part of a window, "+=" for the following ones.  The add is a fire-and-forget RED (no load on
+// the critical path); parts of a window run on the same CTA and are separated by __syncthreads, each address gets
+// at most one add per part, so the result is still deterministic.
+__device__ __forceinline__ void put(double* __restrict__ p, double v, bool accum) {
+  if (accum) atomicAdd(p, v);
+  else *p = v;
+}
+__device__ __forceinline__ void put2(double2* __restrict__ p, double x, double y, bool accum) {
+  if (accum) {
+    atomicAdd(&p->x, x);
+    atomicAdd(&p->y, y);
+  } else {
+    *p = make_double2(x, y);
+  }
+}
+
 // write the sym(21)+b(6) slice a lane holds after the reduction: entries e0..e0+6 of block (p,p)
 __device__ __forceinline__ void write_sym_slice(const double* a, int e0, double* __restrict__ H, double* __restrict__ bp,
-                                                int D, int p) {
+                                                int D, int p, bool accum) {
 #pragma unroll
   for (int k = 0; k < 7; ++k) {
     const int e = e0 + k;
     if (e < 21) {
       const int r = c_sym_r[e], c = c_sym_c[e];
-      H[(size_t)(6 * p + r) * D + 6 * p + c] = a[k];
-      if (r != c) H[(size_t)(6 * p + c) * D + 6 * p + r] = a[k];
+      put(&H[(size_t)(6 * p + r) * D + 6 * p + c], a[k], accum);
+      if (r != c) put(&H[(size_t)(6 * p + c) * D + 6 * p + r], a[k], accum);
     } else if (e < 27) {
-      bp[6 * p + e - 21] = a[k];
+      put(&bp[6 * p + e - 21], a[k], accum);
     }
   }
 }
 
 template <bool MODE_A>
-__global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* __restrict__ fallback, int w_begin, int w_end) {
+__global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_begin, int w_end) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -160,23 +179,34 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
   // register prefetch of the next window's sort keys and pose cache (consumed in its P0)
   uint32_t nx_idx0 = 0u, nx_idx1 = 0u;
   int nx_frame = 0xffff;
-  double nx_c0 = 0.0, nx_c1 = 0.0;
-  auto fetch_next = [&](int wn, int sl) {
-    const int q0 = S.woff[4 * sl], qn = S.woff[4 * sl + 1] - q0, m0 = S.woff[4 * sl + 2], mn = S.woff[4 * sl + 3] - m0;
+  double nx_c0 = 0.0, nx_c1 = 0.0, nx_c2 = 0.0;
+  static_assert(PMAX * kPoseCache + kExCache <= 3 * AT, "pose cache prefetch registers");
+  // factor / line ranges of part `part` of the window in slot `sl`
+  auto seg = [&](int sl, int part, int& q0, int& qn, int& m0, int& mn) {
+    const int a0 = S.woff[4 * sl], an = S.woff[4 * sl + 1] - a0, b0 = S.woff[4 * sl + 2], bn = S.woff[4 * sl + 3] - b0;
+    const int np = max(1, max((an + NF - 1) / NF, (bn + NL - 1) / NL));
+    q0 = a0 + (int)((int64_t)an * part / np), qn = a0 + (int)((int64_t)an * (part + 1) / np) - q0;
+    m0 = b0 + (int)((int64_t)bn * part / np), mn = b0 + (int)((int64_t)bn * (part + 1) / np) - m0;
+    return np;
+  };
+  auto fetch_next = [&](int wn, int sl, int part) {
+    int q0, qn, m0, mn;
+    seg(sl, part, q0, qn, m0, mn);
     nx_idx0 = tid < qn ? A.pf_idx[q0 + tid] : 0u;
     nx_idx1 = tid + AT < qn ? A.pf_idx[q0 + tid + AT] : 0u;
-    nx_frame = tid < mn ? A.lf_frame[m0 + tid] : 0xffff;
+    nx_frame = AT - 1 - tid < mn ? A.lf_frame[m0 + AT - 1 - tid] : 0xffff;
     const double* __restrict__ gc = A.cache + (size_t)wn * cstride;
     nx_c0 = tid < cstride ? gc[tid] : 0.0;
     nx_c1 = tid + AT < cstride ? gc[tid + AT] : 0.0;
+    nx_c2 = tid + 2 * AT < cstride ? gc[tid + 2 * AT] : 0.0;
   };
-  if (w_begin + (int)blockIdx.x < w_end) fetch_next(w_begin + blockIdx.x, 0);
+  if (w_begin + (int)blockIdx.x < w_end) fetch_next(w_begin + blockIdx.x, 0, 0);
 
+  long long tph[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+#define VIML_TICK(k) do { if (A.dbg && tid == 0) { const long long now_ = clock64(); tph[k] += now_ - tlast; tlast = now_; } } while (0)
   int slot = 0;
   for (int w = w_begin + blockIdx.x; w < w_end; w += gridDim.x, ++slot) {
-    const int p0 = S.woff[4 * slot], p1 = S.woff[4 * slot + 1], l0 = S.woff[4 * slot + 2], l1 = S.woff[4 * slot + 3];
     const bool has_next = w + (int)gridDim.x < w_end;
-    const int nf = p1 - p0, nl = l1 - l0;
     if (has_next) {  // pull the next window's per-factor inputs into L2 while this one computes
       const int wn = w + gridDim.x;
       const int q0 = S.woff[4 * slot + 4], q1 = S.woff[4 * slot + 5], m0 = S.woff[4 * slot + 6], m1 = S.woff[4 * slot + 7];
@@ -191,26 +221,23 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
     double* __restrict__ Hll = A.out.H_ll + (size_t)w * F;
     double* __restrict__ bp = A.out.b_p + (size_t)w * D;
     double* __restrict__ bl = A.out.b_l + (size_t)w * F;
-    if (nf > NF || nl > NL) {  // too big for shared memory: zero-fill, flag, let the generic kernel finish it
-      for (int e = tid; e < D * D; e += AT) Hpp[e] = 0.0;
-      for (int e = tid; e < F * D; e += AT) Hlp[e] = 0.0;
-      for (int e = tid; e < F; e += AT) Hll[e] = 0.0, bl[e] = 0.0;
-      for (int e = tid; e < D; e += AT) bp[e] = 0.0;
-      if (tid == 0) fallback[w] = 1;
-      if (has_next) fetch_next(w + gridDim.x, slot + 1);
-      continue;
-    }
+    int p0, nf, l0, nl;
+    const int nparts = seg(slot, 0, p0, nf, l0, nl);
+    for (int part = 0; part < nparts; ++part) {
+    seg(slot, part, p0, nf, l0, nl);
+    const bool accum = part > 0;  // later parts add onto what part 0 wrote
     // ------------------------------------------------------------------ P0: cache + sorts
     {
       if (tid < cstride) S.cache[tid] = nx_c0;
       if (tid + AT < cstride) S.cache[tid + AT] = nx_c1;
+      if (tid + 2 * AT < cstride) S.cache[tid + 2 * AT] = nx_c2;
       uint32_t* z = reinterpret_cast<uint32_t*>(&S.u.cnt);
       for (int e = tid; e < (int)(sizeof(S.u.cnt) / 4); e += AT) z[e] = 0u;
       if (tid == 0) S.next_feature = 0;
     }
     __syncthreads();
     uint32_t fidx[2];
-    int keyA[2], rankA[2], rankB[2], rankD[2];
+    int keyA[2], rankA[2], rankB[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int f = tid + r * AT;
@@ -223,70 +250,51 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
       if (r * AT < nf) {  // warp-uniform: some lane of this warp may be valid
         const unsigned ma = __match_any_sync(0xffffffffu, keyA[r]);
         const unsigned mb = __match_any_sync(0xffffffffu, keyB);
-        const unsigned md = __match_any_sync(0xffffffffu, valid ? hi : 0xffff);
         const unsigned lt = (1u << lane) - 1u;
         rankA[r] = __popc(ma & lt);
         rankB[r] = __popc(mb & lt);
-        rankD[r] = __popc(md & lt);
         const int slab = warp + r * (AT / 32);
         if (valid && rankA[r] == 0) S.u.cnt.cntA[slab * KA + keyA[r]] = (uint16_t)__popc(ma);
         if (valid && rankB[r] == 0) S.u.cnt.cntB[slab * FMAX + keyB] = (uint16_t)__popc(mb);
-        if (valid && rankD[r] == 0) S.u.cnt.cntD[slab * PMAX + hi] = (uint16_t)__popc(md);
       }
     }
+    // line factor t is handled by thread AT-1-t: the second round of point factors uses the LOW threads, so no
+    // thread gets two point factors and a line factor on its critical path
+    const int lt_ = AT - 1 - tid;
     int lframe = 0, rankC = 0;
-    if (tid < NL) {  // warps 0..4 (NL = 160): line factors by frame
-      const bool valid = tid < nl;
+    if (warp >= AT / 32 - LSLABS) {  // line factors by frame (whole warps take part in match_any)
+      const bool valid = lt_ < nl;
       lframe = valid ? nx_frame : 0xffff;
       const unsigned mc = __match_any_sync(0xffffffffu, lframe);
       rankC = __popc(mc & ((1u << lane) - 1u));
-      if (valid && rankC == 0) S.u.cnt.cntC[warp * PMAX + lframe] = (uint16_t)__popc(mc);
+      if (valid && rankC == 0) S.u.cnt.cntC[(AT / 32 - 1 - warp) * PMAX + lframe] = (uint16_t)__popc(mc);
     }
     __syncthreads();
-    // exclusive prefix over slabs for every key (thread per key)
-    for (int e = tid; e < nkeyA + F + 2 * P; e += AT) {
-      if (e < nkeyA) {
-        int run = 0;
-        for (int s = 0; s < SLABS; ++s) {
-          const int c = S.u.cnt.cntA[s * KA + e];
-          S.u.cnt.cntA[s * KA + e] = (uint16_t)run;
-          run += c;
-        }
-        S.totA[e] = (uint16_t)run;
-      } else if (e < nkeyA + F) {
-        const int k = e - nkeyA;
-        int run = 0;
-        for (int s = 0; s < SLABS; ++s) {
-          const int c = S.u.cnt.cntB[s * FMAX + k];
-          S.u.cnt.cntB[s * FMAX + k] = (uint16_t)run;
-          run += c;
-        }
-        S.totB[k] = (uint16_t)run;
-      } else if (e >= nkeyA + F + P) {
-        const int k = e - nkeyA - F - P;
-        int run = 0;
-        for (int s = 0; s < SLABS; ++s) {
-          const int c = S.u.cnt.cntD[s * PMAX + k];
-          S.u.cnt.cntD[s * PMAX + k] = (uint16_t)run;
-          run += c;
-        }
-        S.totD[k] = (uint16_t)run;
-      } else {
-        const int k = e - nkeyA - F;
-        int run = 0;
-        for (int s = 0; s < LSLABS; ++s) {
-          const int c = S.u.cnt.cntC[s * PMAX + k];
-          S.u.cnt.cntC[s * PMAX + k] = (uint16_t)run;
-          run += c;
-        }
-        S.totC[k] = (uint16_t)run;
+    // exclusive prefix over slabs for every key (thread per key); loads are issued together, the running sum
+    // stays in registers (the serial load->store chain of a rolled loop cost ~1 K cycles per window)
+    for (int e = tid; e < nkeyA + F + P; e += AT) {
+      uint16_t* col;
+      int stride, ns;
+      uint16_t* tot;
+      if (e < nkeyA) col = S.u.cnt.cntA + e, stride = KA, ns = SLABS, tot = S.totA + e;
+      else if (e < nkeyA + F) col = S.u.cnt.cntB + (e - nkeyA), stride = FMAX, ns = SLABS, tot = S.totB + (e - nkeyA);
+      else col = S.u.cnt.cntC + (e - nkeyA - F), stride = PMAX, ns = LSLABS, tot = S.totC + (e - nkeyA - F);
+      int c[SLABS];
+#pragma unroll
+      for (int q = 0; q < SLABS; ++q) c[q] = q < ns ? col[q * stride] : 0;
+      int run = 0;
+#pragma unroll
+      for (int q = 0; q < SLABS; ++q) {
+        if (q < ns) col[q * stride] = (uint16_t)run;
+        run += c[q];
       }
+      *tot = (uint16_t)run;
     }
     __syncthreads();
     // exclusive scans over keys: warp 0 -> baseA (+ non-empty pair list), warp 1 -> baseB, warp 2 -> baseC
-    if (warp < 4) {
-      const uint16_t* tot = warp == 0 ? S.totA : (warp == 1 ? S.totB : (warp == 2 ? S.totC : S.totD));
-      uint16_t* base = warp == 0 ? S.baseA : (warp == 1 ? S.baseB : (warp == 2 ? S.baseC : S.baseD));
+    if (warp < 3) {
+      const uint16_t* tot = warp == 0 ? S.totA : (warp == 1 ? S.totB : S.totC);
+      uint16_t* base = warp == 0 ? S.baseA : (warp == 1 ? S.baseB : S.baseC);
       const int n = warp == 0 ? nkeyA : (warp == 1 ? F : P);
       int carry = 0, npairs = 0;
       for (int b0 = 0; b0 < n; b0 += 32) {
@@ -310,6 +318,30 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
         base[n] = (uint16_t)carry;
         if (warp == 0) S.npairs = npairs;
       }
+    } else if (warp == 3) {
+      // records ordered by (hi, lo) WITHOUT another sort: inside one (lo,hi) group the pair-sorted positions are
+      // already contiguous, so  posD = baseD[hi] + sum_{lo' < lo} tot(lo',hi) + (posA - baseA[lo,hi]).
+      // lane = hi: column sums of totA, exclusive scan over hi, then the per-(lo,hi) offsets.
+      const int hi = lane;
+      int col = 0;
+      if (hi < P)
+        for (int lo = 0; lo < hi; ++lo) col += S.totA[lo * P + hi];
+      int inc = col;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (hi < P) {
+        int run = inc - col;
+        S.baseD[hi] = (uint16_t)run;
+        for (int lo = 0; lo < hi; ++lo) {
+          S.offD[lo * P + hi] = (uint16_t)run;
+          run += S.totA[lo * P + hi];
+        }
+      }
+      if (lane == 31) S.baseD[P] = (uint16_t)inc;  // lanes >= P contribute 0: inclusive sum at lane 31 is the total
+      static_assert(PMAX <= 31, "hi scan uses one warp");
     }
     __syncthreads();
     int posA[2];
@@ -324,13 +356,14 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
         const int posB = S.baseB[l] + S.u.cnt.cntB[slab * FMAX + l] + rankB[r];
         S.ridx[posA[r]] = fidx[r];
         S.fperm[posB] = (uint16_t)posA[r];
-        const int hi = max((int)(fidx[r] & 0xff), (int)((fidx[r] >> 8) & 0xff));
-        S.hperm[S.baseD[hi] + S.u.cnt.cntD[slab * PMAX + hi] + rankD[r]] = (uint16_t)posA[r];
+        S.hperm[S.offD[keyA[r]] + posA[r] - S.baseA[keyA[r]]] = (uint16_t)posA[r];
       }
     }
+    VIML_TICK(0);
     int posC = 0;
-    if (tid < nl) posC = S.baseC[lframe] + S.u.cnt.cntC[warp * PMAX + lframe] + rankC;
+    if (lt_ < nl) posC = S.baseC[lframe] + S.u.cnt.cntC[(AT / 32 - 1 - warp) * PMAX + lframe] + rankC;
     __syncthreads();  // count tables are dead from here on (lrec aliases them)
+    VIML_TICK(1);
     // ------------------------------------------------------------------ P1: evaluate, write records
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -361,8 +394,8 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
       strec(S.rec, pos, 15, J.r[0], J.r[1]);
       strec(S.rec, pos, 16, J.d[0], J.d[1]);
     }
-    if (tid < nl) {
-      const int64_t k = (int64_t)l0 + tid;
+    if (lt_ < nl) {
+      const int64_t k = (int64_t)l0 + lt_;
       double g9[9];
 #pragma unroll
       for (int c = 0; c < 9; ++c) g9[c] = A.lf_geom[(size_t)c * A.NL + k];
@@ -376,7 +409,10 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
       for (int c = 0; c < 6; ++c) S.u.lrec[posC * LRECW + c] = make_double2(J.a[0][c], J.a[1][c]);
       S.u.lrec[posC * LRECW + 6] = make_double2(J.r[0], J.r[1]);
     }
+    VIML_TICK(2);
     __syncthreads();
+    VIML_TICK(3);
+    const long long t2a0 = clock64();
     // ------------------------------------------------------------------ P2a: pose blocks, team per target
     const int npairs = S.npairs;
     const int V = 32 + 24 * P + 4 * npairs;
@@ -403,7 +439,7 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
         bf_step<7>(a, 4, m4);
         bf_step<7>(a, 2, m4);
         bf_step<7>(a, 1, m4);
-        if ((t & 7) == 0) write_sym_slice(a, 14 * ((t >> 4) & 1) + 7 * ((t >> 3) & 1), Hpp, bp, D, E);
+        if ((t & 7) == 0) write_sym_slice(a, 14 * ((t >> 4) & 1) + 7 * ((t >> 3) & 1), Hpp, bp, D, E, accum);
       } else if (type == 3) {     // (p,ex) over factors with lo == p or hi == p, 16 lanes
         double a[36];
 #pragma unroll
@@ -431,8 +467,8 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
 #pragma unroll
           for (int k = 0; k < 9; ++k) {
             const int e = e0 + k, r = e / 6, c = e % 6;
-            Hpp[(size_t)(6 * p + r) * D + 6 * E + c] = a[k];
-            Hpp[(size_t)(6 * E + c) * D + 6 * p + r] = a[k];
+            put(&Hpp[(size_t)(6 * p + r) * D + 6 * E + c], a[k], accum);
+            put(&Hpp[(size_t)(6 * E + c) * D + 6 * p + r], a[k], accum);
           }
         }
       } else if (type == 2) {     // (p,p) + b_p over point factors with lo/hi == p and line factors of frame p, 8 lanes
@@ -460,7 +496,7 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
         rs_step<28>(a, (t & 4) != 0, 4, m2);
         rs_step<14>(a, (t & 2) != 0, 2, m2);
         bf_step<7>(a, 1, m2);
-        if ((t & 1) == 0) write_sym_slice(a, 14 * ((t >> 2) & 1) + 7 * ((t >> 1) & 1), Hpp, bp, D, p);
+        if ((t & 1) == 0) write_sym_slice(a, 14 * ((t >> 2) & 1) + 7 * ((t >> 1) & 1), Hpp, bp, D, p, accum);
       } else {                    // (lo,hi) pair block, 4 lanes
         double a[36];
 #pragma unroll
@@ -488,14 +524,15 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
 #pragma unroll
           for (int k = 0; k < 9; ++k) {
             const int e = e0 + k, r = e / 6, c = e % 6;
-            Hpp[(size_t)(6 * lo + r) * D + 6 * hi + c] = a[k];
-            Hpp[(size_t)(6 * hi + c) * D + 6 * lo + r] = a[k];
+            put(&Hpp[(size_t)(6 * lo + r) * D + 6 * hi + c], a[k], accum);
+            put(&Hpp[(size_t)(6 * hi + c) * D + 6 * lo + r], a[k], accum);
           }
         }
       }
     }
+    if (A.dbg && lane == 0) atomicAdd((unsigned long long*)&A.dbg[gridDim.x * 6 + blockIdx.x * 16 + warp], (unsigned long long)(clock64() - t2a0));
     // pose-pair blocks that no factor touches are structural zeros (warp per empty pair)
-    for (int lo = 0; lo < P; ++lo)
+    for (int lo = 0; lo < P && !accum; ++lo)
       for (int hi = lo + 1 + warp; hi < P; hi += AT / 32)
         if (S.totA[lo * P + hi] == 0)
           for (int q = lane; q < 36; q += 32) {
@@ -503,7 +540,9 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
             Hpp[(size_t)(6 * lo + r) * D + 6 * hi + c] = 0.0;
             Hpp[(size_t)(6 * hi + c) * D + 6 * lo + r] = 0.0;
           }
-    if (has_next) fetch_next(w + gridDim.x, slot + 1);
+    VIML_TICK(4);
+    if (part + 1 < nparts) fetch_next(w, slot, part + 1);
+    else if (has_next) fetch_next(w + gridDim.x, slot + 1, 0);
     // ------------------------------------------------------------------ P2b: landmark strips, thread per feature
     for (;;) {
       int base = 0;
@@ -548,71 +587,33 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int* _
         mask |= (1u << j) | (1u << i);
         istart = i;
       }
+      if (accum && istart < 0) continue;  // a later part only touches the features it has factors of
       if (istart >= 0) {
-        row[3 * istart] = make_double2(ai[0], ai[1]);
-        row[3 * istart + 1] = make_double2(ai[2], ai[3]);
-        row[3 * istart + 2] = make_double2(ai[4], ai[5]);
-        mask |= 1u << E;
+        put2(&row[3 * istart], ai[0], ai[1], accum);
+        put2(&row[3 * istart + 1], ai[2], ai[3], accum);
+        put2(&row[3 * istart + 2], ai[4], ai[5], accum);
       }
-      row[3 * E] = make_double2(ae[0], ae[1]);
-      row[3 * E + 1] = make_double2(ae[2], ae[3]);
-      row[3 * E + 2] = make_double2(ae[4], ae[5]);
+      put2(&row[3 * E], ae[0], ae[1], accum);
+      put2(&row[3 * E + 1], ae[2], ae[3], accum);
+      put2(&row[3 * E + 2], ae[4], ae[5], accum);
       mask |= 1u << E;
-      for (int b = 0; b < P; ++b)
-        if (!((mask >> b) & 1u)) {
-          row[3 * b] = make_double2(0.0, 0.0);
-          row[3 * b + 1] = make_double2(0.0, 0.0);
-          row[3 * b + 2] = make_double2(0.0, 0.0);
-        }
-      Hll[l] = dd;
-      bl[l] = dr;
+      if (!accum)
+        for (int b = 0; b < P; ++b)
+          if (!((mask >> b) & 1u)) {
+            row[3 * b] = make_double2(0.0, 0.0);
+            row[3 * b + 1] = make_double2(0.0, 0.0);
+            row[3 * b + 2] = make_double2(0.0, 0.0);
+          }
+      put(&Hll[l], dd, accum);
+      put(&bl[l], dr, accum);
     }
-    __syncthreads();  // shared memory is reused by the next window
+    __syncthreads();  // shared memory is reused by the next part / window
+    VIML_TICK(5);
+    }  // parts
   }
-}
-
-// Generic finish for flagged windows (and nothing else): global atomics on the zero-filled blocks.
-template <bool MODE_A>
-__global__ void __launch_bounds__(256) fallback_kernel(LinearizeArgs A, const int* __restrict__ fallback) {
-  for (int w = blockIdx.x; w < A.W; w += gridDim.x) {
-    if (!fallback[w]) continue;
-    const double* cw = A.cache + (size_t)w * (A.P * kPoseCache + kExCache);
-    const int D = A.D;
-    double* H = A.out.H_pp + (size_t)w * D * D;
-    double* bp = A.out.b_p + (size_t)w * D;
-    for (int64_t k = A.pf_window_offset[w] + threadIdx.x; k < A.pf_window_offset[w + 1]; k += blockDim.x) {
-      const uint32_t pk = A.pf_idx[k];
-      const int i = pk & 0xff, j = (pk >> 8) & 0xff, f = pk >> 16;
-      const double4 ob = reinterpret_cast<const double4*>(A.pf_obs)[k];
-      PointJac J;
-      eval_point(A, cw, i, j, A.inv_depth[(size_t)w * A.F + f], ob.x, ob.y, A.pf_pts_i_z ? A.pf_pts_i_z[k] : 1.0, ob.z,
-                 ob.w, J);
-      if (MODE_A) {
-        if (A.out.pf_residual) reinterpret_cast<double2*>(A.out.pf_residual)[k] = make_double2(J.r[0], J.r[1]);
-        if (A.out.pf_jac_pose_i) store_jac7(A.out.pf_jac_pose_i + 14 * k, J.a);
-        if (A.out.pf_jac_pose_j) store_jac7(A.out.pf_jac_pose_j + 14 * k, J.b);
-        if (A.out.pf_jac_ex) store_jac7(A.out.pf_jac_ex + 14 * k, J.c);
-        if (A.out.pf_jac_feat) reinterpret_cast<double2*>(A.out.pf_jac_feat)[k] = make_double2(J.d[0], J.d[1]);
-      }
-      point_atomics(A, w, i, j, f, J);
-    }
-    if (A.NL > 0)
-      for (int64_t k = A.lf_window_offset[w] + threadIdx.x; k < A.lf_window_offset[w + 1]; k += blockDim.x) {
-        const int frame = A.lf_frame[k];
-        double g9[9];
-#pragma unroll
-        for (int c = 0; c < 9; ++c) g9[c] = A.lf_geom[(size_t)c * A.NL + k];
-        LineJac J;
-        eval_line(A, cw, frame, g9, J);
-        if (MODE_A) {
-          if (A.out.lf_residual) reinterpret_cast<double2*>(A.out.lf_residual)[k] = make_double2(J.r[0], J.r[1]);
-          if (A.out.lf_jac_pose) store_jac7(A.out.lf_jac_pose + 14 * k, J.a);
-        }
-        atomic_block(H, D, 6 * frame, 6 * frame, J.a, J.a, true);
-#pragma unroll
-        for (int r = 0; r < 6; ++r) atomicAdd(bp + 6 * frame + r, J.a[0][r] * J.r[0] + J.a[1][r] * J.r[1]);
-      }
-  }
+  if (A.dbg && tid == 0)
+    for (int k = 0; k < 6; ++k) A.dbg[blockIdx.x * 6 + k] = tph[k];
+#undef VIML_TICK
 }
 
 }  // namespace fused

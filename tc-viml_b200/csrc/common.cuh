@@ -126,8 +126,9 @@ struct LinearizeArgs {  // device pointers only
   const double* lf_geom;
   double* cache;  // [W][P*kPoseCache + kExCache]
   viml_linearize_out out;
-  double sqrt_info, cauchy_a, fx, fy, cx, cy;
+  double sqrt_info, cauchy_a, inv_cauchy_a2, fx, fy, cx, cy;
   uint32_t flags;
+  long long* dbg;  // optional per-CTA phase cycle counters (VIML_PHASE_TIMERS=1), else nullptr
 };
 
 // linearize_kernels.cu

@@ -6,6 +6,9 @@
 //   factor/marginalization_factor.cpp:37-68 (loss), :141-172 (ThreadsConstructA), :267-282 (Schur).
 // The arithmetic is re-organised for the GPU (shared sub-products, reciprocal instead of repeated
 // division, FMA); parity with the oracle is to 1e-9 relative, not bit-exact.
+#include <cstdlib>
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -85,6 +88,24 @@ __global__ void prep_windows_kernel(LinearizeArgs a) {
   }
 }
 
+// 1/x and 1/sqrt(x) from the hardware approximations (2^-23) plus two Newton steps: relative error ~2e-16, a
+// third of the instructions (and of the dependent latency) of the IEEE-rounded division / sqrt sequences.  The
+// parity bar on this path is 1e-9 relative, not bit equality.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  y = y * fma(-0.5 * x * y, y, 1.5);
+  y = y * fma(-0.5 * x * y, y, 1.5);
+  return y;
+}
+
 __device__ __forceinline__ int find_window(const int32_t* __restrict__ off, int W, int64_t k) {
   int lo = 0, hi = W;  // off[lo] <= k < off[hi]
   while (hi - lo > 1) {
@@ -113,7 +134,7 @@ __device__ __forceinline__ void eval_point(const LinearizeArgs& A, const double*
   const double* __restrict__ ci = cw + i * kPoseCache;
   const double* __restrict__ cj = cw + j * kPoseCache;
   const double* __restrict__ ce = cw + A.P * kPoseCache;
-  const double inv_l = 1.0 / lam;
+  const double inv_l = fast_rcp(lam);
   const double cx_ = pix * inv_l, cy_ = piy * inv_l, cz_ = piz * inv_l;  // pts_camera_i (:35)
   double ix, iy, iz;                                                        // pts_imu_i (:36)
   mat3_vec(ce + EC_RIC, cx_, cy_, cz_, ix, iy, iz);
@@ -126,14 +147,14 @@ __device__ __forceinline__ void eval_point(const LinearizeArgs& A, const double*
   mat3_vec(cj + PC_RINV, dx, dy, dz, jx, jy, jz);
   double qx, qy, qz;                                                        // pts_camera_j (:39)
   mat3_vec(ce + EC_RICINV, jx - ce[EC_TIC], jy - ce[EC_TIC + 1], jz - ce[EC_TIC + 2], qx, qy, qz);
-  const double invz = 1.0 / qz;
+  const double invz = fast_rcp(qz);
   const double s = A.sqrt_info;
   double r0 = s * (qx * invz - pjx), r1 = s * (qy * invz - pjy);           // :46-49
   double sc = 1.0;
   if (A.flags & VIML_LOSS_CAUCHY) {                                         // marginalization_factor.cpp:37-67
-    const double cc = 1.0 / (A.cauchy_a * A.cauchy_a);
-    const double rho1 = fmax(2.2250738585072014e-308, 1.0 / (1.0 + (r0 * r0 + r1 * r1) * cc));
-    sc = sqrt(rho1);  // rho[2] < 0 always for Cauchy => residual_scaling = sqrt(rho1), alpha = 0
+    // rho[2] < 0 always for Cauchy => residual_scaling = sqrt(rho1) = 1/sqrt(1 + s/a^2), alpha = 0
+    // (the max(DBL_MIN, .) guard of ceres::CauchyLoss only matters for s > 1e308)
+    sc = fast_rsqrt(fma(r0 * r0 + r1 * r1, A.inv_cauchy_a2, 1.0));
   }
   J.r[0] = sc * r0, J.r[1] = sc * r1;
   // reduce (:72-75) scaled by sqrt_info and the loss factor
@@ -214,20 +235,19 @@ __device__ __forceinline__ void eval_line(const LinearizeArgs& A, const double* 
   mat3_vec(R, g9[3], g9[4], g9[5], ex, ey, ez);
   sx += cf[PC_TL], sy += cf[PC_TL + 1], sz += cf[PC_TL + 2];
   ex += cf[PC_TL], ey += cf[PC_TL + 1], ez += cf[PC_TL + 2];
-  const double isz = 1.0 / sz, iez = 1.0 / ez;
+  const double isz = fast_rcp(sz), iez = fast_rcp(ez);
   // (K*pc).x/(K*pc).z = (fx*X + cx*Z)/Z                                (line_projection_factor.cpp:45-51)
   const double us = (A.fx * sx + A.cx * sz) * isz, vs = (A.fy * sy + A.cy * sz) * isz;
   const double ue = (A.fx * ex + A.cx * ez) * iez, ve = (A.fy * ey + A.cy * ez) * iez;
   const double a = g9[6], b = g9[7], c = g9[8];
-  const double d = a * a + b * b, id = 1.0 / d;
+  const double d = a * a + b * b, id = fast_rcp(d);
   const double mus = (b * b * us - a * b * vs - a * c) * id, mvs = (a * a * vs - a * b * us - b * c) * id;
   const double mue = (b * b * ue - a * b * ve - a * c) * id, mve = (a * a * ve - a * b * ue - b * c) * id;
   const double dus = mus - us, dvs = mvs - vs, due = mue - ue, dve = mve - ve;
   double r0 = sqrt(dus * dus + dvs * dvs), r1 = sqrt(due * due + dve * dve);   // :68-69
   double sc = 1.0;
   if (A.flags & VIML_LOSS_CAUCHY) {
-    const double cc = 1.0 / (A.cauchy_a * A.cauchy_a);
-    sc = sqrt(fmax(2.2250738585072014e-308, 1.0 / (1.0 + (r0 * r0 + r1 * r1) * cc)));
+    sc = fast_rsqrt(fma(r0 * r0 + r1 * r1, A.inv_cauchy_a2, 1.0));
   }
   J.r[0] = sc * r0, J.r[1] = sc * r1;
   const double m2d = -2.0 * id * sc;
@@ -371,8 +391,6 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
   const bool fast = modeB && a.P <= fused::PMAX && a.F <= fused::FMAX && !ctx->force_generic;
   if (fast) {
     // fused CTA-per-window kernel: writes every H/b entry exactly once (no memset), r/J too when asked
-    int* flags = ctx->scratch.take<int>((size_t)a.W);
-    VIML_TRY_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)a.W * sizeof(int), st));
     const size_t smem = sizeof(fused::Smem);
     static bool attr_done = false;
     if (!attr_done) {
@@ -380,17 +398,38 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
       VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(fused::assemble_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_done = true;
     }
-    const int grid = a.W < ctx->sm_count ? a.W : ctx->sm_count;
+    const int grid = a.W < ctx->sm_count ? a.W : ctx->sm_count;   // persistent: one CTA per SM
+    LinearizeArgs a2 = a;
+    long long* dbg = nullptr;
+    if (getenv("VIML_PHASE_TIMERS")) {
+      cudaMalloc((void**)&dbg, sizeof(long long) * 22 * grid);
+      cudaMemsetAsync(dbg, 0, sizeof(long long) * 22 * grid, st);
+    }
+    a2.dbg = dbg;
     for (int wb = 0; wb < a.W; wb += fused::WSLOTS * grid) {   // <= WSLOTS windows per CTA per launch
       const int we = a.W < wb + fused::WSLOTS * grid ? a.W : wb + fused::WSLOTS * grid;
       LaunchScope ls(ctx, K_ASSEMBLE);
-      if (modeA) fused::assemble_kernel<true><<<grid, fused::AT, smem, st>>>(a, flags, wb, we);
-      else fused::assemble_kernel<false><<<grid, fused::AT, smem, st>>>(a, flags, wb, we);
+      if (modeA) fused::assemble_kernel<true><<<grid, fused::AT, smem, st>>>(a2, wb, we);
+      else fused::assemble_kernel<false><<<grid, fused::AT, smem, st>>>(a2, wb, we);
     }
-    {
-      LaunchScope ls(ctx, K_POINTS);  // finishes flagged (over-size) windows only
-      if (modeA) fused::fallback_kernel<true><<<grid, 256, 0, st>>>(a, flags);
-      else fused::fallback_kernel<false><<<grid, 256, 0, st>>>(a, flags);
+    if (dbg) {
+      std::vector<long long> h(22 * grid);
+      cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * 22 * grid, cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      double tot[6] = {0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < grid; ++c)
+        for (int k = 0; k < 6; ++k) tot[k] += (double)h[6 * c + k];
+      const double per = (double)a.W;
+      fprintf(stderr, "[viml phase cycles/window, thread 0] P0(sort,keys) %.0f | P0 tail+barrier %.0f | P1 eval %.0f | P1 barrier wait %.0f | P2a %.0f | P2b+barrier %.0f\n",
+              tot[0] / per, tot[1] / per, tot[2] / per, tot[3] / per, tot[4] / per, tot[5] / per);
+      fprintf(stderr, "[viml P2a cycles/window per warp]");
+      for (int wq = 0; wq < 16; ++wq) {
+        double t = 0;
+        for (int c = 0; c < grid; ++c) t += (double)h[6 * grid + 16 * c + wq];
+        fprintf(stderr, " %.0f", t / per);
+      }
+      fprintf(stderr, "\n");
+      cudaFree(dbg);
     }
   } else {
   if (modeB) {

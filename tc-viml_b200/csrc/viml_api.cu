@@ -219,6 +219,7 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   LinearizeArgs a{};
   a.W = W, a.P = P, a.F = F, a.D = D, a.NP = NP, a.NL = NL;
   a.sqrt_info = ctx->cfg.sqrt_info, a.cauchy_a = ctx->cfg.cauchy_a;
+  a.inv_cauchy_a2 = 1.0 / (ctx->cfg.cauchy_a * ctx->cfg.cauchy_a);
   a.fx = ctx->cfg.fx, a.fy = ctx->cfg.fy, a.cx = ctx->cfg.cx, a.cy = ctx->cfg.cy;
   a.flags = flags;
 
