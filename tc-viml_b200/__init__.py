@@ -24,7 +24,7 @@ ABI_SYMBOLS = (
     "viml_host_alloc", "viml_host_free", "viml_device_alloc", "viml_device_free", "viml_memcpy_h2d",
     "viml_memcpy_d2h", "viml_kernel_launches", "viml_profile_begin", "viml_profile_end", "viml_kernel_name",
     "viml_microbench_fp64", "viml_microbench_dmma", "viml_set_map", "viml_linearize_batch",
-    "viml_marginalize_batch", "viml_line_associate", "viml_allreduce_hb",
+    "viml_marginalize_batch", "viml_line_associate", "viml_assoc_stats", "viml_allreduce_hb",
 )
 
 
@@ -63,6 +63,7 @@ def load_library():
     lib.viml_linearize_batch.argtypes = [C.c_void_p, C.POINTER(_abi.WindowBatch), C.POINTER(_abi.LinearizeOut), C.c_uint32]
     lib.viml_marginalize_batch.argtypes = [C.c_void_p, C.POINTER(_abi.MargBatch), C.POINTER(_abi.MargOut), C.c_uint32]
     lib.viml_line_associate.argtypes = [C.c_void_p, C.POINTER(_abi.AssocQuery), C.POINTER(_abi.AssocOut), C.c_uint32]
+    lib.viml_assoc_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.viml_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     lib.viml_host_free.argtypes = [C.c_void_p]
     lib.viml_device_alloc.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t]
@@ -234,6 +235,11 @@ class Context:
         o.fov_index, o.fov_capacity, o.fov_mask = _abi.ptr(res.get("fov_index")), fov_capacity, _abi.ptr(res.get("fov_mask"))
         self._check(self.lib.viml_line_associate(self.h, C.byref(q), C.byref(o), 0))
         return res
+
+    def assoc_stats(self):
+        g, s = C.c_int64(), C.c_int64()
+        self._check(self.lib.viml_assoc_stats(self.h, C.byref(g), C.byref(s)))
+        return g.value, s.value
 
     def associate_raw(self, q, o, flags):
         self._check(self.lib.viml_line_associate(self.h, C.byref(q), C.byref(o), flags))

@@ -64,9 +64,17 @@ struct viml_ctx {
   // prior map, six SoA planes of n_map doubles
   double* d_map = nullptr;
   int64_t n_map = 0;
+  // spatially sorted copy for the hierarchical cull: Morton order of segment mid-points, tiles of kMapTile
+  // lines with a bounding sphere each (centre xyz + radius), and the original index of every sorted line
+  double* d_map_sorted = nullptr;   // [6][n_map]
+  int32_t* d_map_orig = nullptr;    // [n_map]
+  double* d_tile_sphere = nullptr;  // [n_tiles][4]
+  int64_t n_tiles = 0;
+  unsigned long long* d_assoc_stats = nullptr;  // {gate tests, scored candidates} of the last association call
   DeviceArena in_arena, out_arena, scratch, scratch2;
   void* nccl_lib = nullptr;
   // profiling (viml_profile_begin/end): event pairs per kernel id
+  bool brute_cull = false;     // VIML_BRUTE_CULL=1: the literal all-pairs FoV sweep (roofline accounting, cross-check)
   bool force_generic = false;  // tests: route everything through the generic atomic kernels
   bool prof = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[VIML_NUM_KERNELS];
@@ -106,6 +114,7 @@ struct LaunchScope {
 //   Rl[9]     Ricn^T * Rn^T, Rn = toRotationMatrix(normalized(q))   (line_projection_factor.cpp:31-39)
 //   tl[3]     -Rl*P - Ricn^T*Tic                 (line_projection_factor.cpp:40)
 // Per-window extrinsic cache (24 doubles): tic[3], ric[9], ricinv[9], rtt[3] = ric^T*tic
+constexpr int kMapTile = 256;
 constexpr int kPoseCache = 42;
 constexpr int kExCache = 24;
 constexpr int PC_P = 0, PC_R = 3, PC_RINV = 12, PC_M = 21, PC_RL = 30, PC_TL = 39;
@@ -144,7 +153,11 @@ int viml_launch_marginalize(viml_ctx* ctx, int K, int pos, int m, double eps, co
 struct AssocArgs {  // device pointers only
   int Pq, L;
   int64_t N;
-  const double* map;  // [6][N]
+  const double* map;  // [6][N] original order
+  const double* map_sorted;  // [6][N] Morton order
+  const int32_t* map_orig;   // [N]
+  const double* tile_sphere; // [n_tiles][4]
+  int64_t n_tiles;
   const double* cull_poses;
   const double* match_poses;  // may alias cull_poses
   const double* ex_pose;
@@ -159,6 +172,7 @@ struct AssocArgs {  // device pointers only
   int32_t fov_capacity;
   uint32_t* fov_mask;   // always valid
   int64_t words;        // ceil(N/32)
+  unsigned long long* stats;  // {gate tests, scored}
 };
 // associate_kernels.cu (compiled with -fmad=false)
 int viml_launch_associate(viml_ctx* ctx, const AssocArgs& a);

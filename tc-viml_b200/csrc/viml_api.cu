@@ -4,7 +4,9 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <numeric>
 #include <vector>
 
 #include "common.cuh"
@@ -69,6 +71,7 @@ int viml_create(viml_ctx** out, const viml_config* cfg, int device) {
   ctx->cos_th = cos_threshold(cfg->angle_th);
   ctx->nan_angle_passes = !(3.1415926 > cfg->angle_th);
   if (const char* e = getenv("VIML_FORCE_GENERIC")) ctx->force_generic = e[0] == '1';  // test hook
+  if (const char* e = getenv("VIML_BRUTE_CULL")) ctx->brute_cull = e[0] == '1';
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming) != cudaSuccess ||
@@ -90,6 +93,10 @@ void viml_destroy(viml_ctx* ctx) {
   ctx->scratch.release();
   ctx->scratch2.release();
   if (ctx->d_map) cudaFree(ctx->d_map);
+  if (ctx->d_map_sorted) cudaFree(ctx->d_map_sorted);
+  if (ctx->d_map_orig) cudaFree(ctx->d_map_orig);
+  if (ctx->d_tile_sphere) cudaFree(ctx->d_tile_sphere);
+  if (ctx->d_assoc_stats) cudaFree(ctx->d_assoc_stats);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -178,9 +185,12 @@ int viml_set_map(viml_ctx* ctx, const double* lines, int64_t n) {
   if (!ctx || n < 0 || (n > 0 && !lines)) return VIML_ERR_INVALID;
   VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
   VIML_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (ctx->d_map) cudaFree(ctx->d_map);
-  ctx->d_map = nullptr;
-  ctx->n_map = 0;
+  auto drop = [&](auto*& ptr) {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+  };
+  drop(ctx->d_map), drop(ctx->d_map_sorted), drop(ctx->d_map_orig), drop(ctx->d_tile_sphere);
+  ctx->n_map = 0, ctx->n_tiles = 0;
   if (n == 0) return VIML_OK;
   // AoS rows [sx sy sz ex ey ez] (parameters.cpp:50-59) -> six SoA planes
   std::vector<double> soa((size_t)6 * n);
@@ -188,7 +198,75 @@ int viml_set_map(viml_ctx* ctx, const double* lines, int64_t n) {
     for (int c = 0; c < 6; ++c) soa[(size_t)c * n + j] = lines[6 * j + c];
   VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_map, soa.size() * sizeof(double)));
   VIML_TRY_CUDA(ctx, cudaMemcpy(ctx->d_map, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
+  // Morton order of the segment mid-points (21 bits per axis over the bounding box); one-time ingest cost.
+  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int64_t j = 0; j < n; ++j)
+    for (int c = 0; c < 3; ++c) {
+      const double m = 0.5 * (lines[6 * j + c] + lines[6 * j + 3 + c]);
+      if (std::isfinite(m)) lo[c] = std::min(lo[c], m), hi[c] = std::max(hi[c], m);
+    }
+  auto spread = [](uint64_t v) {  // 21 bits -> every third bit
+    v &= 0x1fffff;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+  };
+  std::vector<uint64_t> key(n);
+  for (int64_t j = 0; j < n; ++j) {
+    uint64_t k = 0;
+    for (int c = 0; c < 3; ++c) {
+      const double m = 0.5 * (lines[6 * j + c] + lines[6 * j + 3 + c]);
+      const double span = hi[c] > lo[c] ? hi[c] - lo[c] : 1.0;
+      double t = std::isfinite(m) ? (m - lo[c]) / span : 0.0;
+      t = std::min(1.0, std::max(0.0, t));
+      k |= spread((uint64_t)(t * 2097151.0)) << c;
+    }
+    key[j] = k;
+  }
+  std::vector<int32_t> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+  std::vector<double> sorted((size_t)6 * n);
+  for (int64_t k = 0; k < n; ++k)
+    for (int c = 0; c < 6; ++c) sorted[(size_t)c * n + k] = lines[6 * (int64_t)order[k] + c];
+  const int64_t nt = (n + kMapTile - 1) / kMapTile;
+  std::vector<double> sph((size_t)nt * 4);
+  for (int64_t t = 0; t < nt; ++t) {
+    const int64_t k0 = t * kMapTile, k1 = std::min<int64_t>(n, k0 + kMapTile);
+    double blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool finite = true;
+    for (int64_t k = k0; k < k1; ++k)
+      for (int c = 0; c < 6; ++c) {
+        const double v = sorted[(size_t)c * n + k];
+        finite &= std::isfinite(v);
+        blo[c % 3] = std::min(blo[c % 3], v), bhi[c % 3] = std::max(bhi[c % 3], v);
+      }
+    double ctr[3], r2 = 0.0;
+    for (int c = 0; c < 3; ++c) ctr[c] = 0.5 * (blo[c] + bhi[c]);
+    for (int64_t k = k0; k < k1; ++k)
+      for (int e = 0; e < 2; ++e) {
+        double d2 = 0.0;
+        for (int c = 0; c < 3; ++c) {
+          const double d = sorted[(size_t)(3 * e + c) * n + k] - ctr[c];
+          d2 += d * d;
+        }
+        r2 = std::max(r2, d2);
+      }
+    // a tile with a non-finite coordinate is never rejected (radius = +inf): the exact test decides
+    sph[4 * t] = ctr[0], sph[4 * t + 1] = ctr[1], sph[4 * t + 2] = ctr[2];
+    sph[4 * t + 3] = finite ? std::sqrt(r2) * (1.0 + 1e-12) : INFINITY;
+  }
+  VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_map_sorted, sorted.size() * sizeof(double)));
+  VIML_TRY_CUDA(ctx, cudaMemcpy(ctx->d_map_sorted, sorted.data(), sorted.size() * sizeof(double), cudaMemcpyHostToDevice));
+  VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_map_orig, (size_t)n * sizeof(int32_t)));
+  VIML_TRY_CUDA(ctx, cudaMemcpy(ctx->d_map_orig, order.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_tile_sphere, sph.size() * sizeof(double)));
+  VIML_TRY_CUDA(ctx, cudaMemcpy(ctx->d_tile_sphere, sph.data(), sph.size() * sizeof(double), cudaMemcpyHostToDevice));
   ctx->n_map = n;
+  ctx->n_tiles = nt;
   return VIML_OK;
 }
 
@@ -375,6 +453,10 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
   const bool dev = (flags & VIML_PTRS_DEVICE) != 0;
   AssocArgs a{};
   a.Pq = Pq, a.L = L, a.N = N, a.map = ctx->d_map, a.words = words;
+  if (!ctx->d_assoc_stats) VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_assoc_stats, 16));
+  VIML_TRY_CUDA(ctx, cudaMemsetAsync(ctx->d_assoc_stats, 0, 16, st));
+  a.stats = ctx->d_assoc_stats;
+  a.map_sorted = ctx->d_map_sorted, a.map_orig = ctx->d_map_orig, a.tile_sphere = ctx->d_tile_sphere, a.n_tiles = ctx->n_tiles;
   a.fov_capacity = out->fov_index ? out->fov_capacity : 0;
   auto pad = [](size_t b) { return DeviceArena::padded(b); };
   const size_t nq = (size_t)Pq * L;
@@ -435,6 +517,18 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
   down(out->fov_mask, a.fov_mask, (size_t)Pq * words * 4);
   VIML_TRY_CUDA(ctx, cudaGetLastError());
   VIML_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+  return VIML_OK;
+}
+
+int viml_assoc_stats(viml_ctx* ctx, int64_t* gate_tests, int64_t* scored) {
+  if (!ctx) return VIML_ERR_INVALID;
+  unsigned long long h[2] = {0, 0};
+  if (ctx->d_assoc_stats) {
+    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_assoc_stats, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    VIML_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  if (gate_tests) *gate_tests = (int64_t)h[0];
+  if (scored) *scored = (int64_t)h[1];
   return VIML_OK;
 }
 

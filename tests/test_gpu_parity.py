@@ -254,6 +254,35 @@ def test_association_synthetic(pkg, orc, ctx, cfg):
     check_assoc(got, ref)
 
 
+def test_hierarchical_cull_equals_brute_force_sweep(pkg, orc, cfg):
+    """The tile-rejection cull (default) and the literal all-pairs sweep (VIML_BRUTE_CULL=1) give identical masks,
+    counts, lists and matches; both equal the oracle on a sample of poses."""
+    synth = pkg.synth
+    ext = (600.0, 600.0, 30.0)
+    lines = synth.make_line_map(100001, seed=51, extent=ext)            # not a multiple of the 256-line tile
+    cull, match, ex, l2d = synth.make_assoc_queries(lines, 70, L=48, n_true=20, seed=52, extent=ext)
+    # a few poses that look at the horizon: huge FoV lists, tiles straddling every frustum plane
+    h = np.sqrt(0.5)
+    cull[3, 3:7] = [h, 0.0, 0.0, h]      # body z (the camera axis, up to the extrinsic) turned horizontal
+    cull[4, 3:7] = [0.0, h, 0.0, h]
+    match[3], match[4] = cull[3], cull[4]
+    res = {}
+    for mode in ("0", "1"):
+        os.environ["VIML_BRUTE_CULL"] = mode
+        try:
+            with pkg.Context(cfg) as cx:
+                cx.set_map(lines)
+                res[mode] = cx.associate(cull, match, ex, l2d, fov_capacity=8192, want_mask=True)
+        finally:
+            del os.environ["VIML_BRUTE_CULL"]
+    for k in res["0"]:
+        assert np.array_equal(res["0"][k], res["1"][k], equal_nan=True), k
+    sel = np.array([0, 3, 4, 69])
+    ref = orc.line_associate(cfg, lines, cull[sel], match[sel], ex[sel], l2d[sel], fov_capacity=8192, want_mask=True, nthreads=8)
+    check_assoc({k: v[sel] for k, v in res["0"].items()}, ref)
+    assert max(res["0"]["fov_count"][3], res["0"]["fov_count"][4]) > 2 * np.median(res["0"]["fov_count"])
+
+
 def test_association_edges(pkg, orc, ctx, cfg):
     synth = pkg.synth
     lines = synth.make_line_map(777, seed=43, extent=(60.0, 60.0, 30.0))   # N not a multiple of 32
