@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_
       prefetch_l2(A.inv_depth + (size_t)wn * F, (size_t)F * 8, tid, AT);
       if (A.pf_pts_i_z) prefetch_l2(A.pf_pts_i_z + q0, (size_t)(q1 - q0) * 8, tid, AT);
       if (A.NL > 0)
-        for (int c = 0; c < 9; ++c) prefetch_l2(A.lf_geom + (size_t)c * A.NL + m0, (size_t)(m1 - m0) * 8, tid, AT);
+        for (int c = 0; c < 9; ++c) prefetch_l2(A.lf_geom + (size_t)c * A.NL_stride + m0, (size_t)(m1 - m0) * 8, tid, AT);
     }
     double* __restrict__ Hpp = A.out.H_pp + (size_t)w * D * D;
     double* __restrict__ Hlp = A.out.H_lp + (size_t)w * F * D;
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_
       const int64_t k = (int64_t)l0 + lt_;
       double g9[9];
 #pragma unroll
-      for (int c = 0; c < 9; ++c) g9[c] = A.lf_geom[(size_t)c * A.NL + k];
+      for (int c = 0; c < 9; ++c) g9[c] = A.lf_geom[(size_t)c * A.NL_stride + k];
       LineJac J;
       eval_line(A, S.cache, lframe, g9, J);
       if (MODE_A) {

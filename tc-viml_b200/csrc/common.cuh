@@ -54,6 +54,7 @@ struct viml_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream2 = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   viml_config cfg{};
   std::string err;
@@ -122,7 +123,9 @@ constexpr int EC_TIC = 0, EC_RIC = 3, EC_RICINV = 12, EC_RTT = 21;
 
 struct LinearizeArgs {  // device pointers only
   int W, P, F, D;
-  int64_t NP, NL;
+  int64_t NP, NL;          // factors covered by this launch
+  int64_t pf_begin, lf_begin;  // first factor covered (chunked launches view a window range of one batch)
+  int64_t NL_stride;       // plane stride of lf_geom (total line factors of the batch)
   const double* poses;
   const double* ex_pose;
   const double* inv_depth;

@@ -327,8 +327,8 @@ __device__ __forceinline__ void point_atomics(const LinearizeArgs& A, int w, int
 
 template <bool MODE_A, bool MODE_B>
 __global__ void __launch_bounds__(128) points_kernel(LinearizeArgs A) {
-  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (k >= A.NP) return;
+  const int64_t k = A.pf_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= A.pf_begin + A.NP) return;
   const int w = find_window(A.pf_window_offset, A.W, k);
   const uint32_t pk = A.pf_idx[k];
   const int i = pk & 0xff, j = (pk >> 8) & 0xff, f = pk >> 16;
@@ -350,13 +350,13 @@ __global__ void __launch_bounds__(128) points_kernel(LinearizeArgs A) {
 
 template <bool MODE_A, bool MODE_B>
 __global__ void __launch_bounds__(128) lines_kernel(LinearizeArgs A) {
-  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (k >= A.NL) return;
+  const int64_t k = A.lf_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= A.lf_begin + A.NL) return;
   const int w = find_window(A.lf_window_offset, A.W, k);
   const int frame = A.lf_frame[k];
   double g9[9];
 #pragma unroll
-  for (int c = 0; c < 9; ++c) g9[c] = A.lf_geom[(size_t)c * A.NL + k];
+  for (int c = 0; c < 9; ++c) g9[c] = A.lf_geom[(size_t)c * A.NL_stride + k];
   const double* cw = A.cache + (size_t)w * (A.P * kPoseCache + kExCache);
   LineJac J;
   eval_line(A, cw, frame, g9, J);

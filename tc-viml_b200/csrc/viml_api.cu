@@ -74,6 +74,7 @@ int viml_create(viml_ctx** out, const viml_config* cfg, int device) {
   if (const char* e = getenv("VIML_BRUTE_CULL")) ctx->brute_cull = e[0] == '1';
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
@@ -100,6 +101,7 @@ void viml_destroy(viml_ctx* ctx) {
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->nccl_lib) dlclose(ctx->nccl_lib);
   delete ctx;
@@ -296,6 +298,7 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
 
   LinearizeArgs a{};
   a.W = W, a.P = P, a.F = F, a.D = D, a.NP = NP, a.NL = NL;
+  a.pf_begin = 0, a.lf_begin = 0, a.NL_stride = NL;
   a.sqrt_info = ctx->cfg.sqrt_info, a.cauchy_a = ctx->cfg.cauchy_a;
   a.inv_cauchy_a2 = 1.0 / (ctx->cfg.cauchy_a * ctx->cfg.cauchy_a);
   a.fx = ctx->cfg.fx, a.fy = ctx->cfg.fy, a.cx = ctx->cfg.cx, a.cy = ctx->cfg.cy;
@@ -331,70 +334,119 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
     return viml_launch_linearize(ctx, a);
   }
 
-  // ---- host pointers: stage in, run, stage out, synchronise ----
-  size_t in_bytes = 0;
+  // ---- host pointers: chunked pipeline  H2D(c+1) | kernels(c) | D2H(c-1)  on three streams ----
+  // Device buffers hold the whole batch at the same absolute positions as the host arrays; a chunk is a range of
+  // windows, its kernels run on a "view" (pointers advanced to the first window of the chunk, factor ranges
+  // absolute).  PCIe is full duplex, so with pinned host memory the call approaches max(H2D, D2H) time.
   auto pad = [](size_t b) { return DeviceArena::padded(b); };
-  in_bytes += pad(n_pose * 8) + pad(n_ex * 8) + pad(n_dep * 8) + 2 * pad((size_t)(W + 1) * 4);
+  size_t in_bytes = pad(n_pose * 8) + pad(n_ex * 8) + pad(n_dep * 8) + 2 * pad((size_t)(W + 1) * 4);
   in_bytes += pad((size_t)NP * 4) + pad((size_t)NP * 32) + pad((size_t)NP * 8);
   in_bytes += pad((size_t)NL * 4) + pad((size_t)NL * 72);
   VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(in_bytes));
-  auto up = [&](const void* src, size_t bytes) -> void* {
-    char* d = ctx->in_arena.take<char>(bytes);
-    if (bytes) cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st);
-    return d;
-  };
-  a.poses = (const double*)up(in->poses, n_pose * 8);
-  a.ex_pose = (const double*)up(in->ex_pose, n_ex * 8);
-  a.inv_depth = (const double*)up(in->inv_depth, n_dep * 8);
-  a.pf_window_offset = (const int32_t*)up(in->pf_window_offset, (size_t)(W + 1) * 4);
-  a.pf_idx = (const uint32_t*)up(in->pf_idx, (size_t)NP * 4);
-  a.pf_obs = (const double*)up(in->pf_obs, (size_t)NP * 32);
-  a.pf_pts_i_z = in->pf_pts_i_z ? (const double*)up(in->pf_pts_i_z, (size_t)NP * 8) : nullptr;
-  if (NL > 0) {
-    a.lf_window_offset = (const int32_t*)up(in->lf_window_offset, (size_t)(W + 1) * 4);
-    a.lf_frame = (const int32_t*)up(in->lf_frame, (size_t)NL * 4);
-    a.lf_geom = (const double*)up(in->lf_geom, (size_t)NL * 72);
-  }
-  VIML_TRY_CUDA(ctx, cudaGetLastError());
+  double* d_poses = ctx->in_arena.take<double>(n_pose);
+  double* d_ex = ctx->in_arena.take<double>(n_ex);
+  double* d_dep = ctx->in_arena.take<double>(n_dep);
+  int32_t* d_poff = ctx->in_arena.take<int32_t>((size_t)W + 1);
+  uint32_t* d_idx = ctx->in_arena.take<uint32_t>((size_t)NP);
+  double* d_obs = ctx->in_arena.take<double>((size_t)NP * 4);
+  double* d_z = in->pf_pts_i_z ? ctx->in_arena.take<double>((size_t)NP) : nullptr;
+  int32_t* d_loff = NL > 0 ? ctx->in_arena.take<int32_t>((size_t)W + 1) : nullptr;
+  int32_t* d_frame = NL > 0 ? ctx->in_arena.take<int32_t>((size_t)NL) : nullptr;
+  double* d_geom = NL > 0 ? ctx->in_arena.take<double>((size_t)NL * 9) : nullptr;
+  a.poses = d_poses, a.ex_pose = d_ex, a.inv_depth = d_dep, a.pf_window_offset = d_poff, a.pf_idx = d_idx;
+  a.pf_obs = d_obs, a.pf_pts_i_z = d_z, a.lf_window_offset = d_loff, a.lf_frame = d_frame, a.lf_geom = d_geom;
 
-  struct Slot { double** dev; double* host; size_t count; };
+  struct Slot { double** dev; double* host; size_t per_window, per_pf, per_lf; };
   std::vector<Slot> slots;
   size_t out_bytes = 0;
-  auto want = [&](double** dslot, double* host, size_t count, bool force) {
+  auto want = [&](double** dslot, double* host, size_t per_window, size_t per_pf, size_t per_lf, bool force) {
     if (host || force) {
-      slots.push_back({dslot, host, count});
-      out_bytes += pad(count * 8);
+      slots.push_back({dslot, host, per_window, per_pf, per_lf});
+      out_bytes += pad((per_window * W + per_pf * NP + per_lf * NL) * 8);
     }
   };
   const bool needH = wantHB || wantS;
   if (wantA) {
-    want(&a.out.pf_residual, out->pf_residual, (size_t)NP * 2, false);
-    want(&a.out.pf_jac_pose_i, out->pf_jac_pose_i, (size_t)NP * 14, false);
-    want(&a.out.pf_jac_pose_j, out->pf_jac_pose_j, (size_t)NP * 14, false);
-    want(&a.out.pf_jac_ex, out->pf_jac_ex, (size_t)NP * 14, false);
-    want(&a.out.pf_jac_feat, out->pf_jac_feat, (size_t)NP * 2, false);
-    want(&a.out.lf_residual, out->lf_residual, (size_t)NL * 2, false);
-    want(&a.out.lf_jac_pose, out->lf_jac_pose, (size_t)NL * 14, false);
+    want(&a.out.pf_residual, out->pf_residual, 0, 2, 0, false);
+    want(&a.out.pf_jac_pose_i, out->pf_jac_pose_i, 0, 14, 0, false);
+    want(&a.out.pf_jac_pose_j, out->pf_jac_pose_j, 0, 14, 0, false);
+    want(&a.out.pf_jac_ex, out->pf_jac_ex, 0, 14, 0, false);
+    want(&a.out.pf_jac_feat, out->pf_jac_feat, 0, 2, 0, false);
+    want(&a.out.lf_residual, out->lf_residual, 0, 0, 2, false);
+    want(&a.out.lf_jac_pose, out->lf_jac_pose, 0, 0, 14, false);
   }
   if (needH) {
-    want(&a.out.H_pp, wantHB ? out->H_pp : nullptr, szHpp, true);
-    want(&a.out.H_lp, wantHB ? out->H_lp : nullptr, szHlp, true);
-    want(&a.out.H_ll, wantHB ? out->H_ll : nullptr, szF, true);
-    want(&a.out.b_p, wantHB ? out->b_p : nullptr, szD, true);
-    want(&a.out.b_l, wantHB ? out->b_l : nullptr, szF, true);
+    want(&a.out.H_pp, wantHB ? out->H_pp : nullptr, (size_t)D * D, 0, 0, true);
+    want(&a.out.H_lp, wantHB ? out->H_lp : nullptr, (size_t)F * D, 0, 0, true);
+    want(&a.out.H_ll, wantHB ? out->H_ll : nullptr, (size_t)F, 0, 0, true);
+    want(&a.out.b_p, wantHB ? out->b_p : nullptr, (size_t)D, 0, 0, true);
+    want(&a.out.b_l, wantHB ? out->b_l : nullptr, (size_t)F, 0, 0, true);
   }
   if (wantS) {
-    want(&a.out.S, out->S, szHpp, true);
-    want(&a.out.g, out->g, szD, true);
+    want(&a.out.S, out->S, (size_t)D * D, 0, 0, true);
+    want(&a.out.g, out->g, (size_t)D, 0, 0, true);
   }
   VIML_TRY_CUDA(ctx, ctx->out_arena.reserve(out_bytes));
-  for (auto& s : slots) *s.dev = ctx->out_arena.take<double>(s.count);
-  int rc = viml_launch_linearize(ctx, a);
+  for (auto& sl : slots) *sl.dev = ctx->out_arena.take<double>(sl.per_window * W + sl.per_pf * NP + sl.per_lf * NL);
+
+  cudaStream_t s_in = ctx->copy_stream, s_out = ctx->copy_stream2;
+  // offsets first (tiny, needed by every chunk); the previous call's work on `st` is already complete (synchronous API)
+  VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_poff, in->pf_window_offset, (size_t)(W + 1) * 4, cudaMemcpyHostToDevice, s_in));
+  if (NL > 0) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_loff, in->lf_window_offset, (size_t)(W + 1) * 4, cudaMemcpyHostToDevice, s_in));
+  const int nchunk = W >= 512 ? 8 : 1;
+  std::vector<cudaEvent_t> ev_in(nchunk), ev_k(nchunk);
+  for (int c = 0; c < nchunk; ++c) {
+    cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_k[c], cudaEventDisableTiming);
+  }
+  int rc = VIML_OK;
+  auto h2d = [&](void* d, const void* h, size_t bytes) {
+    if (bytes) cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s_in);
+  };
+  for (int c = 0; c < nchunk && rc == VIML_OK; ++c) {
+    const int w0 = (int)((int64_t)W * c / nchunk), w1 = (int)((int64_t)W * (c + 1) / nchunk), Wc = w1 - w0;
+    const int64_t pa = in->pf_window_offset[w0], pb = in->pf_window_offset[w1];
+    const int64_t la = NL > 0 ? in->lf_window_offset[w0] : 0, lb = NL > 0 ? in->lf_window_offset[w1] : 0;
+    h2d(d_poses + (size_t)w0 * P * 7, in->poses + (size_t)w0 * P * 7, (size_t)Wc * P * 56);
+    h2d(d_ex + (size_t)w0 * 7, in->ex_pose + (size_t)w0 * 7, (size_t)Wc * 56);
+    h2d(d_dep + (size_t)w0 * F, in->inv_depth + (size_t)w0 * F, (size_t)Wc * F * 8);
+    h2d(d_idx + pa, in->pf_idx + pa, (size_t)(pb - pa) * 4);
+    h2d(d_obs + 4 * pa, in->pf_obs + 4 * pa, (size_t)(pb - pa) * 32);
+    if (d_z) h2d(d_z + pa, in->pf_pts_i_z + pa, (size_t)(pb - pa) * 8);
+    if (lb > la) {
+      h2d(d_frame + la, in->lf_frame + la, (size_t)(lb - la) * 4);
+      for (int k = 0; k < 9; ++k) h2d(d_geom + (size_t)k * NL + la, in->lf_geom + (size_t)k * NL + la, (size_t)(lb - la) * 8);
+    }
+    cudaEventRecord(ev_in[c], s_in);
+    cudaStreamWaitEvent(st, ev_in[c], 0);
+    // view of windows [w0, w1)
+    LinearizeArgs v = a;
+    v.W = Wc, v.NP = pb - pa, v.NL = lb - la, v.pf_begin = pa, v.lf_begin = la;
+    v.poses = a.poses + (size_t)w0 * P * 7, v.ex_pose = a.ex_pose + (size_t)w0 * 7, v.inv_depth = a.inv_depth + (size_t)w0 * F;
+    v.pf_window_offset = a.pf_window_offset + w0;
+    if (NL > 0) v.lf_window_offset = a.lf_window_offset + w0;
+    v.cache = a.cache + (size_t)w0 * (P * kPoseCache + kExCache);
+    for (auto& sl : slots) {
+      double** vd = (double**)((char*)&v.out + ((char*)sl.dev - (char*)&a.out));
+      *vd = *sl.dev + sl.per_window * w0;   // per-factor arrays stay absolute (indexed by the global factor id)
+    }
+    rc = viml_launch_linearize(ctx, v);
+    cudaEventRecord(ev_k[c], st);
+    cudaStreamWaitEvent(s_out, ev_k[c], 0);
+    for (auto& sl : slots)
+      if (sl.host) {
+        const size_t off = sl.per_window * w0 + sl.per_pf * pa + sl.per_lf * la;
+        const size_t cnt = sl.per_window * Wc + sl.per_pf * (pb - pa) + sl.per_lf * (lb - la);
+        if (cnt) cudaMemcpyAsync(sl.host + off, *sl.dev + off, cnt * 8, cudaMemcpyDeviceToHost, s_out);
+      }
+  }
+  cudaError_t e1 = cudaStreamSynchronize(s_out), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(s_in);
+  for (int c = 0; c < nchunk; ++c) cudaEventDestroy(ev_in[c]), cudaEventDestroy(ev_k[c]);
   if (rc != VIML_OK) return rc;
-  for (auto& s : slots)
-    if (s.host && s.count)
-      VIML_TRY_CUDA(ctx, cudaMemcpyAsync(s.host, *s.dev, s.count * 8, cudaMemcpyDeviceToHost, st));
-  VIML_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+  VIML_TRY_CUDA(ctx, e1);
+  VIML_TRY_CUDA(ctx, e2);
+  VIML_TRY_CUDA(ctx, e3);
+  VIML_TRY_CUDA(ctx, cudaGetLastError());
   return VIML_OK;
 }
 
