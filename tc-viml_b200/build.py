@@ -61,6 +61,7 @@ def build_cuda(verbose=False, force=False, ptxas_info=False):
         objs.append(obj)
         if force or _newer([src] + hdrs, obj):
             extra = ["-fmad=false"] if cu in EXACT_TUS else []
+            extra += os.environ.get("VIML_NVCC_EXTRA", "").split()
             if ptxas_info:
                 extra += ["-Xptxas", "-v"]
             _run([nvcc] + NVCC_ARCH + NVCC_COMMON + extra + ["-c", src, "-o", obj], verbose)

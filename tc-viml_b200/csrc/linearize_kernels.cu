@@ -115,6 +115,16 @@ __device__ __forceinline__ int find_window(const int32_t* __restrict__ off, int 
   return lo;
 }
 
+// Window of factor k for a warp of consecutive factors: lane 0's binary search is shared, the other lanes walk
+// forward (a warp of 32 consecutive factors spans one or two windows).
+__device__ __forceinline__ int find_window_warp(const int32_t* __restrict__ off, int W, int64_t k, int64_t k_warp) {
+  int w = 0;
+  if ((threadIdx.x & 31) == 0) w = find_window(off, W, k_warp);
+  w = __shfl_sync(0xffffffffu, w, 0);
+  while (w + 1 < W && off[w + 1] <= k) ++w;
+  return w;
+}
+
 __device__ __forceinline__ void mat3_vec(const double* __restrict__ M, double x, double y, double z, double& ox,
                                          double& oy, double& oz) {
   ox = M[0] * x + M[1] * y + M[2] * z;
@@ -285,6 +295,32 @@ __device__ __forceinline__ void store_jac7(double* __restrict__ dst, const doubl
   d2[6] = make_double2(J[1][5], 0.0);
 }
 
+// Warp-cooperative version: the 32 rows of a warp (32 x 112 B, contiguous in the output array) are first laid out
+// in shared memory (STS.128 at a 7 x 16 B lane stride is conflict-free), then written with fully coalesced
+// 512-byte STG.128 instructions.  Direct per-lane stores touch 32 different lines per instruction and write every
+// sector in two halves; this halves the LSU sector work and gives L2 whole sectors.
+// `stage` is this warp's 3584-byte buffer, `dst` the output row of the warp's first lane, nvalid its live lanes.
+__device__ __forceinline__ void store_jac7_coalesced(double2* __restrict__ stage, double* __restrict__ dst,
+                                                     const double (*J)[6], int lane, int nvalid) {
+  double2* mine = stage + 7 * lane;
+  mine[0] = make_double2(J[0][0], J[0][1]);
+  mine[1] = make_double2(J[0][2], J[0][3]);
+  mine[2] = make_double2(J[0][4], J[0][5]);
+  mine[3] = make_double2(0.0, J[1][0]);
+  mine[4] = make_double2(J[1][1], J[1][2]);
+  mine[5] = make_double2(J[1][3], J[1][4]);
+  mine[6] = make_double2(J[1][5], 0.0);
+  __syncwarp();
+  double2* d2 = reinterpret_cast<double2*>(dst);
+  const int n16 = 7 * nvalid;  // 16-byte units to copy
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    const int e = q * 32 + lane;
+    if (e < n16) d2[e] = stage[e];
+  }
+  __syncwarp();
+}
+
 // H(rows r0.., cols c0..) += X^T Y and its mirror, X,Y 2x6, via global atomics (generic path: used for
 // windows too large for the shared-memory assembly kernel and as the simple reference device path).
 __device__ __forceinline__ void atomic_block(double* __restrict__ H, int D, int r0, int c0, const double (*X)[6],
@@ -326,10 +362,20 @@ __device__ __forceinline__ void point_atomics(const LinearizeArgs& A, int w, int
 }
 
 template <bool MODE_A, bool MODE_B>
-__global__ void __launch_bounds__(128) points_kernel(LinearizeArgs A) {
-  const int64_t k = A.pf_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (k >= A.pf_begin + A.NP) return;
-  const int w = find_window(A.pf_window_offset, A.W, k);
+#ifndef VIML_POINTS_MINB
+#define VIML_POINTS_MINB 4
+#endif
+__global__ void __launch_bounds__(128, VIML_POINTS_MINB) points_kernel(LinearizeArgs A) {
+  __shared__ double2 stage[MODE_A ? 4 * 7 * 32 : 1];
+  const int64_t k_raw = A.pf_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t k_end = A.pf_begin + A.NP;
+  const int lane = threadIdx.x & 31;
+  const int64_t k_warp = k_raw - lane;
+  if (k_warp >= k_end) return;                       // whole warp out of range
+  const int nvalid = (int)min((int64_t)32, k_end - k_warp);
+  const int64_t k = min(k_raw, k_end - 1);           // idle tail lanes recompute the last factor, they store nothing
+  const bool live = k_raw < k_end;
+  const int w = find_window_warp(A.pf_window_offset, A.W, k, k_warp);
   const uint32_t pk = A.pf_idx[k];
   const int i = pk & 0xff, j = (pk >> 8) & 0xff, f = pk >> 16;
   const double4 ob = reinterpret_cast<const double4*>(A.pf_obs)[k];
@@ -339,20 +385,28 @@ __global__ void __launch_bounds__(128) points_kernel(LinearizeArgs A) {
   PointJac J;
   eval_point(A, cw, i, j, lam, ob.x, ob.y, piz, ob.z, ob.w, J);
   if (MODE_A) {
-    if (A.out.pf_residual) reinterpret_cast<double2*>(A.out.pf_residual)[k] = make_double2(J.r[0], J.r[1]);
-    if (A.out.pf_jac_pose_i) store_jac7(A.out.pf_jac_pose_i + 14 * k, J.a);
-    if (A.out.pf_jac_pose_j) store_jac7(A.out.pf_jac_pose_j + 14 * k, J.b);
-    if (A.out.pf_jac_ex) store_jac7(A.out.pf_jac_ex + 14 * k, J.c);
-    if (A.out.pf_jac_feat) reinterpret_cast<double2*>(A.out.pf_jac_feat)[k] = make_double2(J.d[0], J.d[1]);
+    double2* st = stage + (threadIdx.x >> 5) * 7 * 32;
+    if (live && A.out.pf_residual) reinterpret_cast<double2*>(A.out.pf_residual)[k] = make_double2(J.r[0], J.r[1]);
+    if (A.out.pf_jac_pose_i) store_jac7_coalesced(st, A.out.pf_jac_pose_i + 14 * k_warp, J.a, lane, nvalid);
+    if (A.out.pf_jac_pose_j) store_jac7_coalesced(st, A.out.pf_jac_pose_j + 14 * k_warp, J.b, lane, nvalid);
+    if (A.out.pf_jac_ex) store_jac7_coalesced(st, A.out.pf_jac_ex + 14 * k_warp, J.c, lane, nvalid);
+    if (live && A.out.pf_jac_feat) reinterpret_cast<double2*>(A.out.pf_jac_feat)[k] = make_double2(J.d[0], J.d[1]);
   }
-  if (MODE_B) point_atomics(A, w, i, j, f, J);
+  if (MODE_B && live) point_atomics(A, w, i, j, f, J);
 }
 
 template <bool MODE_A, bool MODE_B>
 __global__ void __launch_bounds__(128) lines_kernel(LinearizeArgs A) {
-  const int64_t k = A.lf_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (k >= A.lf_begin + A.NL) return;
-  const int w = find_window(A.lf_window_offset, A.W, k);
+  __shared__ double2 stage[MODE_A ? 4 * 7 * 32 : 1];
+  const int64_t k_raw = A.lf_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t k_end = A.lf_begin + A.NL;
+  const int lane = threadIdx.x & 31;
+  const int64_t k_warp = k_raw - lane;
+  if (k_warp >= k_end) return;
+  const int nvalid = (int)min((int64_t)32, k_end - k_warp);
+  const int64_t k = min(k_raw, k_end - 1);
+  const bool live = k_raw < k_end;
+  const int w = find_window_warp(A.lf_window_offset, A.W, k, k_warp);
   const int frame = A.lf_frame[k];
   double g9[9];
 #pragma unroll
@@ -361,10 +415,11 @@ __global__ void __launch_bounds__(128) lines_kernel(LinearizeArgs A) {
   LineJac J;
   eval_line(A, cw, frame, g9, J);
   if (MODE_A) {
-    if (A.out.lf_residual) reinterpret_cast<double2*>(A.out.lf_residual)[k] = make_double2(J.r[0], J.r[1]);
-    if (A.out.lf_jac_pose) store_jac7(A.out.lf_jac_pose + 14 * k, J.a);
+    if (live && A.out.lf_residual) reinterpret_cast<double2*>(A.out.lf_residual)[k] = make_double2(J.r[0], J.r[1]);
+    if (A.out.lf_jac_pose)
+      store_jac7_coalesced(stage + (threadIdx.x >> 5) * 7 * 32, A.out.lf_jac_pose + 14 * k_warp, J.a, lane, nvalid);
   }
-  if (MODE_B) {
+  if (MODE_B && live) {
     const int D = A.D;
     double* H = A.out.H_pp + (size_t)w * D * D;
     double* bp = A.out.b_p + (size_t)w * D;
