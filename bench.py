@@ -330,6 +330,24 @@ def main():
                         "step_ms_with_linearize": msS / K}
         for p in dS.values():
             ctx.device_free(p)
+        # cfg 4: marginalisation / Schur stress, 10 keyframes + 2000 landmarks per window (all starting in frame 0);
+        # windows scaled to 256 per GPU to keep input generation short (per-window work is what cfg 4 fixes)
+        b4 = synth.make_windows(256, seed=0x5EED + 4 + rank, P=11, F=2000, all_start_zero=True, lines_per_frame=0)
+        d4 = {k: ctx.to_device(v) for k, v in b4.arrays().items() if v is not None}
+        sh4 = b4.out_shapes()
+        o4 = {k: ctx.device_alloc(int(np.prod(sh4[k])) * 8) for k in ("H_pp", "H_lp", "H_ll", "b_p", "b_l", "S", "g")}
+        s4, so4 = b4.struct(d4), abi.out_struct(o4)
+        ms4, prof4 = timed_device(lambda: ctx.linearize_raw(s4, so4, flagsS | abi.PTRS_DEVICE), max(3, K // 4), 3)
+        n4 = max(3, K // 4)
+        p4 = prof4.get("schur_landmarks", (ms4, n4))
+        fl4 = (2.0 * b4.D * b4.D * b4.F + 2.0 * b4.D * b4.F) * b4.W
+        out["schur_cfg4"] = {"shape": f"{b4.W} windows/GPU x (10 kf + 1, {b4.F} landmarks, {b4.NP // b4.W} factors/window)",
+                             "factors_per_s": sum_over_ranks(float(b4.NP)) / (ms4 / n4 * 1e-3), "ms_per_step": ms4 / n4,
+                             "windows_per_s": sum_over_ranks(float(b4.W)) / (ms4 / n4 * 1e-3),
+                             "schur_ms_per_launch": p4[0] / p4[1], "schur_tflops": fl4 / (p4[0] / p4[1] * 1e-3) / 1e12,
+                             "kernel_ms_per_step": {k: v[0] / n4 for k, v in prof4.items()}}
+        for p in list(d4.values()) + list(o4.values()):
+            ctx.device_free(p)
         out["fp64_peaks"] = dict(zip(("dfma_tflops", "dmul_dadd_tops", "dmma_tflops"), ctx.microbench_fp64()))
     for p in list(d_in.values()) + list(d_out.values()):
         ctx.device_free(p)

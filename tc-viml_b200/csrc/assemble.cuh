@@ -155,7 +155,10 @@ __device__ __forceinline__ void write_sym_slice(const double* a, int e0, double*
   }
 }
 
-template <bool MODE_A>
+// BIGF: more features per window than the shared-memory feature tables hold (F > FMAX, e.g. the 2000-landmark
+// marginalisation stress): the per-feature sort and P2b are skipped; every factor adds its landmark terms with
+// RED.ADD.F64 onto rows the launcher zero-filled (their summation order is then not reproducible bit for bit).
+template <bool MODE_A, bool BIGF>
 __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_begin, int w_end) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_
       const int i = fidx[r] & 0xff, j = (fidx[r] >> 8) & 0xff, l = fidx[r] >> 16;
       const int lo = min(i, j), hi = max(i, j);
       keyA[r] = valid ? lo * P + hi : 0xffff;
-      const int keyB = valid ? l : 0xffff;
+      const int keyB = (valid && !BIGF) ? l : 0xffff;
       if (r * AT < nf) {  // warp-uniform: some lane of this warp may be valid
         const unsigned ma = __match_any_sync(0xffffffffu, keyA[r]);
         const unsigned mb = __match_any_sync(0xffffffffu, keyB);
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_
         rankB[r] = __popc(mb & lt);
         const int slab = warp + r * (AT / 32);
         if (valid && rankA[r] == 0) S.u.cnt.cntA[slab * KA + keyA[r]] = (uint16_t)__popc(ma);
-        if (valid && rankB[r] == 0) S.u.cnt.cntB[slab * FMAX + keyB] = (uint16_t)__popc(mb);
+        if (!BIGF && valid && rankB[r] == 0) S.u.cnt.cntB[slab * FMAX + keyB] = (uint16_t)__popc(mb);
       }
     }
     // line factor t is handled by thread AT-1-t: the second round of point factors uses the LOW threads, so no
@@ -272,13 +275,14 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_
     __syncthreads();
     // exclusive prefix over slabs for every key (thread per key); loads are issued together, the running sum
     // stays in registers (the serial load->store chain of a rolled loop cost ~1 K cycles per window)
-    for (int e = tid; e < nkeyA + F + P; e += AT) {
+    const int Fs = BIGF ? 0 : F;  // feature keys handled in shared memory
+    for (int e = tid; e < nkeyA + Fs + P; e += AT) {
       uint16_t* col;
       int stride, ns;
       uint16_t* tot;
       if (e < nkeyA) col = S.u.cnt.cntA + e, stride = KA, ns = SLABS, tot = S.totA + e;
-      else if (e < nkeyA + F) col = S.u.cnt.cntB + (e - nkeyA), stride = FMAX, ns = SLABS, tot = S.totB + (e - nkeyA);
-      else col = S.u.cnt.cntC + (e - nkeyA - F), stride = PMAX, ns = LSLABS, tot = S.totC + (e - nkeyA - F);
+      else if (e < nkeyA + Fs) col = S.u.cnt.cntB + (e - nkeyA), stride = FMAX, ns = SLABS, tot = S.totB + (e - nkeyA);
+      else col = S.u.cnt.cntC + (e - nkeyA - Fs), stride = PMAX, ns = LSLABS, tot = S.totC + (e - nkeyA - Fs);
       int c[SLABS];
 #pragma unroll
       for (int q = 0; q < SLABS; ++q) c[q] = q < ns ? col[q * stride] : 0;
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_
     if (warp < 3) {
       const uint16_t* tot = warp == 0 ? S.totA : (warp == 1 ? S.totB : S.totC);
       uint16_t* base = warp == 0 ? S.baseA : (warp == 1 ? S.baseB : S.baseC);
-      const int n = warp == 0 ? nkeyA : (warp == 1 ? F : P);
+      const int n = warp == 0 ? nkeyA : (warp == 1 ? Fs : P);
       int carry = 0, npairs = 0;
       for (int b0 = 0; b0 < n; b0 += 32) {
         const int k = b0 + lane;
@@ -353,9 +357,8 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_
         const int slab = warp + r * (AT / 32);
         const int l = fidx[r] >> 16;
         posA[r] = S.baseA[keyA[r]] + S.u.cnt.cntA[slab * KA + keyA[r]] + rankA[r];
-        const int posB = S.baseB[l] + S.u.cnt.cntB[slab * FMAX + l] + rankB[r];
         S.ridx[posA[r]] = fidx[r];
-        S.fperm[posB] = (uint16_t)posA[r];
+        if (!BIGF) S.fperm[S.baseB[l] + S.u.cnt.cntB[slab * FMAX + l] + rankB[r]] = (uint16_t)posA[r];
         S.hperm[S.offD[keyA[r]] + posA[r] - S.baseA[keyA[r]]] = (uint16_t)posA[r];
       }
     }
@@ -393,6 +396,17 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_
       for (int c = 0; c < 6; ++c) strec(S.rec, pos, 9 + c, J.c[0][c], J.c[1][c]);
       strec(S.rec, pos, 15, J.r[0], J.r[1]);
       strec(S.rec, pos, 16, J.d[0], J.d[1]);
+      if (BIGF) {  // landmark row terms straight from registers (rows were zero-filled by the launcher)
+        double* row = Hlp + (size_t)l * D;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          atomicAdd(row + 6 * i + c, J.d[0] * J.a[0][c] + J.d[1] * J.a[1][c]);
+          atomicAdd(row + 6 * E + c, J.d[0] * J.c[0][c] + J.d[1] * J.c[1][c]);
+          row[6 * j + c] = J.d[0] * J.b[0][c] + J.d[1] * J.b[1][c];   // unique per (landmark, frame)
+        }
+        atomicAdd(Hll + l, J.d[0] * J.d[0] + J.d[1] * J.d[1]);
+        atomicAdd(bl + l, J.d[0] * J.r[0] + J.d[1] * J.r[1]);
+      }
     }
     if (lt_ < nl) {
       const int64_t k = (int64_t)l0 + lt_;
@@ -544,7 +558,7 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_
     if (part + 1 < nparts) fetch_next(w, slot, part + 1);
     else if (has_next) fetch_next(w + gridDim.x, slot + 1, 0);
     // ------------------------------------------------------------------ P2b: landmark strips, thread per feature
-    for (;;) {
+    for (; !BIGF;) {
       int base = 0;
       if (lane == 0) base = atomicAdd(&S.next_feature, 32);
       base = __shfl_sync(0xffffffffu, base, 0);

@@ -443,15 +443,24 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
     LaunchScope ls(ctx, K_PREP);
     prep_windows_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a);
   }
-  const bool fast = modeB && a.P <= fused::PMAX && a.F <= fused::FMAX && !ctx->force_generic;
+  const bool fast = modeB && a.P <= fused::PMAX && !ctx->force_generic;
+  const bool bigf = a.F > fused::FMAX;
   if (fast) {
     // fused CTA-per-window kernel: writes every H/b entry exactly once (no memset), r/J too when asked
     const size_t smem = sizeof(fused::Smem);
     static bool attr_done = false;
     if (!attr_done) {
-      VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(fused::assemble_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(fused::assemble_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(fused::assemble_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(fused::assemble_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(fused::assemble_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(fused::assemble_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_done = true;
+    }
+    if (bigf) {  // landmark rows are accumulated with REDs: they start from zero
+      const size_t W = a.W, D = a.D, F = a.F;
+      VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.H_lp, 0, W * F * D * sizeof(double), st));
+      VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.H_ll, 0, W * F * sizeof(double), st));
+      VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.b_l, 0, W * F * sizeof(double), st));
     }
     const int grid = a.W < ctx->sm_count ? a.W : ctx->sm_count;   // persistent: one CTA per SM
     LinearizeArgs a2 = a;
@@ -464,8 +473,10 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
     for (int wb = 0; wb < a.W; wb += fused::WSLOTS * grid) {   // <= WSLOTS windows per CTA per launch
       const int we = a.W < wb + fused::WSLOTS * grid ? a.W : wb + fused::WSLOTS * grid;
       LaunchScope ls(ctx, K_ASSEMBLE);
-      if (modeA) fused::assemble_kernel<true><<<grid, fused::AT, smem, st>>>(a2, wb, we);
-      else fused::assemble_kernel<false><<<grid, fused::AT, smem, st>>>(a2, wb, we);
+      if (modeA && bigf) fused::assemble_kernel<true, true><<<grid, fused::AT, smem, st>>>(a2, wb, we);
+      else if (modeA) fused::assemble_kernel<true, false><<<grid, fused::AT, smem, st>>>(a2, wb, we);
+      else if (bigf) fused::assemble_kernel<false, true><<<grid, fused::AT, smem, st>>>(a2, wb, we);
+      else fused::assemble_kernel<false, false><<<grid, fused::AT, smem, st>>>(a2, wb, we);
     }
     if (dbg) {
       std::vector<long long> h(22 * grid);

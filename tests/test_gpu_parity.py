@@ -100,6 +100,11 @@ def test_marginalisation_stress_shape(pkg, orc, ctx, cfg):
     abi = pkg._abi
     b = pkg.synth.make_windows(3, seed=109, P=11, F=400, all_start_zero=True, lines_per_frame=0)
     check_linearize(pkg, orc, ctx, cfg, b, abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY)
+    # the full cfg-4 window shape: 2000 landmarks, ~11000 factors per window (fused kernel in its many-feature mode:
+    # 16 accumulating parts per window, landmark rows by RED), DMMA Schur with K = 2000
+    b = pkg.synth.make_windows(2, seed=115, P=11, F=2000, all_start_zero=True, lines_per_frame=3)
+    assert np.diff(b.pf_window_offset).min() > 9000
+    check_linearize(pkg, orc, ctx, cfg, b, abi.OUT_RESIDUAL_JACOBIAN | abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY)
 
 
 def test_bad_arguments(pkg, ctx, cfg):
