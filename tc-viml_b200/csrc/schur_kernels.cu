@@ -112,6 +112,118 @@ __global__ void __launch_bounds__(SWARPS * 32) schur_dmma_kernel(int F, int D, c
   if (diag && tid < nr) g[(size_t)w * D + r0 + tid] = b_p[(size_t)w * D + r0 + tid] - gacc;
 }
 
+// ---- D <= 72 (one tile, the sliding-window case): split-K over the 8 warps ------------------------------------
+// Each warp owns every 8x8 sub-tile of the upper triangle (45 x 2 accumulator registers per lane) for its share
+// of the landmarks: one row fragment per 8-column block is loaded once per 4 landmarks and feeds both operand
+// roles (A = W^T/L, B = W) of up to 9 MMAs each, there is no block barrier in the main loop, and the next
+// 4 rows are prefetched into registers while the current ones are multiplied.  The 8 partial triangles are summed
+// through shared memory at the end.
+constexpr int kSplitStageLd = 76;
+__global__ void __launch_bounds__(SWARPS * 32) schur_splitk_kernel(int F, int D, const double* __restrict__ H_pp,
+                                                                   const double* __restrict__ H_lp,
+                                                                   const double* __restrict__ H_ll,
+                                                                   const double* __restrict__ b_p,
+                                                                   const double* __restrict__ b_l, double* __restrict__ S,
+                                                                   double* __restrict__ g, double eps) {
+  __shared__ double stage[SWARPS][4 * kSplitStageLd + 8];   // 4 landmark rows (padded stride) + inv[4] + b[4]
+  __shared__ double sAcc[45 * 64 + 72];                      // cross-warp sum of the 45 sub-tiles + g
+  const int w = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kq = lane & 3, mq = lane >> 2;
+  const double* __restrict__ Hl = H_lp + (size_t)w * F * D;
+  const double* __restrict__ Ll = H_ll + (size_t)w * F;
+  const double* __restrict__ Bl = b_l + (size_t)w * F;
+  double* st = stage[warp];
+  double acc[45][2];
+#pragma unroll
+  for (int i = 0; i < 45; ++i) acc[i][0] = acc[i][1] = 0.0;
+  double gacc[3] = {0.0, 0.0, 0.0};
+  const int nsteps = (F + 3) / 4;
+  // register prefetch of one step: 4 rows x 72 columns = 288 doubles = 9 per lane, plus L and b for lanes 0..3
+  double pre[9], preL = 0.0, preB = 0.0;
+  auto fetch = [&](int step) {
+    const int l0 = 4 * step;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+      const int e = q * 32 + lane, r = e / 72, c = e % 72;
+      pre[q] = (l0 + r < F && c < D) ? Hl[(size_t)(l0 + r) * D + c] : 0.0;
+    }
+    if (lane < 4) {
+      preL = l0 + lane < F ? Ll[l0 + lane] : 0.0;
+      preB = l0 + lane < F ? Bl[l0 + lane] : 0.0;
+    }
+  };
+  if (warp < nsteps) fetch(warp);
+  for (int step = warp; step < nsteps; step += SWARPS) {
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+      const int e = q * 32 + lane, r = e / 72, c = e % 72;
+      st[r * kSplitStageLd + c] = pre[q];
+    }
+    if (lane < 4) {
+      st[4 * kSplitStageLd + lane] = (preL > eps) ? 1.0 / preL : 0.0;
+      st[4 * kSplitStageLd + 4 + lane] = preB;
+    }
+    __syncwarp();
+    if (step + SWARPS < nsteps) fetch(step + SWARPS);
+    const double inv = st[4 * kSplitStageLd + kq];
+    double fb[9], fa[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      fb[t] = st[kq * kSplitStageLd + 8 * t + mq];
+      fa[t] = fb[t] * inv;
+    }
+    int idx = 0;
+#pragma unroll
+    for (int tr = 0; tr < 9; ++tr)
+#pragma unroll
+      for (int tc = tr; tc < 9; ++tc, ++idx) dmma(acc[idx][0], acc[idx][1], fa[tr], fb[tc]);
+    // g: lanes own rows lane, lane+32, lane+64
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double s = st[4 * kSplitStageLd + k] * st[4 * kSplitStageLd + 4 + k];
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (lane + 32 * q < 72) gacc[q] = fma(st[k * kSplitStageLd + lane + 32 * q], s, gacc[q]);
+    }
+    __syncwarp();
+  }
+  // cross-warp reduction (once per window)
+  for (int e = tid; e < 45 * 64 + 72; e += SWARPS * 32) sAcc[e] = 0.0;
+  __syncthreads();
+  for (int turn = 0; turn < SWARPS; ++turn) {
+    if (warp == turn) {
+#pragma unroll
+      for (int i = 0; i < 45; ++i) {
+        sAcc[i * 64 + mq * 8 + 2 * kq] += acc[i][0];
+        sAcc[i * 64 + mq * 8 + 2 * kq + 1] += acc[i][1];
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (lane + 32 * q < 72) sAcc[45 * 64 + lane + 32 * q] += gacc[q];
+    }
+    __syncthreads();
+  }
+  const double* __restrict__ Hp = H_pp + (size_t)w * D * D;
+  double* __restrict__ So = S + (size_t)w * D * D;
+  for (int e = tid; e < D * D; e += SWARPS * 32) {
+    const int r = e / D, c = e % D;
+    const int rr = r <= c ? r : c, cc = r <= c ? c : r;     // value lives in the upper triangle
+    const int tr = rr >> 3, tc = cc >> 3;
+    // sub-tile index in the (tr <= tc) enumeration: sum_{k<tr} (9-k) + (tc - tr)
+    const int idx = tr * 9 - (tr * (tr - 1)) / 2 + (tc - tr);
+    double v;
+    if (tr == tc) {
+      // a diagonal sub-tile holds the full 8x8 (both triangles were computed)
+      v = sAcc[idx * 64 + (r & 7) * 8 + (c & 7)];
+    } else {
+      v = sAcc[idx * 64 + (rr & 7) * 8 + (cc & 7)];
+    }
+    So[e] = Hp[e] - v;
+  }
+  for (int e = tid; e < D; e += SWARPS * 32) g[(size_t)w * D + e] = b_p[(size_t)w * D + e] - sAcc[45 * 64 + e];
+}
+
 // ---- DMMA peak (for the roofline denominator of this kernel) ----
 __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, double a, double b, int iters) {
   double c[8][2];
@@ -132,6 +244,11 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, double a, d
 int viml_launch_schur(viml_ctx* ctx, int W, int F, int D, const double* H_pp, const double* H_lp, const double* H_ll,
                       const double* b_p, const double* b_l, double* S, double* g, double eps) {
   const int ntile = (D + TS - 1) / TS;
+  if (ntile == 1) {   // sliding-window case: split-K kernel, one CTA per window
+    LaunchScope ls(ctx, K_SCHUR);
+    schur_splitk_kernel<<<(unsigned)W, SWARPS * 32, 0, ctx->stream>>>(F, D, H_pp, H_lp, H_ll, b_p, b_l, S, g, eps);
+    return VIML_OK;
+  }
   dim3 grid((unsigned)(ntile * (ntile + 1) / 2), (unsigned)W);
   LaunchScope ls(ctx, K_SCHUR);
   schur_dmma_kernel<<<grid, SWARPS * 32, 0, ctx->stream>>>(F, D, H_pp, H_lp, H_ll, b_p, b_l, S, g, eps, ntile);
