@@ -63,7 +63,7 @@ def load_library():
     lib.viml_linearize_batch.argtypes = [C.c_void_p, C.POINTER(_abi.WindowBatch), C.POINTER(_abi.LinearizeOut), C.c_uint32]
     lib.viml_marginalize_batch.argtypes = [C.c_void_p, C.POINTER(_abi.MargBatch), C.POINTER(_abi.MargOut), C.c_uint32]
     lib.viml_line_associate.argtypes = [C.c_void_p, C.POINTER(_abi.AssocQuery), C.POINTER(_abi.AssocOut), C.c_uint32]
-    lib.viml_assoc_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.viml_assoc_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 4
     lib.viml_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     lib.viml_host_free.argtypes = [C.c_void_p]
     lib.viml_device_alloc.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t]
@@ -237,9 +237,9 @@ class Context:
         return res
 
     def assoc_stats(self):
-        g, s = C.c_int64(), C.c_int64()
-        self._check(self.lib.viml_assoc_stats(self.h, C.byref(g), C.byref(s)))
-        return g.value, s.value
+        v = [C.c_int64() for _ in range(4)]
+        self._check(self.lib.viml_assoc_stats(self.h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)   # gate tests, gated pairs, overlap-scored, distance-scored
 
     def associate_raw(self, q, o, flags):
         self._check(self.lib.viml_line_associate(self.h, C.byref(q), C.byref(o), flags))

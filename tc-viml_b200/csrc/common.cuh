@@ -71,7 +71,7 @@ struct viml_ctx {
   int32_t* d_map_orig = nullptr;    // [n_map]
   double* d_tile_sphere = nullptr;  // [n_tiles][4]
   int64_t n_tiles = 0;
-  unsigned long long* d_assoc_stats = nullptr;  // {gate tests, scored candidates} of the last association call
+  unsigned long long* d_assoc_stats = nullptr;  // {gate tests, gated pairs, overlap-scored, distance-scored} of the last association call
   DeviceArena in_arena, out_arena, scratch, scratch2;
   void* nccl_lib = nullptr;
   // profiling (viml_profile_begin/end): event pairs per kernel id
@@ -175,7 +175,7 @@ struct AssocArgs {  // device pointers only
   int32_t fov_capacity;
   uint32_t* fov_mask;   // always valid
   int64_t words;        // ceil(N/32)
-  unsigned long long* stats;  // {gate tests, scored}
+  unsigned long long* stats;  // {gate tests, gated, overlap-scored, distance-scored}
 };
 // associate_kernels.cu (compiled with -fmad=false)
 int viml_launch_associate(viml_ctx* ctx, const AssocArgs& a);

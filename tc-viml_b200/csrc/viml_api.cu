@@ -505,8 +505,8 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
   const bool dev = (flags & VIML_PTRS_DEVICE) != 0;
   AssocArgs a{};
   a.Pq = Pq, a.L = L, a.N = N, a.map = ctx->d_map, a.words = words;
-  if (!ctx->d_assoc_stats) VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_assoc_stats, 16));
-  VIML_TRY_CUDA(ctx, cudaMemsetAsync(ctx->d_assoc_stats, 0, 16, st));
+  if (!ctx->d_assoc_stats) VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_assoc_stats, 32));
+  VIML_TRY_CUDA(ctx, cudaMemsetAsync(ctx->d_assoc_stats, 0, 32, st));
   a.stats = ctx->d_assoc_stats;
   a.map_sorted = ctx->d_map_sorted, a.map_orig = ctx->d_map_orig, a.tile_sphere = ctx->d_tile_sphere, a.n_tiles = ctx->n_tiles;
   a.fov_capacity = out->fov_index ? out->fov_capacity : 0;
@@ -572,15 +572,18 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
   return VIML_OK;
 }
 
-int viml_assoc_stats(viml_ctx* ctx, int64_t* gate_tests, int64_t* scored) {
+int viml_assoc_stats(viml_ctx* ctx, int64_t* gate_tests, int64_t* gated, int64_t* overlap_scored,
+                     int64_t* distance_scored) {
   if (!ctx) return VIML_ERR_INVALID;
-  unsigned long long h[2] = {0, 0};
+  unsigned long long h[4] = {0, 0, 0, 0};
   if (ctx->d_assoc_stats) {
-    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_assoc_stats, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_assoc_stats, 32, cudaMemcpyDeviceToHost, ctx->stream));
     VIML_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   if (gate_tests) *gate_tests = (int64_t)h[0];
-  if (scored) *scored = (int64_t)h[1];
+  if (gated) *gated = (int64_t)h[1];
+  if (overlap_scored) *overlap_scored = (int64_t)h[2];
+  if (distance_scored) *distance_scored = (int64_t)h[3];
   return VIML_OK;
 }
 
