@@ -322,6 +322,72 @@ def test_association_angle_threshold_variants(pkg, orc):
         check_assoc(got, ref)
 
 
+def test_association_pruning_adversarial(pkg, orc):
+    """The match kernel drops pairs through conservative overlap / distance bounds before the exact arithmetic.
+    Queries built ON the thresholds: sub-segments of the projected map lines whose overlap sits within 1e-9 ... 1e-3
+    of overlap_th on either side, over-long queries (the detected line becomes line2), exactly / nearly vertical and
+    (near) zero-length segments, 3 px parallel offsets, duplicated map lines (distance ties -> list order)."""
+    synth = pkg.synth
+    ext = (300.0, 300.0, 30.0)
+    lines = synth.make_line_map(20000, seed=51, extent=ext)
+    lines = np.concatenate([lines, lines[:800]])                      # exact duplicates: equal distances
+    cull, match, ex, l2d = synth.make_assoc_queries(lines, 16, L=300, n_true=150, seed=52, extent=ext)
+    rng = np.random.Generator(np.random.PCG64(53))
+    for ang, ov in ((0.18, 0.8), (0.1, 0.5), (0.3, 0.0), (0.18, 1.0)):
+        cfg = synth.euroc_config(angle_th=ang, overlap_th=ov)
+        with pkg.Context(cfg) as cx:
+            cx.set_map(lines)
+            base = cx.associate(cull, None, ex, l2d)
+            q = l2d.copy()
+            for p in range(q.shape[0]):
+                segs = base["projected"][p][base["match_index"][p] >= 0]
+                if len(segs) == 0:
+                    continue
+                for i in range(q.shape[1]):
+                    s = segs[i % len(segs)]
+                    S, E = s[:2], s[2:]
+                    d = E - S
+                    Ls = np.hypot(*d)
+                    if not np.isfinite(Ls) or Ls < 1e-6:
+                        continue
+                    u, n = d / Ls, np.array([-d[1], d[0]]) / Ls
+                    eps = (0.0, 1e-9, -1e-9, 1e-6, -1e-6, 1e-4, -1e-4, 1e-3, -1e-3)[rng.integers(9)]
+                    f = min(max(ov + eps, 1e-3), 1.0)
+                    mode = i % 10
+                    if mode == 0:
+                        a, b = S, E
+                    elif mode == 1:                                   # shorter query inside the candidate
+                        a, b = S, S + f * Ls * u
+                    elif mode == 2:                                   # hangs over the end, overlap part = f * L
+                        a = S + (1 - f) * Ls * u
+                        b = a + (f * Ls + 40.0) * u * (0.5 if f * Ls + 40.0 > Ls else 1.0)
+                    elif mode == 3:                                   # longer query: candidate / query = f
+                        ext_ = Ls / f - Ls
+                        a, b = S - 0.3 * ext_ * u, E + 0.7 * ext_ * u
+                    elif mode == 4:                                   # exactly vertical through the midpoint
+                        mid = 0.5 * (S + E)
+                        a, b = mid - [0, 0.4 * Ls], mid + [0, 0.4 * Ls]
+                    elif mode == 5:                                   # nearly vertical
+                        mid = 0.5 * (S + E)
+                        a, b = mid - [5e-5, 0.4 * Ls], mid + [5e-5, 0.4 * Ls]
+                    elif mode == 6:                                   # (near) zero length
+                        mid = 0.5 * (S + E)
+                        a, b = mid, mid + (1e-5 * u if i % 20 == 6 else 0.0)
+                    elif mode == 7:                                   # parallel, 3 px off, same extent
+                        a, b = S + 3 * n, E + 3 * n
+                    elif mode == 8:                                   # reversed direction, float32-rounded
+                        a, b = E.astype(np.float32), S.astype(np.float32)
+                    else:                                             # rotated by about angle_th
+                        c, si = np.cos(ang * (1 + eps)), np.sin(ang * (1 + eps))
+                        r = np.array([c * d[0] - si * d[1], si * d[0] + c * d[1]])
+                        a, b = S, S + r
+                    q[p, i] = [a[0], a[1], b[0], b[1]]
+            got = cx.associate(cull, None, ex, q, want_mask=True)
+        ref = orc.line_associate(cfg, lines, cull, None, ex, q, want_mask=True, nthreads=8)
+        check_assoc(got, ref)
+        assert ov >= 1.0 or (ref["match_index"] >= 0).mean() > 0.3
+
+
 def test_association_sweep_properties_large(pkg, orc, ctx, cfg):
     """cfg-3 geometry at 1/4 of the map and 1/16 of the poses: oracle on a sample of poses + invariants."""
     synth = pkg.synth
