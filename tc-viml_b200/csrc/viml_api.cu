@@ -216,12 +216,16 @@ int viml_set_map(viml_ctx* ctx, const double* lines, int64_t n) {
     v = (v | v << 2) & 0x1249249249249249ull;
     return v;
   };
+  // one scale for the three axes: cubic cells, so a flat map (x, y extent >> z extent) is split in x and y first
+  double span = 0.0;
+  for (int c = 0; c < 3; ++c)
+    if (hi[c] > lo[c]) span = std::max(span, hi[c] - lo[c]);
+  if (!(span > 0.0)) span = 1.0;
   std::vector<uint64_t> key(n);
   for (int64_t j = 0; j < n; ++j) {
     uint64_t k = 0;
     for (int c = 0; c < 3; ++c) {
       const double m = 0.5 * (lines[6 * j + c] + lines[6 * j + 3 + c]);
-      const double span = hi[c] > lo[c] ? hi[c] - lo[c] : 1.0;
       double t = std::isfinite(m) ? (m - lo[c]) / span : 0.0;
       t = std::min(1.0, std::max(0.0, t));
       k |= spread((uint64_t)(t * 2097151.0)) << c;
