@@ -399,10 +399,24 @@ def main():
                       "reference_equivalent": {"tops": ref_equiv_tops, "frac_of_peak": (ref_equiv_tops / fp["dmul_dadd_tops"]) if fp.get("dmul_dadd_tops") else None,
                                                "note": "the reference scores every gated pair (170 ops each); pairs whose distance lower bound cannot beat the current best, or whose overlap already fails, skip the rest here; results identical"},
                       "avg_launch_ms": match_ms, "peak_source": "viml_microbench_fp64 on this device, same run"}
+        # end to end: host buffers (pinned) in and out through the C-ABI call, copies inside the timed region
+        hin = {k: pkg.pinned_like(v) for k, v in (("cull", cull), ("ex", ex), ("l2d", l2d))}
+        res_p = {"match_index": pkg.PinnedArray((Pq, L), np.int32), "err": pkg.PinnedArray((Pq, L, 3), np.float32),
+                 "projected": pkg.PinnedArray((Pq, L, 4), np.float64), "fov_count": pkg.PinnedArray((Pq,), np.int32)}
+        qh, oh = abi.AssocQuery(), abi.AssocOut()
+        qh.n_poses, qh.lines_per_pose = Pq, L
+        qh.cull_poses, qh.match_poses, qh.ex_pose, qh.lines2d, qh.n_lines2d = (abi.ptr(hin["cull"].array), None, abi.ptr(hin["ex"].array),
+                                                                                 abi.ptr(hin["l2d"].array), None)
+        oh.match_index, oh.err, oh.projected, oh.fov_count = (abi.ptr(res_p[k].array) for k in ("match_index", "err", "projected", "fov_count"))
+        oh.fov_index, oh.fov_capacity, oh.fov_mask = None, 0, None
+        ctx.associate_raw(qh, oh, 0)
+        barrier()
         t0 = time.perf_counter()
-        for _ in range(2):
-            res = ctx.associate(cull, None, ex, l2d)
-        e_ms_a = max_over_ranks((time.perf_counter() - t0) * 1e3) / 2
+        for _ in range(a_steps):
+            ctx.associate_raw(qh, oh, 0)
+        e_ms_a = max_over_ranks((time.perf_counter() - t0) * 1e3) / a_steps
+        res = {k: v.array for k, v in res_p.items()}
+        assert np.array_equal(res["match_index"], mi)
         out["assoc"] = {"metric": "line_associations_per_s", "value": n_assoc / (msQ * 1e-3), "unit": "assoc/s",
                         "ms_per_step": msQ, "steps": a_steps,
                         "config": {"workload": f"cfg3: {N} map lines x {Pq} poses/GPU x {L} 2D lines/pose, cull pose == match pose",
@@ -416,7 +430,7 @@ def main():
                         "roofline": match_roof,
                         "kernel_ms_per_step": {k: v[0] / a_steps for k, v in profQ.items()},
                         "e2e": {"value": n_assoc / (e_ms_a * 1e-3), "unit": "assoc/s", "ms_per_step": e_ms_a,
-                                "h2d_bytes_per_step": int(cull.nbytes + ex.nbytes + l2d.nbytes),
+                                "h2d_bytes_per_step": int(cull.nbytes + ex.nbytes + l2d.nbytes + res["projected"].nbytes),  # incl. the caller's projected[] (unmatched entries are preserved)
                                 "d2h_bytes_per_step": int(res["match_index"].nbytes + res["err"].nbytes + res["projected"].nbytes + res["fov_count"].nbytes)}}
         out["gpu_launches_assoc_per_step"] = 6
         if rank == 0 and not args.skip_cpu:
