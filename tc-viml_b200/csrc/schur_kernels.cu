@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(SWARPS * 32) schur_dmma_kernel(int F, int D, c
 // 4 rows are prefetched into registers while the current ones are multiplied.  The 8 partial triangles are summed
 // through shared memory at the end.
 constexpr int kSplitStageLd = 76;
+constexpr int kSplitAcc = 45 * 64 + 72;   // doubles per warp slab: 45 upper-triangle 8x8 sub-tiles + g
 __global__ void __launch_bounds__(SWARPS * 32) schur_splitk_kernel(int F, int D, const double* __restrict__ H_pp,
                                                                    const double* __restrict__ H_lp,
                                                                    const double* __restrict__ H_ll,
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(SWARPS * 32) schur_splitk_kernel(int F, int D,
                                                                    const double* __restrict__ b_l, double* __restrict__ S,
                                                                    double* __restrict__ g, double eps) {
   __shared__ double stage[SWARPS][4 * kSplitStageLd + 8];   // 4 landmark rows (padded stride) + inv[4] + b[4]
-  __shared__ double sAcc[45 * 64 + 72];                      // cross-warp sum of the 45 sub-tiles + g
+  extern __shared__ double sAcc[];                           // [SWARPS][kSplitAcc]: every warp's 45 sub-tiles + g
   const int w = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int kq = lane & 3, mq = lane >> 2;
@@ -188,40 +189,54 @@ __global__ void __launch_bounds__(SWARPS * 32) schur_splitk_kernel(int F, int D,
     }
     __syncwarp();
   }
-  // cross-warp reduction (once per window)
-  for (int e = tid; e < 45 * 64 + 72; e += SWARPS * 32) sAcc[e] = 0.0;
-  __syncthreads();
-  for (int turn = 0; turn < SWARPS; ++turn) {
-    if (warp == turn) {
+  // cross-warp reduction (once per window): every warp parks its partial sums in its own slab (no turn-taking),
+  // the S / g writers add the SWARPS slabs
+  {
+    double* mine = sAcc + warp * kSplitAcc;
 #pragma unroll
-      for (int i = 0; i < 45; ++i) {
-        sAcc[i * 64 + mq * 8 + 2 * kq] += acc[i][0];
-        sAcc[i * 64 + mq * 8 + 2 * kq + 1] += acc[i][1];
-      }
+    for (int i = 0; i < 45; ++i)
+      *reinterpret_cast<double2*>(mine + i * 64 + mq * 8 + 2 * kq) = make_double2(acc[i][0], acc[i][1]);
 #pragma unroll
-      for (int q = 0; q < 3; ++q)
-        if (lane + 32 * q < 72) sAcc[45 * 64 + lane + 32 * q] += gacc[q];
-    }
-    __syncthreads();
+    for (int q = 0; q < 3; ++q)
+      if (lane + 32 * q < 72) mine[45 * 64 + lane + 32 * q] = gacc[q];
   }
+  // H_pp of this window is fetched while the slabs settle (the accumulator registers are free now): the S loop
+  // below then has no global-load latency on its critical path
   const double* __restrict__ Hp = H_pp + (size_t)w * D * D;
   double* __restrict__ So = S + (size_t)w * D * D;
-  for (int e = tid; e < D * D; e += SWARPS * 32) {
+  constexpr int kHp = (72 * 72 + SWARPS * 32 - 1) / (SWARPS * 32);
+  double hp[kHp];
+#pragma unroll
+  for (int i = 0; i < kHp; ++i) {
+    const int e = tid + i * SWARPS * 32;
+    hp[i] = e < D * D ? Hp[e] : 0.0;
+  }
+  __syncthreads();
+  // slabs 1.. are folded into slab 0 in slab order (consecutive threads, consecutive words: conflict-free); the
+  // symmetric read-out below, whose lower-triangle half is strided, then touches one slab instead of SWARPS
+  for (int off = tid; off < kSplitAcc; off += SWARPS * 32) {
+    double v = sAcc[off];
+#pragma unroll
+    for (int k = 1; k < SWARPS; ++k) v += sAcc[k * kSplitAcc + off];
+    sAcc[off] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kHp; ++i) {
+    const int e = tid + i * SWARPS * 32;
+    if (e >= D * D) break;
     const int r = e / D, c = e % D;
     const int rr = r <= c ? r : c, cc = r <= c ? c : r;     // value lives in the upper triangle
     const int tr = rr >> 3, tc = cc >> 3;
     // sub-tile index in the (tr <= tc) enumeration: sum_{k<tr} (9-k) + (tc - tr)
     const int idx = tr * 9 - (tr * (tr - 1)) / 2 + (tc - tr);
-    double v;
-    if (tr == tc) {
-      // a diagonal sub-tile holds the full 8x8 (both triangles were computed)
-      v = sAcc[idx * 64 + (r & 7) * 8 + (c & 7)];
-    } else {
-      v = sAcc[idx * 64 + (rr & 7) * 8 + (cc & 7)];
-    }
-    So[e] = Hp[e] - v;
+    // a diagonal sub-tile holds the full 8x8 (both triangles were computed)
+    const int off = tr == tc ? idx * 64 + (r & 7) * 8 + (c & 7) : idx * 64 + (rr & 7) * 8 + (cc & 7);
+    So[e] = hp[i] - sAcc[off];
   }
-  for (int e = tid; e < D; e += SWARPS * 32) g[(size_t)w * D + e] = b_p[(size_t)w * D + e] - sAcc[45 * 64 + e];
+  for (int e = tid; e < D; e += SWARPS * 32) {
+    g[(size_t)w * D + e] = b_p[(size_t)w * D + e] - sAcc[45 * 64 + e];
+  }
 }
 
 // ---- DMMA peak (for the roofline denominator of this kernel) ----
@@ -246,7 +261,9 @@ int viml_launch_schur(viml_ctx* ctx, int W, int F, int D, const double* H_pp, co
   const int ntile = (D + TS - 1) / TS;
   if (ntile == 1) {   // sliding-window case: split-K kernel, one CTA per window
     LaunchScope ls(ctx, K_SCHUR);
-    schur_splitk_kernel<<<(unsigned)W, SWARPS * 32, 0, ctx->stream>>>(F, D, H_pp, H_lp, H_ll, b_p, b_l, S, g, eps);
+    const int smem = SWARPS * kSplitAcc * (int)sizeof(double);
+    if (cudaFuncSetAttribute(schur_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return VIML_ERR_CUDA;
+    schur_splitk_kernel<<<(unsigned)W, SWARPS * 32, smem, ctx->stream>>>(F, D, H_pp, H_lp, H_ll, b_p, b_l, S, g, eps);
     return VIML_OK;
   }
   dim3 grid((unsigned)(ntile * (ntile + 1) / 2), (unsigned)W);
