@@ -72,6 +72,12 @@ __device__ __forceinline__ void strec(double2* __restrict__ rec, int pos, int k,
   rec[pos * RECW + k] = make_double2(x, y);
 }
 
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
 // reduce-scatter step: N live values -> N/2, lanes with bit w keep the upper half
 template <int N>
 __device__ __forceinline__ void rs_step(double* a, bool up, int w, unsigned mask) {
@@ -346,6 +352,7 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_
       }
       if (lane == 31) S.baseD[P] = (uint16_t)inc;  // lanes >= P contribute 0: inclusive sum at lane 31 is the total
       static_assert(PMAX <= 31, "hi scan uses one warp");
+      static_assert(PMAX + 1 < AT / 32, "P2a: one warp per pose, one for the extrinsic block, at least one helper");
     }
     __syncthreads();
     int posA[2];
@@ -426,134 +433,120 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_
     VIML_TICK(2);
     __syncthreads();
     VIML_TICK(3);
+    // ------------------------------------------------------------------ P2a: pose blocks on the FP64 tensor pipe
+    // Every 6x6 block of H_pp is a sum over factors of X^T Y with X, Y 2x6 Jacobian blocks: two factors make one
+    // K = 4 step of mma.m8n8k4.f64 (C[m][n] += sum_k A[m][k] B[k][n], A[m][k] = X[k][m], B[k][n] = Y[k][n]); lane
+    // (g = lane >> 2, k = lane & 3) holds column g of row k & 1 of factor k >> 1 for both operand layouts, so one
+    // 8-byte shared-memory load per lane is a whole fragment and the same register serves X as A and as B.  Column
+    // 6 of a fragment carries the residual, which makes column 6 of X^T [X | r] the gradient block for free.
+    //   warp p < P : pose p.  lo list (pair-sorted, contiguous): (p,p) += X^T X, (p,ex) += X^T Z, (p,hi) += X^T Y per
+    //                (p,hi) segment; hi list (through hperm): (p,p) += Y^T Y, (p,ex) += Y^T Z; line factors of frame
+    //                p: (p,p) += L^T L.  One warp owns all of pose p's blocks: single writer, no reduction.
+    //   warp P     : (ex,ex) + b_ex over every point factor.
+    //   warps > P  : structural zeros of untouched pair blocks, then straight on to P2b.
     const long long t2a0 = clock64();
-    // ------------------------------------------------------------------ P2a: pose blocks, team per target
-    const int npairs = S.npairs;
-    const int V = 32 + 24 * P + 4 * npairs;
-    for (int vw = warp; vw * 32 < V; vw += AT / 32) {
-      const int v = vw * 32 + lane;
-      int type, t, tgt;
-      if (v < 32) type = 4, t = v, tgt = E;
-      else if (v < 32 + 16 * P) type = 3, t = (v - 32) & 15, tgt = (v - 32) >> 4;
-      else if (v < 32 + 24 * P) type = 2, t = (v - 32 - 16 * P) & 7, tgt = (v - 32 - 16 * P) >> 3;
-      else type = 1, t = (v - 32 - 24 * P) & 3, tgt = (v - 32 - 24 * P) >> 2;
-      const unsigned m4 = __ballot_sync(0xffffffffu, type == 4), m3 = __ballot_sync(0xffffffffu, type == 3);
-      const unsigned m2 = __ballot_sync(0xffffffffu, type == 2), m1 = __ballot_sync(0xffffffffu, type == 1);
-      if (type == 4) {            // (ex,ex) + b_ex over all point factors, 32 lanes
-        double a[28];
-#pragma unroll
-        for (int k = 0; k < 28; ++k) a[k] = 0.0;
-        for (int pos = t; pos < nf; pos += 32) {
-          double2 X[6];
-          load_ex(S.rec, pos, X);
-          acc_sym(a, X, ldrec(S.rec, pos, 15));
-        }
-        rs_step<28>(a, (t & 16) != 0, 16, m4);
-        rs_step<14>(a, (t & 8) != 0, 8, m4);
-        bf_step<7>(a, 4, m4);
-        bf_step<7>(a, 2, m4);
-        bf_step<7>(a, 1, m4);
-        if ((t & 7) == 0) write_sym_slice(a, 14 * ((t >> 4) & 1) + 7 * ((t >> 3) & 1), Hpp, bp, D, E, accum);
-      } else if (type == 3) {     // (p,ex) over factors with lo == p or hi == p, 16 lanes
-        double a[36];
-#pragma unroll
-        for (int k = 0; k < 36; ++k) a[k] = 0.0;
-        const int p = tgt;
-        for (int pos = S.baseA[p * P] + t, end = S.baseA[(p + 1) * P]; pos < end; pos += 16) {
-          double2 X[6], Y[6];
-          load_lo(S.rec, pos, X);
-          load_ex(S.rec, pos, Y);
-          acc_full(a, X, Y);
-        }
-        for (int k = S.baseD[p] + t, end = S.baseD[p + 1]; k < end; k += 16) {
-          const int pos = S.hperm[k];
-          double2 X[6], Y[6];
-          load_hi(S.rec, pos, X);
-          load_ex(S.rec, pos, Y);
-          acc_full(a, X, Y);
-        }
-        rs_step<36>(a, (t & 8) != 0, 8, m3);
-        rs_step<18>(a, (t & 4) != 0, 4, m3);
-        bf_step<9>(a, 2, m3);
-        bf_step<9>(a, 1, m3);
-        if ((t & 3) == 0) {
-          const int e0 = 18 * ((t >> 3) & 1) + 9 * ((t >> 2) & 1);
-#pragma unroll
-          for (int k = 0; k < 9; ++k) {
-            const int e = e0 + k, r = e / 6, c = e % 6;
-            put(&Hpp[(size_t)(6 * p + r) * D + 6 * E + c], a[k], accum);
-            put(&Hpp[(size_t)(6 * E + c) * D + 6 * p + r], a[k], accum);
+    {
+      const int g = lane >> 2, krow = lane & 1, kf = (lane >> 1) & 1;
+      const int c2 = 2 * (lane & 3);                       // accumulator columns c2, c2 + 1 of row g
+      // double offsets inside a record for the fragment kinds (column 7 is always zero)
+      const int offX = (g < 6 ? g : 15) * 2 + krow;                                 // lo block | r
+      const int offZ = (g < 6 ? 9 + g : 15) * 2 + krow;                             // ex block | r
+      const int offY = (g < 3 ? g : (g < 6 ? g + 3 : 15)) * 2 + krow;               // hi block (-lo translation, hi rotation) | r
+      const double sgnY = g < 3 ? -1.0 : 1.0;
+      const bool col_ok = g < 7;
+      const double* __restrict__ recd = reinterpret_cast<const double*>(S.rec);
+      auto store_block = [&](int rb, int cb, double v0, double v1, bool mirror) {
+        if (g < 6 && c2 < 6) {
+          put(&Hpp[(size_t)(6 * rb + g) * D + 6 * cb + c2], v0, accum);
+          put(&Hpp[(size_t)(6 * rb + g) * D + 6 * cb + c2 + 1], v1, accum);
+          if (mirror) {
+            put(&Hpp[(size_t)(6 * cb + c2) * D + 6 * rb + g], v0, accum);
+            put(&Hpp[(size_t)(6 * cb + c2 + 1) * D + 6 * rb + g], v1, accum);
           }
         }
-      } else if (type == 2) {     // (p,p) + b_p over point factors with lo/hi == p and line factors of frame p, 8 lanes
-        double a[28];
-#pragma unroll
-        for (int k = 0; k < 28; ++k) a[k] = 0.0;
-        const int p = tgt;
-        for (int pos = S.baseA[p * P] + t, end = S.baseA[(p + 1) * P]; pos < end; pos += 8) {
-          double2 X[6];
-          load_lo(S.rec, pos, X);
-          acc_sym(a, X, ldrec(S.rec, pos, 15));
+      };
+      // Two K-steps (four factors) per iteration on two accumulator sets: the loads of both steps are issued before
+      // the first mma, and consecutive mma on one block do not wait for each other.
+      if (warp < P) {
+        const int p = warp;
+        double pp0 = 0.0, pp1 = 0.0, pe0 = 0.0, pe1 = 0.0, qq0 = 0.0, qq1 = 0.0, qe0 = 0.0, qe1 = 0.0;
+        for (int hi = p + 1; hi < P; ++hi) {
+          const int key = p * P + hi, n = S.totA[key];
+          if (n == 0) continue;
+          const int b0 = S.baseA[key], end = b0 + n;
+          double ph0 = 0.0, ph1 = 0.0, qh0 = 0.0, qh1 = 0.0;
+          for (int q = b0; q < end; q += 4) {
+            const int posa = q + kf, posb = q + 2 + kf;
+            const bool oka = col_ok && posa < end, okb = col_ok && posb < end;
+            const double* ra = recd + (size_t)posa * (2 * RECW);
+            const double* rb = recd + (size_t)posb * (2 * RECW);
+            const double xa = oka ? ra[offX] : 0.0, za = oka ? ra[offZ] : 0.0, ya = oka ? sgnY * ra[offY] : 0.0;
+            const double xb = okb ? rb[offX] : 0.0, zb = okb ? rb[offZ] : 0.0, yb = okb ? sgnY * rb[offY] : 0.0;
+            dmma(pp0, pp1, xa, xa);
+            dmma(pe0, pe1, xa, za);
+            dmma(ph0, ph1, xa, ya);
+            dmma(qq0, qq1, xb, xb);
+            dmma(qe0, qe1, xb, zb);
+            dmma(qh0, qh1, xb, yb);
+          }
+          store_block(p, hi, ph0 + qh0, ph1 + qh1, true);
         }
-        for (int k = S.baseD[p] + t, end = S.baseD[p + 1]; k < end; k += 8) {
-          const int pos = S.hperm[k];
-          double2 X[6];
-          load_hi(S.rec, pos, X);
-          acc_sym(a, X, ldrec(S.rec, pos, 15));
+        for (int q = S.baseD[p], end = S.baseD[p + 1]; q < end; q += 4) {
+          const bool oka = col_ok && q + kf < end, okb = col_ok && q + 2 + kf < end;
+          const int posa = oka ? S.hperm[q + kf] : 0, posb = okb ? S.hperm[q + 2 + kf] : 0;
+          const double* ra = recd + (size_t)posa * (2 * RECW);
+          const double* rb = recd + (size_t)posb * (2 * RECW);
+          const double ya = oka ? sgnY * ra[offY] : 0.0, za = oka ? ra[offZ] : 0.0;
+          const double yb = okb ? sgnY * rb[offY] : 0.0, zb = okb ? rb[offZ] : 0.0;
+          dmma(pp0, pp1, ya, ya);
+          dmma(pe0, pe1, ya, za);
+          dmma(qq0, qq1, yb, yb);
+          dmma(qe0, qe1, yb, zb);
         }
-        for (int pos = S.baseC[p] + t, end = S.baseC[p + 1]; pos < end; pos += 8) {
-          double2 X[6];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) X[k] = S.u.lrec[pos * LRECW + k];
-          acc_sym(a, X, S.u.lrec[pos * LRECW + 6]);
-        }
-        rs_step<28>(a, (t & 4) != 0, 4, m2);
-        rs_step<14>(a, (t & 2) != 0, 2, m2);
-        bf_step<7>(a, 1, m2);
-        if ((t & 1) == 0) write_sym_slice(a, 14 * ((t >> 2) & 1) + 7 * ((t >> 1) & 1), Hpp, bp, D, p, accum);
-      } else {                    // (lo,hi) pair block, 4 lanes
-        double a[36];
-#pragma unroll
-        for (int k = 0; k < 36; ++k) a[k] = 0.0;
-        const bool live = tgt < npairs;
-        const int key = live ? S.pairs[tgt] : 0;
-        const int lo = key / P, hi = key % P;
-        if (live) {
-          const int b0 = S.baseA[key];
-          for (int pos = b0 + t, end = b0 + S.totA[key]; pos < end; pos += 4) {
-            double2 X[6], Y[6];
-            load_lo(S.rec, pos, X);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              Y[k] = make_double2(-X[k].x, -X[k].y);
-              Y[3 + k] = ldrec(S.rec, pos, 6 + k);
-            }
-            acc_full(a, X, Y);
+        {
+          const double* lrd = reinterpret_cast<const double*>(S.u.lrec);
+          for (int q = S.baseC[p], end = S.baseC[p + 1]; q < end; q += 4) {
+            const bool oka = col_ok && q + kf < end, okb = col_ok && q + 2 + kf < end;
+            const double la = oka ? lrd[(size_t)(q + kf) * (2 * LRECW) + 2 * g + krow] : 0.0;   // columns 0..5 = J, 6 = r
+            const double lb = okb ? lrd[(size_t)(q + 2 + kf) * (2 * LRECW) + 2 * g + krow] : 0.0;
+            dmma(pp0, pp1, la, la);
+            dmma(qq0, qq1, lb, lb);
           }
         }
-        rs_step<36>(a, (t & 2) != 0, 2, m1);
-        rs_step<18>(a, (t & 1) != 0, 1, m1);
-        if (live) {
-          const int e0 = 9 * t;
+        pp0 += qq0, pp1 += qq1, pe0 += qe0, pe1 += qe1;
+        store_block(p, p, pp0, pp1, false);                 // the tile holds both triangles (bitwise symmetric)
+        if (g < 6 && c2 == 6) put(&bp[6 * p + g], pp0, accum);
+        store_block(p, E, pe0, pe1, true);
+      } else if (warp == P) {
+        double e0[4] = {0, 0, 0, 0}, e1[4] = {0, 0, 0, 0};
+        for (int q = 0; q < nf; q += 8) {
+          double z[4];
 #pragma unroll
-          for (int k = 0; k < 9; ++k) {
-            const int e = e0 + k, r = e / 6, c = e % 6;
-            put(&Hpp[(size_t)(6 * lo + r) * D + 6 * hi + c], a[k], accum);
-            put(&Hpp[(size_t)(6 * hi + c) * D + 6 * lo + r], a[k], accum);
+          for (int u = 0; u < 4; ++u) {
+            const int pos = q + 2 * u + kf;
+            z[u] = (col_ok && pos < nf) ? recd[(size_t)pos * (2 * RECW) + offZ] : 0.0;
           }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dmma(e0[u], e1[u], z[u], z[u]);
         }
+        const double ee0 = (e0[0] + e0[1]) + (e0[2] + e0[3]), ee1 = (e1[0] + e1[1]) + (e1[2] + e1[3]);
+        store_block(E, E, ee0, ee1, false);
+        if (g < 6 && c2 == 6) put(&bp[6 * E + g], ee0, accum);
+      } else if (!accum) {
+        // pose-pair blocks that no factor touches are structural zeros
+        const int nh = AT / 32 - (P + 1), h = warp - (P + 1);
+        int e = 0;
+        for (int lo = 0; lo < P; ++lo)
+          for (int hi = lo + 1; hi < P; ++hi)
+            if (S.totA[lo * P + hi] == 0 && (e++ % nh) == h)
+              for (int q = lane; q < 36; q += 32) {
+                const int r = q / 6, c = q % 6;
+                Hpp[(size_t)(6 * lo + r) * D + 6 * hi + c] = 0.0;
+                Hpp[(size_t)(6 * hi + c) * D + 6 * lo + r] = 0.0;
+              }
       }
     }
     if (A.dbg && lane == 0) atomicAdd((unsigned long long*)&A.dbg[gridDim.x * 6 + blockIdx.x * 16 + warp], (unsigned long long)(clock64() - t2a0));
-    // pose-pair blocks that no factor touches are structural zeros (warp per empty pair)
-    for (int lo = 0; lo < P && !accum; ++lo)
-      for (int hi = lo + 1 + warp; hi < P; hi += AT / 32)
-        if (S.totA[lo * P + hi] == 0)
-          for (int q = lane; q < 36; q += 32) {
-            const int r = q / 6, c = q % 6;
-            Hpp[(size_t)(6 * lo + r) * D + 6 * hi + c] = 0.0;
-            Hpp[(size_t)(6 * hi + c) * D + 6 * lo + r] = 0.0;
-          }
     VIML_TICK(4);
     if (part + 1 < nparts) fetch_next(w, slot, part + 1);
     else if (has_next) fetch_next(w + gridDim.x, slot + 1, 0);
