@@ -161,6 +161,201 @@ __device__ __forceinline__ void write_sym_slice(const double* a, int e0, double*
   }
 }
 
+// P0 sorts on a workspace WS (the fused kernel's Smem or the plan kernel's PlanSmem: same member names).  The count
+// tables S.u.cnt must be zero on entry (and a barrier passed); on return every thread holds the record positions of
+// its two point factors (posA) and of its line factor (posC), S.fperm / S.hperm / base* / tot* are filled and a
+// barrier is still needed before they are read.
+template <bool BIGF, bool WITH_RIDX, class WS>
+__device__ __forceinline__ void p0_sort(WS& S, int tid, int P, int F, int nf, int nl, uint32_t idx0, uint32_t idx1, int frame,
+                                        uint32_t (&fidx)[2], int (&posA)[2], int& lframe, int& posC) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const int nkeyA = P * P;
+  int keyA[2], rankA[2], rankB[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int f = tid + r * AT;
+    const bool valid = f < nf;
+    fidx[r] = r == 0 ? idx0 : idx1;
+    const int i = fidx[r] & 0xff, j = (fidx[r] >> 8) & 0xff, l = fidx[r] >> 16;
+    const int lo = min(i, j), hi = max(i, j);
+    keyA[r] = valid ? lo * P + hi : 0xffff;
+    const int keyB = (valid && !BIGF) ? l : 0xffff;
+    if (r * AT < nf) {  // warp-uniform: some lane of this warp may be valid
+      const unsigned ma = __match_any_sync(0xffffffffu, keyA[r]);
+      const unsigned mb = __match_any_sync(0xffffffffu, keyB);
+      const unsigned lt = (1u << lane) - 1u;
+      rankA[r] = __popc(ma & lt);
+      rankB[r] = __popc(mb & lt);
+      const int slab = warp + r * (AT / 32);
+      if (valid && rankA[r] == 0) S.u.cnt.cntA[slab * KA + keyA[r]] = (uint16_t)__popc(ma);
+      if (!BIGF && valid && rankB[r] == 0) S.u.cnt.cntB[slab * FMAX + keyB] = (uint16_t)__popc(mb);
+    }
+  }
+  // line factor t is handled by thread AT-1-t: the second round of point factors uses the LOW threads, so no
+  // thread gets two point factors and a line factor on its critical path
+  const int lt_ = AT - 1 - tid;
+  int rankC = 0;
+  lframe = 0;
+  if (warp >= AT / 32 - LSLABS) {  // line factors by frame (whole warps take part in match_any)
+    const bool valid = lt_ < nl;
+    lframe = valid ? frame : 0xffff;
+    const unsigned mc = __match_any_sync(0xffffffffu, lframe);
+    rankC = __popc(mc & ((1u << lane) - 1u));
+    if (valid && rankC == 0) S.u.cnt.cntC[(AT / 32 - 1 - warp) * PMAX + lframe] = (uint16_t)__popc(mc);
+  }
+  __syncthreads();
+  // exclusive prefix over slabs for every key (thread per key); loads are issued together, the running sum
+  // stays in registers (the serial load->store chain of a rolled loop cost ~1 K cycles per window)
+  const int Fs = BIGF ? 0 : F;  // feature keys handled in shared memory
+  for (int e = tid; e < nkeyA + Fs + P; e += AT) {
+    uint16_t* col;
+    int stride, ns;
+    uint16_t* tot;
+    if (e < nkeyA) col = S.u.cnt.cntA + e, stride = KA, ns = SLABS, tot = S.totA + e;
+    else if (e < nkeyA + Fs) col = S.u.cnt.cntB + (e - nkeyA), stride = FMAX, ns = SLABS, tot = S.totB + (e - nkeyA);
+    else col = S.u.cnt.cntC + (e - nkeyA - Fs), stride = PMAX, ns = LSLABS, tot = S.totC + (e - nkeyA - Fs);
+    int c[SLABS];
+#pragma unroll
+    for (int q = 0; q < SLABS; ++q) c[q] = q < ns ? col[q * stride] : 0;
+    int run = 0;
+#pragma unroll
+    for (int q = 0; q < SLABS; ++q) {
+      if (q < ns) col[q * stride] = (uint16_t)run;
+      run += c[q];
+    }
+    *tot = (uint16_t)run;
+  }
+  __syncthreads();
+  // exclusive scans over keys: warp 0 -> baseA (+ non-empty pair list), warp 1 -> baseB, warp 2 -> baseC
+  if (warp < 3) {
+    const uint16_t* tot = warp == 0 ? S.totA : (warp == 1 ? S.totB : S.totC);
+    uint16_t* base = warp == 0 ? S.baseA : (warp == 1 ? S.baseB : S.baseC);
+    const int n = warp == 0 ? nkeyA : (warp == 1 ? Fs : P);
+    int carry = 0, npairs = 0;
+    for (int b0 = 0; b0 < n; b0 += 32) {
+      const int k = b0 + lane;
+      const int v = k < n ? tot[k] : 0;
+      int inc = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (k < n) base[k] = (uint16_t)(carry + inc - v);
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+      if (warp == 0) {
+        const unsigned nz = __ballot_sync(0xffffffffu, v > 0);
+        if (v > 0) S.pairs[npairs + __popc(nz & ((1u << lane) - 1u))] = (uint16_t)k;
+        npairs += __popc(nz);
+      }
+    }
+    if (lane == 0) {
+      base[n] = (uint16_t)carry;
+      if (warp == 0) S.npairs = npairs;
+    }
+  } else if (warp == 3) {
+    // records ordered by (hi, lo) WITHOUT another sort: inside one (lo,hi) group the pair-sorted positions are
+    // already contiguous, so  posD = baseD[hi] + sum_{lo' < lo} tot(lo',hi) + (posA - baseA[lo,hi]).
+    // lane = hi: column sums of totA, exclusive scan over hi, then the per-(lo,hi) offsets.
+    const int hi = lane;
+    int col = 0;
+    if (hi < P)
+      for (int lo = 0; lo < hi; ++lo) col += S.totA[lo * P + hi];
+    int inc = col;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (hi < P) {
+      int run = inc - col;
+      S.baseD[hi] = (uint16_t)run;
+      for (int lo = 0; lo < hi; ++lo) {
+        S.offD[lo * P + hi] = (uint16_t)run;
+        run += S.totA[lo * P + hi];
+      }
+    }
+    if (lane == 31) S.baseD[P] = (uint16_t)inc;  // lanes >= P contribute 0: inclusive sum at lane 31 is the total
+    static_assert(PMAX <= 31, "hi scan uses one warp");
+    static_assert(PMAX + 1 < AT / 32, "P2a: one warp per pose, one for the extrinsic block, at least one helper");
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int f = tid + r * AT;
+    posA[r] = 0;
+    if (f < nf) {
+      const int slab = warp + r * (AT / 32);
+      const int l = fidx[r] >> 16;
+      posA[r] = S.baseA[keyA[r]] + S.u.cnt.cntA[slab * KA + keyA[r]] + rankA[r];
+      if (WITH_RIDX) S.ridx[posA[r]] = fidx[r];
+      if (!BIGF) S.fperm[S.baseB[l] + S.u.cnt.cntB[slab * FMAX + l] + rankB[r]] = (uint16_t)posA[r];
+      S.hperm[S.offD[keyA[r]] + posA[r] - S.baseA[keyA[r]]] = (uint16_t)posA[r];
+    }
+  }
+  posC = 0;
+  if (lt_ < nl) posC = S.baseC[lframe] + S.u.cnt.cntC[(AT / 32 - 1 - warp) * PMAX + lframe] + rankC;
+}
+
+// Layout of one window's sort plan in HBM (uint16 units), written by plan_kernel for single-part windows.
+constexpr int kPlanPosA = 0, kPlanFperm = NF, kPlanHperm = 2 * NF, kPlanPosC = 3 * NF, kPlanTab = 3 * NF + NL;
+constexpr int kPlanTabN = (KA + 1) + KA + (FMAX + 1) + (PMAX + 1) + (PMAX + 1);   // baseA, totA, baseB, baseC, baseD
+constexpr int kPlanStride = (kPlanTab + kPlanTabN + 7) / 8 * 8;
+
+struct PlanSmem {
+  struct {
+    struct {
+      uint16_t cntA[SLABS * KA];
+      uint16_t cntB[SLABS * FMAX];
+      uint16_t cntC[LSLABS * PMAX];
+    } cnt;
+  } u;
+  uint16_t fperm[NF], hperm[NF];
+  uint16_t baseA[KA + 1], totA[KA], baseB[FMAX + 1], totB[FMAX], baseC[PMAX + 1], totC[PMAX], baseD[PMAX + 1], offD[KA], pairs[KA];
+  uint32_t ridx[1];
+  int npairs;
+};
+
+// table entry e of the plan <-> the workspace arrays
+template <class WS>
+__device__ __forceinline__ uint16_t* plan_tab(WS& S, int e) {
+  if (e < KA + 1) return S.baseA + e;
+  e -= KA + 1;
+  if (e < KA) return S.totA + e;
+  e -= KA;
+  if (e < FMAX + 1) return S.baseB + e;
+  e -= FMAX + 1;
+  if (e < PMAX + 1) return S.baseC + e;
+  e -= PMAX + 1;
+  return S.baseD + e;
+}
+
+// The sorts of a window depend on its factor indices only, and inside the persistent fused kernel (one CTA per SM)
+// their ~10 barriers are pure latency.  This kernel runs them ahead for every single-part window with several CTAs
+// per SM; the fused kernel then just copies ~5.5 KB of positions and tables.
+__global__ void __launch_bounds__(AT, 4) plan_kernel(LinearizeArgs A, uint16_t* __restrict__ plan) {
+  __shared__ PlanSmem S;
+  const int tid = threadIdx.x, w = blockIdx.x;
+  const int a0 = A.pf_window_offset[w], nf = A.pf_window_offset[w + 1] - a0;
+  const int b0 = A.NL > 0 ? A.lf_window_offset[w] : 0, nl = A.NL > 0 ? A.lf_window_offset[w + 1] - b0 : 0;
+  if (nf > NF || nl > NL) return;   // multi-part window: sorted part by part inside the fused kernel
+  uint32_t* z = reinterpret_cast<uint32_t*>(&S.u.cnt);
+  for (int e = tid; e < (int)(sizeof(S.u.cnt) / 4); e += AT) z[e] = 0u;
+  const uint32_t idx0 = tid < nf ? A.pf_idx[a0 + tid] : 0u, idx1 = tid + AT < nf ? A.pf_idx[a0 + tid + AT] : 0u;
+  const int frame = AT - 1 - tid < nl ? A.lf_frame[b0 + AT - 1 - tid] : 0xffff;
+  __syncthreads();
+  uint32_t fidx[2];
+  int posA[2], lframe, posC;
+  p0_sort<false, false>(S, tid, A.P, A.F, nf, nl, idx0, idx1, frame, fidx, posA, lframe, posC);
+  __syncthreads();
+  uint16_t* __restrict__ out = plan + (size_t)w * kPlanStride;
+  if (tid < nf) out[kPlanPosA + tid] = (uint16_t)posA[0];
+  if (tid + AT < nf) out[kPlanPosA + tid + AT] = (uint16_t)posA[1];
+  if (AT - 1 - tid < nl) out[kPlanPosC + AT - 1 - tid] = (uint16_t)posC;
+  for (int e = tid; e < nf; e += AT) out[kPlanFperm + e] = S.fperm[e], out[kPlanHperm + e] = S.hperm[e];
+  for (int e = tid; e < kPlanTabN; e += AT) out[kPlanTab + e] = *plan_tab(S, e);
+}
+
 // BIGF: more features per window than the shared-memory feature tables hold (F > FMAX, e.g. the 2000-landmark
 // marginalisation stress): the per-feature sort and P2b are skipped; every factor adds its landmark terms with
 // RED.ADD.F64 onto rows the launcher zero-filled (their summation order is then not reproducible bit for bit).
@@ -170,7 +365,6 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = A.P, F = A.F, D = A.D, E = A.P;
-  const int nkeyA = P * P;
   const int cstride = P * kPoseCache + kExCache;
 
   // stage this CTA's CSR offsets once so that per-window address generation never waits on HBM
@@ -194,6 +388,10 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_
   auto seg = [&](int sl, int part, int& q0, int& qn, int& m0, int& mn) {
     const int a0 = S.woff[4 * sl], an = S.woff[4 * sl + 1] - a0, b0 = S.woff[4 * sl + 2], bn = S.woff[4 * sl + 3] - b0;
     const int np = max(1, max((an + NF - 1) / NF, (bn + NL - 1) / NL));
+    if (np == 1) {   // the common case: no 64-bit divisions on the per-window path
+      q0 = a0, qn = an, m0 = b0, mn = bn;
+      return 1;
+    }
     q0 = a0 + (int)((int64_t)an * part / np), qn = a0 + (int)((int64_t)an * (part + 1) / np) - q0;
     m0 = b0 + (int)((int64_t)bn * part / np), mn = b0 + (int)((int64_t)bn * (part + 1) / np) - m0;
     return np;
@@ -221,6 +419,7 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_
       const int q0 = S.woff[4 * slot + 4], q1 = S.woff[4 * slot + 5], m0 = S.woff[4 * slot + 6], m1 = S.woff[4 * slot + 7];
       prefetch_l2(A.pf_obs + (size_t)q0 * 4, (size_t)(q1 - q0) * 32, tid, AT);
       prefetch_l2(A.inv_depth + (size_t)wn * F, (size_t)F * 8, tid, AT);
+      if (A.plan) prefetch_l2(A.plan + (size_t)wn * kPlanStride, (size_t)kPlanStride * 2, tid, AT);
       if (A.pf_pts_i_z) prefetch_l2(A.pf_pts_i_z + q0, (size_t)(q1 - q0) * 8, tid, AT);
       if (A.NL > 0)
         for (int c = 0; c < 9; ++c) prefetch_l2(A.lf_geom + (size_t)c * A.NL_stride + m0, (size_t)(m1 - m0) * 8, tid, AT);
@@ -235,143 +434,42 @@ __global__ void __launch_bounds__(AT, 1) assemble_kernel(LinearizeArgs A, int w_
     for (int part = 0; part < nparts; ++part) {
     seg(slot, part, p0, nf, l0, nl);
     const bool accum = part > 0;  // later parts add onto what part 0 wrote
-    // ------------------------------------------------------------------ P0: cache + sorts
+    // ------------------------------------------------------------------ P0: cache + sorts (or the precomputed plan)
+    const bool planned = !BIGF && A.plan != nullptr && nparts == 1;
     {
       if (tid < cstride) S.cache[tid] = nx_c0;
       if (tid + AT < cstride) S.cache[tid + AT] = nx_c1;
       if (tid + 2 * AT < cstride) S.cache[tid + 2 * AT] = nx_c2;
-      uint32_t* z = reinterpret_cast<uint32_t*>(&S.u.cnt);
-      for (int e = tid; e < (int)(sizeof(S.u.cnt) / 4); e += AT) z[e] = 0u;
       if (tid == 0) S.next_feature = 0;
     }
-    __syncthreads();
     uint32_t fidx[2];
-    int keyA[2], rankA[2], rankB[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int f = tid + r * AT;
-      const bool valid = f < nf;
-      fidx[r] = r == 0 ? nx_idx0 : nx_idx1;
-      const int i = fidx[r] & 0xff, j = (fidx[r] >> 8) & 0xff, l = fidx[r] >> 16;
-      const int lo = min(i, j), hi = max(i, j);
-      keyA[r] = valid ? lo * P + hi : 0xffff;
-      const int keyB = (valid && !BIGF) ? l : 0xffff;
-      if (r * AT < nf) {  // warp-uniform: some lane of this warp may be valid
-        const unsigned ma = __match_any_sync(0xffffffffu, keyA[r]);
-        const unsigned mb = __match_any_sync(0xffffffffu, keyB);
-        const unsigned lt = (1u << lane) - 1u;
-        rankA[r] = __popc(ma & lt);
-        rankB[r] = __popc(mb & lt);
-        const int slab = warp + r * (AT / 32);
-        if (valid && rankA[r] == 0) S.u.cnt.cntA[slab * KA + keyA[r]] = (uint16_t)__popc(ma);
-        if (!BIGF && valid && rankB[r] == 0) S.u.cnt.cntB[slab * FMAX + keyB] = (uint16_t)__popc(mb);
-      }
-    }
-    // line factor t is handled by thread AT-1-t: the second round of point factors uses the LOW threads, so no
-    // thread gets two point factors and a line factor on its critical path
-    const int lt_ = AT - 1 - tid;
-    int lframe = 0, rankC = 0;
-    if (warp >= AT / 32 - LSLABS) {  // line factors by frame (whole warps take part in match_any)
-      const bool valid = lt_ < nl;
-      lframe = valid ? nx_frame : 0xffff;
-      const unsigned mc = __match_any_sync(0xffffffffu, lframe);
-      rankC = __popc(mc & ((1u << lane) - 1u));
-      if (valid && rankC == 0) S.u.cnt.cntC[(AT / 32 - 1 - warp) * PMAX + lframe] = (uint16_t)__popc(mc);
-    }
-    __syncthreads();
-    // exclusive prefix over slabs for every key (thread per key); loads are issued together, the running sum
-    // stays in registers (the serial load->store chain of a rolled loop cost ~1 K cycles per window)
-    const int Fs = BIGF ? 0 : F;  // feature keys handled in shared memory
-    for (int e = tid; e < nkeyA + Fs + P; e += AT) {
-      uint16_t* col;
-      int stride, ns;
-      uint16_t* tot;
-      if (e < nkeyA) col = S.u.cnt.cntA + e, stride = KA, ns = SLABS, tot = S.totA + e;
-      else if (e < nkeyA + Fs) col = S.u.cnt.cntB + (e - nkeyA), stride = FMAX, ns = SLABS, tot = S.totB + (e - nkeyA);
-      else col = S.u.cnt.cntC + (e - nkeyA - Fs), stride = PMAX, ns = LSLABS, tot = S.totC + (e - nkeyA - Fs);
-      int c[SLABS];
-#pragma unroll
-      for (int q = 0; q < SLABS; ++q) c[q] = q < ns ? col[q * stride] : 0;
-      int run = 0;
-#pragma unroll
-      for (int q = 0; q < SLABS; ++q) {
-        if (q < ns) col[q * stride] = (uint16_t)run;
-        run += c[q];
-      }
-      *tot = (uint16_t)run;
-    }
-    __syncthreads();
-    // exclusive scans over keys: warp 0 -> baseA (+ non-empty pair list), warp 1 -> baseB, warp 2 -> baseC
-    if (warp < 3) {
-      const uint16_t* tot = warp == 0 ? S.totA : (warp == 1 ? S.totB : S.totC);
-      uint16_t* base = warp == 0 ? S.baseA : (warp == 1 ? S.baseB : S.baseC);
-      const int n = warp == 0 ? nkeyA : (warp == 1 ? Fs : P);
-      int carry = 0, npairs = 0;
-      for (int b0 = 0; b0 < n; b0 += 32) {
-        const int k = b0 + lane;
-        const int v = k < n ? tot[k] : 0;
-        int inc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, inc, d);
-          if (lane >= d) inc += t;
-        }
-        if (k < n) base[k] = (uint16_t)(carry + inc - v);
-        carry += __shfl_sync(0xffffffffu, inc, 31);
-        if (warp == 0) {
-          const unsigned nz = __ballot_sync(0xffffffffu, v > 0);
-          if (v > 0) S.pairs[npairs + __popc(nz & ((1u << lane) - 1u))] = (uint16_t)k;
-          npairs += __popc(nz);
-        }
-      }
-      if (lane == 0) {
-        base[n] = (uint16_t)carry;
-        if (warp == 0) S.npairs = npairs;
-      }
-    } else if (warp == 3) {
-      // records ordered by (hi, lo) WITHOUT another sort: inside one (lo,hi) group the pair-sorted positions are
-      // already contiguous, so  posD = baseD[hi] + sum_{lo' < lo} tot(lo',hi) + (posA - baseA[lo,hi]).
-      // lane = hi: column sums of totA, exclusive scan over hi, then the per-(lo,hi) offsets.
-      const int hi = lane;
-      int col = 0;
-      if (hi < P)
-        for (int lo = 0; lo < hi; ++lo) col += S.totA[lo * P + hi];
-      int inc = col;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-      }
-      if (hi < P) {
-        int run = inc - col;
-        S.baseD[hi] = (uint16_t)run;
-        for (int lo = 0; lo < hi; ++lo) {
-          S.offD[lo * P + hi] = (uint16_t)run;
-          run += S.totA[lo * P + hi];
-        }
-      }
-      if (lane == 31) S.baseD[P] = (uint16_t)inc;  // lanes >= P contribute 0: inclusive sum at lane 31 is the total
-      static_assert(PMAX <= 31, "hi scan uses one warp");
-      static_assert(PMAX + 1 < AT / 32, "P2a: one warp per pose, one for the extrinsic block, at least one helper");
-    }
-    __syncthreads();
-    int posA[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int f = tid + r * AT;
-      posA[r] = 0;
-      if (f < nf) {
-        const int slab = warp + r * (AT / 32);
-        const int l = fidx[r] >> 16;
-        posA[r] = S.baseA[keyA[r]] + S.u.cnt.cntA[slab * KA + keyA[r]] + rankA[r];
-        S.ridx[posA[r]] = fidx[r];
-        if (!BIGF) S.fperm[S.baseB[l] + S.u.cnt.cntB[slab * FMAX + l] + rankB[r]] = (uint16_t)posA[r];
-        S.hperm[S.offD[keyA[r]] + posA[r] - S.baseA[keyA[r]]] = (uint16_t)posA[r];
-      }
+    int posA[2], lframe, posC;
+    const int lt_ = AT - 1 - tid;   // line factor t is handled by thread AT-1-t
+    if (planned) {
+      const uint16_t* __restrict__ pl = A.plan + (size_t)w * kPlanStride;
+      fidx[0] = nx_idx0, fidx[1] = nx_idx1;
+      lframe = lt_ < nl ? nx_frame : 0xffff;
+      // all loads first (one L2 round trip; the row was prefetched into L2 during the previous window)
+      static_assert(NF / 2 <= AT && kPlanTabN <= AT, "plan copy: one element per thread");
+      const uint32_t* __restrict__ fp = reinterpret_cast<const uint32_t*>(pl + kPlanFperm);
+      const uint32_t* __restrict__ hp = reinterpret_cast<const uint32_t*>(pl + kPlanHperm);
+      const int pa0 = tid < nf ? pl[kPlanPosA + tid] : 0, pa1 = tid + AT < nf ? pl[kPlanPosA + tid + AT] : 0;
+      const int pc = lt_ < nl ? pl[kPlanPosC + lt_] : 0;
+      const bool cp = tid < (nf + 1) / 2;
+      const uint32_t wf = cp ? fp[tid] : 0u, wh = cp ? hp[tid] : 0u;
+      const uint16_t tb = tid < kPlanTabN ? pl[kPlanTab + tid] : (uint16_t)0;
+      posA[0] = pa0, posA[1] = pa1, posC = pc;
+      if (cp) reinterpret_cast<uint32_t*>(S.fperm)[tid] = wf, reinterpret_cast<uint32_t*>(S.hperm)[tid] = wh;
+      if (tid < kPlanTabN) *plan_tab(S, tid) = tb;
+      if (tid < nf) S.ridx[pa0] = fidx[0];
+      if (tid + AT < nf) S.ridx[pa1] = fidx[1];
+    } else {
+      uint32_t* z = reinterpret_cast<uint32_t*>(&S.u.cnt);
+      for (int e = tid; e < (int)(sizeof(S.u.cnt) / 4); e += AT) z[e] = 0u;
+      __syncthreads();
+      p0_sort<BIGF, true>(S, tid, P, F, nf, nl, nx_idx0, nx_idx1, nx_frame, fidx, posA, lframe, posC);
     }
     VIML_TICK(0);
-    int posC = 0;
-    if (lt_ < nl) posC = S.baseC[lframe] + S.u.cnt.cntC[(AT / 32 - 1 - warp) * PMAX + lframe] + rankC;
     __syncthreads();  // count tables are dead from here on (lrec aliases them)
     VIML_TICK(1);
     // ------------------------------------------------------------------ P1: evaluate, write records

@@ -72,7 +72,7 @@ struct viml_ctx {
   double* d_tile_sphere = nullptr;  // [n_tiles][4]
   int64_t n_tiles = 0;
   unsigned long long* d_assoc_stats = nullptr;  // {gate tests, gated pairs, overlap-scored, distance-scored} of the last association call
-  DeviceArena in_arena, out_arena, scratch, scratch2;
+  DeviceArena in_arena, out_arena, scratch, scratch2, scratch3;
   void* nccl_lib = nullptr;
   // profiling (viml_profile_begin/end): event pairs per kernel id
   bool brute_cull = false;     // VIML_BRUTE_CULL=1: the literal all-pairs FoV sweep (roofline accounting, cross-check)
@@ -83,7 +83,7 @@ struct viml_ctx {
 
 enum KernelId {
   K_PREP = 0, K_POINTS, K_LINES, K_ASSEMBLE, K_SCHUR, K_CAMPOSE, K_CULL, K_SCAN, K_FILL, K_PROJECT, K_MATCH,
-  K_MARG, K_MICRO, K_COUNT
+  K_MARG, K_MICRO, K_PLAN, K_COUNT
 };
 static_assert(K_COUNT <= VIML_NUM_KERNELS, "raise VIML_NUM_KERNELS");
 
@@ -137,6 +137,7 @@ struct LinearizeArgs {  // device pointers only
   const int32_t* lf_frame;
   const double* lf_geom;
   double* cache;  // [W][P*kPoseCache + kExCache]
+  uint16_t* plan;  // fused kernel: per-window sort plan written by plan_kernel (launcher scratch), or nullptr
   viml_linearize_out out;
   double sqrt_info, cauchy_a, inv_cauchy_a2, fx, fy, cx, cy;
   uint32_t flags;

@@ -464,6 +464,13 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
     }
     const int grid = a.W < ctx->sm_count ? a.W : ctx->sm_count;   // persistent: one CTA per SM
     LinearizeArgs a2 = a;
+    a2.plan = nullptr;
+    if (!bigf && !getenv("VIML_NO_PLAN")) {   // sorts of all single-part windows ahead of the fused kernel
+      VIML_TRY_CUDA(ctx, ctx->scratch3.reserve(DeviceArena::padded((size_t)a.W * fused::kPlanStride * sizeof(uint16_t))));
+      a2.plan = ctx->scratch3.take<uint16_t>((size_t)a.W * fused::kPlanStride);
+      LaunchScope ls(ctx, K_PLAN);
+      fused::plan_kernel<<<a.W, fused::AT, 0, st>>>(a2, a2.plan);
+    }
     long long* dbg = nullptr;
     if (getenv("VIML_PHASE_TIMERS")) {
       cudaMalloc((void**)&dbg, sizeof(long long) * 22 * grid);

@@ -93,6 +93,7 @@ void viml_destroy(viml_ctx* ctx) {
   ctx->out_arena.release();
   ctx->scratch.release();
   ctx->scratch2.release();
+  ctx->scratch3.release();
   if (ctx->d_map) cudaFree(ctx->d_map);
   if (ctx->d_map_sorted) cudaFree(ctx->d_map_sorted);
   if (ctx->d_map_orig) cudaFree(ctx->d_map_orig);
@@ -178,7 +179,7 @@ const char* viml_kernel_name(int id) {
   static const char* names[VIML_NUM_KERNELS] = {"prep_windows", "linearize_points", "linearize_lines", "assemble_hb",
                                                 "schur_landmarks", "assoc_cam_pose", "assoc_cull", "assoc_scan",
                                                 "assoc_fill_list", "assoc_project", "assoc_match", "marginalize_dense",
-                                                "microbench", "", "", ""};
+                                                "microbench", "plan_windows", "", ""};
   return (id >= 0 && id < VIML_NUM_KERNELS) ? names[id] : "";
 }
 
