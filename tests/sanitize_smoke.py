@@ -23,5 +23,7 @@ with pkg.Context(cfg) as ctx:
     lines = synth.make_line_map(3000, seed=5, extent=(120.0, 120.0, 30.0))
     cull, match, ex, l2d = synth.make_assoc_queries(lines, 3, L=20, n_true=8, seed=6, extent=(120.0, 120.0, 30.0))
     ctx.set_map(lines)
-    ctx.associate(cull, match, ex, l2d, fov_capacity=256, want_mask=True)
+    ctx.associate(cull, match, ex, l2d, fov_capacity=256, want_mask=True)                # few poses: 64-thread match CTAs
+    cull, match, ex, l2d = synth.make_assoc_queries(lines, 130, L=40, n_true=16, seed=7, extent=(120.0, 120.0, 30.0))
+    ctx.associate(cull, None, ex, l2d)                                                   # >= 128 poses: 320-thread match CTAs
 print("sanitize_smoke: done")
