@@ -407,3 +407,43 @@ def test_association_sweep_properties_large(pkg, orc, ctx, cfg):
     ref = orc.line_associate(cfg, lines, cull[sel], None, ex[sel], l2d[sel], fov_capacity=4096, want_mask=True, nthreads=8)
     sub = {k: v[sel] for k, v in got.items()}
     check_assoc(sub, ref)
+
+
+def test_allreduce_hb_two_gpus(pkg, cfg):
+    """viml_allreduce_hb (the C++ hosts' all-reduce of partial [S | g]) with raw ncclComm_t handles: one
+    process, two contexts on two devices, one thread per device.  Skipped on a single-GPU box."""
+    import ctypes
+    import threading
+    import torch   # loads the bundled libnccl into the process, which is what the library dlopens
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    nccl = ctypes.CDLL("libnccl.so.2")
+    comms = (ctypes.c_void_p * 2)()
+    devs = (ctypes.c_int * 2)(0, 1)
+    assert nccl.ncclCommInitAll(comms, 2, devs) == 0
+    n = 72 * 72 + 72
+    parts = [np.arange(n, dtype=np.float64) * (k + 1) + 0.25 * k for k in range(2)]
+    ctxs = [pkg.Context(cfg, device=k) for k in range(2)]
+    bufs = [c.to_device(p) for c, p in zip(ctxs, parts)]
+    for c in ctxs:
+        c.sync()
+    rcs = [None, None]
+
+    def run(k):
+        rcs[k] = ctxs[k].lib.viml_allreduce_hb(ctxs[k].h, comms[k], bufs[k], n)
+        ctxs[k].sync()
+
+    th = [threading.Thread(target=run, args=(k,)) for k in range(2)]
+    [t.start() for t in th]
+    [t.join(timeout=60) for t in th]
+    assert rcs == [0, 0]
+    for k in range(2):
+        got = np.empty(n)
+        ctxs[k].d2h(got, bufs[k])
+        ctxs[k].sync()
+        assert np.array_equal(got, parts[0] + parts[1])
+        ctxs[k].device_free(bufs[k])
+    for k in range(2):
+        nccl.ncclCommDestroy(ctypes.c_void_p(comms[k]))
+    for c in ctxs:
+        c.close() if hasattr(c, "close") else None
