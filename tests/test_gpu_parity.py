@@ -95,6 +95,33 @@ def test_batch_shapes_and_edges(pkg, orc, ctx, cfg):
         check_linearize(pkg, orc, c2, cfg2, synth.make_windows(4, seed=108), allf)
 
 
+def test_fused_path_extremes(pkg, orc, ctx, cfg):
+    """Limits of the fused kernel's static layout (12 poses = 12 pose warps, 160 features), degenerate pair structures
+    and empty factor classes, with and without the per-factor outputs (both template instantiations)."""
+    abi, synth = pkg._abi, pkg.synth
+    hb = abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
+    allf = hb | abi.OUT_RESIDUAL_JACOBIAN
+    for flags in (hb, allf):
+        check_linearize(pkg, orc, ctx, cfg, synth.make_windows(6, seed=121, P=12, F=160, lines_per_frame=12), flags)
+        check_linearize(pkg, orc, ctx, cfg, synth.make_windows(5, seed=122, P=2, F=9, lines_per_frame=1, start_max=0), flags)
+        check_linearize(pkg, orc, ctx, cfg, synth.make_windows(4, seed=123, P=3, F=150, lines_per_frame=0, start_max=0), flags)
+    # only line factors: every pose-pair block, every landmark row is a structural zero
+    b = synth.make_windows(4, seed=124)
+    only_lines = abi.Batch(b.poses, b.ex_pose, b.inv_depth, np.zeros(5, dtype=np.int32), b.pf_idx[:0], b.pf_obs[:0],
+                           b.lf_window_offset, b.lf_frame, b.lf_geom)
+    got, _ = check_linearize(pkg, orc, ctx, cfg, only_lines, abi.OUT_HB | abi.LOSS_CAUCHY)
+    assert np.all(got["H_lp"] == 0.0) and np.all(got["H_ll"] == 0.0)
+    # one pose pair carries every factor (all features start in frame 0 and are seen once more, in frame 1)
+    b = synth.make_windows(3, seed=125, P=11, F=150, all_start_zero=True, max_len=2)
+    check_linearize(pkg, orc, ctx, cfg, b, hb)
+    # bit-reproducible: same inputs, same bits (single writer per entry, fixed summation order)
+    b = synth.make_windows(16, seed=126)
+    a1 = ctx.linearize(b, hb)
+    a2 = ctx.linearize(b, hb)
+    for k in a1:
+        assert np.array_equal(a1[k], a2[k]), k
+
+
 def test_marginalisation_stress_shape(pkg, orc, ctx, cfg):
     """cfg-4 shape at a size the dense oracle finishes in seconds: all landmarks start in frame 0."""
     abi = pkg._abi
