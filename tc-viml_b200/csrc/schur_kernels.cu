@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(SWARPS * 32) schur_dmma_kernel(int F, int D, c
 // through shared memory at the end.
 constexpr int kSplitStageLd = 76;
 constexpr int kSplitAcc = 45 * 64 + 72;   // doubles per warp slab: 45 upper-triangle 8x8 sub-tiles + g
-__global__ void __launch_bounds__(SWARPS * 32) schur_splitk_kernel(int F, int D, const double* __restrict__ H_pp,
+__global__ void __launch_bounds__(SWARPS * 32) schur_splitk_kernel(int W, int F, int D, const double* __restrict__ H_pp,
                                                                    const double* __restrict__ H_lp,
                                                                    const double* __restrict__ H_ll,
                                                                    const double* __restrict__ b_p,
@@ -128,20 +128,20 @@ __global__ void __launch_bounds__(SWARPS * 32) schur_splitk_kernel(int F, int D,
                                                                    double* __restrict__ g, double eps) {
   __shared__ double stage[SWARPS][4 * kSplitStageLd + 8];   // 4 landmark rows (padded stride) + inv[4] + b[4]
   extern __shared__ double sAcc[];                           // [SWARPS][kSplitAcc]: every warp's 45 sub-tiles + g
-  const int w = blockIdx.x;
+  // persistent: one CTA per SM walks the windows; the first landmark rows of the NEXT window are fetched before the
+  // epilogue of the current one, so neither the CTA launch nor the first HBM round trip is exposed per window
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int kq = lane & 3, mq = lane >> 2;
-  const double* __restrict__ Hl = H_lp + (size_t)w * F * D;
-  const double* __restrict__ Ll = H_ll + (size_t)w * F;
-  const double* __restrict__ Bl = b_l + (size_t)w * F;
   double* st = stage[warp];
-  double acc[45][2];
-#pragma unroll
-  for (int i = 0; i < 45; ++i) acc[i][0] = acc[i][1] = 0.0;
-  double gacc[3] = {0.0, 0.0, 0.0};
   const int nsteps = (F + 3) / 4;
   // register prefetch of one step: 4 rows x 72 columns = 288 doubles = 9 per lane, plus L and b for lanes 0..3
   double pre[9], preL = 0.0, preB = 0.0;
+  const double* __restrict__ Hl = nullptr;
+  const double* __restrict__ Ll = nullptr;
+  const double* __restrict__ Bl = nullptr;
+  auto window = [&](int w) {
+    Hl = H_lp + (size_t)w * F * D, Ll = H_ll + (size_t)w * F, Bl = b_l + (size_t)w * F;
+  };
   auto fetch = [&](int step) {
     const int l0 = 4 * step;
 #pragma unroll
@@ -154,7 +154,15 @@ __global__ void __launch_bounds__(SWARPS * 32) schur_splitk_kernel(int F, int D,
       preB = l0 + lane < F ? Bl[l0 + lane] : 0.0;
     }
   };
-  if (warp < nsteps) fetch(warp);
+  if ((int)blockIdx.x < W) {
+    window(blockIdx.x);
+    if (warp < nsteps) fetch(warp);
+  }
+  for (int w = blockIdx.x; w < W; w += gridDim.x) {
+  double acc[45][2];
+#pragma unroll
+  for (int i = 0; i < 45; ++i) acc[i][0] = acc[i][1] = 0.0;
+  double gacc[3] = {0.0, 0.0, 0.0};
   for (int step = warp; step < nsteps; step += SWARPS) {
 #pragma unroll
     for (int q = 0; q < 9; ++q) {
@@ -188,6 +196,10 @@ __global__ void __launch_bounds__(SWARPS * 32) schur_splitk_kernel(int F, int D,
         if (lane + 32 * q < 72) gacc[q] = fma(st[k * kSplitStageLd + lane + 32 * q], s, gacc[q]);
     }
     __syncwarp();
+  }
+  if (w + (int)gridDim.x < W) {   // first step of the next window, in flight during the epilogue
+    window(w + gridDim.x);
+    if (warp < nsteps) fetch(warp);
   }
   // cross-warp reduction (once per window): every warp parks its partial sums in its own slab (no turn-taking),
   // the S / g writers add the SWARPS slabs
@@ -237,6 +249,8 @@ __global__ void __launch_bounds__(SWARPS * 32) schur_splitk_kernel(int F, int D,
   for (int e = tid; e < D; e += SWARPS * 32) {
     g[(size_t)w * D + e] = b_p[(size_t)w * D + e] - sAcc[45 * 64 + e];
   }
+  __syncthreads();   // the slabs and the stages are reused by the next window
+  }
 }
 
 // ---- DMMA peak (for the roofline denominator of this kernel) ----
@@ -263,7 +277,8 @@ int viml_launch_schur(viml_ctx* ctx, int W, int F, int D, const double* H_pp, co
     LaunchScope ls(ctx, K_SCHUR);
     const int smem = SWARPS * kSplitAcc * (int)sizeof(double);
     if (cudaFuncSetAttribute(schur_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return VIML_ERR_CUDA;
-    schur_splitk_kernel<<<(unsigned)W, SWARPS * 32, smem, ctx->stream>>>(F, D, H_pp, H_lp, H_ll, b_p, b_l, S, g, eps);
+    const int grid = W < ctx->sm_count ? W : ctx->sm_count;
+    schur_splitk_kernel<<<(unsigned)grid, SWARPS * 32, smem, ctx->stream>>>(W, F, D, H_pp, H_lp, H_ll, b_p, b_l, S, g, eps);
     return VIML_OK;
   }
   dim3 grid((unsigned)(ntile * (ntile + 1) / 2), (unsigned)W);
