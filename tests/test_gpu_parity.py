@@ -120,6 +120,15 @@ def test_fused_path_extremes(pkg, orc, ctx, cfg):
     a2 = ctx.linearize(b, hb)
     for k in a1:
         assert np.array_equal(a1[k], a2[k]), k
+    # the sorts run ahead in plan_kernel or, for multi-part windows, inside the fused kernel: same code, same positions,
+    # same bits (VIML_NO_PLAN=1 is the test hook that forces the in-kernel sorts everywhere)
+    os.environ["VIML_NO_PLAN"] = "1"
+    try:
+        a3 = ctx.linearize(b, hb)
+    finally:
+        del os.environ["VIML_NO_PLAN"]
+    for k in a1:
+        assert np.array_equal(a1[k], a3[k]), k
 
 
 def test_marginalisation_stress_shape(pkg, orc, ctx, cfg):
