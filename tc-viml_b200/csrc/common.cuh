@@ -56,6 +56,8 @@ struct viml_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaStream_t copy_stream2 = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  cudaStream_t aux_stream = nullptr;            // plan_kernel runs here, beside prep_windows_kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   viml_config cfg{};
   std::string err;
   int64_t launches = 0;
@@ -91,19 +93,20 @@ static_assert(K_COUNT <= VIML_NUM_KERNELS, "raise VIML_NUM_KERNELS");
 struct LaunchScope {
   viml_ctx* ctx;
   cudaEvent_t stop = nullptr;
-  LaunchScope(viml_ctx* c, int id) : ctx(c) {
+  cudaStream_t on;
+  LaunchScope(viml_ctx* c, int id, cudaStream_t st = nullptr) : ctx(c), on(st ? st : c->stream) {
     ctx->launches++;
     if (ctx->prof) {
       cudaEvent_t a, b;
       cudaEventCreate(&a);
       cudaEventCreate(&b);
-      cudaEventRecord(a, ctx->stream);
+      cudaEventRecord(a, on);
       ctx->prof_events[id].emplace_back(a, b);
       stop = b;
     }
   }
   ~LaunchScope() {
-    if (stop) cudaEventRecord(stop, ctx->stream);
+    if (stop) cudaEventRecord(stop, on);
   }
 };
 

@@ -438,13 +438,28 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
   cudaStream_t st = ctx->stream;
   const bool modeA = (a.flags & VIML_OUT_RESIDUAL_JACOBIAN) != 0;
   const bool modeB = (a.flags & (VIML_OUT_HB | VIML_OUT_SCHUR)) != 0;
+  const bool fast = modeB && a.P <= fused::PMAX && !ctx->force_generic;
+  const bool bigf = a.F > fused::FMAX;
+  // The window sorts (plan_kernel) depend on the factor indices only, the pose cache (prep_windows_kernel) on the states
+  // only: the two short kernels run side by side on two streams and meet before the fused kernel.
+  uint16_t* plan = nullptr;
+  if (fast && !bigf && !getenv("VIML_NO_PLAN")) {
+    VIML_TRY_CUDA(ctx, ctx->scratch3.reserve(DeviceArena::padded((size_t)a.W * fused::kPlanStride * sizeof(uint16_t))));
+    plan = ctx->scratch3.take<uint16_t>((size_t)a.W * fused::kPlanStride);
+    VIML_TRY_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    VIML_TRY_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    {
+      LaunchScope ls(ctx, K_PLAN, ctx->aux_stream);
+      fused::plan_kernel<<<a.W, fused::AT, 0, ctx->aux_stream>>>(a, plan);
+    }
+    VIML_TRY_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+  }
   {
     const int64_t total = (int64_t)a.W * (a.P + 1);
     LaunchScope ls(ctx, K_PREP);
     prep_windows_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a);
   }
-  const bool fast = modeB && a.P <= fused::PMAX && !ctx->force_generic;
-  const bool bigf = a.F > fused::FMAX;
+  if (plan) VIML_TRY_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
   if (fast) {
     // fused CTA-per-window kernel: writes every H/b entry exactly once (no memset), r/J too when asked
     const size_t smem = sizeof(fused::Smem);
@@ -464,13 +479,7 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
     }
     const int grid = a.W < ctx->sm_count ? a.W : ctx->sm_count;   // persistent: one CTA per SM
     LinearizeArgs a2 = a;
-    a2.plan = nullptr;
-    if (!bigf && !getenv("VIML_NO_PLAN")) {   // sorts of all single-part windows ahead of the fused kernel
-      VIML_TRY_CUDA(ctx, ctx->scratch3.reserve(DeviceArena::padded((size_t)a.W * fused::kPlanStride * sizeof(uint16_t))));
-      a2.plan = ctx->scratch3.take<uint16_t>((size_t)a.W * fused::kPlanStride);
-      LaunchScope ls(ctx, K_PLAN);
-      fused::plan_kernel<<<a.W, fused::AT, 0, st>>>(a2, a2.plan);
-    }
+    a2.plan = plan;
     long long* dbg = nullptr;
     if (getenv("VIML_PHASE_TIMERS")) {
       cudaMalloc((void**)&dbg, sizeof(long long) * 22 * grid);

@@ -76,7 +76,10 @@ int viml_create(viml_ctx** out, const viml_config* cfg, int device) {
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return VIML_ERR_CUDA;
   }
@@ -101,6 +104,9 @@ void viml_destroy(viml_ctx* ctx) {
   if (ctx->d_assoc_stats) cudaFree(ctx->d_assoc_stats);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
