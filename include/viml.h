@@ -99,6 +99,10 @@ const char* viml_kernel_name(int kernel_id);
 int viml_microbench_fp64(viml_ctx* ctx, double* dfma_tflops, double* dmul_dadd_tops);
 /* FP64 tensor-core peak: mma.sync m8n8k4.f64 (DMMA), 512 flop per warp instruction.                 */
 int viml_microbench_dmma(viml_ctx* ctx, double* dmma_tflops);
+/* Self-test of the association kernels' division with a hoisted reciprocal (the bit-exact contract of
+ * viml_line_associate rests on it): computes a[k] / b[k] both ways on the device for n HOST pairs and returns the
+ * number of quotients that differ in any bit (NaN == NaN). Must be 0. */
+int viml_selftest_division(viml_ctx* ctx, const double* a, const double* b, int64_t n, int64_t* mismatches);
 
 /* ---- prior line map -------------------------------------------------------------------------- */
 /* lines_xyzxyz: N rows of [sx sy sz ex ey ez] exactly as line_3d.txt (parameters.cpp:50-59).

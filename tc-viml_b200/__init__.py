@@ -23,7 +23,7 @@ ABI_SYMBOLS = (
     "viml_abi_version", "viml_create", "viml_destroy", "viml_last_error", "viml_sync", "viml_stream",
     "viml_host_alloc", "viml_host_free", "viml_device_alloc", "viml_device_free", "viml_memcpy_h2d",
     "viml_memcpy_d2h", "viml_kernel_launches", "viml_profile_begin", "viml_profile_end", "viml_kernel_name",
-    "viml_microbench_fp64", "viml_microbench_dmma", "viml_set_map", "viml_linearize_batch",
+    "viml_microbench_fp64", "viml_microbench_dmma", "viml_selftest_division", "viml_set_map", "viml_linearize_batch",
     "viml_marginalize_batch", "viml_line_associate", "viml_assoc_stats", "viml_allreduce_hb",
 )
 
@@ -56,6 +56,7 @@ def load_library():
     lib.viml_profile_end.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.viml_microbench_fp64.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.viml_microbench_dmma.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.viml_selftest_division.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.viml_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_abi.Config), C.c_int]
     lib.viml_destroy.argtypes = [C.c_void_p]
     lib.viml_sync.argtypes = [C.c_void_p]
@@ -235,6 +236,13 @@ class Context:
         o.fov_index, o.fov_capacity, o.fov_mask = _abi.ptr(res.get("fov_index")), fov_capacity, _abi.ptr(res.get("fov_mask"))
         self._check(self.lib.viml_line_associate(self.h, C.byref(q), C.byref(o), 0))
         return res
+
+    def selftest_division(self, a, b):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        m = C.c_int64()
+        self._check(self.lib.viml_selftest_division(self.h, _abi.ptr(a), _abi.ptr(b), a.size, C.byref(m)))
+        return m.value
 
     def assoc_stats(self):
         v = [C.c_int64() for _ in range(4)]

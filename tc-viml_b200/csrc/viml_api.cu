@@ -583,6 +583,26 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
   return VIML_OK;
 }
 
+int viml_selftest_division(viml_ctx* ctx, const double* a, const double* b, int64_t n, int64_t* mismatches) {
+  if (!ctx) return VIML_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!a || !b)) || !mismatches) return fail(ctx, VIML_ERR_INVALID, "bad division self-test arguments");
+  VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+  VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(2 * DeviceArena::padded((size_t)n * 8) + 256));
+  double* da = ctx->in_arena.take<double>((size_t)n);
+  double* db = ctx->in_arena.take<double>((size_t)n);
+  unsigned long long* dm = ctx->in_arena.take<unsigned long long>(1);
+  VIML_TRY_CUDA(ctx, cudaMemcpyAsync(da, a, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  VIML_TRY_CUDA(ctx, cudaMemcpyAsync(db, b, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  VIML_TRY_CUDA(ctx, cudaMemsetAsync(dm, 0, 8, ctx->stream));
+  const int rc = viml_launch_divcheck(ctx, da, db, n, dm);
+  if (rc != VIML_OK) return rc;
+  unsigned long long h = 0;
+  VIML_TRY_CUDA(ctx, cudaMemcpyAsync(&h, dm, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VIML_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *mismatches = (int64_t)h;
+  return VIML_OK;
+}
+
 int viml_assoc_stats(viml_ctx* ctx, int64_t* gate_tests, int64_t* gated, int64_t* overlap_scored,
                      int64_t* distance_scored) {
   if (!ctx) return VIML_ERR_INVALID;

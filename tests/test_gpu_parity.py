@@ -358,6 +358,30 @@ def test_association_angle_threshold_variants(pkg, orc):
         check_assoc(got, ref)
 
 
+def test_division_with_hoisted_reciprocal_is_exact(ctx):
+    """div_by (associate_kernels.cu) replays the compiler's division fast path with the reciprocal part computed once
+    per divisor and falls back to `/` outside a narrower exponent range: every quotient must equal a / b bit for bit,
+    over pixel-scale values, random bit patterns, subnormals, huge values, zeros, infinities and NaNs."""
+    rng = np.random.Generator(np.random.PCG64(61))
+    n = 1 << 21
+    a = [rng.uniform(-2000, 2000, n), rng.uniform(0, 1e6, n) * rng.uniform(0, 1, n) ** 8]
+    b = [rng.uniform(1e-3, 2000, n), rng.uniform(0, 800, n)]
+    bits = rng.integers(0, 1 << 63, n, dtype=np.int64) * rng.choice([-1, 1], n)      # any finite / inf / NaN pattern
+    a.append(bits.view(np.float64))
+    b.append((rng.integers(0, 1 << 63, n, dtype=np.int64)).view(np.float64))
+    mant = 1.0 + rng.integers(0, 16, n) * 2.0 ** -52                                  # mantissas next to 1 and 2
+    mant2 = 2.0 - rng.integers(1, 16, n) * 2.0 ** -52
+    a.append(np.concatenate([mant[: n // 2], mant2[n // 2:]]) * 2.0 ** rng.integers(-1030, 1020, n).astype(np.float64))
+    b.append(np.concatenate([mant2[: n // 2], mant[n // 2:]]) * 2.0 ** rng.integers(-1030, 1020, n).astype(np.float64))
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308,
+                        1.0, 10.0, 12.0, 3.0, 1e-200, 1e200])
+    a.append(np.repeat(special, special.size))
+    b.append(np.tile(special, special.size))
+    with np.errstate(all="ignore"):
+        for x, y in zip(a, b):
+            assert ctx.selftest_division(x, y) == 0
+
+
 def test_association_pruning_adversarial(pkg, orc):
     """The match kernel drops pairs through conservative overlap / distance bounds before the exact arithmetic.
     Queries built ON the thresholds: sub-segments of the projected map lines whose overlap sits within 1e-9 ... 1e-3
