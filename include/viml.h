@@ -233,8 +233,8 @@ typedef struct viml_assoc_out {
 
 int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_assoc_out* out,
                         uint32_t flags);
-/* Work counters of the last viml_line_associate call (synchronises): gate_tests = sum over queries of the FoV list
- * length (CalAngleDist evaluations), gated = pairs that passed the angle gate (what the reference runs CalEulerDist
+/* Work counters of the last viml_line_associate call (synchronises): gate_tests = CalAngleDist evaluations executed (the
+ * angular bins a 2D line's window touches; the reference evaluates the whole FoV list per line), gated = pairs that passed the angle gate (what the reference runs CalEulerDist
  * on), overlap_scored = pairs that survived the distance lower bound and ran the overlap half of CalEulerDist,
  * distance_scored = pairs whose overlap passed and ran the distance half.  For roofline accounting. */
 int viml_assoc_stats(viml_ctx* ctx, int64_t* gate_tests, int64_t* gated, int64_t* overlap_scored,
