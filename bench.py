@@ -432,7 +432,7 @@ def main():
                         "roofline": match_roof,
                         "kernel_ms_per_step": {k: v[0] / a_steps for k, v in profQ.items()},
                         "e2e": {"value": n_assoc / (e_ms_a * 1e-3), "unit": "assoc/s", "ms_per_step": e_ms_a,
-                                "h2d_bytes_per_step": int(cull.nbytes + ex.nbytes + l2d.nbytes + res["projected"].nbytes),  # incl. the caller's projected[] (unmatched entries are preserved)
+                                "h2d_bytes_per_step": int(cull.nbytes + ex.nbytes + l2d.nbytes),
                                 "d2h_bytes_per_step": int(res["match_index"].nbytes + res["err"].nbytes + res["projected"].nbytes + res["fov_count"].nbytes)}}
         out["gpu_launches_assoc_per_step"] = 6
         if rank == 0 and not args.skip_cpu:

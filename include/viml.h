@@ -215,8 +215,9 @@ typedef struct viml_assoc_query {
 
 /* match_index: MAP index of the chosen 3D line, -1 = none (est.cpp:869-878 / :703-713).
  * err: {errA, errD, overlap} as the reference's Vector3f (-1,-1,-1 when unmatched).
- * projected: the chosen candidate's projected 2D segment (xx,yy,xx_,yy_ / clipped endpoint), untouched
- *            when unmatched.
+ * projected: the chosen candidate's projected 2D segment (xx,yy,xx_,yy_ / clipped endpoint); for an unmatched
+ *            query the detected line itself (est.cpp:874 returns detectLine).  Queries past n_lines2d[p] are not
+ *            processed: their match_index / err / projected entries keep the caller's content.
  * fov_count [Pq]; fov_index [Pq][fov_capacity] = map indices in map order (the WorldLinesInFOV list);
  * a list longer than fov_capacity is truncated in the output only (fov_count still exact, matching
  * still uses the full list).  fov_mask: [Pq][ceil(N/32)] bitset, bit j of word j/32.              */

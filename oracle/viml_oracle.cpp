@@ -960,6 +960,8 @@ int correspondence(const viml_config* cfg, const CamPose& cp, const double* map,
   }
   if (choose_index == -1) {                                                                 // :869
     err[0] = err[1] = err[2] = -1;
+    if (projected)                                                                          // :874 returns detectLine itself
+      projected[0] = l2d[0], projected[1] = l2d[1], projected[2] = l2d[2], projected[3] = l2d[3];
     return -1;
   }
   err[0] = error[0], err[1] = error[1], err[2] = error[2];
@@ -1013,7 +1015,7 @@ extern "C" int orc_line_associate(const viml_config* cfg, const double* map, int
       const size_t o = (size_t)p * L + l;
       if (out->match_index) out->match_index[o] = idx;
       if (out->err) out->err[3 * o] = err[0], out->err[3 * o + 1] = err[1], out->err[3 * o + 2] = err[2];
-      if (out->projected && idx >= 0) std::memcpy(out->projected + 4 * o, proj, sizeof(proj));
+      if (out->projected) std::memcpy(out->projected + 4 * o, proj, sizeof(proj));
     }
   });
   return VIML_OK;

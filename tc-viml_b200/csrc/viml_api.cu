@@ -559,13 +559,13 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
   a.fov_count = ctx->out_arena.take<int32_t>(Pq);
   a.fov_index = cap ? ctx->out_arena.take<int32_t>((size_t)Pq * cap) : nullptr;
   a.fov_mask = ctx->out_arena.take<uint32_t>((size_t)Pq * words);
-  if (out->projected)  // unmatched entries keep the caller's content
-    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.projected, out->projected, nq * 32, cudaMemcpyHostToDevice, st));
+
   if (out->fov_index && cap)  // entries past fov_count keep the caller's content
     VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.fov_index, out->fov_index, (size_t)Pq * cap * 4, cudaMemcpyHostToDevice, st));
   if (out->match_index && q->n_lines2d) {  // ragged queries past n_lines2d keep the caller's content
     VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.match_index, out->match_index, nq * 4, cudaMemcpyHostToDevice, st));
     if (out->err) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.err, out->err, nq * 12, cudaMemcpyHostToDevice, st));
+    if (out->projected) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.projected, out->projected, nq * 32, cudaMemcpyHostToDevice, st));
   }
   int rc = viml_launch_associate(ctx, a);
   if (rc != VIML_OK) return rc;

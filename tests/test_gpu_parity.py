@@ -289,6 +289,8 @@ def test_association_synthetic(pkg, orc, ctx, cfg):
     ref = orc.line_associate(cfg, lines, cull, match, ex, l2d, fov_capacity=2048, want_mask=True, nthreads=8)
     exact = check_assoc(got, ref)
     assert (ref["match_index"] >= 0).mean() > 0.2 and exact > 0.99
+    um = ref["match_index"] == -1   # an unmatched query returns the detected line itself (est.cpp:874)
+    assert um.any() and np.array_equal(got["projected"][um], l2d[um]) and np.array_equal(ref["projected"][um], l2d[um])
     # same pose for cull and match (match_poses = NULL), as the cfg-3 sweep does
     got = ctx.associate(cull, None, ex, l2d)
     ref = orc.line_associate(cfg, lines, cull, None, ex, l2d, nthreads=8)
