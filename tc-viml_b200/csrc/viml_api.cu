@@ -537,19 +537,26 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
     a.fov_count = out->fov_count ? out->fov_count : ctx->out_arena.take<int32_t>(Pq);
     return viml_launch_associate(ctx, a);
   }
+  // Host buffers: poses are independent, so a large query is run as a pipeline of pose chunks -- all uploads are queued
+  // on the copy stream up front (one event per chunk), chunk c's kernels wait for its upload only, and its results go
+  // back on the second copy stream while chunk c + 1 computes.
   VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(4 * pad((size_t)Pq * 56) + pad(nq * 32) + pad((size_t)Pq * 4)));
+  cudaStream_t cs = ctx->copy_stream, ds = ctx->copy_stream2;
+  const int C = Pq >= 512 ? 4 : 1;
   auto up = [&](const void* src, size_t bytes) -> void* {
     char* d = ctx->in_arena.take<char>(bytes);
-    if (bytes) cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st);
+    if (bytes) cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, cs);
     return d;
   };
+  VIML_TRY_CUDA(ctx, cudaEventRecord(ctx->ev_a, st));   // the copy stream starts after whatever the caller queued before
+  VIML_TRY_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_a, 0));
   a.cull_poses = (const double*)up(q->cull_poses, (size_t)Pq * 56);
   a.match_poses = q->match_poses ? (const double*)up(q->match_poses, (size_t)Pq * 56) : a.cull_poses;
   a.ex_pose = (const double*)up(q->ex_pose, (size_t)Pq * 56);
   a.cull_ex_pose = q->cull_ex_pose ? (const double*)up(q->cull_ex_pose, (size_t)Pq * 56) : a.ex_pose;
-  a.lines2d = (const double*)up(q->lines2d, nq * 32);
   a.n_lines2d = q->n_lines2d ? (const int32_t*)up(q->n_lines2d, (size_t)Pq * 4) : nullptr;
-  VIML_TRY_CUDA(ctx, cudaGetLastError());
+  double* d_l2d = ctx->in_arena.take<double>(nq * 4);
+  a.lines2d = d_l2d;
   const size_t cap = a.fov_capacity;
   VIML_TRY_CUDA(ctx, ctx->out_arena.reserve(pad(nq * 4) + pad(nq * 12) + pad(nq * 32) + pad((size_t)Pq * 4) +
                                             pad((size_t)Pq * cap * 4) + pad((size_t)Pq * words * 4)));
@@ -559,27 +566,58 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
   a.fov_count = ctx->out_arena.take<int32_t>(Pq);
   a.fov_index = cap ? ctx->out_arena.take<int32_t>((size_t)Pq * cap) : nullptr;
   a.fov_mask = ctx->out_arena.take<uint32_t>((size_t)Pq * words);
-
   if (out->fov_index && cap)  // entries past fov_count keep the caller's content
-    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.fov_index, out->fov_index, (size_t)Pq * cap * 4, cudaMemcpyHostToDevice, st));
+    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.fov_index, out->fov_index, (size_t)Pq * cap * 4, cudaMemcpyHostToDevice, cs));
   if (out->match_index && q->n_lines2d) {  // ragged queries past n_lines2d keep the caller's content
-    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.match_index, out->match_index, nq * 4, cudaMemcpyHostToDevice, st));
-    if (out->err) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.err, out->err, nq * 12, cudaMemcpyHostToDevice, st));
-    if (out->projected) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.projected, out->projected, nq * 32, cudaMemcpyHostToDevice, st));
+    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.match_index, out->match_index, nq * 4, cudaMemcpyHostToDevice, cs));
+    if (out->err) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.err, out->err, nq * 12, cudaMemcpyHostToDevice, cs));
+    if (out->projected) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.projected, out->projected, nq * 32, cudaMemcpyHostToDevice, cs));
   }
-  int rc = viml_launch_associate(ctx, a);
-  if (rc != VIML_OK) return rc;
+  std::vector<cudaEvent_t> ev_in(C), ev_k(C);
+  auto chunk = [&](int c, int& p0, int& p1) { p0 = (int)((int64_t)Pq * c / C), p1 = (int)((int64_t)Pq * (c + 1) / C); };
+  for (int c = 0; c < C; ++c) {
+    int p0, p1;
+    chunk(c, p0, p1);
+    cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_k[c], cudaEventDisableTiming);
+    const size_t o = (size_t)p0 * L * 4, n = (size_t)(p1 - p0) * L * 4;
+    if (n) cudaMemcpyAsync(d_l2d + o, q->lines2d + o, n * 8, cudaMemcpyHostToDevice, cs);
+    cudaEventRecord(ev_in[c], cs);
+  }
+  int rc = VIML_OK;
   auto down = [&](void* host, const void* d, size_t bytes) {
-    if (host && bytes) cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, st);
+    if (host && bytes) cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, ds);
   };
-  down(out->match_index, a.match_index, nq * 4);
-  down(out->err, a.err, nq * 12);
-  down(out->projected, a.projected, nq * 32);
-  down(out->fov_count, a.fov_count, (size_t)Pq * 4);
-  down(out->fov_index, a.fov_index, (size_t)Pq * cap * 4);
-  down(out->fov_mask, a.fov_mask, (size_t)Pq * words * 4);
+  for (int c = 0; c < C && rc == VIML_OK; ++c) {
+    int p0, p1;
+    chunk(c, p0, p1);
+    cudaStreamWaitEvent(st, ev_in[c], 0);
+    AssocArgs v = a;   // view of poses [p0, p1)
+    v.Pq = p1 - p0;
+    v.cull_poses = a.cull_poses + (size_t)p0 * 7, v.match_poses = a.match_poses + (size_t)p0 * 7;
+    v.ex_pose = a.ex_pose + (size_t)p0 * 7, v.cull_ex_pose = a.cull_ex_pose + (size_t)p0 * 7;
+    v.lines2d = a.lines2d + (size_t)p0 * L * 4, v.n_lines2d = a.n_lines2d ? a.n_lines2d + p0 : nullptr;
+    v.match_index = a.match_index + (size_t)p0 * L, v.err = a.err + (size_t)p0 * L * 3, v.projected = a.projected + (size_t)p0 * L * 4;
+    v.fov_count = a.fov_count + p0, v.fov_index = a.fov_index ? a.fov_index + (size_t)p0 * cap : nullptr;
+    v.fov_mask = a.fov_mask + (size_t)p0 * words;
+    if (v.Pq > 0) rc = viml_launch_associate(ctx, v);
+    cudaEventRecord(ev_k[c], st);
+    cudaStreamWaitEvent(ds, ev_k[c], 0);
+    const size_t np = (size_t)(p1 - p0), nqc = np * L;
+    down(out->match_index ? out->match_index + (size_t)p0 * L : nullptr, v.match_index, nqc * 4);
+    down(out->err ? out->err + (size_t)p0 * L * 3 : nullptr, v.err, nqc * 12);
+    down(out->projected ? out->projected + (size_t)p0 * L * 4 : nullptr, v.projected, nqc * 32);
+    down(out->fov_count ? out->fov_count + p0 : nullptr, v.fov_count, np * 4);
+    down(out->fov_index ? out->fov_index + (size_t)p0 * cap : nullptr, v.fov_index, np * cap * 4);
+    down(out->fov_mask ? out->fov_mask + (size_t)p0 * words : nullptr, v.fov_mask, np * words * 4);
+  }
+  cudaError_t e1 = cudaStreamSynchronize(ds), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(cs);
+  for (int c = 0; c < C; ++c) cudaEventDestroy(ev_in[c]), cudaEventDestroy(ev_k[c]);
+  if (rc != VIML_OK) return rc;
+  VIML_TRY_CUDA(ctx, e1);
+  VIML_TRY_CUDA(ctx, e2);
+  VIML_TRY_CUDA(ctx, e3);
   VIML_TRY_CUDA(ctx, cudaGetLastError());
-  VIML_TRY_CUDA(ctx, cudaStreamSynchronize(st));
   return VIML_OK;
 }
 
