@@ -32,6 +32,24 @@ if os.path.exists(src):
                 f"`profiles/launches_{tag}.csv`.\n\n| kernel | launches | total us | avg us | share of captured time |\n|---|---|---|---|---|\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {n} | {t:.1f} | {t / n:.1f} | {100 * t / tot:.1f} % |\n")
+        # the headline step = prep_windows + plan + assemble<0,0> on the full 4096-window batch: the same kernels also run
+        # on the 512-window chunks of the e2e leg, so take the largest launches of each (one per timed step)
+        per = collections.defaultdict(list)
+        for r in rows[1:]:
+            if len(r) >= len(hdr) and r[ci["Metric Name"]] == "gpu__time_duration.sum":
+                v = float(r[ci["Metric Value"]].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r[ci["Metric Unit"]], 1e-3)
+                per[re.sub(r"\(.*", "", r[ci["Kernel Name"]]).replace("<unnamed>::", "")].append(v)
+        pick = {}
+        for name, key in (("assemble", "assemble_kernel<0, 0>"), ("plan", "plan_kernel"), ("prep", "prep_windows_kernel")):
+            cand = [v for k, vs in per.items() if key in k for v in vs]
+            if cand:
+                top = sorted(cand, reverse=True)[:5]
+                pick[name] = sum(top) / len(top)
+        if len(pick) == 3:
+            tot3 = sum(pick.values())
+            f.write("\nHeadline step (full-size launches only, mean of the 5 largest of each kernel): " + ", ".join(
+                f"{k} {v:.1f} us = {100 * v / tot3:.1f} %" for k, v in pick.items()) +
+                ". `bench.py` (CUDA events, warm) reports 85 / 11 / 4 % (`roofline.kernel_ms_per_step`; there plan and prep run side by side on two streams and each takes a little longer).\n")
 
 want = [("gpu__time_duration.sum", "duration"), ("launch__registers_per_thread", "regs/thread"),
         ("launch__grid_size", "grid"), ("launch__block_size", "block"),
