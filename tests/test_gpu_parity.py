@@ -347,6 +347,24 @@ def test_association_edges(pkg, orc, ctx, cfg):
     assert np.all(got["match_index"] == -1) and np.all(got["fov_count"] == 0)
 
 
+def test_association_long_fov_lists(pkg, orc, ctx, cfg):
+    """FoV lists longer than the match kernel's shared-memory stage (2048 candidate directions): the tail of the list
+    is gated straight from the candidate arrays; same bits as the oracle, and the winners do come from the tail."""
+    synth = pkg.synth
+    ext = (70.0, 70.0, 30.0)
+    lines = synth.make_line_map(9000, seed=71, extent=ext)
+    cull, match, ex, l2d = synth.make_assoc_queries(lines, 130, L=48, n_true=24, seed=72, extent=ext)
+    ctx.set_map(lines)
+    got = ctx.associate(cull, match, ex, l2d, fov_capacity=8192, want_mask=True)
+    assert got["fov_count"].max() > 2600
+    sel = np.argsort(-got["fov_count"])[:6]                       # the longest lists
+    ref = orc.line_associate(cfg, lines, cull[sel], match[sel], ex[sel], l2d[sel], fov_capacity=8192, want_mask=True, nthreads=8)
+    sub = {k: v[sel] for k, v in got.items()}
+    check_assoc(sub, ref)
+    pos = [np.searchsorted(sub["fov_index"][i, :sub["fov_count"][i]], sub["match_index"][i][sub["match_index"][i] >= 0]) for i in range(len(sel))]
+    assert max(p.max() for p in pos if len(p)) >= 2048           # some matches sit beyond the staged part of the list
+
+
 def test_association_angle_threshold_variants(pkg, orc):
     synth = pkg.synth
     lines = synth.make_line_map(20000, seed=45, extent=(300.0, 300.0, 30.0))
