@@ -141,7 +141,8 @@ def line_correspondence(cfg, pose, ex, lines, fov, line2d):
     return idx, err, proj
 
 
-def line_associate(cfg, lines, cull_poses, match_poses, ex_pose, lines2d, n_lines2d=None, fov_capacity=0, want_mask=False, nthreads=1):
+def line_associate(cfg, lines, cull_poses, match_poses, ex_pose, lines2d, n_lines2d=None, fov_capacity=0, want_mask=False, nthreads=1,
+                   cull_ex_pose=None):
     """Oracle counterpart of Context.associate: dict(match_index, err, projected, fov_count, fov_index, fov_mask)."""
     abi = _abi()
     lines = np.ascontiguousarray(lines, dtype=np.float64)
@@ -152,6 +153,8 @@ def line_associate(cfg, lines, cull_poses, match_poses, ex_pose, lines2d, n_line
     q.cull_poses, q.match_poses, q.ex_pose, q.lines2d = [abi.ptr(k) for k in keep]
     nl = None if n_lines2d is None else np.ascontiguousarray(n_lines2d, dtype=np.int32)
     q.n_lines2d = abi.ptr(nl)
+    cex = None if cull_ex_pose is None else np.ascontiguousarray(cull_ex_pose, dtype=np.float64)
+    q.cull_ex_pose = abi.ptr(cex)
     N = len(lines)
     res = {"match_index": np.full((Pq, L), -2, dtype=np.int32), "err": np.full((Pq, L, 3), np.nan, dtype=np.float32),
            "projected": np.full((Pq, L, 4), np.nan), "fov_count": np.zeros(Pq, dtype=np.int32)}

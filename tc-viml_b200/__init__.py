@@ -214,7 +214,7 @@ class Context:
         return res
 
     def associate(self, cull_poses, match_poses, ex_pose, lines2d, n_lines2d=None, fov_capacity=0,
-                  want_mask=False):
+                  want_mask=False, cull_ex_pose=None):
         """viml_line_associate with host buffers; returns dict of numpy outputs."""
         keep = [None if x is None else np.ascontiguousarray(x, dtype=np.float64)
                 for x in (cull_poses, match_poses, ex_pose, lines2d)]
@@ -224,6 +224,8 @@ class Context:
         q.cull_poses, q.match_poses, q.ex_pose, q.lines2d = [_abi.ptr(k) for k in keep]
         nl = None if n_lines2d is None else np.ascontiguousarray(n_lines2d, dtype=np.int32)
         q.n_lines2d = _abi.ptr(nl)
+        cex = None if cull_ex_pose is None else np.ascontiguousarray(cull_ex_pose, dtype=np.float64)
+        q.cull_ex_pose = _abi.ptr(cex)
         res = {"match_index": np.full((Pq, L), -2, dtype=np.int32),
                "err": np.full((Pq, L, 3), np.nan, dtype=np.float32),
                "projected": np.full((Pq, L, 4), np.nan), "fov_count": np.zeros(Pq, dtype=np.int32)}

@@ -347,6 +347,28 @@ def test_association_edges(pkg, orc, ctx, cfg):
     assert np.all(got["match_index"] == -1) and np.all(got["fov_count"] == 0)
 
 
+def test_association_frame_entry_extrinsic(pkg, orc, ctx, cfg):
+    """UpdateLinesInFoV runs at frame entry with the extrinsic of that moment (est.cpp:385), the match with the
+    re-optimised one: cull_ex_pose != ex_pose, with and without a separate match pose, host chunks included (640 poses)."""
+    synth = pkg.synth
+    ext = (400.0, 400.0, 30.0)
+    lines = synth.make_line_map(40000, seed=81, extent=ext)
+    cull, match, ex, l2d = synth.make_assoc_queries(lines, 640, L=24, n_true=12, seed=82, extent=ext)
+    rng = np.random.Generator(np.random.PCG64(83))
+    cex = ex.copy()
+    cex[:, :3] += 0.01 * rng.standard_normal((len(ex), 3))
+    cex[:, 3:] += 0.002 * rng.standard_normal((len(ex), 4))        # un-normalised on purpose: the path normalises
+    ctx.set_map(lines)
+    sel = np.array([0, 1, 159, 160, 319, 320, 479, 480, 639])       # both sides of every host-pipeline chunk boundary
+    for m in (match, None):
+        got = ctx.associate(cull, m, ex, l2d, fov_capacity=1024, want_mask=True, cull_ex_pose=cex)
+        ref = orc.line_associate(cfg, lines, cull[sel], None if m is None else m[sel], ex[sel], l2d[sel], fov_capacity=1024,
+                                 want_mask=True, nthreads=8, cull_ex_pose=cex[sel])
+        check_assoc({k: v[sel] for k, v in got.items()}, ref)
+    plain = ctx.associate(cull, match, ex, l2d, fov_capacity=1024)
+    assert not np.array_equal(plain["fov_count"], got["fov_count"]) or not np.array_equal(plain["fov_index"], got["fov_index"])
+
+
 def test_association_long_fov_lists(pkg, orc, ctx, cfg):
     """FoV lists longer than the match kernel's shared-memory stage (2048 candidate directions): the tail of the list
     is gated straight from the candidate arrays; same bits as the oracle, and the winners do come from the tail."""
