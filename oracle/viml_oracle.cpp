@@ -874,6 +874,8 @@ int correspondence(const viml_config* cfg, const CamPose& cp, const double* map,
   Line2D projectedLine{};
   if (fov_n == 0) {                                                                         // :703-713
     err[0] = err[1] = err[2] = -1;
+    if (projected)                                                                          // :709 returns detectLine itself
+      projected[0] = l2d[0], projected[1] = l2d[1], projected[2] = l2d[2], projected[3] = l2d[3];
     return -1;
   }
   for (int i = 0; i < fov_n; ++i) {                                                         // :715

@@ -1,0 +1,717 @@
+// assemble2.cuh — fused "evaluate + loss-correct + J^T J / J^T r" for batches of windows (mode B of viml_linearize_batch).
+// Included by linearize_kernels.cu after eval_point / eval_line.
+//
+// What the reference does per window (marginalization_factor.cpp:3-69, :141-172): evaluate every factor into heap
+// Jacobian blocks, then 4 pthreads scatter J_i^T J_j into private dense pos x pos matrices.  Here Jacobians never
+// leave the SM and there is no CTA-wide phase structure: a window is cut into TASKS that warps execute on their own.
+//
+//   plan_kernel (indices only)   features are ordered by anchor pose; a task is a run of consecutive features
+//       (<= 32 features, ~88 factors); inside a task the factors are ordered by (anchor i, observing frame j) and
+//       every (i, j) SEGMENT is padded to an even length.  The plan is a list of 32-bit slots
+//       (factor id | feature slot | i | j) plus one record per task.
+//   assemble_kernel, one CTA (8 warps) per window, two CTAs per SM.  A warp takes a task and streams its slots
+//   32 at a time:
+//     1. lane = factor: residual, Jacobians, Cauchy correction in registers (eval_point).
+//     2. landmark row of the factor's feature: the d^T J_j block is unique to the factor and goes straight to
+//        H_lp; d^T J_i, d^T J_ex, d^T d, d^T r are summed over the feature's factors in a warp-private
+//        shared-memory row (all factors of a feature belong to one task: plain read-modify-write, no atomics).
+//     3. pose part on the FP64 tensor pipe: the factor's 16 distinct columns U = [A | a_rot | b_rot | J_ex | r]
+//        (the pose-j translation block is -A) go to a warp-private stage; two factors of one segment form one
+//        K = 4 step of mma.sync.m8n8k4.f64 and the upper triangle of the 16 x 16 Gram matrix U^T U costs three
+//        DMMA per step.  Every block of H_pp the two factors touch — (i,i), (j,j), (i,j), (i,ex), (j,ex), (ex,ex),
+//        b_i, b_j, b_ex — is a signed sub-block of that Gram matrix.
+//     4. at the end of a segment the j-role entries and the (i,j) block are added to the window's block-upper
+//        accumulator in shared memory (shared-memory FP64 add = CAS loop; balanced over the lanes through a
+//        192-double patch and a compile-time destination table); the i-role and extrinsic entries keep
+//        accumulating in registers until the anchor changes.
+//   When the window's tasks are done the CTA expands the block-upper accumulator to the full symmetric D x D
+//   matrix in the (now dead) warp work areas and writes it with ONE cp.async.bulk shared->global (TMA bulk store).
+//
+// Precondition of the fused path (it is the reference's factor structure, estimator.cpp:1735-1770): every feature
+// has ONE anchor pose i, each (feature, j) pair occurs once, i != j, indices in range.  plan_kernel checks it; a
+// window that violates it is zero-filled here and assembled by irregular_kernel with global atomics instead.
+// The order in which segments reach the shared accumulator is not fixed: H_pp / b_p are reproducible to rounding
+// (~1e-16 relative), not bit for bit; H_lp, H_ll, b_l and the per-factor outputs are bit-reproducible.
+#pragma once
+
+namespace stream {
+
+constexpr int PMAX = 12;       // poses per window on the fused path (4-bit i/j, 12-bit observation masks)
+constexpr int FMAXP = 4096;    // features per window the plan kernel's shared tables are sized for
+constexpr int PT = 256;        // plan_kernel threads
+constexpr int TASK_T = 88;     // target point factors per task
+constexpr int TASK_F = 32;     // features per task
+constexpr int LTASK = 96;      // line slots per line task
+constexpr int AW = 8;          // warps per assemble CTA
+constexpr int WORK_D = 1152;   // doubles of private work area per warp: stage 512 | landmark rows 448 | patch 192
+constexpr int LACC_W = 14;     // landmark row: d^T J_i (6) | d^T J_ex (6) | d^T d | d^T r
+
+struct PlanPtrs {
+  int4* hdr;          // [W] {n_tasks, n_lslots, irregular, 0}
+  int4* tasks;        // {slot_begin, n_slots, feat_begin, n_feats}; window w starts at task_base(w)
+  uint32_t* slots;    // [2 NP] factor id (16) | feature slot in task (5) | i (4) | j (4); id 0xffff = padding
+  uint32_t* finfo;    // [W F] anchor-sorted features: feature (16) | observation mask (12) | anchor (4)
+  uint32_t* lslots;   // [2 NL] line id (16) | frame (8)
+  int* any_irregular;
+};
+
+__host__ __device__ inline int task_base(int a0_rel, int w, int F) { return a0_rel / 64 + w * (F / TASK_F + 2); }
+
+// ------------------------------------------------------------------------------------------------ plan
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += t;
+  }
+  return v;
+}
+
+// One CTA per window.  Dynamic shared memory: fmask[F] u32 | fanchor[F] u32 | cexcl[F+1] u32 | ford[F] u16 | fid[F*P] u16
+__global__ void __launch_bounds__(PT) plan_kernel(LinearizeArgs A, PlanPtrs PL) {
+  extern __shared__ __align__(16) unsigned char plan_raw[];
+  __shared__ int gcount[PMAX + 2], grun[PMAX + 2], lcount[PMAX + 1], lrun[PMAX + 1];
+  __shared__ int s_bad, s_ntasks, s_nlslots;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, w = blockIdx.x;
+  const int P = A.P, F = A.F;
+  uint32_t* fmask = reinterpret_cast<uint32_t*>(plan_raw);
+  uint32_t* fanchor = fmask + F;
+  uint32_t* cexcl = fanchor + F;
+  uint16_t* ford = reinterpret_cast<uint16_t*>(cexcl + F + 1);
+  uint16_t* fid = ford + ((F + 1) & ~1);
+  const int a0 = A.pf_window_offset[w], nf = A.pf_window_offset[w + 1] - a0;
+  const int b0 = A.NL > 0 ? A.lf_window_offset[w] : 0, nl = A.NL > 0 ? A.lf_window_offset[w + 1] - b0 : 0;
+  const int a0r = a0 - (int)A.pf_begin, b0r = b0 - (int)A.lf_begin;
+  for (int f = tid; f < F; f += PT) fmask[f] = 0u, fanchor[f] = 0xffu;
+  for (int e = tid; e < F * P; e += PT) fid[e] = 0xffff;
+  if (tid < PMAX + 2) gcount[tid] = 0;
+  if (tid < PMAX + 1) lcount[tid] = 0;
+  if (tid == 0) s_bad = (nf > 65534 || nl > 65534 || nf < 0 || nl < 0) ? 1 : 0, s_ntasks = 0, s_nlslots = 0;
+  __syncthreads();
+  const int nfs = s_bad ? 0 : nf;
+  for (int k = tid; k < nfs; k += PT) {
+    const uint32_t ix = A.pf_idx[a0 + k];
+    const int i = ix & 0xff, j = (ix >> 8) & 0xff, l = ix >> 16;
+    if (i >= P || j >= P || l >= F || i == j) {
+      s_bad = 1;
+      continue;
+    }
+    const uint32_t old = atomicOr(&fmask[l], 1u << j);
+    const uint32_t an = atomicCAS(&fanchor[l], 0xffu, (uint32_t)i);
+    if (((old >> j) & 1u) || (an != 0xffu && an != (uint32_t)i)) s_bad = 1;
+    fid[l * P + j] = (uint16_t)k;
+  }
+  __syncthreads();
+  if (s_bad) {   // zero-filled by assemble_kernel, assembled by irregular_kernel
+    if (tid == 0) {
+      PL.hdr[w] = make_int4(0, 0, 1, 0);
+      atomicOr(PL.any_irregular, 1);
+    }
+    return;
+  }
+  uint32_t* lsl = PL.lslots + 2 * (size_t)b0r;
+  if (warp == 0) {
+    // features ordered by anchor (stable in the feature index); features without a factor come last
+    for (int f0 = 0; f0 < F; f0 += 32) {
+      const int f = f0 + lane;
+      const int key = f < F ? (fanchor[f] == 0xffu ? P : (int)fanchor[f]) : 64 + lane;
+      const unsigned m = __match_any_sync(0xffffffffu, key);
+      if (f < F && (m & ((1u << lane) - 1u)) == 0u) gcount[key] += __popc(m);
+      __syncwarp();
+    }
+    {
+      const int c = lane <= P ? gcount[lane] : 0;
+      const int inc = warp_incl_scan(c, lane);
+      if (lane <= P) grun[lane] = inc - c;
+    }
+    __syncwarp();
+    for (int f0 = 0; f0 < F; f0 += 32) {
+      const int f = f0 + lane;
+      const int key = f < F ? (fanchor[f] == 0xffu ? P : (int)fanchor[f]) : 64 + lane;
+      const unsigned m = __match_any_sync(0xffffffffu, key);
+      const int rank = __popc(m & ((1u << lane) - 1u));
+      if (f < F) ford[grun[key] + rank] = (uint16_t)f;
+      __syncwarp();
+      if (f < F && rank == 0) grun[key] += __popc(m);
+      __syncwarp();
+    }
+    // exclusive prefix of the factor counts in that order
+    int carry = 0;
+    for (int p0 = 0; p0 < F; p0 += 32) {
+      const int p = p0 + lane;
+      const int c = p < F ? __popc(fmask[ford[p]]) : 0;
+      const int inc = warp_incl_scan(c, lane);
+      if (p < F) cexcl[p] = (uint32_t)(carry + inc - c);
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) cexcl[F] = (uint32_t)carry;
+    __syncwarp();
+    // greedy cut into tasks: as many consecutive features as fit TASK_T factors, at most TASK_F, at least one
+    const int tb = task_base(a0r, w, F);
+    int pos = 0, t = 0;
+    while (pos < F) {
+      const int p = pos + lane;
+      const int c = p < F ? (int)(cexcl[p + 1] - cexcl[p]) : 0x10000;
+      const int inc = warp_incl_scan(c, lane);
+      const unsigned okm = __ballot_sync(0xffffffffu, inc <= TASK_T && p < F);
+      int n = okm == 0xffffffffu ? 32 : __ffs(~okm) - 1;
+      n = max(n, 1);
+      n = min(n, F - pos);
+      if (lane == 0) PL.tasks[tb + t] = make_int4(2 * (int)cexcl[pos], 0, pos, n);
+      pos += n, ++t;
+    }
+    if (lane == 0) s_ntasks = t;
+  } else if (warp == 1 && nl > 0) {
+    // line factors ordered by frame, every frame's run padded to an even length
+    bool bad = false;
+    for (int k0 = 0; k0 < nl; k0 += 32) {
+      const int k = k0 + lane;
+      int key = k < nl ? A.lf_frame[b0 + k] : 64 + lane;
+      if (k < nl && (key < 0 || key >= P)) bad = true, key = 96 + lane;
+      const unsigned m = __match_any_sync(0xffffffffu, key);
+      if (k < nl && key < P && (m & ((1u << lane) - 1u)) == 0u) lcount[key] += __popc(m);
+      __syncwarp();
+    }
+    if (__any_sync(0xffffffffu, bad)) {
+      if (lane == 0) s_bad = 1;
+    } else {
+      const int c = lane < P ? ((lcount[lane] + 1) & ~1) : 0;
+      const int inc = warp_incl_scan(c, lane);
+      if (lane < P) {
+        lrun[lane] = inc - c;
+        if (lcount[lane] & 1) lsl[inc - 1] = 0xffffu | ((uint32_t)lane << 16);   // padding slot of this frame
+      }
+      if (lane == 31) s_nlslots = inc;
+      __syncwarp();
+      for (int k0 = 0; k0 < nl; k0 += 32) {
+        const int k = k0 + lane;
+        const int key = k < nl ? A.lf_frame[b0 + k] : 64 + lane;
+        const unsigned m = __match_any_sync(0xffffffffu, key);
+        const int rank = __popc(m & ((1u << lane) - 1u));
+        if (k < nl) lsl[lrun[key] + rank] = (uint32_t)k | ((uint32_t)key << 16);
+        __syncwarp();
+        if (k < nl && rank == 0) lrun[key] += __popc(m);
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+  if (s_bad) {
+    if (tid == 0) {
+      PL.hdr[w] = make_int4(0, 0, 1, 0);
+      atomicOr(PL.any_irregular, 1);
+    }
+    return;
+  }
+  // slots of every task: lane = feature of the task; segments (i, j) in order, padded to even length
+  const int tb = task_base(a0r, w, F), nt = s_ntasks;
+  uint32_t* sl_w = PL.slots + 2 * (size_t)a0r;
+  for (int t = warp; t < nt; t += PT / 32) {
+    int4 tk = PL.tasks[tb + t];
+    const int p = tk.z + lane;
+    const bool on = lane < tk.w;
+    const int l = on ? ford[p] : 0;
+    const uint32_t m = on ? fmask[l] : 0u;
+    const int an = (on && m) ? (int)fanchor[l] : 0xff;
+    if (on) PL.finfo[(size_t)w * F + p] = (uint32_t)l | (m << 16) | ((uint32_t)(an & 15) << 28);
+    uint32_t* sl = sl_w + tk.x;
+    int off = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int i = 0; i < P; ++i) {
+      if (!__any_sync(0xffffffffu, an == i)) continue;
+      for (int j = 0; j < P; ++j) {
+        const bool mine = an == i && ((m >> j) & 1u);
+        const unsigned b = __ballot_sync(0xffffffffu, mine);
+        if (!b) continue;
+        const int n = __popc(b);
+        const uint32_t key = ((uint32_t)i << 21) | ((uint32_t)j << 25);
+        if (mine) sl[off + __popc(b & lt)] = (uint32_t)fid[l * P + j] | ((uint32_t)lane << 16) | key;
+        if ((n & 1) && lane == 0) sl[off + n] = 0xffffu | key;
+        off += (n + 1) & ~1;
+      }
+    }
+    if (lane == 0) PL.tasks[tb + t].y = off;
+  }
+  if (tid == 0) PL.hdr[w] = make_int4(nt, s_nlslots, 0, 0);
+}
+
+// ------------------------------------------------------------------------------------------------ scatter tables
+// The Gram matrix of U = [A(0-2) | a_rot(3-5) | b_rot(6-8) | Z(9-14) | r(15)] lives in three 8x8 tiles (rows 0-7 x
+// cols 0-7, rows 0-7 x cols 8-15, rows 8-15 x cols 8-15).  A table entry sends patch[src] (tile*64 + row*8 + col) to
+// one destination: kind selects the block (lo = min(i,j) role, hi role, extrinsic), off the entry inside it.
+enum Kind { K_LL = 0, K_HH, K_LH, K_LE, K_HE, K_EE, K_BL, K_BH, K_BE, K_NKIND };
+
+struct Tables {
+  uint32_t seg[128];   // per segment: hi-role blocks and the (lo,hi) block (99 entries)
+  uint32_t lo[96];     // per anchor change: lo-role and extrinsic blocks (90 entries)
+  uint32_t line[32];   // line factors of one frame: (p,p) upper + b_p (27 entries)
+};
+
+constexpr uint32_t tab_entry(int R, int C, int kind, int off, bool neg) {
+  const int tile = (R < 8 && C < 8) ? 0 : (R < 8 ? 1 : 2);
+  return 0x80000000u | (uint32_t)(tile * 64 + (R & 7) * 8 + (C & 7)) | ((uint32_t)kind << 8) | ((uint32_t)off << 12) |
+         (neg ? (1u << 18) : 0u);
+}
+
+constexpr Tables make_tables() {
+  Tables T{};
+  int ns = 0, nlo = 0, nli = 0;
+  // columns: A r = 0..2, X (a_rot) 3..5, B (b_rot) 6..8, Z 9..14, res 15
+  for (int r = 0; r < 3; ++r) {
+    for (int c = r; c < 3; ++c) {   // (A_r, A_c)
+      T.lo[nlo++] = tab_entry(r, c, K_LL, r * 6 + c, false);
+      T.seg[ns++] = tab_entry(r, c, K_HH, r * 6 + c, false);
+      T.seg[ns++] = tab_entry(r, c, K_LH, r * 6 + c, true);
+      if (r != c) T.seg[ns++] = tab_entry(r, c, K_LH, c * 6 + r, true);
+    }
+    for (int c = 0; c < 3; ++c) {
+      T.lo[nlo++] = tab_entry(r, 3 + c, K_LL, r * 6 + 3 + c, false);       // (A_r, X_c)
+      T.seg[ns++] = tab_entry(r, 3 + c, K_LH, (3 + c) * 6 + r, true);
+      T.seg[ns++] = tab_entry(r, 6 + c, K_LH, r * 6 + 3 + c, false);       // (A_r, B_c)
+      T.seg[ns++] = tab_entry(r, 6 + c, K_HH, r * 6 + 3 + c, true);
+    }
+    for (int c = 0; c < 6; ++c) {                                          // (A_r, Z_c)
+      T.lo[nlo++] = tab_entry(r, 9 + c, K_LE, r * 6 + c, false);
+      T.seg[ns++] = tab_entry(r, 9 + c, K_HE, r * 6 + c, true);
+    }
+    T.lo[nlo++] = tab_entry(r, 15, K_BL, r, false);                        // (A_r, res)
+    T.seg[ns++] = tab_entry(r, 15, K_BH, r, true);
+  }
+  for (int r = 0; r < 3; ++r) {
+    for (int c = r; c < 3; ++c) T.lo[nlo++] = tab_entry(3 + r, 3 + c, K_LL, (3 + r) * 6 + 3 + c, false);   // (X, X)
+    for (int c = 0; c < 3; ++c) T.seg[ns++] = tab_entry(3 + r, 6 + c, K_LH, (3 + r) * 6 + 3 + c, false);   // (X, B)
+    for (int c = 0; c < 6; ++c) T.lo[nlo++] = tab_entry(3 + r, 9 + c, K_LE, (3 + r) * 6 + c, false);       // (X, Z)
+    T.lo[nlo++] = tab_entry(3 + r, 15, K_BL, 3 + r, false);
+  }
+  for (int r = 0; r < 3; ++r) {
+    for (int c = r; c < 3; ++c) T.seg[ns++] = tab_entry(6 + r, 6 + c, K_HH, (3 + r) * 6 + 3 + c, false);   // (B, B)
+    for (int c = 0; c < 6; ++c) T.seg[ns++] = tab_entry(6 + r, 9 + c, K_HE, (3 + r) * 6 + c, false);       // (B, Z)
+    T.seg[ns++] = tab_entry(6 + r, 15, K_BH, 3 + r, false);
+  }
+  for (int r = 0; r < 6; ++r) {
+    for (int c = r; c < 6; ++c) T.lo[nlo++] = tab_entry(9 + r, 9 + c, K_EE, r * 6 + c, false);             // (Z, Z)
+    T.lo[nlo++] = tab_entry(9 + r, 15, K_BE, r, false);
+  }
+  // line factors: columns 0..5 = J, 6 = residual (tile 0 only)
+  for (int r = 0; r < 6; ++r) {
+    for (int c = r; c < 6; ++c) T.line[nli++] = tab_entry(r, c, K_LL, r * 6 + c, false);
+    T.line[nli++] = tab_entry(r, 6, K_BL, r, false);
+  }
+  return T;
+}
+__constant__ Tables c_tables = make_tables();
+static_assert(make_tables().seg[98] != 0u && make_tables().seg[99] == 0u, "99 per-segment destinations");
+static_assert(make_tables().lo[89] != 0u && make_tables().lo[90] == 0u, "90 per-anchor destinations");
+static_assert(make_tables().line[26] != 0u && make_tables().line[27] == 0u, "27 line destinations");
+
+// ------------------------------------------------------------------------------------------------ device helpers
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// index of block (br, bc), br <= bc, in the block-upper layout with NB blocks per side
+__device__ __forceinline__ int blk(int br, int bc, int NB) { return br * NB - (br * (br - 1)) / 2 + (bc - br); }
+
+// stage: 16 records x 16 units (unit = one column as (row 0, row 1), 16 bytes).  Unit c of record f sits at
+// f*16 + (c ^ swz(f)) so that the half-warp record stores and the LDS.64 fragment loads are both conflict-free.
+__device__ __forceinline__ int swz(int f) { return ((f & 1) << 2) ^ ((f >> 1) & 3); }
+
+template <int ROUNDS>
+__device__ __forceinline__ void scatter(const double* __restrict__ patch, const uint32_t (&tab)[ROUNDS], double* __restrict__ Hc,
+                                        int mybase) {
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const uint32_t e = tab[r];
+    const int base = __shfl_sync(0xffffffffu, mybase, (e >> 8) & 15);
+    if (e >> 31) {
+      const double v = patch[e & 0xff];
+      atomicAdd(&Hc[base + ((e >> 12) & 63)], ((e >> 18) & 1u) ? -v : v);
+    }
+  }
+}
+
+// lane k < K_NKIND: offset of destination kind k in the block-upper accumulator for segment (lo, hi)
+__device__ __forceinline__ int kind_base(int lane, int lo, int hi, int NB, int boff) {
+  const int e = NB - 1;
+  switch (lane) {
+    case K_LL: return blk(lo, lo, NB) * 36;
+    case K_HH: return blk(hi, hi, NB) * 36;
+    case K_LH: return blk(lo, hi, NB) * 36;
+    case K_LE: return blk(lo, e, NB) * 36;
+    case K_HE: return blk(hi, e, NB) * 36;
+    case K_EE: return blk(e, e, NB) * 36;
+    case K_BL: return boff + 6 * lo;
+    case K_BH: return boff + 6 * hi;
+    case K_BE: return boff + 6 * e;
+    default: return 0;
+  }
+}
+
+__device__ __forceinline__ void put_patch(double* __restrict__ patch, int lane, const double (&G)[6]) {
+  // lane holds rows g = lane>>2, columns 2*(lane&3) + {0,1} of each tile
+  double2* p2 = reinterpret_cast<double2*>(patch);
+  const int o = (lane >> 2) * 4 + (lane & 3);
+  p2[o] = make_double2(G[0], G[1]);
+  p2[32 + o] = make_double2(G[2], G[3]);
+  p2[64 + o] = make_double2(G[4], G[5]);
+}
+
+// ------------------------------------------------------------------------------------------------ assemble
+template <bool MODE_A>
+__global__ void __launch_bounds__(AW * 32, 2) assemble_kernel(LinearizeArgs A, PlanPtrs PL, int use_tma) {
+  extern __shared__ __align__(16) unsigned char asm_raw[];
+  __shared__ int s_next;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, w = blockIdx.x;
+  const int P = A.P, F = A.F, D = A.D, NB = P + 1;
+  const int nblk = NB * (NB + 1) / 2, boff = nblk * 36;
+  const int hc_n = (boff + D + 1) & ~1;
+  const int cstride = P * kPoseCache + kExCache;
+  double* __restrict__ Hc = reinterpret_cast<double*>(asm_raw);
+  double* __restrict__ cache = Hc + hc_n;
+  double* __restrict__ work0 = cache + cstride;
+  double* __restrict__ stage = work0 + warp * WORK_D;
+  double* __restrict__ lacc = stage + 512;
+  double* __restrict__ patch = lacc + 448;
+
+  const int4 hdr = PL.hdr[w];
+  const int a0 = A.pf_window_offset[w];
+  const int b0 = A.NL > 0 ? A.lf_window_offset[w] : 0;
+  double* __restrict__ Hpp = A.out.H_pp + (size_t)w * D * D;
+  double* __restrict__ Hlp = A.out.H_lp + (size_t)w * F * D;
+  double* __restrict__ Hll = A.out.H_ll + (size_t)w * F;
+  double* __restrict__ bp = A.out.b_p + (size_t)w * D;
+  double* __restrict__ bl = A.out.b_l + (size_t)w * F;
+  if (hdr.z) {   // irregular window: zero here, irregular_kernel adds with global atomics
+    for (int e = tid; e < D * D; e += AW * 32) Hpp[e] = 0.0;
+    for (int e = tid; e < F * D; e += AW * 32) Hlp[e] = 0.0;
+    for (int e = tid; e < F; e += AW * 32) Hll[e] = 0.0, bl[e] = 0.0;
+    for (int e = tid; e < D; e += AW * 32) bp[e] = 0.0;
+    return;
+  }
+  for (int e = tid; e < hc_n; e += AW * 32) Hc[e] = 0.0;
+  {
+    const double* __restrict__ gc = A.cache + (size_t)w * cstride;
+    for (int e = tid; e < cstride; e += AW * 32) cache[e] = gc[e];
+  }
+  if (tid == 0) s_next = 0;
+  uint32_t tab_seg[4], tab_lo[3], tab_line[1];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) tab_seg[r] = c_tables.seg[32 * r + lane];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) tab_lo[r] = c_tables.lo[32 * r + lane];
+  tab_line[0] = c_tables.line[lane];
+  __syncthreads();
+
+  const int ntask = hdr.x, nlsl = hdr.y, nltask = (nlsl + LTASK - 1) / LTASK;
+  const int tb = task_base(a0 - (int)A.pf_begin, w, F);
+  const uint32_t* __restrict__ sl_w = PL.slots + 2 * (size_t)(a0 - (int)A.pf_begin);
+  const uint32_t* __restrict__ lsl_w = PL.lslots + 2 * (size_t)(b0 - (int)A.lf_begin);
+  // fragment geometry of mma.m8n8k4: lane (g, kk) holds column g of row kk&1 of factor kk>>1 (A and B operand alike)
+  const int g = lane >> 2, kk = lane & 3;
+  const unsigned full = 0xffffffffu;
+
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&s_next, 1);
+    t = __shfl_sync(full, t, 0);
+    if (t >= ntask + nltask) break;
+    if (t < ntask) {
+      // ================================================================== point task
+      const int4 tk = PL.tasks[tb + t];
+      const int n_slots = tk.y, n_feats = tk.w;
+      const uint32_t fi = lane < n_feats ? PL.finfo[(size_t)w * F + tk.z + lane] : 0u;
+      {
+        double2* z = reinterpret_cast<double2*>(lacc);
+#pragma unroll
+        for (int q = 0; q < 7; ++q) z[q * 32 + lane] = make_double2(0.0, 0.0);
+      }
+      __syncwarp();
+      const uint32_t* __restrict__ sl = sl_w + tk.x;
+      double G[6] = {0, 0, 0, 0, 0, 0}, R[6] = {0, 0, 0, 0, 0, 0};
+      uint32_t nsw = lane < n_slots ? sl[lane] : 0xffffu;
+      for (int c0 = 0; c0 < n_slots; c0 += 32) {
+        const uint32_t sw_ = nsw;
+        nsw = c0 + 32 + lane < n_slots ? sl[c0 + 32 + lane] : 0xffffu;
+        const bool valid = (sw_ & 0xffffu) != 0xffffu;
+        const int lf = (sw_ >> 16) & 31, i = (sw_ >> 21) & 15, j = (sw_ >> 25) & 15;
+        const int l = __shfl_sync(full, fi, lf) & 0xffff;
+        PointJac J;
+        if (valid) {
+          const int64_t k = (int64_t)a0 + (sw_ & 0xffffu);
+          const double4 ob = reinterpret_cast<const double4*>(A.pf_obs)[k];
+          const double piz = A.pf_pts_i_z ? A.pf_pts_i_z[k] : 1.0;
+          const double lam = A.inv_depth[(size_t)w * F + l];
+          eval_point(A, cache, i, j, lam, ob.x, ob.y, piz, ob.z, ob.w, J);
+          if (MODE_A) {
+            if (A.out.pf_residual) reinterpret_cast<double2*>(A.out.pf_residual)[k] = make_double2(J.r[0], J.r[1]);
+            if (A.out.pf_jac_pose_i) store_jac7(A.out.pf_jac_pose_i + 14 * k, J.a);
+            if (A.out.pf_jac_pose_j) store_jac7(A.out.pf_jac_pose_j + 14 * k, J.b);
+            if (A.out.pf_jac_ex) store_jac7(A.out.pf_jac_ex + 14 * k, J.c);
+            if (A.out.pf_jac_feat) reinterpret_cast<double2*>(A.out.pf_jac_feat)[k] = make_double2(J.d[0], J.d[1]);
+          }
+          // the factor's own block of the landmark row: d^T J_j  (unique per (feature, j))
+          double2* row = reinterpret_cast<double2*>(Hlp + (size_t)l * D + 6 * j);
+          row[0] = make_double2(J.d[0] * J.b[0][0] + J.d[1] * J.b[1][0], J.d[0] * J.b[0][1] + J.d[1] * J.b[1][1]);
+          row[1] = make_double2(J.d[0] * J.b[0][2] + J.d[1] * J.b[1][2], J.d[0] * J.b[0][3] + J.d[1] * J.b[1][3]);
+          row[2] = make_double2(J.d[0] * J.b[0][4] + J.d[1] * J.b[1][4], J.d[0] * J.b[0][5] + J.d[1] * J.b[1][5]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) J.a[0][c] = J.a[1][c] = J.b[0][c] = J.b[1][c] = J.c[0][c] = J.c[1][c] = 0.0;
+          J.r[0] = J.r[1] = J.d[0] = J.d[1] = 0.0;
+        }
+        // landmark row sums: lanes of one segment have distinct features; lanes that share a feature take turns
+        {
+          const unsigned grp = __match_any_sync(full, valid ? lf : 32 + lane);
+          const int rank = __popc(grp & ((1u << lane) - 1u));
+          const int rounds = __reduce_max_sync(full, valid ? __popc(grp) : 0);
+          double* __restrict__ la = lacc + lf * LACC_W;
+          for (int r = 0; r < rounds; ++r) {
+            if (valid && rank == r) {
+#pragma unroll
+              for (int c = 0; c < 6; ++c) {
+                la[c] += J.d[0] * J.a[0][c] + J.d[1] * J.a[1][c];
+                la[6 + c] += J.d[0] * J.c[0][c] + J.d[1] * J.c[1][c];
+              }
+              la[12] += J.d[0] * J.d[0] + J.d[1] * J.d[1];
+              la[13] += J.d[0] * J.r[0] + J.d[1] * J.r[1];
+            }
+            __syncwarp();
+          }
+        }
+        // segment ends: bit q of bnd = the slot after lane q belongs to another segment (or the task ends)
+        const uint32_t key = sw_ >> 21;
+        uint32_t nk = __shfl_down_sync(full, key, 1);
+        const uint32_t nk31 = __shfl_sync(full, nsw >> 21, 0);
+        if (lane == 31) nk = nk31;
+        if (c0 + lane + 1 >= n_slots) nk = 0xffffffffu;
+        const unsigned bnd = __ballot_sync(full, key != nk);
+        const bool swp = i > j;   // lo role is pose j
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          if (c0 + 16 * h >= n_slots) break;
+          if ((lane >> 4) == h) {
+            const int f = lane & 15, sx = swz(f);
+            double2* rec = reinterpret_cast<double2*>(stage) + f * 16;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) rec[c ^ sx] = swp ? make_double2(J.b[0][c], J.b[1][c]) : make_double2(J.a[0][c], J.a[1][c]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              rec[(6 + c) ^ sx] = swp ? make_double2(J.a[0][3 + c], J.a[1][3 + c]) : make_double2(J.b[0][3 + c], J.b[1][3 + c]);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) rec[(9 + c) ^ sx] = make_double2(J.c[0][c], J.c[1][c]);
+            rec[15 ^ sx] = make_double2(J.r[0], J.r[1]);
+          }
+          __syncwarp();
+#pragma unroll 1
+          for (int s = 0; s < 8; ++s) {
+            const int la_ = 16 * h + 2 * s;
+            if (c0 + la_ >= n_slots) break;
+            const int f = 2 * s + (kk >> 1), sx = swz(f);
+            const double* __restrict__ rec = stage + f * 32 + (kk & 1);
+            const double u0 = rec[2 * (g ^ sx)], u1 = rec[2 * ((8 + g) ^ sx)];
+            dmma(G[0], G[1], u0, u0);
+            dmma(G[2], G[3], u0, u1);
+            dmma(G[4], G[5], u1, u1);
+            if ((bnd >> (la_ + 1)) & 1u) {
+              const uint32_t kseg = __shfl_sync(full, key, la_), knext = __shfl_sync(full, nk, la_ + 1);
+              const int si = kseg & 15, sj = (kseg >> 4) & 15;
+              const int lo = min(si, sj), hi = max(si, sj);
+              const int mybase = kind_base(lane, lo, hi, NB, boff);
+              put_patch(patch, lane, G);
+              __syncwarp();
+              scatter<4>(patch, tab_seg, Hc, mybase);
+#pragma unroll
+              for (int q = 0; q < 6; ++q) R[q] += G[q], G[q] = 0.0;
+              const bool lo_ends = knext == 0xffffffffu || min((int)(knext & 15), (int)((knext >> 4) & 15)) != lo;
+              if (lo_ends) {
+                __syncwarp();
+                put_patch(patch, lane, R);
+                __syncwarp();
+                scatter<3>(patch, tab_lo, Hc, mybase);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) R[q] = 0.0;
+              }
+              __syncwarp();
+            }
+          }
+          __syncwarp();
+        }
+      }
+      // rows of the task's features: anchor block, extrinsic block, structural zeros (the observing frames' blocks
+      // were written by the factors), H_ll, b_l
+      __syncwarp();
+      {
+        const int upr = 3 * NB, total = n_feats * upr;
+        for (int idx0 = 0; idx0 < total; idx0 += 32) {
+          const int idx = idx0 + lane;
+          const int f = min(idx / upr, n_feats - 1), u = idx - (idx / upr) * upr;
+          const uint32_t info = __shfl_sync(full, fi, f);
+          if (idx < total) {
+            const int l = info & 0xffff, b = u / 3, part = u - 3 * b;
+            const uint32_t m = (info >> 16) & 0xfffu;
+            const int an = m ? (int)(info >> 28) : -1;
+            double2* dst = reinterpret_cast<double2*>(Hlp + (size_t)l * D) + u;
+            const double* __restrict__ la = lacc + f * LACC_W;
+            if (b == an) *dst = make_double2(la[2 * part], la[2 * part + 1]);
+            else if (b == P) *dst = make_double2(la[6 + 2 * part], la[6 + 2 * part + 1]);
+            else if (!((m >> b) & 1u)) *dst = make_double2(0.0, 0.0);
+          }
+        }
+        if (lane < n_feats) {
+          const int l = fi & 0xffff;
+          Hll[l] = lacc[lane * LACC_W + 12];
+          bl[l] = lacc[lane * LACC_W + 13];
+        }
+      }
+      __syncwarp();
+    } else {
+      // ================================================================== line task
+      const int t0 = (t - ntask) * LTASK, n_slots = min(LTASK, nlsl - t0);
+      const uint32_t* __restrict__ sl = lsl_w + t0;
+      double G[6] = {0, 0, 0, 0, 0, 0};
+      uint32_t nsw = lane < n_slots ? sl[lane] : 0xffffu;
+      for (int c0 = 0; c0 < n_slots; c0 += 32) {
+        const uint32_t sw_ = nsw;
+        nsw = c0 + 32 + lane < n_slots ? sl[c0 + 32 + lane] : 0xffffu;
+        const bool valid = (sw_ & 0xffffu) != 0xffffu;
+        const int frame = (sw_ >> 16) & 0xff;
+        LineJac J;
+        if (valid) {
+          const int64_t k = (int64_t)b0 + (sw_ & 0xffffu);
+          double g9[9];
+#pragma unroll
+          for (int c = 0; c < 9; ++c) g9[c] = A.lf_geom[(size_t)c * A.NL_stride + k];
+          eval_line(A, cache, frame, g9, J);
+          if (MODE_A) {
+            if (A.out.lf_residual) reinterpret_cast<double2*>(A.out.lf_residual)[k] = make_double2(J.r[0], J.r[1]);
+            if (A.out.lf_jac_pose) store_jac7(A.out.lf_jac_pose + 14 * k, J.a);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) J.a[0][c] = J.a[1][c] = 0.0;
+          J.r[0] = J.r[1] = 0.0;
+        }
+        const uint32_t key = sw_ >> 16;
+        uint32_t nk = __shfl_down_sync(full, key, 1);
+        const uint32_t nk31 = __shfl_sync(full, nsw >> 16, 0);
+        if (lane == 31) nk = nk31;
+        if (c0 + lane + 1 >= n_slots) nk = 0xffffffffu;
+        const unsigned bnd = __ballot_sync(full, key != nk);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          if (c0 + 16 * h >= n_slots) break;
+          if ((lane >> 4) == h) {
+            const int f = lane & 15, sx = swz(f);
+            double2* rec = reinterpret_cast<double2*>(stage) + f * 16;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) rec[c ^ sx] = make_double2(J.a[0][c], J.a[1][c]);
+            rec[6 ^ sx] = make_double2(J.r[0], J.r[1]);
+            rec[7 ^ sx] = make_double2(0.0, 0.0);
+          }
+          __syncwarp();
+#pragma unroll 1
+          for (int s = 0; s < 8; ++s) {
+            const int la_ = 16 * h + 2 * s;
+            if (c0 + la_ >= n_slots) break;
+            const int f = 2 * s + (kk >> 1), sx = swz(f);
+            const double u0 = stage[f * 32 + (kk & 1) + 2 * (g ^ sx)];
+            dmma(G[0], G[1], u0, u0);
+            if ((bnd >> (la_ + 1)) & 1u) {
+              const int fr = __shfl_sync(full, key, la_) & 0xff;
+              const int mybase = kind_base(lane, fr, fr, NB, boff);
+              put_patch(patch, lane, G);
+              __syncwarp();
+              scatter<1>(patch, tab_line, Hc, mybase);
+              G[0] = G[1] = 0.0;
+              __syncwarp();
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // expand the block-upper accumulator to the full symmetric matrix (+ b_p behind it) in the warps' work areas
+  double* __restrict__ Hf = work0;
+  for (int e = tid; e < D * D; e += AW * 32) {
+    const int r = e / D, c = e - r * D;
+    const int br = r / 6, bc = c / 6, rr = r - 6 * br, cc = c - 6 * bc;
+    double v;
+    if (br < bc) v = Hc[blk(br, bc, NB) * 36 + rr * 6 + cc];
+    else if (br > bc) v = Hc[blk(bc, br, NB) * 36 + cc * 6 + rr];
+    else v = Hc[blk(br, br, NB) * 36 + (rr <= cc ? rr * 6 + cc : cc * 6 + rr)];
+    Hf[e] = v;
+  }
+  for (int e = tid; e < D; e += AW * 32) Hf[D * D + e] = Hc[boff + e];
+  if (use_tma) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(Hf);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(Hpp), "r"(s0), "r"((uint32_t)(D * D * 8))
+                   : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(bp), "r"(s0 + (uint32_t)(D * D * 8)),
+                   "r"((uint32_t)(D * 8))
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  } else {
+    __syncthreads();
+    for (int e = tid; e < D * D; e += AW * 32) Hpp[e] = Hf[e];
+    for (int e = tid; e < D; e += AW * 32) bp[e] = Hf[D * D + e];
+  }
+}
+
+// Windows the plan rejected (a feature with two anchors, a repeated (feature, j), i == j, indices out of range):
+// every factor adds its blocks with global atomics onto the zeros assemble_kernel wrote.  Exits at once when the
+// batch has no such window.
+template <bool MODE_A>
+__global__ void __launch_bounds__(128) irregular_kernel(LinearizeArgs A, PlanPtrs PL) {
+  if (!*PL.any_irregular) return;
+  const int cstride = A.P * kPoseCache + kExCache;
+  for (int w = blockIdx.x; w < A.W; w += gridDim.x) {
+    if (!PL.hdr[w].z) continue;
+    const double* cw = A.cache + (size_t)w * cstride;
+    const int a0 = A.pf_window_offset[w], a1 = A.pf_window_offset[w + 1];
+    for (int64_t k = a0 + threadIdx.x; k < a1; k += blockDim.x) {
+      const uint32_t pk = A.pf_idx[k];
+      const int i = pk & 0xff, j = (pk >> 8) & 0xff, f = pk >> 16;
+      if (i >= A.P || j >= A.P || f >= A.F) continue;   // out-of-range indices are dropped, never dereferenced
+      const double4 ob = reinterpret_cast<const double4*>(A.pf_obs)[k];
+      const double piz = A.pf_pts_i_z ? A.pf_pts_i_z[k] : 1.0;
+      PointJac J;
+      eval_point(A, cw, i, j, A.inv_depth[(size_t)w * A.F + f], ob.x, ob.y, piz, ob.z, ob.w, J);
+      if (MODE_A) {
+        if (A.out.pf_residual) reinterpret_cast<double2*>(A.out.pf_residual)[k] = make_double2(J.r[0], J.r[1]);
+        if (A.out.pf_jac_pose_i) store_jac7(A.out.pf_jac_pose_i + 14 * k, J.a);
+        if (A.out.pf_jac_pose_j) store_jac7(A.out.pf_jac_pose_j + 14 * k, J.b);
+        if (A.out.pf_jac_ex) store_jac7(A.out.pf_jac_ex + 14 * k, J.c);
+        if (A.out.pf_jac_feat) reinterpret_cast<double2*>(A.out.pf_jac_feat)[k] = make_double2(J.d[0], J.d[1]);
+      }
+      point_atomics(A, w, i, j, f, J);
+    }
+    if (A.NL > 0) {
+      const int b0 = A.lf_window_offset[w], b1 = A.lf_window_offset[w + 1];
+      for (int64_t k = b0 + threadIdx.x; k < b1; k += blockDim.x) {
+        const int frame = A.lf_frame[k];
+        if (frame < 0 || frame >= A.P) continue;
+        double g9[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) g9[c] = A.lf_geom[(size_t)c * A.NL_stride + k];
+        LineJac J;
+        eval_line(A, cw, frame, g9, J);
+        if (MODE_A) {
+          if (A.out.lf_residual) reinterpret_cast<double2*>(A.out.lf_residual)[k] = make_double2(J.r[0], J.r[1]);
+          if (A.out.lf_jac_pose) store_jac7(A.out.lf_jac_pose + 14 * k, J.a);
+        }
+        line_atomics(A, w, frame, J);
+      }
+    }
+  }
+}
+
+}  // namespace stream

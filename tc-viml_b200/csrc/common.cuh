@@ -67,6 +67,7 @@ struct viml_ctx {
   // prior map, six SoA planes of n_map doubles
   double* d_map = nullptr;
   int64_t n_map = 0;
+  bool map_set = false;   // viml_set_map was called (an empty map is legal)
   // spatially sorted copy for the hierarchical cull: Morton order of segment mid-points, tiles of kMapTile
   // lines with a bounding sphere each (centre xyz + radius), and the original index of every sorted line
   double* d_map_sorted = nullptr;   // [6][n_map]
@@ -85,7 +86,7 @@ struct viml_ctx {
 
 enum KernelId {
   K_PREP = 0, K_POINTS, K_LINES, K_ASSEMBLE, K_SCHUR, K_CAMPOSE, K_CULL, K_SCAN, K_FILL, K_PROJECT, K_MATCH,
-  K_MARG, K_MICRO, K_PLAN, K_COUNT
+  K_MARG, K_MICRO, K_PLAN, K_IRREGULAR, K_COUNT
 };
 static_assert(K_COUNT <= VIML_NUM_KERNELS, "raise VIML_NUM_KERNELS");
 
@@ -140,11 +141,9 @@ struct LinearizeArgs {  // device pointers only
   const int32_t* lf_frame;
   const double* lf_geom;
   double* cache;  // [W][P*kPoseCache + kExCache]
-  uint16_t* plan;  // fused kernel: per-window sort plan written by plan_kernel (launcher scratch), or nullptr
   viml_linearize_out out;
   double sqrt_info, cauchy_a, inv_cauchy_a2, fx, fy, cx, cy;
   uint32_t flags;
-  long long* dbg;  // optional per-CTA phase cycle counters (VIML_PHASE_TIMERS=1), else nullptr
 };
 
 // linearize_kernels.cu

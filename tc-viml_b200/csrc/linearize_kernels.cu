@@ -361,6 +361,17 @@ __device__ __forceinline__ void point_atomics(const LinearizeArgs& A, int w, int
   atomicAdd(A.out.b_l + (size_t)w * A.F + f, J.d[0] * J.r[0] + J.d[1] * J.r[1]);
 }
 
+// Generic accumulation of one line factor: (frame, frame) block and b.
+__device__ __forceinline__ void line_atomics(const LinearizeArgs& A, int w, int frame, const LineJac& J) {
+  const int D = A.D;
+  double* H = A.out.H_pp + (size_t)w * D * D;
+  double* bp = A.out.b_p + (size_t)w * D;
+  const int of = 6 * frame;
+  atomic_block(H, D, of, of, J.a, J.a, true);
+#pragma unroll
+  for (int r = 0; r < 6; ++r) atomicAdd(bp + of + r, J.a[0][r] * J.r[0] + J.a[1][r] * J.r[1]);
+}
+
 template <bool MODE_A, bool MODE_B>
 #ifndef VIML_POINTS_MINB
 #define VIML_POINTS_MINB 4
@@ -419,18 +430,10 @@ __global__ void __launch_bounds__(128) lines_kernel(LinearizeArgs A) {
     if (A.out.lf_jac_pose)
       store_jac7_coalesced(stage + (threadIdx.x >> 5) * 7 * 32, A.out.lf_jac_pose + 14 * k_warp, J.a, lane, nvalid);
   }
-  if (MODE_B && live) {
-    const int D = A.D;
-    double* H = A.out.H_pp + (size_t)w * D * D;
-    double* bp = A.out.b_p + (size_t)w * D;
-    const int of = 6 * frame;
-    atomic_block(H, D, of, of, J.a, J.a, true);
-#pragma unroll
-    for (int r = 0; r < 6; ++r) atomicAdd(bp + of + r, J.a[0][r] * J.r[0] + J.a[1][r] * J.r[1]);
-  }
+  if (MODE_B && live) line_atomics(A, w, frame, J);
 }
 
-#include "assemble.cuh"
+#include "assemble2.cuh"
 
 }  // namespace
 
@@ -438,19 +441,31 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
   cudaStream_t st = ctx->stream;
   const bool modeA = (a.flags & VIML_OUT_RESIDUAL_JACOBIAN) != 0;
   const bool modeB = (a.flags & (VIML_OUT_HB | VIML_OUT_SCHUR)) != 0;
-  const bool fast = modeB && a.P <= fused::PMAX && !ctx->force_generic;
-  const bool bigf = a.F > fused::FMAX;
-  // The window sorts (plan_kernel) depend on the factor indices only, the pose cache (prep_windows_kernel) on the states
-  // only: the two short kernels run side by side on two streams and meet before the fused kernel.
-  uint16_t* plan = nullptr;
-  if (fast && !bigf && !getenv("VIML_NO_PLAN")) {
-    VIML_TRY_CUDA(ctx, ctx->scratch3.reserve(DeviceArena::padded((size_t)a.W * fused::kPlanStride * sizeof(uint16_t))));
-    plan = ctx->scratch3.take<uint16_t>((size_t)a.W * fused::kPlanStride);
+  // fused path: plan_kernel + assemble_kernel (assemble2.cuh); anything outside its static limits goes through the
+  // generic atomic kernels
+  const size_t plan_smem = (size_t)a.F * 8 + ((size_t)a.F + 1) * 4 + (((size_t)a.F + 1) & ~(size_t)1) * 2 + (size_t)a.F * a.P * 2 + 16;
+  const bool fast = modeB && a.P <= stream::PMAX && a.F <= stream::FMAXP && plan_smem <= 200 * 1024 && !ctx->force_generic;
+  stream::PlanPtrs PL{};
+  if (fast) {
+    const size_t n_tasks = (size_t)a.NP / 64 + (size_t)a.W * (a.F / stream::TASK_F + 2) + 2;
+    auto pad = [](size_t b) { return DeviceArena::padded(b); };
+    VIML_TRY_CUDA(ctx, ctx->scratch3.reserve(pad((size_t)a.W * 16) + pad(n_tasks * 16) + pad((size_t)a.NP * 8 + 8) +
+                                             pad((size_t)a.W * a.F * 4 + 4) + pad((size_t)a.NL * 8 + 8) + pad(4)));
+    PL.hdr = ctx->scratch3.take<int4>((size_t)a.W);
+    PL.tasks = ctx->scratch3.take<int4>(n_tasks);
+    PL.slots = ctx->scratch3.take<uint32_t>((size_t)a.NP * 2 + 2);
+    PL.finfo = ctx->scratch3.take<uint32_t>((size_t)a.W * a.F + 1);
+    PL.lslots = ctx->scratch3.take<uint32_t>((size_t)a.NL * 2 + 2);
+    PL.any_irregular = ctx->scratch3.take<int>(1);
+    // the plan depends on the factor indices only, the pose cache (prep_windows_kernel) on the states only: the two
+    // short kernels run side by side on two streams and meet before the fused kernel
     VIML_TRY_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
     VIML_TRY_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    VIML_TRY_CUDA(ctx, cudaMemsetAsync(PL.any_irregular, 0, 4, ctx->aux_stream));
+    VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(stream::plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem));
     {
       LaunchScope ls(ctx, K_PLAN, ctx->aux_stream);
-      fused::plan_kernel<<<a.W, fused::AT, 0, ctx->aux_stream>>>(a, plan);
+      stream::plan_kernel<<<a.W, stream::PT, plan_smem, ctx->aux_stream>>>(a, PL);
     }
     VIML_TRY_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
   }
@@ -459,83 +474,49 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
     LaunchScope ls(ctx, K_PREP);
     prep_windows_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a);
   }
-  if (plan) VIML_TRY_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
   if (fast) {
-    // fused CTA-per-window kernel: writes every H/b entry exactly once (no memset), r/J too when asked
-    const size_t smem = sizeof(fused::Smem);
-    static bool attr_done = false;
-    if (!attr_done) {
-      VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(fused::assemble_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(fused::assemble_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(fused::assemble_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(fused::assemble_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_done = true;
-    }
-    if (bigf) {  // landmark rows are accumulated with REDs: they start from zero
-      const size_t W = a.W, D = a.D, F = a.F;
-      VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.H_lp, 0, W * F * D * sizeof(double), st));
-      VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.H_ll, 0, W * F * sizeof(double), st));
-      VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.b_l, 0, W * F * sizeof(double), st));
-    }
-    const int grid = a.W < ctx->sm_count ? a.W : ctx->sm_count;   // persistent: one CTA per SM
-    LinearizeArgs a2 = a;
-    a2.plan = plan;
-    long long* dbg = nullptr;
-    if (getenv("VIML_PHASE_TIMERS")) {
-      cudaMalloc((void**)&dbg, sizeof(long long) * 22 * grid);
-      cudaMemsetAsync(dbg, 0, sizeof(long long) * 22 * grid, st);
-    }
-    a2.dbg = dbg;
-    for (int wb = 0; wb < a.W; wb += fused::WSLOTS * grid) {   // <= WSLOTS windows per CTA per launch
-      const int we = a.W < wb + fused::WSLOTS * grid ? a.W : wb + fused::WSLOTS * grid;
+    VIML_TRY_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    // one CTA per window, two CTAs per SM; every H/b entry is written exactly once (no memset)
+    const int NB = a.P + 1, nblk = NB * (NB + 1) / 2;
+    const size_t smem = ((size_t)((nblk * 36 + a.D + 1) & ~1) + (size_t)a.P * kPoseCache + kExCache + (size_t)stream::AW * stream::WORK_D) * 8;
+    const int use_tma = ((((uintptr_t)a.out.H_pp) | ((uintptr_t)a.out.b_p)) & 15) == 0 ? 1 : 0;
+    // the attribute is per device: set on every call (a process may hold contexts on several devices)
+    VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(stream::assemble_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(stream::assemble_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
       LaunchScope ls(ctx, K_ASSEMBLE);
-      if (modeA && bigf) fused::assemble_kernel<true, true><<<grid, fused::AT, smem, st>>>(a2, wb, we);
-      else if (modeA) fused::assemble_kernel<true, false><<<grid, fused::AT, smem, st>>>(a2, wb, we);
-      else if (bigf) fused::assemble_kernel<false, true><<<grid, fused::AT, smem, st>>>(a2, wb, we);
-      else fused::assemble_kernel<false, false><<<grid, fused::AT, smem, st>>>(a2, wb, we);
+      if (modeA) stream::assemble_kernel<true><<<a.W, stream::AW * 32, smem, st>>>(a, PL, use_tma);
+      else stream::assemble_kernel<false><<<a.W, stream::AW * 32, smem, st>>>(a, PL, use_tma);
     }
-    if (dbg) {
-      std::vector<long long> h(22 * grid);
-      cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * 22 * grid, cudaMemcpyDeviceToHost, st);
-      cudaStreamSynchronize(st);
-      double tot[6] = {0, 0, 0, 0, 0, 0};
-      for (int c = 0; c < grid; ++c)
-        for (int k = 0; k < 6; ++k) tot[k] += (double)h[6 * c + k];
-      const double per = (double)a.W;
-      fprintf(stderr, "[viml phase cycles/window, thread 0] P0(sort,keys) %.0f | P0 tail+barrier %.0f | P1 eval %.0f | P1 barrier wait %.0f | P2a %.0f | P2b+barrier %.0f\n",
-              tot[0] / per, tot[1] / per, tot[2] / per, tot[3] / per, tot[4] / per, tot[5] / per);
-      fprintf(stderr, "[viml P2a cycles/window per warp]");
-      for (int wq = 0; wq < 16; ++wq) {
-        double t = 0;
-        for (int c = 0; c < grid; ++c) t += (double)h[6 * grid + 16 * c + wq];
-        fprintf(stderr, " %.0f", t / per);
-      }
-      fprintf(stderr, "\n");
-      cudaFree(dbg);
+    {
+      const int grid = a.W < 4 * ctx->sm_count ? a.W : 4 * ctx->sm_count;
+      LaunchScope ls(ctx, K_IRREGULAR);
+      if (modeA) stream::irregular_kernel<true><<<grid, 128, 0, st>>>(a, PL);
+      else stream::irregular_kernel<false><<<grid, 128, 0, st>>>(a, PL);
     }
   } else {
-  if (modeB) {
-    const size_t W = a.W, D = a.D, F = a.F;
-    VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.H_pp, 0, W * D * D * sizeof(double), st));
-    VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.H_lp, 0, W * F * D * sizeof(double), st));
-    VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.H_ll, 0, W * F * sizeof(double), st));
-    VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.b_p, 0, W * D * sizeof(double), st));
-    VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.b_l, 0, W * F * sizeof(double), st));
-  }
-  if (a.NP > 0) {
-    const unsigned grid = (unsigned)((a.NP + 127) / 128);
-    LaunchScope ls(ctx, K_POINTS);
-    if (modeA && modeB) points_kernel<true, true><<<grid, 128, 0, st>>>(a);
-    else if (modeA) points_kernel<true, false><<<grid, 128, 0, st>>>(a);
-    else if (modeB) points_kernel<false, true><<<grid, 128, 0, st>>>(a);
-  }
-  if (a.NL > 0) {
-    const unsigned grid = (unsigned)((a.NL + 127) / 128);
-    LaunchScope ls(ctx, K_LINES);
-    if (modeA && modeB) lines_kernel<true, true><<<grid, 128, 0, st>>>(a);
-    else if (modeA) lines_kernel<true, false><<<grid, 128, 0, st>>>(a);
-    else if (modeB) lines_kernel<false, true><<<grid, 128, 0, st>>>(a);
-  }
+    if (modeB) {
+      const size_t W = a.W, D = a.D, F = a.F;
+      VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.H_pp, 0, W * D * D * sizeof(double), st));
+      VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.H_lp, 0, W * F * D * sizeof(double), st));
+      VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.H_ll, 0, W * F * sizeof(double), st));
+      VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.b_p, 0, W * D * sizeof(double), st));
+      VIML_TRY_CUDA(ctx, cudaMemsetAsync(a.out.b_l, 0, W * F * sizeof(double), st));
+    }
+    if (a.NP > 0) {
+      const unsigned grid = (unsigned)((a.NP + 127) / 128);
+      LaunchScope ls(ctx, K_POINTS);
+      if (modeA && modeB) points_kernel<true, true><<<grid, 128, 0, st>>>(a);
+      else if (modeA) points_kernel<true, false><<<grid, 128, 0, st>>>(a);
+      else if (modeB) points_kernel<false, true><<<grid, 128, 0, st>>>(a);
+    }
+    if (a.NL > 0) {
+      const unsigned grid = (unsigned)((a.NL + 127) / 128);
+      LaunchScope ls(ctx, K_LINES);
+      if (modeA && modeB) lines_kernel<true, true><<<grid, 128, 0, st>>>(a);
+      else if (modeA) lines_kernel<true, false><<<grid, 128, 0, st>>>(a);
+      else if (modeB) lines_kernel<false, true><<<grid, 128, 0, st>>>(a);
+    }
   }
   if (a.flags & VIML_OUT_SCHUR) {
     const double eps = 1e-8;  // MarginalizationInfo::eps (marginalization_factor.h:70)

@@ -185,7 +185,7 @@ const char* viml_kernel_name(int id) {
   static const char* names[VIML_NUM_KERNELS] = {"prep_windows", "linearize_points", "linearize_lines", "assemble_hb",
                                                 "schur_landmarks", "assoc_cam_pose", "assoc_cull", "assoc_scan",
                                                 "assoc_fill_list", "assoc_project", "assoc_match", "marginalize_dense",
-                                                "microbench", "plan_windows", "", ""};
+                                                "microbench", "plan_windows", "assemble_irregular", ""};
   return (id >= 0 && id < VIML_NUM_KERNELS) ? names[id] : "";
 }
 
@@ -200,6 +200,7 @@ int viml_set_map(viml_ctx* ctx, const double* lines, int64_t n) {
   };
   drop(ctx->d_map), drop(ctx->d_map_sorted), drop(ctx->d_map_orig), drop(ctx->d_tile_sphere);
   ctx->n_map = 0, ctx->n_tiles = 0;
+  ctx->map_set = true;
   if (n == 0) return VIML_OK;
   // AoS rows [sx sy sz ex ey ez] (parameters.cpp:50-59) -> six SoA planes
   std::vector<double> soa((size_t)6 * n);
@@ -345,6 +346,27 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
     return viml_launch_linearize(ctx, a);
   }
 
+  // host pointers: the packed indices and CSR offsets are validated before anything is launched (device pointers cannot
+  // be read here; on that path plan_kernel routes windows with bad indices to the generic kernel, which drops them)
+  {
+    const int32_t* po = in->pf_window_offset;
+    bool ok = po[0] == 0 && po[W] == NP;
+    for (int w = 0; w < W && ok; ++w) ok = po[w] <= po[w + 1];
+    if (NL > 0) {
+      const int32_t* lo = in->lf_window_offset;
+      ok = ok && lo[0] == 0 && lo[W] == NL;
+      for (int w = 0; w < W && ok; ++w) ok = lo[w] <= lo[w + 1];
+    }
+    if (!ok) return fail(ctx, VIML_ERR_INVALID, "window offsets are not a CSR of the factor arrays (offset[0] == 0, non-decreasing, offset[W] == n_factors)");
+    uint32_t bad = 0;
+    const uint32_t uP = (uint32_t)P, uF = (uint32_t)F;
+    for (int64_t k = 0; k < NP; ++k) {
+      const uint32_t ix = in->pf_idx[k];
+      bad |= (uint32_t)((ix & 0xffu) >= uP) | (uint32_t)(((ix >> 8) & 0xffu) >= uP) | (uint32_t)((ix >> 16) >= uF);
+    }
+    for (int64_t k = 0; k < NL; ++k) bad |= (uint32_t)((uint32_t)in->lf_frame[k] >= uP);
+    if (bad) return fail(ctx, VIML_ERR_INVALID, "factor index out of range (pose index >= poses_per_window, feature >= feats_per_window or line frame >= poses_per_window)");
+  }
   // ---- host pointers: chunked pipeline  H2D(c+1) | kernels(c) | D2H(c-1)  on three streams ----
   // Device buffers hold the whole batch at the same absolute positions as the host arrays; a chunk is a range of
   // windows, its kernels run on a "view" (pointers advanced to the first window of the chunk, factor ranges
@@ -503,9 +525,7 @@ int viml_marginalize_batch(viml_ctx* ctx, const viml_marg_batch* in, const viml_
 int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_assoc_out* out, uint32_t flags) {
   if (!ctx) return VIML_ERR_INVALID;
   if (!q || !out) return fail(ctx, VIML_ERR_INVALID, "null query or output struct");
-  if (!ctx->d_map && ctx->n_map == 0 && !(flags & 0x80000000u)) {
-    // an empty map is legal (every query is unmatched) but it must have been set
-  }
+  if (!ctx->map_set) return fail(ctx, VIML_ERR_NOMAP, "viml_line_associate before viml_set_map (an empty map is legal, but it must be set)");
   const int Pq = q->n_poses, L = q->lines_per_pose;
   if (Pq < 0 || L < 0 || !q->cull_poses || !q->ex_pose || (L > 0 && !q->lines2d))
     return fail(ctx, VIML_ERR_INVALID, "bad association query");
