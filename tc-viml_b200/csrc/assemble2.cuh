@@ -6,10 +6,10 @@
 // leave the SM and there is no CTA-wide phase structure: a window is cut into TASKS that warps execute on their own.
 //
 //   plan_kernel (indices only)   features are ordered by anchor pose; a task is a run of consecutive features
-//       (<= 32 features, ~88 factors); inside a task the factors are ordered by (anchor i, observing frame j) and
+//       (<= 24 features, ~88 factors); inside a task the factors are ordered by (anchor i, observing frame j) and
 //       every (i, j) SEGMENT is padded to an even length.  The plan is a list of 32-bit slots
 //       (factor id | feature slot | i | j) plus one record per task.
-//   assemble_kernel, one CTA (8 warps) per window, two CTAs per SM.  A warp takes a task and streams its slots
+//   assemble_kernel, one CTA (6 warps) per window, two CTAs per SM.  A warp takes a task and streams its slots
 //   32 at a time:
 //     1. lane = factor: residual, Jacobians, Cauchy correction in registers (eval_point).
 //     2. landmark row of the factor's feature: the d^T J_j block is unique to the factor and goes straight to
@@ -40,11 +40,13 @@ constexpr int PMAX = 12;       // poses per window on the fused path (4-bit i/j,
 constexpr int FMAXP = 4096;    // features per window the plan kernel's shared tables are sized for
 constexpr int PT = 256;        // plan_kernel threads
 constexpr int TASK_T = 88;     // target point factors per task
-constexpr int TASK_F = 32;     // features per task
-constexpr int LTASK = 96;      // line slots per line task
-constexpr int AW = 8;          // warps per assemble CTA
-constexpr int WORK_D = 1152;   // doubles of private work area per warp: stage 512 | landmark rows 448 | patch 192
+constexpr int TASK_F = 24;     // features per task
+constexpr int LTASK = 32;      // line slots per line task
+constexpr int AW = 6;          // warps per assemble CTA (2 CTAs x 6 warps = 3 warps per scheduler at <= 168 registers)
 constexpr int LACC_W = 14;     // landmark row: d^T J_i (6) | d^T J_ex (6) | d^T d | d^T r
+constexpr int STAGE_D = 1024;  // stage: 32 records x 32 doubles
+constexpr int LACC_D = TASK_F * LACC_W;
+constexpr int WORK_D = STAGE_D + LACC_D + 192;   // doubles of private work area per warp: stage | landmark rows | patch
 
 struct PlanPtrs {
   int4* hdr;          // [W] {n_tasks, n_lslots, irregular, 0}
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(PT) plan_kernel(LinearizeArgs A, PlanPtrs PL) 
       const int p = pos + lane;
       const int c = p < F ? (int)(cexcl[p + 1] - cexcl[p]) : 0x10000;
       const int inc = warp_incl_scan(c, lane);
-      const unsigned okm = __ballot_sync(0xffffffffu, inc <= TASK_T && p < F);
+      const unsigned okm = __ballot_sync(0xffffffffu, inc <= TASK_T && p < F && lane < TASK_F);
       int n = okm == 0xffffffffu ? 32 : __ffs(~okm) - 1;
       n = max(n, 1);
       n = min(n, F - pos);
@@ -299,10 +301,12 @@ constexpr Tables make_tables() {
   }
   return T;
 }
-__constant__ Tables c_tables = make_tables();
+// read once per CTA with lane-indexed (coalesced) loads: global memory, not __constant__ (divergent constant reads replay)
+__device__ const Tables g_tables = make_tables();
 static_assert(make_tables().seg[98] != 0u && make_tables().seg[99] == 0u, "99 per-segment destinations");
 static_assert(make_tables().lo[89] != 0u && make_tables().lo[90] == 0u, "90 per-anchor destinations");
 static_assert(make_tables().line[26] != 0u && make_tables().line[27] == 0u, "27 line destinations");
+
 
 // ------------------------------------------------------------------------------------------------ device helpers
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
@@ -314,10 +318,13 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 // index of block (br, bc), br <= bc, in the block-upper layout with NB blocks per side
 __device__ __forceinline__ int blk(int br, int bc, int NB) { return br * NB - (br * (br - 1)) / 2 + (bc - br); }
 
-// stage: 16 records x 16 units (unit = one column as (row 0, row 1), 16 bytes).  Unit c of record f sits at
-// f*16 + (c ^ swz(f)) so that the half-warp record stores and the LDS.64 fragment loads are both conflict-free.
+// stage: 32 records x 16 units (unit = one column as (row 0, row 1), 16 bytes).  Unit c of record f sits at
+// f*16 + (c ^ swz(f)) so that the record stores (STS.128, a quarter warp per wavefront) and the LDS.64 fragment loads
+// (a half warp = two records per wavefront) are both conflict-free.
 __device__ __forceinline__ int swz(int f) { return ((f & 1) << 2) ^ ((f >> 1) & 3); }
 
+// One scatter round per table word: patch[src] goes to Hc[base(kind) + off] with a shared-memory FP64 add (CAS loop).
+// Lane k < K_NKIND holds the base of destination kind k in `mybase`.
 template <int ROUNDS>
 __device__ __forceinline__ void scatter(const double* __restrict__ patch, const uint32_t (&tab)[ROUNDS], double* __restrict__ Hc,
                                         int mybase) {
@@ -332,21 +339,13 @@ __device__ __forceinline__ void scatter(const double* __restrict__ patch, const 
   }
 }
 
-// lane k < K_NKIND: offset of destination kind k in the block-upper accumulator for segment (lo, hi)
-__device__ __forceinline__ int kind_base(int lane, int lo, int hi, int NB, int boff) {
+// Per-lane selectors of kind_base: which pose (0 = lo, 1 = hi, 2 = extrinsic) is the block row / column of kind `lane`.
+//   kind      LL HH LH LE HE EE BL BH BE
+//   row        0  1  0  0  1  2  0  1  2      col   0  1  1  2  2  2  -  -  -
+__device__ __forceinline__ int kind_base(int rs, int cs, bool isb, int lo, int hi, int NB, int boff) {
   const int e = NB - 1;
-  switch (lane) {
-    case K_LL: return blk(lo, lo, NB) * 36;
-    case K_HH: return blk(hi, hi, NB) * 36;
-    case K_LH: return blk(lo, hi, NB) * 36;
-    case K_LE: return blk(lo, e, NB) * 36;
-    case K_HE: return blk(hi, e, NB) * 36;
-    case K_EE: return blk(e, e, NB) * 36;
-    case K_BL: return boff + 6 * lo;
-    case K_BH: return boff + 6 * hi;
-    case K_BE: return boff + 6 * e;
-    default: return 0;
-  }
+  const int x = rs == 0 ? lo : (rs == 1 ? hi : e), y = cs == 0 ? lo : (cs == 1 ? hi : e);
+  return isb ? boff + 6 * x : blk(x, y, NB) * 36;
 }
 
 __device__ __forceinline__ void put_patch(double* __restrict__ patch, int lane, const double (&G)[6]) {
@@ -360,9 +359,10 @@ __device__ __forceinline__ void put_patch(double* __restrict__ patch, int lane, 
 
 // ------------------------------------------------------------------------------------------------ assemble
 template <bool MODE_A>
-__global__ void __launch_bounds__(AW * 32, 2) assemble_kernel(LinearizeArgs A, PlanPtrs PL, int use_tma) {
+__global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, int use_tma) {
   extern __shared__ __align__(16) unsigned char asm_raw[];
   __shared__ int s_next;
+  constexpr int NT = AW * 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, w = blockIdx.x;
   const int P = A.P, F = A.F, D = A.D, NB = P + 1;
   const int nblk = NB * (NB + 1) / 2, boff = nblk * 36;
@@ -372,8 +372,8 @@ __global__ void __launch_bounds__(AW * 32, 2) assemble_kernel(LinearizeArgs A, P
   double* __restrict__ cache = Hc + hc_n;
   double* __restrict__ work0 = cache + cstride;
   double* __restrict__ stage = work0 + warp * WORK_D;
-  double* __restrict__ lacc = stage + 512;
-  double* __restrict__ patch = lacc + 448;
+  double* __restrict__ lacc = stage + STAGE_D;
+  double* __restrict__ patch = lacc + LACC_D;
 
   const int4 hdr = PL.hdr[w];
   const int a0 = A.pf_window_offset[w];
@@ -384,24 +384,28 @@ __global__ void __launch_bounds__(AW * 32, 2) assemble_kernel(LinearizeArgs A, P
   double* __restrict__ bp = A.out.b_p + (size_t)w * D;
   double* __restrict__ bl = A.out.b_l + (size_t)w * F;
   if (hdr.z) {   // irregular window: zero here, irregular_kernel adds with global atomics
-    for (int e = tid; e < D * D; e += AW * 32) Hpp[e] = 0.0;
-    for (int e = tid; e < F * D; e += AW * 32) Hlp[e] = 0.0;
-    for (int e = tid; e < F; e += AW * 32) Hll[e] = 0.0, bl[e] = 0.0;
-    for (int e = tid; e < D; e += AW * 32) bp[e] = 0.0;
+    for (int e = tid; e < D * D; e += NT) Hpp[e] = 0.0;
+    for (int e = tid; e < F * D; e += NT) Hlp[e] = 0.0;
+    for (int e = tid; e < F; e += NT) Hll[e] = 0.0, bl[e] = 0.0;
+    for (int e = tid; e < D; e += NT) bp[e] = 0.0;
     return;
   }
-  for (int e = tid; e < hc_n; e += AW * 32) Hc[e] = 0.0;
   {
-    const double* __restrict__ gc = A.cache + (size_t)w * cstride;
-    for (int e = tid; e < cstride; e += AW * 32) cache[e] = gc[e];
+    double2* z = reinterpret_cast<double2*>(Hc);
+    for (int e = tid; e < hc_n / 2; e += NT) z[e] = make_double2(0.0, 0.0);
+    const double2* __restrict__ gc = reinterpret_cast<const double2*>(A.cache + (size_t)w * cstride);
+    double2* c2 = reinterpret_cast<double2*>(cache);
+    for (int e = tid; e < cstride / 2; e += NT) c2[e] = gc[e];
   }
   if (tid == 0) s_next = 0;
   uint32_t tab_seg[4], tab_lo[3], tab_line[1];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) tab_seg[r] = c_tables.seg[32 * r + lane];
+  for (int r = 0; r < 4; ++r) tab_seg[r] = g_tables.seg[32 * r + lane];
 #pragma unroll
-  for (int r = 0; r < 3; ++r) tab_lo[r] = c_tables.lo[32 * r + lane];
-  tab_line[0] = c_tables.line[lane];
+  for (int r = 0; r < 3; ++r) tab_lo[r] = g_tables.lo[32 * r + lane];
+  tab_line[0] = g_tables.line[lane];
+  const int kb_rs = lane < K_NKIND ? (0x24904 >> (2 * lane)) & 3 : 0, kb_cs = lane < K_NKIND ? (0xA94 >> (2 * lane)) & 3 : 0;
+  const bool kb_isb = lane >= K_BL && lane < K_NKIND;
   __syncthreads();
 
   const int ntask = hdr.x, nlsl = hdr.y, nltask = (nlsl + LTASK - 1) / LTASK;
@@ -410,7 +414,13 @@ __global__ void __launch_bounds__(AW * 32, 2) assemble_kernel(LinearizeArgs A, P
   const uint32_t* __restrict__ lsl_w = PL.lslots + 2 * (size_t)(b0 - (int)A.lf_begin);
   // fragment geometry of mma.m8n8k4: lane (g, kk) holds column g of row kk&1 of factor kk>>1 (A and B operand alike)
   const int g = lane >> 2, kk = lane & 3;
+  const int gx = g ^ ((kk >> 1) << 2);
+  const double* __restrict__ frag0 = stage + (kk >> 1) * 32 + (kk & 1);   // record 2s + (kk>>1), row kk&1
   const unsigned full = 0xffffffffu;
+  // landmark-row units of this lane: u = lane and lane + 32 (a row has 3 NB <= 39 units of 16 bytes)
+  const int upr = 3 * NB;
+  const int ru1 = lane + 32, rb0 = (lane * 11) >> 5, rb1 = (ru1 * 43) >> 7;
+  const int rp0 = lane - 3 * rb0, rp1 = ru1 - 3 * rb1;
 
   for (;;) {
     int t = 0;
@@ -424,8 +434,7 @@ __global__ void __launch_bounds__(AW * 32, 2) assemble_kernel(LinearizeArgs A, P
       const uint32_t fi = lane < n_feats ? PL.finfo[(size_t)w * F + tk.z + lane] : 0u;
       {
         double2* z = reinterpret_cast<double2*>(lacc);
-#pragma unroll
-        for (int q = 0; q < 7; ++q) z[q * 32 + lane] = make_double2(0.0, 0.0);
+        for (int q = lane; q < LACC_D / 2; q += 32) z[q] = make_double2(0.0, 0.0);
       }
       __syncwarp();
       const uint32_t* __restrict__ sl = sl_w + tk.x;
@@ -435,65 +444,39 @@ __global__ void __launch_bounds__(AW * 32, 2) assemble_kernel(LinearizeArgs A, P
         const uint32_t sw_ = nsw;
         nsw = c0 + 32 + lane < n_slots ? sl[c0 + 32 + lane] : 0xffffu;
         const bool valid = (sw_ & 0xffffu) != 0xffffu;
-        const int lf = (sw_ >> 16) & 31, i = (sw_ >> 21) & 15, j = (sw_ >> 25) & 15;
-        const int l = __shfl_sync(full, fi, lf) & 0xffff;
-        PointJac J;
-        if (valid) {
-          const int64_t k = (int64_t)a0 + (sw_ & 0xffffu);
-          const double4 ob = reinterpret_cast<const double4*>(A.pf_obs)[k];
-          const double piz = A.pf_pts_i_z ? A.pf_pts_i_z[k] : 1.0;
-          const double lam = A.inv_depth[(size_t)w * F + l];
-          eval_point(A, cache, i, j, lam, ob.x, ob.y, piz, ob.z, ob.w, J);
-          if (MODE_A) {
-            if (A.out.pf_residual) reinterpret_cast<double2*>(A.out.pf_residual)[k] = make_double2(J.r[0], J.r[1]);
-            if (A.out.pf_jac_pose_i) store_jac7(A.out.pf_jac_pose_i + 14 * k, J.a);
-            if (A.out.pf_jac_pose_j) store_jac7(A.out.pf_jac_pose_j + 14 * k, J.b);
-            if (A.out.pf_jac_ex) store_jac7(A.out.pf_jac_ex + 14 * k, J.c);
-            if (A.out.pf_jac_feat) reinterpret_cast<double2*>(A.out.pf_jac_feat)[k] = make_double2(J.d[0], J.d[1]);
-          }
-          // the factor's own block of the landmark row: d^T J_j  (unique per (feature, j))
-          double2* row = reinterpret_cast<double2*>(Hlp + (size_t)l * D + 6 * j);
-          row[0] = make_double2(J.d[0] * J.b[0][0] + J.d[1] * J.b[1][0], J.d[0] * J.b[0][1] + J.d[1] * J.b[1][1]);
-          row[1] = make_double2(J.d[0] * J.b[0][2] + J.d[1] * J.b[1][2], J.d[0] * J.b[0][3] + J.d[1] * J.b[1][3]);
-          row[2] = make_double2(J.d[0] * J.b[0][4] + J.d[1] * J.b[1][4], J.d[0] * J.b[0][5] + J.d[1] * J.b[1][5]);
-        } else {
-#pragma unroll
-          for (int c = 0; c < 6; ++c) J.a[0][c] = J.a[1][c] = J.b[0][c] = J.b[1][c] = J.c[0][c] = J.c[1][c] = 0.0;
-          J.r[0] = J.r[1] = J.d[0] = J.d[1] = 0.0;
-        }
-        // landmark row sums: lanes of one segment have distinct features; lanes that share a feature take turns
+        const int lf = (sw_ >> 16) & 31;
         {
-          const unsigned grp = __match_any_sync(full, valid ? lf : 32 + lane);
-          const int rank = __popc(grp & ((1u << lane) - 1u));
-          const int rounds = __reduce_max_sync(full, valid ? __popc(grp) : 0);
-          double* __restrict__ la = lacc + lf * LACC_W;
-          for (int r = 0; r < rounds; ++r) {
-            if (valid && rank == r) {
-#pragma unroll
-              for (int c = 0; c < 6; ++c) {
-                la[c] += J.d[0] * J.a[0][c] + J.d[1] * J.a[1][c];
-                la[6 + c] += J.d[0] * J.c[0][c] + J.d[1] * J.c[1][c];
-              }
-              la[12] += J.d[0] * J.d[0] + J.d[1] * J.d[1];
-              la[13] += J.d[0] * J.r[0] + J.d[1] * J.r[1];
+          const int i = (sw_ >> 21) & 15, j = (sw_ >> 25) & 15;
+          const int l = __shfl_sync(full, fi, lf) & 0xffff;
+          PointJac J;
+          if (valid) {
+            const int64_t k = (int64_t)a0 + (sw_ & 0xffffu);
+            const double4 ob = reinterpret_cast<const double4*>(A.pf_obs)[k];
+            const double piz = A.pf_pts_i_z ? A.pf_pts_i_z[k] : 1.0;
+            const double lam = A.inv_depth[(size_t)w * F + l];
+            eval_point(A, cache, i, j, lam, ob.x, ob.y, piz, ob.z, ob.w, J);
+            if (MODE_A) {
+              if (A.out.pf_residual) reinterpret_cast<double2*>(A.out.pf_residual)[k] = make_double2(J.r[0], J.r[1]);
+              if (A.out.pf_jac_pose_i) store_jac7(A.out.pf_jac_pose_i + 14 * k, J.a);
+              if (A.out.pf_jac_pose_j) store_jac7(A.out.pf_jac_pose_j + 14 * k, J.b);
+              if (A.out.pf_jac_ex) store_jac7(A.out.pf_jac_ex + 14 * k, J.c);
+              if (A.out.pf_jac_feat) reinterpret_cast<double2*>(A.out.pf_jac_feat)[k] = make_double2(J.d[0], J.d[1]);
             }
-            __syncwarp();
+            // the factor's own block of the landmark row: d^T J_j  (unique per (feature, j))
+            double2* row = reinterpret_cast<double2*>(Hlp + (size_t)l * D + 6 * j);
+            row[0] = make_double2(J.d[0] * J.b[0][0] + J.d[1] * J.b[1][0], J.d[0] * J.b[0][1] + J.d[1] * J.b[1][1]);
+            row[1] = make_double2(J.d[0] * J.b[0][2] + J.d[1] * J.b[1][2], J.d[0] * J.b[0][3] + J.d[1] * J.b[1][3]);
+            row[2] = make_double2(J.d[0] * J.b[0][4] + J.d[1] * J.b[1][4], J.d[0] * J.b[0][5] + J.d[1] * J.b[1][5]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) J.a[0][c] = J.a[1][c] = J.b[0][c] = J.b[1][c] = J.c[0][c] = J.c[1][c] = 0.0;
+            J.r[0] = J.r[1] = J.d[0] = J.d[1] = 0.0;
           }
-        }
-        // segment ends: bit q of bnd = the slot after lane q belongs to another segment (or the task ends)
-        const uint32_t key = sw_ >> 21;
-        uint32_t nk = __shfl_down_sync(full, key, 1);
-        const uint32_t nk31 = __shfl_sync(full, nsw >> 21, 0);
-        if (lane == 31) nk = nk31;
-        if (c0 + lane + 1 >= n_slots) nk = 0xffffffffu;
-        const unsigned bnd = __ballot_sync(full, key != nk);
-        const bool swp = i > j;   // lo role is pose j
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          if (c0 + 16 * h >= n_slots) break;
-          if ((lane >> 4) == h) {
-            const int f = lane & 15, sx = swz(f);
-            double2* rec = reinterpret_cast<double2*>(stage) + f * 16;
+          // record -> stage (the lo role is the smaller pose index)
+          {
+            const bool swp = i > j;
+            const int sx = swz(lane);
+            double2* rec = reinterpret_cast<double2*>(stage) + lane * 16;
 #pragma unroll
             for (int c = 0; c < 6; ++c) rec[c ^ sx] = swp ? make_double2(J.b[0][c], J.b[1][c]) : make_double2(J.a[0][c], J.a[1][c]);
 #pragma unroll
@@ -503,80 +486,120 @@ __global__ void __launch_bounds__(AW * 32, 2) assemble_kernel(LinearizeArgs A, P
             for (int c = 0; c < 6; ++c) rec[(9 + c) ^ sx] = make_double2(J.c[0][c], J.c[1][c]);
             rec[15 ^ sx] = make_double2(J.r[0], J.r[1]);
           }
-          __syncwarp();
-#pragma unroll 1
-          for (int s = 0; s < 8; ++s) {
-            const int la_ = 16 * h + 2 * s;
-            if (c0 + la_ >= n_slots) break;
-            const int f = 2 * s + (kk >> 1), sx = swz(f);
-            const double* __restrict__ rec = stage + f * 32 + (kk & 1);
-            const double u0 = rec[2 * (g ^ sx)], u1 = rec[2 * ((8 + g) ^ sx)];
-            dmma(G[0], G[1], u0, u0);
-            dmma(G[2], G[3], u0, u1);
-            dmma(G[4], G[5], u1, u1);
-            if ((bnd >> (la_ + 1)) & 1u) {
-              const uint32_t kseg = __shfl_sync(full, key, la_), knext = __shfl_sync(full, nk, la_ + 1);
-              const int si = kseg & 15, sj = (kseg >> 4) & 15;
-              const int lo = min(si, sj), hi = max(si, sj);
-              const int mybase = kind_base(lane, lo, hi, NB, boff);
-              put_patch(patch, lane, G);
-              __syncwarp();
-              scatter<4>(patch, tab_seg, Hc, mybase);
+          // landmark row sums: lanes of one segment have distinct features; lanes that share a feature take turns
+          {
+            const unsigned grp = __match_any_sync(full, valid ? lf : 32 + lane);
+            const int rank = __popc(grp & ((1u << lane) - 1u));
+            const int rounds = __reduce_max_sync(full, valid ? __popc(grp) : 0);
+            double v[LACC_W];
 #pragma unroll
-              for (int q = 0; q < 6; ++q) R[q] += G[q], G[q] = 0.0;
-              const bool lo_ends = knext == 0xffffffffu || min((int)(knext & 15), (int)((knext >> 4) & 15)) != lo;
-              if (lo_ends) {
-                __syncwarp();
-                put_patch(patch, lane, R);
-                __syncwarp();
-                scatter<3>(patch, tab_lo, Hc, mybase);
+            for (int c = 0; c < 6; ++c) {
+              v[c] = J.d[0] * J.a[0][c] + J.d[1] * J.a[1][c];
+              v[6 + c] = J.d[0] * J.c[0][c] + J.d[1] * J.c[1][c];
+            }
+            v[12] = J.d[0] * J.d[0] + J.d[1] * J.d[1];
+            v[13] = J.d[0] * J.r[0] + J.d[1] * J.r[1];
+            double2* __restrict__ la = reinterpret_cast<double2*>(lacc + lf * LACC_W);
+            for (int r = 0; r < rounds; ++r) {
+              if (valid && rank == r) {
 #pragma unroll
-                for (int q = 0; q < 6; ++q) R[q] = 0.0;
+                for (int c = 0; c < LACC_W / 2; ++c) {
+                  double2 o = la[c];
+                  o.x += v[2 * c], o.y += v[2 * c + 1];
+                  la[c] = o;
+                }
               }
               __syncwarp();
             }
           }
-          __syncwarp();
         }
-      }
-      // rows of the task's features: anchor block, extrinsic block, structural zeros (the observing frames' blocks
-      // were written by the factors), H_ll, b_l
-      __syncwarp();
-      {
-        const int upr = 3 * NB, total = n_feats * upr;
-        for (int idx0 = 0; idx0 < total; idx0 += 32) {
-          const int idx = idx0 + lane;
-          const int f = min(idx / upr, n_feats - 1), u = idx - (idx / upr) * upr;
-          const uint32_t info = __shfl_sync(full, fi, f);
-          if (idx < total) {
-            const int l = info & 0xffff, b = u / 3, part = u - 3 * b;
-            const uint32_t m = (info >> 16) & 0xfffu;
-            const int an = m ? (int)(info >> 28) : -1;
-            double2* dst = reinterpret_cast<double2*>(Hlp + (size_t)l * D) + u;
-            const double* __restrict__ la = lacc + f * LACC_W;
-            if (b == an) *dst = make_double2(la[2 * part], la[2 * part + 1]);
-            else if (b == P) *dst = make_double2(la[6 + 2 * part], la[6 + 2 * part + 1]);
-            else if (!((m >> b) & 1u)) *dst = make_double2(0.0, 0.0);
+        __syncwarp();
+        // segment ends: bit q of bnd = the slot after lane q belongs to another segment (or the task ends)
+        const uint32_t key = sw_ >> 21;
+        uint32_t nk = __shfl_down_sync(full, key, 1);
+        const uint32_t nk31 = __shfl_sync(full, nsw >> 21, 0);
+        if (lane == 31) nk = nk31;
+        if (c0 + lane + 1 >= n_slots) nk = 0xffffffffu;
+        const unsigned bnd = __ballot_sync(full, key != nk);
+        const int nks = min(16, (n_slots - c0) >> 1);
+        int s = 0;
+        while (s < nks) {
+          const unsigned rem = bnd >> (2 * s + 1);   // bit 2q: the segment ends after K-step s + q
+          const int q_end = rem ? ((__ffs(rem) - 1) >> 1) : 32;
+          const bool ends = s + q_end < nks;
+          const int s_end = ends ? s + q_end + 1 : nks;
+#pragma unroll 2
+          for (; s < s_end; ++s) {
+            const double* __restrict__ p = frag0 + s * 64 + 2 * (gx ^ (s & 3));
+            const double u0 = p[0], u1 = p[16];
+            dmma(G[0], G[1], u0, u0);
+            dmma(G[2], G[3], u0, u1);
+            dmma(G[4], G[5], u1, u1);
+          }
+          if (ends) {
+            const int la_ = 2 * s - 2;   // first lane of the segment's last K-step
+            const uint32_t kseg = __shfl_sync(full, key, la_), knext = __shfl_sync(full, nk, la_ + 1);
+            const int si = kseg & 15, sj = (kseg >> 4) & 15;
+            const int lo = min(si, sj), hi = max(si, sj);
+            const int mybase = kind_base(kb_rs, kb_cs, kb_isb, lo, hi, NB, boff);
+            put_patch(patch, lane, G);
+            __syncwarp();
+            scatter<4>(patch, tab_seg, Hc, mybase);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) R[q] += G[q], G[q] = 0.0;
+            const bool lo_ends = knext == 0xffffffffu || min((int)(knext & 15), (int)((knext >> 4) & 15)) != lo;
+            if (lo_ends) {
+              __syncwarp();
+              put_patch(patch, lane, R);
+              __syncwarp();
+              scatter<3>(patch, tab_lo, Hc, mybase);
+#pragma unroll
+              for (int q = 0; q < 6; ++q) R[q] = 0.0;
+            }
+            __syncwarp();
           }
         }
-        if (lane < n_feats) {
-          const int l = fi & 0xffff;
-          Hll[l] = lacc[lane * LACC_W + 12];
-          bl[l] = lacc[lane * LACC_W + 13];
+        __syncwarp();   // the stage is rewritten by the next chunk
+      }
+      // rows of the task's features: anchor block, extrinsic block, structural zeros (the observing frames' blocks
+      // were written by the factors), H_ll, b_l.  One feature per iteration, lane = 16-byte unit of the row.
+      for (int f = 0; f < n_feats; ++f) {
+        const uint32_t info = __shfl_sync(full, fi, f);
+        const int l = info & 0xffff;
+        const uint32_t m = (info >> 16) & 0xfffu;
+        const int an = m ? (int)(info >> 28) : -1;
+        double2* __restrict__ dst = reinterpret_cast<double2*>(Hlp + (size_t)l * D);
+        const double2* __restrict__ la = reinterpret_cast<const double2*>(lacc + f * LACC_W);
+        {
+          double2 v = make_double2(0.0, 0.0);
+          bool wr = true;
+          if (rb0 == an) v = la[rp0];
+          else if (rb0 == P) v = la[3 + rp0];
+          else if ((m >> rb0) & 1u) wr = false;
+          if (wr && lane < upr) dst[lane] = v;
         }
+        if (ru1 < upr) {
+          double2 v = make_double2(0.0, 0.0);
+          bool wr = true;
+          if (rb1 == an) v = la[rp1];
+          else if (rb1 == P) v = la[3 + rp1];
+          else if ((m >> rb1) & 1u) wr = false;
+          if (wr) dst[ru1] = v;
+        }
+      }
+      if (lane < n_feats) {
+        const int l = fi & 0xffff;
+        Hll[l] = lacc[lane * LACC_W + 12];
+        bl[l] = lacc[lane * LACC_W + 13];
       }
       __syncwarp();
     } else {
       // ================================================================== line task
       const int t0 = (t - ntask) * LTASK, n_slots = min(LTASK, nlsl - t0);
-      const uint32_t* __restrict__ sl = lsl_w + t0;
-      double G[6] = {0, 0, 0, 0, 0, 0};
-      uint32_t nsw = lane < n_slots ? sl[lane] : 0xffffu;
-      for (int c0 = 0; c0 < n_slots; c0 += 32) {
-        const uint32_t sw_ = nsw;
-        nsw = c0 + 32 + lane < n_slots ? sl[c0 + 32 + lane] : 0xffffu;
-        const bool valid = (sw_ & 0xffffu) != 0xffffu;
-        const int frame = (sw_ >> 16) & 0xff;
+      const uint32_t sw_ = lane < n_slots ? lsl_w[t0 + lane] : 0xffffu;
+      const bool valid = (sw_ & 0xffffu) != 0xffffu;
+      const int frame = (sw_ >> 16) & 0xff;
+      {
         LineJac J;
         if (valid) {
           const int64_t k = (int64_t)b0 + (sw_ & 0xffffu);
@@ -593,59 +616,54 @@ __global__ void __launch_bounds__(AW * 32, 2) assemble_kernel(LinearizeArgs A, P
           for (int c = 0; c < 6; ++c) J.a[0][c] = J.a[1][c] = 0.0;
           J.r[0] = J.r[1] = 0.0;
         }
-        const uint32_t key = sw_ >> 16;
-        uint32_t nk = __shfl_down_sync(full, key, 1);
-        const uint32_t nk31 = __shfl_sync(full, nsw >> 16, 0);
-        if (lane == 31) nk = nk31;
-        if (c0 + lane + 1 >= n_slots) nk = 0xffffffffu;
-        const unsigned bnd = __ballot_sync(full, key != nk);
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          if (c0 + 16 * h >= n_slots) break;
-          if ((lane >> 4) == h) {
-            const int f = lane & 15, sx = swz(f);
-            double2* rec = reinterpret_cast<double2*>(stage) + f * 16;
+        const int sx = swz(lane);
+        double2* rec = reinterpret_cast<double2*>(stage) + lane * 16;
 #pragma unroll
-            for (int c = 0; c < 6; ++c) rec[c ^ sx] = make_double2(J.a[0][c], J.a[1][c]);
-            rec[6 ^ sx] = make_double2(J.r[0], J.r[1]);
-            rec[7 ^ sx] = make_double2(0.0, 0.0);
-          }
-          __syncwarp();
-#pragma unroll 1
-          for (int s = 0; s < 8; ++s) {
-            const int la_ = 16 * h + 2 * s;
-            if (c0 + la_ >= n_slots) break;
-            const int f = 2 * s + (kk >> 1), sx = swz(f);
-            const double u0 = stage[f * 32 + (kk & 1) + 2 * (g ^ sx)];
-            dmma(G[0], G[1], u0, u0);
-            if ((bnd >> (la_ + 1)) & 1u) {
-              const int fr = __shfl_sync(full, key, la_) & 0xff;
-              const int mybase = kind_base(lane, fr, fr, NB, boff);
-              put_patch(patch, lane, G);
-              __syncwarp();
-              scatter<1>(patch, tab_line, Hc, mybase);
-              G[0] = G[1] = 0.0;
-              __syncwarp();
-            }
-          }
-          __syncwarp();
+        for (int c = 0; c < 6; ++c) rec[c ^ sx] = make_double2(J.a[0][c], J.a[1][c]);
+        rec[6 ^ sx] = make_double2(J.r[0], J.r[1]);
+        rec[7 ^ sx] = make_double2(0.0, 0.0);
+      }
+      __syncwarp();
+      const uint32_t key = sw_ >> 16;
+      uint32_t nk = __shfl_down_sync(full, key, 1);
+      if (lane + 1 >= n_slots) nk = 0xffffffffu;
+      const unsigned bnd = __ballot_sync(full, key != nk);
+      const int nks = n_slots >> 1;
+      double G[6] = {0, 0, 0, 0, 0, 0};
+      int s = 0;
+      while (s < nks) {
+        const unsigned rem = bnd >> (2 * s + 1);
+        const int s_end = min(nks, s + ((__ffs(rem) - 1) >> 1) + 1);   // a line task always ends on a segment end
+        for (; s < s_end; ++s) {
+          const double u0 = frag0[s * 64 + 2 * (gx ^ (s & 3))];
+          dmma(G[0], G[1], u0, u0);
         }
+        const int fr = __shfl_sync(full, key, 2 * s - 2) & 0xff;
+        const int mybase = kind_base(kb_rs, kb_cs, kb_isb, fr, fr, NB, boff);
+        put_patch(patch, lane, G);
+        __syncwarp();
+        scatter<1>(patch, tab_line, Hc, mybase);
+        G[0] = G[1] = 0.0;
+        __syncwarp();
       }
     }
   }
   __syncthreads();
   // expand the block-upper accumulator to the full symmetric matrix (+ b_p behind it) in the warps' work areas
   double* __restrict__ Hf = work0;
-  for (int e = tid; e < D * D; e += AW * 32) {
-    const int r = e / D, c = e - r * D;
-    const int br = r / 6, bc = c / 6, rr = r - 6 * br, cc = c - 6 * bc;
-    double v;
-    if (br < bc) v = Hc[blk(br, bc, NB) * 36 + rr * 6 + cc];
-    else if (br > bc) v = Hc[blk(bc, br, NB) * 36 + cc * 6 + rr];
-    else v = Hc[blk(br, br, NB) * 36 + (rr <= cc ? rr * 6 + cc : cc * 6 + rr)];
-    Hf[e] = v;
+  {
+    int r = tid / D, c = tid - r * D;
+    const int dr = NT / D, dc = NT - dr * D;
+    for (int e = tid; e < D * D; e += NT) {
+      const int br = (r * 43) >> 8, bc = (c * 43) >> 8, rr = r - 6 * br, cc = c - 6 * bc;
+      const int lo = min(br, bc), hi = max(br, bc);
+      const bool tr = br > bc || (br == bc && rr > cc);
+      Hf[e] = Hc[blk(lo, hi, NB) * 36 + (tr ? cc * 6 + rr : rr * 6 + cc)];
+      c += dc, r += dr;
+      if (c >= D) c -= D, ++r;
+    }
   }
-  for (int e = tid; e < D; e += AW * 32) Hf[D * D + e] = Hc[boff + e];
+  for (int e = tid; e < D; e += NT) Hf[D * D + e] = Hc[boff + e];
   if (use_tma) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -661,8 +679,8 @@ __global__ void __launch_bounds__(AW * 32, 2) assemble_kernel(LinearizeArgs A, P
     }
   } else {
     __syncthreads();
-    for (int e = tid; e < D * D; e += AW * 32) Hpp[e] = Hf[e];
-    for (int e = tid; e < D; e += AW * 32) bp[e] = Hf[D * D + e];
+    for (int e = tid; e < D * D; e += NT) Hpp[e] = Hf[e];
+    for (int e = tid; e < D; e += NT) bp[e] = Hf[D * D + e];
   }
 }
 

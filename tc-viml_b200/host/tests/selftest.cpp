@@ -254,6 +254,38 @@ static void test_factors(const viml_config& cfg) {
       orc_line_evaluate(lf->pts_start.data(), lf->pts_end.data(), lf->line_param.data(), K.m, Ric.m, Tic.data(), lp, ro, jo);
       CHECK(rel_err(r, ro, 2) < 1e-9 && rel_err(J, Jo, 14) < 1e-9);
     }
+    // What ceres::Solve does: ResidualBlock::Evaluate hands out pointers into the minimizer's own state vector, never
+    // the user's arrays.  Copies of the evaluation point must be served from the batch (no per-factor launch) ...
+    {
+      batch.PrepareForEvaluation(true, true);
+      const long before = batch.served();
+      for (size_t k = 0; k < fs.size(); ++k) {
+        double cp[4][7];
+        for (int b = 0; b < 4; ++b) std::memcpy(cp[b], ps[k][b], (b == 3 ? 1 : 7) * sizeof(double));
+        const double* params[4] = {cp[0], cp[1], cp[2], cp[3]};
+        double r[2], ro[2], J[4][14], Jo[4][14];
+        double *jp[4] = {J[0], J[1], J[2], J[3]}, *jo[4] = {Jo[0], Jo[1], Jo[2], Jo[3]};
+        fs[k]->Evaluate(params, r, jp);
+        orc_projection_evaluate(fs[k]->pts_i.data(), fs[k]->pts_j.data(), cfg.sqrt_info, params, ro, jo);
+        CHECK(rel_err(r, ro, 2) < 1e-9 && rel_err(J[0], Jo[0], 14) < 1e-9 && rel_err(J[3], Jo[3], 2) < 1e-9);
+      }
+      CHECK(batch.served() - before == (long)fs.size());
+      // ... and a state that is NOT the evaluation point must not be (it is evaluated on its own, correctly)
+      double cp[4][7];
+      for (int b = 0; b < 4; ++b) std::memcpy(cp[b], ps[0][b], (b == 3 ? 1 : 7) * sizeof(double));
+      cp[1][1] += 0.02;
+      const double* params[4] = {cp[0], cp[1], cp[2], cp[3]};
+      double r[2], ro[2], J[4][14], Jo[4][14];
+      double *jp[4] = {J[0], J[1], J[2], J[3]}, *jo[4] = {Jo[0], Jo[1], Jo[2], Jo[3]};
+      const long b2 = batch.served();
+      fs[0]->Evaluate(params, r, jp);
+      orc_projection_evaluate(fs[0]->pts_i.data(), fs[0]->pts_j.data(), cfg.sqrt_info, params, ro, jo);
+      CHECK(batch.served() == b2 && rel_err(r, ro, 2) < 1e-9 && rel_err(J[1], Jo[1], 14) < 1e-9);
+      batch.Invalidate();
+      const double* up[4] = {ps[0][0], ps[0][1], ps[0][2], ps[0][3]};
+      fs[0]->Evaluate(up, r, jp);
+      CHECK(batch.served() == b2);
+    }
     for (auto* f : fs) delete f;
     delete lf;
   }

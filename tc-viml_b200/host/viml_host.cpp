@@ -295,13 +295,17 @@ void LinearizationBatch::PrepareForEvaluation(bool /*evaluate_jacobians*/, bool 
   out.lf_residual = r_lf_, out.lf_jac_pose = jp_;
   last_rc_ = viml_linearize_batch(ctx, &in, &out, VIML_OUT_RESIDUAL_JACOBIAN);
   check_rc(last_rc_, "viml_linearize_batch");
+  snap_poses_.swap(poses), snap_lam_.swap(lam), snap_ex_.swap(ex);
   valid_ = true;
 }
 
 bool LinearizationBatch::fetch(const ProjectionFactor* f, double const* const* parameters, double* residuals, double** jacobians) const {
   if (!valid_) return false;
   const PF& e = pf_[f->slot_];
-  if (parameters[0] != e.pi || parameters[1] != e.pj || parameters[2] != e.ex || parameters[3] != e.feat) return false;
+  // same evaluation point?  compared by value (56-byte blocks), not by address: see snap_poses_ in viml_host.h
+  if (std::memcmp(parameters[0], &snap_poses_[7 * (size_t)e.i], 56) || std::memcmp(parameters[1], &snap_poses_[7 * (size_t)e.j], 56) ||
+      std::memcmp(parameters[2], snap_ex_.data(), 56) || std::memcmp(parameters[3], &snap_lam_[(size_t)e.l], 8))
+    return false;
   const size_t k = (size_t)f->slot_;
   residuals[0] = r_pf_[2 * k], residuals[1] = r_pf_[2 * k + 1];
   if (jacobians) {
@@ -310,15 +314,17 @@ bool LinearizationBatch::fetch(const ProjectionFactor* f, double const* const* p
     if (jacobians[2]) std::memcpy(jacobians[2], je_ + 14 * k, 112);
     if (jacobians[3]) std::memcpy(jacobians[3], jl_ + 2 * k, 16);
   }
+  ++served_;
   return true;
 }
 bool LinearizationBatch::fetch(const LineProjectionFactor* f, double const* const* parameters, double* residuals, double** jacobians) const {
   if (!valid_) return false;
   const LF& e = lf_[f->slot_];
-  if (parameters[0] != e.pose) return false;
+  if (std::memcmp(parameters[0], &snap_poses_[7 * (size_t)e.frame], 56)) return false;
   const size_t k = (size_t)f->slot_;
   residuals[0] = r_lf_[2 * k], residuals[1] = r_lf_[2 * k + 1];
   if (jacobians) std::memcpy(jacobians[0], jp_ + 14 * k, 112);
+  ++served_;
   return true;
 }
 

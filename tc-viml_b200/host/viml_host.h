@@ -160,9 +160,13 @@ class LinearizationBatch : public ceres::EvaluationCallback {
   void AddResidualBlock(ProjectionFactor* f, double* pose_i, double* pose_j, double* ex_pose, double* feature);
   void AddResidualBlock(LineProjectionFactor* f, double* pose);
   void PrepareForEvaluation(bool evaluate_jacobians, bool new_evaluation_point) override;
+  // Call when the solve has returned: later Evaluate calls (e.g. ResidualBlockInfo::Evaluate at other states) must not be
+  // served from the last evaluation point by accident.  (fetch also compares the parameter VALUES, so this is belt and braces.)
+  void Invalidate() { valid_ = false; }
   int num_point_factors() const { return (int)pf_.size(); }
   int num_line_factors() const { return (int)lf_.size(); }
   int last_error() const { return last_rc_; }
+  long served() const { return served_; }   // Evaluate calls answered from the batch so far (tests, diagnostics)
 
  private:
   friend class ProjectionFactor;
@@ -178,7 +182,12 @@ class LinearizationBatch : public ceres::EvaluationCallback {
   std::vector<double*> poses_, feats_;
   std::unordered_map<double*, int> pose_id_, feat_id_;
   double* ex_ = nullptr;
+  // values of the registered blocks at the last PrepareForEvaluation: during ceres::Solve the pointers handed to
+  // Evaluate are the minimizer's own state vector (ResidualBlock::Evaluate passes parameter_block->state()), not the
+  // user's arrays, so a factor is served by slot when the VALUES it is asked at equal the evaluation point
+  std::vector<double> snap_poses_, snap_lam_, snap_ex_;
   bool valid_ = false;
+  mutable long served_ = 0;
   int last_rc_ = 0;
   // pinned result buffers
   double *r_pf_ = nullptr, *ji_ = nullptr, *jj_ = nullptr, *je_ = nullptr, *jl_ = nullptr, *r_lf_ = nullptr, *jp_ = nullptr;
