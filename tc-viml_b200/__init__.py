@@ -15,7 +15,7 @@ from ._abi import (LOSS_CAUCHY, OUT_HB, OUT_RESIDUAL_JACOBIAN, OUT_SCHUR, PTRS_D
                    make_config)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libviml_b200.so")
+LIB_PATH = os.environ.get("VIML_LIB_PATH") or os.path.join(_HERE, "libviml_b200.so")   # override: A/B runs of kernel variants
 _LIB = None
 
 # every symbol include/viml.h declares

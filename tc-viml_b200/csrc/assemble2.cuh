@@ -6,10 +6,10 @@
 // leave the SM and there is no CTA-wide phase structure: a window is cut into TASKS that warps execute on their own.
 //
 //   plan_kernel (indices only)   features are ordered by anchor pose; a task is a run of consecutive features
-//       (<= 24 features, ~88 factors); inside a task the factors are ordered by (anchor i, observing frame j) and
+//       (<= 16 features, ~60 factors); inside a task the factors are ordered by (anchor i, observing frame j) and
 //       every (i, j) SEGMENT is padded to an even length.  The plan is a list of 32-bit slots
 //       (factor id | feature slot | i | j) plus one record per task.
-//   assemble_kernel, one CTA (6 warps) per window, two CTAs per SM.  A warp takes a task and streams its slots
+//   assemble_kernel, one CTA (4 warps) per window, three CTAs per SM.  A warp takes a task and streams its slots
 //   32 at a time:
 //     1. lane = factor: residual, Jacobians, Cauchy correction in registers (eval_point).
 //     2. landmark row of the factor's feature: the d^T J_j block is unique to the factor and goes straight to
@@ -21,9 +21,9 @@
 //        DMMA per step.  Every block of H_pp the two factors touch — (i,i), (j,j), (i,j), (i,ex), (j,ex), (ex,ex),
 //        b_i, b_j, b_ex — is a signed sub-block of that Gram matrix.
 //     4. at the end of a segment the j-role entries and the (i,j) block are added to the window's block-upper
-//        accumulator in shared memory (shared-memory FP64 add = CAS loop; balanced over the lanes through a
-//        192-double patch and a compile-time destination table); the i-role and extrinsic entries keep
-//        accumulating in registers until the anchor changes.
+//        accumulator in shared memory (shared-memory FP64 add = compare-and-swap loop; balanced over the
+//        lanes through a 192-double patch and a compile-time destination table); the i-role and extrinsic entries
+//        keep accumulating in registers until the anchor changes.
 //   When the window's tasks are done the CTA expands the block-upper accumulator to the full symmetric D x D
 //   matrix in the (now dead) warp work areas and writes it with ONE cp.async.bulk shared->global (TMA bulk store).
 //
@@ -38,11 +38,11 @@ namespace stream {
 
 constexpr int PMAX = 12;       // poses per window on the fused path (4-bit i/j, 12-bit observation masks)
 constexpr int FMAXP = 4096;    // features per window the plan kernel's shared tables are sized for
-constexpr int PT = 256;        // plan_kernel threads
-constexpr int TASK_T = 88;     // target point factors per task
-constexpr int TASK_F = 24;     // features per task
+constexpr int PT = 64;         // plan_kernel threads (warp 0 orders the features, warp 1 the line factors)
+constexpr int TASK_T = 60;     // target point factors per task (two 32-slot chunks with the segment padding)
+constexpr int TASK_F = 16;     // features per task
 constexpr int LTASK = 32;      // line slots per line task
-constexpr int AW = 6;          // warps per assemble CTA (2 CTAs x 6 warps = 3 warps per scheduler at <= 168 registers)
+constexpr int AW = 4;          // warps per assemble CTA (3 CTAs x 4 warps per SM = 3 warps per scheduler at <= 168 registers)
 constexpr int LACC_W = 14;     // landmark row: d^T J_i (6) | d^T J_ex (6) | d^T d | d^T r
 constexpr int STAGE_D = 1024;  // stage: 32 records x 32 doubles
 constexpr int LACC_D = TASK_F * LACC_W;
@@ -255,50 +255,70 @@ constexpr uint32_t tab_entry(int R, int C, int kind, int off, bool neg) {
          (neg ? (1u << 18) : 0u);
 }
 
+// Destination (kind, off) of Gram entry (R, C), R <= C, for the three roles; the tables are emitted ordered by destination
+// (kind, then offset) so that the 32 lanes of a scatter round add to runs of consecutive doubles of at most three blocks:
+// the shared-memory read-modify-write of a round is then (nearly) bank-conflict free.
+constexpr int col_type(int c) { return c < 3 ? 0 : (c < 6 ? 1 : (c < 9 ? 2 : (c < 15 ? 3 : 4))); }   // A X B Z res
+constexpr int col_sub(int c) { return c < 3 ? c : (c < 6 ? c - 3 : (c < 9 ? c - 6 : (c < 15 ? c - 9 : 0))); }
+
 constexpr Tables make_tables() {
   Tables T{};
   int ns = 0, nlo = 0, nli = 0;
-  // columns: A r = 0..2, X (a_rot) 3..5, B (b_rot) 6..8, Z 9..14, res 15
-  for (int r = 0; r < 3; ++r) {
-    for (int c = r; c < 3; ++c) {   // (A_r, A_c)
-      T.lo[nlo++] = tab_entry(r, c, K_LL, r * 6 + c, false);
-      T.seg[ns++] = tab_entry(r, c, K_HH, r * 6 + c, false);
-      T.seg[ns++] = tab_entry(r, c, K_LH, r * 6 + c, true);
-      if (r != c) T.seg[ns++] = tab_entry(r, c, K_LH, c * 6 + r, true);
+  // every (kind, off) in destination order; for each, the (R, C, sign) that feeds it
+  for (int kind = 0; kind < K_NKIND; ++kind)
+    for (int off = 0; off < 36; ++off) {
+      const bool vec = kind >= K_BL;
+      if (vec && off >= 6) continue;
+      const int dr = vec ? off : off / 6, dc = vec ? 0 : off % 6;
+      for (int R = 0; R < 16; ++R)
+        for (int C = R; C < 16; ++C) {
+          const int tr = col_type(R), tc = col_type(C), r = col_sub(R), c = col_sub(C);
+          // contributions of Gram entry (R, C) — see the role algebra in the header of this file
+          bool hit = false, neg = false;
+          if (tr == 0 && tc == 0) {            // (A_r, A_c), r <= c
+            if (kind == K_LL || kind == K_HH) hit = dr == r && dc == c;
+            if (kind == K_LH) hit = (dr == r && dc == c) || (dr == c && dc == r), neg = true;
+          } else if (tr == 0 && tc == 1) {     // (A_r, X_c)
+            if (kind == K_LL) hit = dr == r && dc == 3 + c;
+            if (kind == K_LH) hit = dr == 3 + c && dc == r, neg = true;
+          } else if (tr == 0 && tc == 2) {     // (A_r, B_c)
+            if (kind == K_LH) hit = dr == r && dc == 3 + c;
+            if (kind == K_HH) hit = dr == r && dc == 3 + c, neg = true;
+          } else if (tr == 0 && tc == 3) {     // (A_r, Z_c)
+            if (kind == K_LE) hit = dr == r && dc == c;
+            if (kind == K_HE) hit = dr == r && dc == c, neg = true;
+          } else if (tr == 0 && tc == 4) {     // (A_r, res)
+            if (kind == K_BL) hit = dr == r;
+            if (kind == K_BH) hit = dr == r, neg = true;
+          } else if (tr == 1 && tc == 1) {     // (X, X)
+            if (kind == K_LL) hit = dr == 3 + r && dc == 3 + c;
+          } else if (tr == 1 && tc == 2) {     // (X, B)
+            if (kind == K_LH) hit = dr == 3 + r && dc == 3 + c;
+          } else if (tr == 1 && tc == 3) {     // (X, Z)
+            if (kind == K_LE) hit = dr == 3 + r && dc == c;
+          } else if (tr == 1 && tc == 4) {
+            if (kind == K_BL) hit = dr == 3 + r;
+          } else if (tr == 2 && tc == 2) {     // (B, B)
+            if (kind == K_HH) hit = dr == 3 + r && dc == 3 + c;
+          } else if (tr == 2 && tc == 3) {     // (B, Z)
+            if (kind == K_HE) hit = dr == 3 + r && dc == c;
+          } else if (tr == 2 && tc == 4) {
+            if (kind == K_BH) hit = dr == 3 + r;
+          } else if (tr == 3 && tc == 3) {     // (Z, Z)
+            if (kind == K_EE) hit = dr == r && dc == c;
+          } else if (tr == 3 && tc == 4) {
+            if (kind == K_BE) hit = dr == r;
+          }
+          if (!hit) continue;
+          const bool per_segment = kind == K_HH || kind == K_LH || kind == K_HE || kind == K_BH;
+          if (per_segment) T.seg[ns++] = tab_entry(R, C, kind, off, neg);
+          else T.lo[nlo++] = tab_entry(R, C, kind, off, neg);
+        }
     }
-    for (int c = 0; c < 3; ++c) {
-      T.lo[nlo++] = tab_entry(r, 3 + c, K_LL, r * 6 + 3 + c, false);       // (A_r, X_c)
-      T.seg[ns++] = tab_entry(r, 3 + c, K_LH, (3 + c) * 6 + r, true);
-      T.seg[ns++] = tab_entry(r, 6 + c, K_LH, r * 6 + 3 + c, false);       // (A_r, B_c)
-      T.seg[ns++] = tab_entry(r, 6 + c, K_HH, r * 6 + 3 + c, true);
-    }
-    for (int c = 0; c < 6; ++c) {                                          // (A_r, Z_c)
-      T.lo[nlo++] = tab_entry(r, 9 + c, K_LE, r * 6 + c, false);
-      T.seg[ns++] = tab_entry(r, 9 + c, K_HE, r * 6 + c, true);
-    }
-    T.lo[nlo++] = tab_entry(r, 15, K_BL, r, false);                        // (A_r, res)
-    T.seg[ns++] = tab_entry(r, 15, K_BH, r, true);
-  }
-  for (int r = 0; r < 3; ++r) {
-    for (int c = r; c < 3; ++c) T.lo[nlo++] = tab_entry(3 + r, 3 + c, K_LL, (3 + r) * 6 + 3 + c, false);   // (X, X)
-    for (int c = 0; c < 3; ++c) T.seg[ns++] = tab_entry(3 + r, 6 + c, K_LH, (3 + r) * 6 + 3 + c, false);   // (X, B)
-    for (int c = 0; c < 6; ++c) T.lo[nlo++] = tab_entry(3 + r, 9 + c, K_LE, (3 + r) * 6 + c, false);       // (X, Z)
-    T.lo[nlo++] = tab_entry(3 + r, 15, K_BL, 3 + r, false);
-  }
-  for (int r = 0; r < 3; ++r) {
-    for (int c = r; c < 3; ++c) T.seg[ns++] = tab_entry(6 + r, 6 + c, K_HH, (3 + r) * 6 + 3 + c, false);   // (B, B)
-    for (int c = 0; c < 6; ++c) T.seg[ns++] = tab_entry(6 + r, 9 + c, K_HE, (3 + r) * 6 + c, false);       // (B, Z)
-    T.seg[ns++] = tab_entry(6 + r, 15, K_BH, 3 + r, false);
-  }
-  for (int r = 0; r < 6; ++r) {
-    for (int c = r; c < 6; ++c) T.lo[nlo++] = tab_entry(9 + r, 9 + c, K_EE, r * 6 + c, false);             // (Z, Z)
-    T.lo[nlo++] = tab_entry(9 + r, 15, K_BE, r, false);
-  }
   // line factors: columns 0..5 = J, 6 = residual (tile 0 only)
-  for (int r = 0; r < 6; ++r) {
+  for (int r = 0; r < 6; ++r)
     for (int c = r; c < 6; ++c) T.line[nli++] = tab_entry(r, c, K_LL, r * 6 + c, false);
-    T.line[nli++] = tab_entry(r, 6, K_BL, r, false);
-  }
+  for (int r = 0; r < 6; ++r) T.line[nli++] = tab_entry(r, 6, K_BL, r, false);
   return T;
 }
 // read once per CTA with lane-indexed (coalesced) loads: global memory, not __constant__ (divergent constant reads replay)
@@ -324,20 +344,37 @@ __device__ __forceinline__ int blk(int br, int bc, int NB) { return br * NB - (b
 __device__ __forceinline__ int swz(int f) { return ((f & 1) << 2) ^ ((f >> 1) & 3); }
 
 // One scatter round per table word: patch[src] goes to Hc[base(kind) + off] with a shared-memory FP64 add (CAS loop).
-// Lane k < K_NKIND holds the base of destination kind k in `mybase`.
+// Lane k < K_NKIND holds the base of destination kind k in `mybase`.  The table words are decoded once per kernel.
+struct Dest {
+  int src;        // double index in the patch, -1 = no entry
+  int off;        // offset inside the destination block
+  int kind;
+  unsigned sign;  // 0x80000000 to negate
+};
+__device__ __forceinline__ Dest decode(uint32_t e) {
+  Dest d;
+  d.src = (e >> 31) ? (int)(e & 0xff) : -1;
+  d.off = (e >> 12) & 63;
+  d.kind = (e >> 8) & 15;
+  d.sign = ((e >> 18) & 1u) << 31;
+  return d;
+}
 template <int ROUNDS>
-__device__ __forceinline__ void scatter(const double* __restrict__ patch, const uint32_t (&tab)[ROUNDS], double* __restrict__ Hc,
+__device__ __forceinline__ void scatter(const double* __restrict__ patch, const Dest (&tab)[ROUNDS], double* __restrict__ Hc,
                                         int mybase) {
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
-    const uint32_t e = tab[r];
-    const int base = __shfl_sync(0xffffffffu, mybase, (e >> 8) & 15);
-    if (e >> 31) {
-      const double v = patch[e & 0xff];
-      atomicAdd(&Hc[base + ((e >> 12) & 63)], ((e >> 18) & 1u) ? -v : v);
+    const int base = __shfl_sync(0xffffffffu, mybase, tab[r].kind);
+    if (tab[r].src >= 0) {
+      const double v = patch[tab[r].src];
+      atomicAdd(&Hc[base + tab[r].off], __hiloint2double(__double2hiint(v) ^ (int)tab[r].sign, __double2loint(v)));
     }
   }
 }
+// (Measured and dropped, round 2: per-pose spin locks with plain read-modify-write under the lock — 0.72 vs 0.56 ms for
+// the compare-and-swap adds; taking entries out with a 64-bit exchange + sentinel so that the rounds of a flush pipeline —
+// 0.68 ms, the per-round address/value registers spill at the 168-register cap; prefetching the next chunk's factor inputs
+// into registers — spills as well.)
 
 // Per-lane selectors of kind_base: which pose (0 = lo, 1 = hi, 2 = extrinsic) is the block row / column of kind `lane`.
 //   kind      LL HH LH LE HE EE BL BH BE
@@ -398,12 +435,12 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
     for (int e = tid; e < cstride / 2; e += NT) c2[e] = gc[e];
   }
   if (tid == 0) s_next = 0;
-  uint32_t tab_seg[4], tab_lo[3], tab_line[1];
+  Dest tab_seg[4], tab_lo[3], tab_line[1];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) tab_seg[r] = g_tables.seg[32 * r + lane];
+  for (int r = 0; r < 4; ++r) tab_seg[r] = decode(g_tables.seg[32 * r + lane]);
 #pragma unroll
-  for (int r = 0; r < 3; ++r) tab_lo[r] = g_tables.lo[32 * r + lane];
-  tab_line[0] = g_tables.line[lane];
+  for (int r = 0; r < 3; ++r) tab_lo[r] = decode(g_tables.lo[32 * r + lane]);
+  tab_line[0] = decode(g_tables.line[lane]);
   const int kb_rs = lane < K_NKIND ? (0x24904 >> (2 * lane)) & 3 : 0, kb_cs = lane < K_NKIND ? (0xA94 >> (2 * lane)) & 3 : 0;
   const bool kb_isb = lane >= K_BL && lane < K_NKIND;
   __syncthreads();
@@ -571,20 +608,16 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
         double2* __restrict__ dst = reinterpret_cast<double2*>(Hlp + (size_t)l * D);
         const double2* __restrict__ la = reinterpret_cast<const double2*>(lacc + f * LACC_W);
         {
-          double2 v = make_double2(0.0, 0.0);
-          bool wr = true;
-          if (rb0 == an) v = la[rp0];
-          else if (rb0 == P) v = la[3 + rp0];
-          else if ((m >> rb0) & 1u) wr = false;
-          if (wr && lane < upr) dst[lane] = v;
+          const bool ia = rb0 == an, ie = rb0 == P;
+          double2 v = la[ia ? rp0 : 3 + rp0];
+          if (!(ia || ie)) v = make_double2(0.0, 0.0);
+          if ((ia || ie || !((m >> rb0) & 1u)) && lane < upr) dst[lane] = v;
         }
-        if (ru1 < upr) {
-          double2 v = make_double2(0.0, 0.0);
-          bool wr = true;
-          if (rb1 == an) v = la[rp1];
-          else if (rb1 == P) v = la[3 + rp1];
-          else if ((m >> rb1) & 1u) wr = false;
-          if (wr) dst[ru1] = v;
+        {
+          const bool ia = rb1 == an, ie = rb1 == P;
+          double2 v = la[ia ? rp1 : 3 + rp1];
+          if (!(ia || ie)) v = make_double2(0.0, 0.0);
+          if ((ia || ie || !((m >> rb1) & 1u)) && ru1 < upr) dst[ru1] = v;
         }
       }
       if (lane < n_feats) {
@@ -651,6 +684,11 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
   __syncthreads();
   // expand the block-upper accumulator to the full symmetric matrix (+ b_p behind it) in the warps' work areas
   double* __restrict__ Hf = work0;
+  const bool staged = D * D + D <= AW * WORK_D;   // P = 12 does not fit: written straight from the accumulator
+  if (!staged) {
+    Hf = Hpp;
+    use_tma = 0;
+  }
   {
     int r = tid / D, c = tid - r * D;
     const int dr = NT / D, dc = NT - dr * D;
@@ -663,7 +701,11 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
       if (c >= D) c -= D, ++r;
     }
   }
-  for (int e = tid; e < D; e += NT) Hf[D * D + e] = Hc[boff + e];
+  if (staged) {
+    for (int e = tid; e < D; e += NT) Hf[D * D + e] = Hc[boff + e];
+  } else {
+    for (int e = tid; e < D; e += NT) bp[e] = Hc[boff + e];
+  }
   if (use_tma) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -677,7 +719,7 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
-  } else {
+  } else if (staged) {
     __syncthreads();
     for (int e = tid; e < D * D; e += NT) Hpp[e] = Hf[e];
     for (int e = tid; e < D; e += NT) bp[e] = Hf[D * D + e];
