@@ -10,12 +10,17 @@ One JSON line on rank 0.  A step = one pass of the hot path over one batch:
   BASELINE.json configs[1]: 4096 independent EuRoC-shaped windows per GPU, every ProjectionFactor and
   LineProjectionFactor evaluated with the Cauchy loss correction and assembled into the block-structured
   H = J^T J, b = J^T r of its window (viml_linearize_batch, VIML_OUT_HB | VIML_LOSS_CAUCHY).
-`value` times it with inputs resident in HBM (CUDA events on the context stream); `e2e` is the same call with
-pinned HOST buffers (H2D of all inputs and D2H of all H/b blocks inside the timed region).  The `assoc`
-object reports the second BASELINE metric (2D-3D line associations/s, configs[2]) the same way, `schur`
-the landmark Schur complement (configs[3] shape), `mode_a` the per-factor r/J output mode.
+`value` times it with inputs resident in HBM (CUDA events on the context stream).  `e2e` is the drop-in call a host
+makes with pinned HOST buffers, H2D of all inputs and D2H of the result inside the timed region; the result it asks
+for is what MarginalizationInfo::marginalize / the solver consume, the landmark-eliminated S, g
+(VIML_OUT_SCHUR: evaluate + assemble + Schur; 42 KB per window back instead of the 131 KB of mostly-zero blocks);
+`e2e_hb` is the same with the full H/b blocks shipped.  Further objects: `parity` (oracle check of this run's outputs),
+`mode_a`, `schur`, `schur_cfg4` (configs[3] at 4096 windows), `cfg5a` (configs[4]: 65536 windows split over the
+GPUs, strong scaling), `assoc` (second BASELINE metric, configs[2]), `huge_window` (configs[4]: one 201-pose window,
+partial [S|g] all-reduced with viml_allreduce_hb), `single_window` (configs[0] through the Ceres bridge).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -32,6 +37,8 @@ import __graft_entry__ as ge  # noqa: E402
 # SURVEY.md §8(d) algorithmic bytes
 B_POINT_A, B_LINE_A = 412, 204            # mode A: inputs + r/J outputs per factor
 B_POINT_IN, B_LINE_IN = 44, 76            # mode B inputs per factor
+WORKLOAD = ("cfg2: 4096 EuRoC-shaped windows/GPU (11 poses, 150 features, ~560 ProjectionFactors + 110 "
+            "LineProjectionFactors each): Evaluate + loss correction + H/b assembly")
 
 
 def window_bytes(P, F):
@@ -95,24 +102,42 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
-def cpu_linearize_rate(orc, cfg, batch, flags, nthreads, target_s=12.0):
-    """Oracle (= the reference's CPU algorithm) on a bounded sample of the same workload."""
+def tile_batch(abi, b, times):
+    """`times` copies of the windows of b, one after the other (independent windows: the work per window is what the
+    BASELINE configs fix; generating 65536 distinct windows in numpy would take minutes for milliseconds of timed work)."""
+    if times == 1:
+        return b
+    def offs(o):
+        step = int(o[-1])
+        return np.concatenate([o[:-1] + k * step for k in range(times)] + [np.array([times * step], dtype=o.dtype)]).astype(np.int32)
+    z = None if b.pf_pts_i_z is None else np.tile(b.pf_pts_i_z, times)
+    return abi.Batch(np.tile(b.poses, (times, 1, 1)), np.tile(b.ex_pose, (times, 1)), np.tile(b.inv_depth, (times, 1)),
+                     offs(b.pf_window_offset), np.tile(b.pf_idx, times), np.tile(b.pf_obs, (times, 1)),
+                     offs(b.lf_window_offset), np.tile(b.lf_frame, times), np.tile(b.lf_geom, (1, times)), z)
+
+
+def cpu_linearize_rate(orc, cfg, batch, flags, nthreads, target_s=12.0, keep=False):
+    """Oracle (= the reference's CPU algorithm) on a bounded sample of the same workload.  Returns (factors/s, windows in
+    the sample, seconds, last result or None)."""
     probe = batch.slice_windows(0, min(batch.W, 2 * nthreads))
     t0 = time.perf_counter()
     orc.linearize_batch(cfg, probe, flags, nthreads=nthreads)
     dt = max(time.perf_counter() - t0, 1e-6)
-    nwin = int(min(batch.W, max(2 * nthreads, probe.W * target_s / dt)))
+    nwin = int(min(batch.W, max(2 * nthreads, 256 if keep else 0, probe.W * target_s / dt)))
     sample = batch.slice_windows(0, nwin)
     reps, dt = 0, 0.0
+    res = sample.alloc_out(flags, fill=0.0)   # allocated once, outside the timed loop
     t0 = time.perf_counter()
     while dt < target_s and reps < 64:   # repeat the sample until ~target_s of wall time has been measured
-        orc.linearize_batch(cfg, sample, flags, nthreads=nthreads)
+        orc.linearize_batch(cfg, sample, flags, nthreads=nthreads, out=res)
         reps += 1
         dt = time.perf_counter() - t0
-    return (sample.NP + sample.NL) * reps / dt, nwin, dt
+    return (sample.NP + sample.NL) * reps / dt, nwin, dt, (res if keep else None)
 
 
 def run_reference(args):
+    """The reference's CPU path for the SAME batch and the same call as the native arm's `e2e`: all 4096 windows per step,
+    Evaluate + loss correction + dense A/b by the ThreadsConstructA rule + landmark Schur complement, all host threads."""
     rank, _, world = dist_env()
     if rank != 0:
         return
@@ -120,37 +145,68 @@ def run_reference(args):
     abi, synth = pkg._abi, pkg.synth
     cfg = synth.euroc_config()
     nthreads = orc.hardware_threads()
-    flags = abi.OUT_HB | abi.LOSS_CAUCHY
-    nwin = max(2 * nthreads, 64)
-    batch = synth.make_windows(nwin, seed=0x5EED + 2)
-    # size the per-step sample so the whole run stays within a few minutes
+    flags = abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
+    batch = synth.make_windows(args.windows, seed=0x5EED + 2)
+    steps, warm = args.steps, args.warmup
+    bufs = batch.alloc_out(flags, fill=0.0)
     t0 = time.perf_counter()
-    orc.linearize_batch(cfg, batch, flags, nthreads=nthreads)
-    dt = time.perf_counter() - t0
-    budget = 120.0 / max(args.steps + args.warmup, 1)
-    scale = int(max(1, min(16, budget / max(dt, 1e-6))))
-    if scale > 1:
-        batch = synth.make_windows(nwin * scale, seed=0x5EED + 2)
-    for _ in range(args.warmup):
-        orc.linearize_batch(cfg, batch, flags, nthreads=nthreads)
+    orc.linearize_batch(cfg, batch, flags, nthreads=nthreads, out=bufs)
+    dt1 = time.perf_counter() - t0
+    if dt1 * (steps + warm) > 240.0:     # keep the whole run within a few minutes on a slow host
+        steps = max(3, int(240.0 / dt1) - warm)
+    for _ in range(max(warm - 1, 0)):
+        orc.linearize_batch(cfg, batch, flags, nthreads=nthreads, out=bufs)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        orc.linearize_batch(cfg, batch, flags, nthreads=nthreads)
+    for _ in range(steps):
+        orc.linearize_batch(cfg, batch, flags, nthreads=nthreads, out=bufs)
     dt = time.perf_counter() - t0
     factors = batch.NP + batch.NL
-    val = factors * args.steps / dt
-    sample = f"{batch.W} of 4096 windows per step ({factors} factors), Evaluate + Cauchy correction + ThreadsConstructA-rule dense A/b"
+    val = factors * steps / dt
+    sample = (f"all {batch.W} windows per step ({factors} factors): Evaluate + Cauchy correction + ThreadsConstructA-rule dense A/b + "
+              f"landmark Schur complement; {steps} timed steps")
     print(json.dumps({
         "impl": "reference", "metric": "linearized_factors_per_s", "value": val, "unit": "factors/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2: 4096 EuRoC-shaped windows/GPU (11 poses, 150 features, ~560 ProjectionFactors + 110 "
-                               "LineProjectionFactors each): Evaluate + loss correction + H/b assembly", "sample": sample},
+        "config": {"workload": WORKLOAD, "windows": batch.W, "sample": sample},
         "cpu_baseline": {"value": val, "unit": "factors/s", "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "factors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference needs Eigen/Ceres/ROS and cannot be built here; this is the dependency-free oracle port of its "
                 "CPU algorithm, std::thread over windows on all host threads",
     }))
+
+
+def nccl_bootstrap(torch, dist, world, rank):
+    """A raw ncclComm_t for viml_allreduce_hb: ncclGetUniqueId on rank 0, broadcast over the existing process group,
+    ncclCommInitRank on every rank (the library dlopens the same libnccl.so.2 torch has loaded)."""
+    try:
+        nccl = ctypes.CDLL("libnccl.so.2")
+    except OSError:
+        import glob
+        import site
+        cand = []
+        for sp in site.getsitepackages():
+            cand += glob.glob(os.path.join(sp, "nvidia", "nccl", "lib", "libnccl.so.2"))
+        if not cand:
+            return None, None
+        nccl = ctypes.CDLL(cand[0])
+
+    class UniqueId(ctypes.Structure):
+        _fields_ = [("internal", ctypes.c_byte * 128)]
+
+    uid = UniqueId()
+    if rank == 0:
+        assert nccl.ncclGetUniqueId(ctypes.byref(uid)) == 0
+    t = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+    raw = bytes(t.cpu().numpy().tolist())
+    ctypes.memmove(ctypes.byref(uid), raw, 128)
+    comm = ctypes.c_void_p()
+    nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UniqueId, ctypes.c_int]
+    rc = nccl.ncclCommInitRank(ctypes.byref(comm), world, uid, rank)
+    if rc != 0:
+        return None, None
+    return nccl, comm
 
 
 def main():
@@ -202,12 +258,13 @@ def main():
         return float(t.item())
 
     pkg = ge.load_package()
-    abi, synth = pkg._abi, pkg.synth
+    abi, synth, parity = pkg._abi, pkg.synth, pkg.parity
     cfg = synth.euroc_config()
     ctx = pkg.Context(cfg, device=local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
     hbm_peak, peak_src = peaks()
     K, Wm = args.steps, args.warmup
+    do_cpu = rank == 0 and world == 1 and not args.skip_cpu
 
     def timed_device(fn, steps, warm):
         """K launches of fn on the context stream between two CUDA events, barrier+sync on both sides,
@@ -227,10 +284,33 @@ def main():
         barrier()
         return max_over_ranks(e0.elapsed_time(e1)), prof
 
+    def timed_host(fn, steps, warm=2):
+        for _ in range(warm):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
+        barrier()
+        return ms
+
+    def free_all(*ds):
+        for d in ds:
+            for p in d.values():
+                ctx.device_free(p)
+
+    def fetch(shape, dptr, dtype=np.float64):
+        a = np.empty(shape, dtype=dtype)
+        ctx.d2h(a, dptr)
+        ctx.sync()
+        return a
+
     # ------------------------------------------------------------------ linearise (headline)
     batch = synth.make_windows(args.windows, seed=0x5EED + 2 + rank)
     factors = batch.NP + batch.NL
     flags = abi.OUT_HB | abi.LOSS_CAUCHY
+    flagsS = abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
     d_in = {k: ctx.to_device(v) for k, v in batch.arrays().items() if v is not None}
     shapes = batch.out_shapes()
     d_out = {k: ctx.device_alloc(int(np.prod(shapes[k])) * 8) for k in ("H_pp", "H_lp", "H_ll", "b_p", "b_l")}
@@ -255,51 +335,75 @@ def main():
           "assemble_hb": step_bytes, "linearize_lines": batch.NL * B_LINE_IN, "prep_windows": batch.W * shared_in}
     dom_bytes = kb.get(dom_name, step_bytes)
     achieved = dom_bytes / (dom_ms / dom_n * 1e-3) / 1e9
+    ncu_traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        ncu_traffic = json.load(open(tpath)).get(dom_name)
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": None,
+                "traffic_note": "DRAM bytes are not measurable inside a plain run; the ncu --set full capture of this kernel for "
+                                "the same command is in profiles/ (value under ncu_dram_bytes_per_launch when committed)",
+                "ncu_dram_bytes_per_launch": ncu_traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms / dom_n,
                 "step_algorithmic_bytes": step_bytes, "step_frac": step_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
                 "kernel_ms_per_step": {k: v[0] / K for k, v in prof.items()}}
-    ncu_traffic = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(ncu_traffic):
-        roofline["traffic"] = json.load(open(ncu_traffic)).get(dom_name)
+    H_dev = {k: fetch(shapes[k], d_out[k]) for k in d_out}     # this run's device-resident outputs, for the parity check
 
-    # ------------------------------------------------------------------ e2e: same call, pinned host buffers
+    # ------------------------------------------------------------------ e2e: the drop-in call, pinned host buffers
     pins = {k: pkg.pinned_like(v) for k, v in batch.arrays().items() if v is not None}
-    pouts = {k: pkg.PinnedArray(shapes[k], np.float64) for k in d_out}
     hb = abi.Batch(**{k: p.array for k, p in pins.items()})
-    ho = {k: p.array for k, p in pouts.items()}
     h2d = sum(p.nbytes for p in pins.values())
-    d2h = sum(p.nbytes for p in pouts.values())
-    for _ in range(2):
-        ctx.linearize(hb, flags, out=ho)
-    barrier()
     e_steps = max(3, min(K, 10))
-    t0 = time.perf_counter()
-    for _ in range(e_steps):
-        ctx.linearize(hb, flags, out=ho)
-    e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e_steps
-    barrier()
+    pS = {k: pkg.PinnedArray(shapes[k], np.float64) for k in ("S", "g")}
+    hoS = {k: p.array for k, p in pS.items()}
+    e_ms = timed_host(lambda: ctx.linearize(hb, abi.OUT_SCHUR | abi.LOSS_CAUCHY, out=hoS), e_steps)
     e2e = {"value": total_factors / (e_ms * 1e-3), "unit": "factors/s", "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(d2h), "ms_per_step": e_ms, "steps": e_steps,
-           "api": "viml_linearize_batch(host pointers, VIML_OUT_HB|VIML_LOSS_CAUCHY)"}
-    # spot check against the device-resident run so the e2e path is the same computation
-    chk = np.empty(shapes["b_p"])
-    ctx.d2h(chk, d_out["b_p"])
-    ctx.sync()
-    assert np.allclose(chk, ho["b_p"], rtol=1e-9, atol=1e-6 * np.abs(chk).max()), "e2e and device-resident results differ"
-    for p in list(pins.values()) + list(pouts.values()):
+           "d2h_bytes_per_step": int(sum(p.nbytes for p in pS.values())), "ms_per_step": e_ms, "steps": e_steps,
+           "api": "viml_linearize_batch(host pointers, VIML_OUT_SCHUR|VIML_LOSS_CAUCHY): evaluate + assemble + landmark Schur, S and g back"}
+    S_host = {k: v.copy() for k, v in hoS.items()}
+    pH = {k: pkg.PinnedArray(shapes[k], np.float64) for k in d_out}
+    hoH = {k: p.array for k, p in pH.items()}
+    e_ms_hb = timed_host(lambda: ctx.linearize(hb, flags, out=hoH), max(3, e_steps // 2))
+    e2e_hb = {"value": total_factors / (e_ms_hb * 1e-3), "unit": "factors/s", "h2d_bytes_per_step": int(h2d),
+              "d2h_bytes_per_step": int(sum(p.nbytes for p in pH.values())), "ms_per_step": e_ms_hb,
+              "api": "viml_linearize_batch(host pointers, VIML_OUT_HB|VIML_LOSS_CAUCHY): every H/b block shipped"}
+    # the host-pointer path is the same computation as the device-resident one
+    for k in ("b_p", "H_ll"):
+        assert parity.unit_err(k, hoH[k], H_dev[k]) < 1e-12, "e2e and device-resident results differ"
+    for p in list(pins.values()) + list(pS.values()) + list(pH.values()):
         p.free()
 
     out = {"metric": "linearized_factors_per_s", "value": value, "unit": "factors/s", "n_gpus": world, "steps": K,
            "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "cfg2: 4096 EuRoC-shaped windows/GPU (11 poses, 150 features, ~560 ProjectionFactors + 110 "
-                                  "LineProjectionFactors each): Evaluate + loss correction + H/b assembly",
+           "config": {"workload": WORKLOAD,
                       "windows_per_gpu": batch.W, "point_factors_per_gpu": batch.NP, "line_factors_per_gpu": batch.NL,
                       "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (step_bytes / 1e6),
                       "parallelism": f"{world} GPU(s), windows sharded, no data-path collective"},
-           "roofline": roofline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks}
+           "roofline": roofline, "e2e": e2e, "e2e_hb": e2e_hb, "gpu_launches": gpu_launches, "clocks": clocks}
+
+    # ------------------------------------------------------------------ CPU baseline + parity of THIS run's outputs (rank 0, N=1)
+    if do_cpu:
+        orc = ge.load_oracle()
+        nt = orc.hardware_threads()
+        rate, nwin, dt, ref = cpu_linearize_rate(orc, cfg, batch, flagsS, nt, keep=True)
+        out["cpu_baseline"] = {"value": rate, "unit": "factors/s", "cores": nt, "kind": "port",
+                               "sample": f"{nwin} of {batch.W} windows, all {nt} host threads, {dt:.1f} s; oracle port of the reference's "
+                                         "Evaluate + loss correction + ThreadsConstructA dense A/b + landmark Schur"}
+        r1, n1, d1, _ = cpu_linearize_rate(orc, cfg, batch, flagsS, 1, target_s=4.0)
+        out["cpu_baseline"]["single_thread_factors_per_s"] = r1
+        errs = {}
+        for k in ("H_pp", "H_lp", "H_ll", "b_p", "b_l"):
+            errs[k] = parity.unit_err(k, H_dev[k][:nwin], ref[k])
+        for k in ("S", "g"):
+            errs[k] = parity.unit_err(k, S_host[k][:nwin], ref[k])
+        assert max(errs.values()) < 1e-9, errs
+        out["parity"] = {"parity_checked_windows": nwin, "tolerance": 1e-9,
+                         "norm": "per unit: 6x6 block (H_pp, S), 6-vector (b_p, g), landmark row (H_lp), window (H_ll, b_l)",
+                         "max_unit_err": errs, "oracle": "oracle/viml_oracle.cpp (parity unpinned: see DESIGN.md)"}
+    elif rank == 0:
+        out["cpu_baseline"] = None
+    del H_dev, S_host
 
     if not args.skip_extras:
         # ---------------- mode A (per-factor r/J for the Ceres shim)
@@ -315,10 +419,8 @@ def main():
                                       "achieved": (batch.NP * B_POINT_A) / (pa[0] / pa[1] * 1e-3) / 1e9, "peak": hbm_peak,
                                       "unit": "GB/s", "frac": (batch.NP * B_POINT_A) / (pa[0] / pa[1] * 1e-3) / 1e9 / hbm_peak,
                                       "step_frac": bytesA / (msA / K * 1e-3) / 1e9 / hbm_peak}}
-        for p in dA.values():
-            ctx.device_free(p)
-        # ---------------- landmark Schur (cfg-4 shape, windows scaled to fit the step budget)
-        flagsS = abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
+        free_all(dA)
+        # ---------------- linearise + landmark Schur, device resident (cfg-2 shape)
         dS = {k: ctx.device_alloc(int(np.prod(shapes[k])) * 8) for k in ("S", "g")}
         sS = abi.out_struct({**d_out, **dS})
         msS, profS = timed_device(lambda: ctx.linearize_raw(s_in, sS, flagsS | abi.PTRS_DEVICE), K, Wm)
@@ -327,30 +429,87 @@ def main():
         fl = (2.0 * D * D * F + 2.0 * D * F) * batch.W
         out["schur"] = {"windows_per_s": sum_over_ranks(float(batch.W)) / (ps[0] / ps[1] * 1e-3), "ms_per_launch": ps[0] / ps[1],
                         "gflops": fl / (ps[0] / ps[1] * 1e-3) / 1e9, "shape": f"{batch.W} windows x (D={D}, {F} landmarks)",
-                        "step_ms_with_linearize": msS / K}
-        for p in dS.values():
-            ctx.device_free(p)
-        # cfg 4: marginalisation / Schur stress, 10 keyframes + 2000 landmarks per window (all starting in frame 0);
-        # windows scaled to 256 per GPU to keep input generation short (per-window work is what cfg 4 fixes)
-        b4 = synth.make_windows(256, seed=0x5EED + 4 + rank, P=11, F=2000, all_start_zero=True, lines_per_frame=0)
+                        "step_ms_with_linearize": msS / K, "kernel_ms_per_step": {k: v[0] / K for k, v in profS.items()}}
+        free_all(dS)
+    free_all(d_in, d_out)
+
+    if not args.skip_extras:
+        # ---------------- cfg 4: marginalisation / Schur stress, 4096 windows x (10 keyframes + 1, 2000 landmarks all starting in
+        # frame 0): 256 distinct windows generated, tiled x16 (independent windows; per-window work is what cfg 4 fixes)
+        b4s = synth.make_windows(256, seed=0x5EED + 4 + rank, P=11, F=2000, all_start_zero=True, lines_per_frame=0)
+        b4 = tile_batch(abi, b4s, 16)
         d4 = {k: ctx.to_device(v) for k, v in b4.arrays().items() if v is not None}
         sh4 = b4.out_shapes()
         o4 = {k: ctx.device_alloc(int(np.prod(sh4[k])) * 8) for k in ("H_pp", "H_lp", "H_ll", "b_p", "b_l", "S", "g")}
         s4, so4 = b4.struct(d4), abi.out_struct(o4)
-        ms4, prof4 = timed_device(lambda: ctx.linearize_raw(s4, so4, flagsS | abi.PTRS_DEVICE), max(3, K // 4), 3)
-        n4 = max(3, K // 4)
+        n4 = 3
+        ms4, prof4 = timed_device(lambda: ctx.linearize_raw(s4, so4, flagsS | abi.PTRS_DEVICE), n4, 3)
         p4 = prof4.get("schur_landmarks", (ms4, n4))
+        pa4 = prof4.get("assemble_hb", (ms4, n4))
         fl4 = (2.0 * b4.D * b4.D * b4.F + 2.0 * b4.D * b4.F) * b4.W
-        out["schur_cfg4"] = {"shape": f"{b4.W} windows/GPU x (10 kf + 1, {b4.F} landmarks, {b4.NP // b4.W} factors/window)",
+        sin4, sout4 = window_bytes(b4.P, b4.F)
+        bytes4 = b4.NP * B_POINT_IN + b4.W * (sin4 + sout4)
+        out["schur_cfg4"] = {"shape": f"{b4.W} windows/GPU x (10 kf + 1, {b4.F} landmarks, {b4.NP // b4.W} factors/window); 256 distinct windows tiled x16",
                              "factors_per_s": sum_over_ranks(float(b4.NP)) / (ms4 / n4 * 1e-3), "ms_per_step": ms4 / n4,
                              "windows_per_s": sum_over_ranks(float(b4.W)) / (ms4 / n4 * 1e-3),
                              "schur_ms_per_launch": p4[0] / p4[1], "schur_tflops": fl4 / (p4[0] / p4[1] * 1e-3) / 1e12,
+                             "assemble_roofline": {"bound": "hbm", "kernel": "assemble_hb", "algorithmic_bytes_per_launch": bytes4,
+                                                   "achieved": bytes4 / (pa4[0] / pa4[1] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                                   "frac": bytes4 / (pa4[0] / pa4[1] * 1e-3) / 1e9 / hbm_peak},
                              "kernel_ms_per_step": {k: v[0] / n4 for k, v in prof4.items()}}
-        for p in list(d4.values()) + list(o4.values()):
-            ctx.device_free(p)
+        if do_cpu:
+            orc = ge.load_oracle()
+            nt = orc.hardware_threads()
+            # (i) the structured landmark Schur of the oracle port on the cfg-4 window shape, all host threads
+            smp = b4s.slice_windows(0, min(b4s.W, 2 * nt))
+            t0 = time.perf_counter()
+            orc.linearize_batch(cfg, smp, abi.OUT_HB | abi.LOSS_CAUCHY, nthreads=nt)
+            t_hb = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            refS = orc.linearize_batch(cfg, smp, flagsS, nthreads=nt)
+            t_s = time.perf_counter() - t0
+            gotS = fetch(sh4["S"], o4["S"])[:smp.W]
+            e4 = parity.unit_err("S", gotS, refS["S"])
+            assert e4 < 1e-9, e4
+            # (ii) the reference's literal algorithm, eig(Amm) of the dense pos x pos system (marginalization_factor.cpp:267-282):
+            # cubic in the landmark count, timed single-thread on a reduced L and extrapolated
+            Lr = 200
+            br = synth.make_windows(1, seed=77, P=11, F=Lr, all_start_zero=True, lines_per_frame=0)
+            A, bb = orc.window_dense(cfg, br, 0, abi.OUT_HB | abi.LOSS_CAUCHY)
+            pos = A.shape[0]
+            perm = np.concatenate([np.arange(br.D, pos), np.arange(br.D)])   # landmarks first = the marginalised block
+            A, bb = A[np.ix_(perm, perm)], bb[perm]
+            t0 = time.perf_counter()
+            orc.marginalize_dense(A, bb, Lr)
+            t_dense = time.perf_counter() - t0
+            out["schur_cfg4"]["cpu_baseline"] = {
+                "structured": {"windows_per_s": smp.W / max(t_s, 1e-9), "schur_only_windows_per_s": smp.W / max(t_s - t_hb, 1e-9),
+                               "cores": nt, "kind": "port", "sample": f"{smp.W} cfg-4 windows: Evaluate + H/b + structured landmark Schur"},
+                "literal_dense": {"seconds_per_window_at_L": t_dense, "L": Lr, "cores": 1, "kind": "port",
+                                  "extrapolated_seconds_per_window_at_2000": t_dense * (2015.0 / (Lr + 15.0)) ** 3,
+                                  "note": "SelfAdjointEigenSolver stand-in (cyclic Jacobi) on the dense (L+72) system; O(L^3)"},
+                "parity_checked_windows": smp.W, "S_max_unit_err": e4}
+        free_all(d4, o4)
+        del b4, b4s
+
+        # ---------------- cfg 5a: 65536 windows partitioned over the GPUs (strong scaling: total work fixed)
+        tot5 = 65536
+        per = tot5 // world
+        b5 = tile_batch(abi, synth.make_windows(4096, seed=0x5EED + 5 + rank), max(1, per // 4096))
+        d5 = {k: ctx.to_device(v) for k, v in b5.arrays().items() if v is not None}
+        sh5 = b5.out_shapes()
+        o5 = {k: ctx.device_alloc(int(np.prod(sh5[k])) * 8) for k in ("H_pp", "H_lp", "H_ll", "b_p", "b_l")}
+        s5, so5 = b5.struct(d5), abi.out_struct(o5)
+        ms5, prof5 = timed_device(lambda: ctx.linearize_raw(s5, so5, flags | abi.PTRS_DEVICE), 3, 3)
+        f5 = sum_over_ranks(float(b5.NP + b5.NL))
+        out["cfg5a"] = {"metric": "linearized_factors_per_s", "value": f5 / (ms5 / 3 * 1e-3), "unit": "factors/s", "scaling": "strong",
+                        "windows_total": int(sum_over_ranks(float(b5.W))), "windows_per_gpu": b5.W, "n_gpus": world, "ms_per_step": ms5 / 3,
+                        "config": "cfg5a: 65536 EuRoC-shaped windows partitioned over the GPUs (4096 distinct windows per rank, tiled), "
+                                  "device resident, no data-path collective",
+                        "kernel_ms_per_step": {k: v[0] / 3 for k, v in prof5.items()}}
+        free_all(d5, o5)
+        del b5
         out["fp64_peaks"] = dict(zip(("dfma_tflops", "dmul_dadd_tops", "dmma_tflops"), ctx.microbench_fp64()))
-    for p in list(d_in.values()) + list(d_out.values()):
-        ctx.device_free(p)
 
     # ------------------------------------------------------------------ association (second metric)
     if not args.skip_assoc and not args.skip_extras:
@@ -374,11 +533,9 @@ def main():
         a_steps = max(3, min(K, 5))
         msQ, profQ = timed_device(lambda: ctx.associate_raw(q, o, abi.PTRS_DEVICE), a_steps, 3)
         msQ /= a_steps
-        cnt = np.empty(Pq, dtype=np.int32)
-        mi = np.empty((Pq, L), dtype=np.int32)
-        ctx.d2h(cnt, do["fov_count"])
-        ctx.d2h(mi, do["match_index"])
-        ctx.sync()
+        cnt = fetch((Pq,), do["fov_count"], np.int32)
+        mi = fetch((Pq, L), do["match_index"], np.int32)
+        err_d = fetch((Pq, L, 3), do["err"], np.float32)
         n_assoc = sum_over_ranks(float(Pq * L))
         fp = out.get("fp64_peaks", {})
         pc = profQ.get("assoc_cull", (msQ, 1))
@@ -411,12 +568,7 @@ def main():
                                                                                  abi.ptr(hin["l2d"].array), None)
         oh.match_index, oh.err, oh.projected, oh.fov_count = (abi.ptr(res_p[k].array) for k in ("match_index", "err", "projected", "fov_count"))
         oh.fov_index, oh.fov_capacity, oh.fov_mask = None, 0, None
-        ctx.associate_raw(qh, oh, 0)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(a_steps):
-            ctx.associate_raw(qh, oh, 0)
-        e_ms_a = max_over_ranks((time.perf_counter() - t0) * 1e3) / a_steps
+        e_ms_a = timed_host(lambda: ctx.associate_raw(qh, oh, 0), a_steps, warm=1)
         res = {k: v.array for k, v in res_p.items()}
         assert np.array_equal(res["match_index"], mi)
         out["assoc"] = {"metric": "line_associations_per_s", "value": n_assoc / (msQ * 1e-3), "unit": "assoc/s",
@@ -442,13 +594,22 @@ def main():
             t0 = time.perf_counter()
             orc.line_associate(cfg, lines, cull[:npose], None, ex[:npose], l2d[:npose], nthreads=nt)
             dt = time.perf_counter() - t0
-            if dt < 5.0:   # scale the sample to ~10 s of wall time
-                npose = int(min(Pq, npose * 10.0 / max(dt, 1e-3)))
-                t0 = time.perf_counter()
-                orc.line_associate(cfg, lines, cull[:npose], None, ex[:npose], l2d[:npose], nthreads=nt)
-                dt = time.perf_counter() - t0
+            npose = int(min(Pq, max(npose, npose * 20.0 / max(dt, 1e-3))))   # ~20 s of CPU work, or every pose if that is less
+            t0 = time.perf_counter()
+            ref = orc.line_associate(cfg, lines, cull[:npose], None, ex[:npose], l2d[:npose], nthreads=nt)
+            dt = time.perf_counter() - t0
             out["assoc"]["cpu_baseline"] = {"value": npose * L / dt, "unit": "assoc/s", "cores": nt, "kind": "port",
                                             "sample": f"{npose} of {Pq} poses against the full {N}-line map ({dt:.1f} s)"}
+            # bit-exact parity of this run's device results on every pose the CPU leg covered
+            assert np.array_equal(mi[:npose], ref["match_index"]), "association indices differ from the oracle"
+            assert np.array_equal(cnt[:npose], ref["fov_count"]), "FoV counts differ from the oracle"
+            assert np.array_equal(err_d[:npose, :, 1:], ref["err"][..., 1:]), "errD / overlap differ from the oracle"
+            assert np.array_equal(res["projected"][:npose], ref["projected"]), "projected segments differ from the oracle"
+            out["assoc"]["parity_checked_poses"] = npose
+            out["assoc"]["parity"] = "match_index, fov_count, errD, overlap, projected bit-exact against the oracle on those poses"
+        for p in list(hin.values()) + list(res_p.values()):
+            p.free()
+        free_all(dq, do)
 
     # ------------------------------------------------------------------ one huge window (cfg 5b): partial [S|g] + all-reduce
     if not args.skip_extras:
@@ -462,35 +623,46 @@ def main():
         so.S, so.g = sg.data_ptr(), sg.data_ptr() + Dh * Dh * 8
         sh = part.struct(dh_in)
         fl = abi.OUT_SCHUR | abi.LOSS_CAUCHY | abi.PTRS_DEVICE
+        nccl, comm = (None, None)
+        if world > 1:
+            nccl, comm = nccl_bootstrap(torch, dist, world, rank)
+        via = "none (1 GPU)"
+        if world > 1:
+            via = ("viml_allreduce_hb (raw ncclComm_t, ncclAllReduce(sum, f64) of [S|g] on the context stream)" if comm
+                   else "torch.distributed all_reduce (raw NCCL bootstrap failed)")
 
         def huge_step():
             ctx.linearize_raw(sh, so, fl)
             if world > 1:
-                with torch.cuda.stream(stream):
-                    dist.all_reduce(sg)
+                if comm:
+                    rc = ctx.lib.viml_allreduce_hb(ctx.h, comm, ctypes.c_void_p(sg.data_ptr()), Dh * Dh + Dh)
+                    assert rc == 0, rc
+                else:
+                    with torch.cuda.stream(stream):
+                        dist.all_reduce(sg)
 
         h_steps = max(3, min(K, 5))
         msH, profH = timed_device(huge_step, h_steps, 3)
         out["huge_window"] = {"factors_per_s": (huge.NP + huge.NL) / (msH / h_steps * 1e-3), "ms_per_step": msH / h_steps,
                               "shape": f"1 window, {huge.P} poses, {huge.F} landmarks, {huge.NP}+{huge.NL} factors, split by landmark over {world} GPU(s)",
-                              "allreduce_doubles": int(Dh * Dh + Dh) if world > 1 else 0,
-                              "collective": "NCCL all-reduce(sum, f64) of [S|g] via torch.distributed" if world > 1 else "none (1 GPU)",
-                              "kernel_ms_per_step": {k: v[0] / h_steps for k, v in profH.items()}}
-        for p in dh_in.values():
-            ctx.device_free(p)
+                              "landmarks_per_rank": int(part.F), "allreduce_doubles": int(Dh * Dh + Dh) if world > 1 else 0,
+                              "collective": via, "kernel_ms_per_step": {k: v[0] / h_steps for k, v in profH.items()}}
+        if comm:
+            ctx.sync()
+            nccl.ncclCommDestroy(comm)
+        free_all(dh_in)
 
-    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
-    if rank == 0 and world == 1 and not args.skip_cpu:
-        orc = ge.load_oracle()
-        nt = orc.hardware_threads()
-        rate, nwin, dt = cpu_linearize_rate(orc, cfg, batch, flags, nt)
-        out["cpu_baseline"] = {"value": rate, "unit": "factors/s", "cores": nt, "kind": "port",
-                               "sample": f"{nwin} of {batch.W} windows, all {nt} host threads, {dt:.1f} s; oracle port of the reference's "
-                                         "Evaluate + loss correction + ThreadsConstructA dense A/b"}
-        r1, n1, d1 = cpu_linearize_rate(orc, cfg, batch, flags, 1, target_s=4.0)
-        out["cpu_baseline"]["single_thread_factors_per_s"] = r1
-    elif rank == 0:
-        out["cpu_baseline"] = None
+    # ------------------------------------------------------------------ cfg 1 through the drop-in path (Ceres bridge), rank 0
+    if rank == 0 and not args.skip_extras:
+        exe = os.path.join(ROOT, "tc-viml_b200", "build", "selftest")
+        try:
+            r = subprocess.run([exe, "--bench-cfg1", "200"], capture_output=True, text=True, timeout=300,
+                               env={**os.environ, "CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)).split(",")[0]})
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+            out["single_window"] = json.loads(line)
+            out["single_window"].pop("sink", None)
+        except Exception as e:   # the bench line must still be printed
+            out["single_window"] = {"error": repr(e)[:200]}
 
     ctx.close()
     if world > 1:

@@ -65,9 +65,10 @@ def line_evaluate(ps, pe, abc, K, bcR, bcT, pose, want_jac=True):
     return r, J
 
 
-def linearize_batch(cfg, batch, flags, nthreads=1):
-    """Oracle counterpart of Context.linearize: returns dict of numpy outputs."""
-    bufs = batch.alloc_out(flags, fill=0.0)
+def linearize_batch(cfg, batch, flags, nthreads=1, out=None):
+    """Oracle counterpart of Context.linearize: returns dict of numpy outputs (`out`: reuse buffers of an earlier call, so
+    that a timed loop does not pay for the allocation)."""
+    bufs = batch.alloc_out(flags, fill=0.0) if out is None else out
     s = batch.struct()
     o = _abi().out_struct(bufs)
     rc = lib().orc_linearize_batch(C.byref(cfg), C.byref(s), C.byref(o), C.c_uint32(flags), C.c_int(nthreads))

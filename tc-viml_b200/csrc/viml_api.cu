@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
+#include <ctime>
 #include <numeric>
 #include <vector>
 
@@ -299,6 +300,8 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
       (NP > 0 && (!in->pf_idx || !in->pf_obs)) || (NL > 0 && (!in->lf_window_offset || !in->lf_frame || !in->lf_geom)))
     return fail(ctx, VIML_ERR_INVALID, "null input array");
   const int D = 6 * (P + 1);
+  timespec ts_begin;
+  clock_gettime(CLOCK_MONOTONIC, &ts_begin);
   const bool dev = (flags & VIML_PTRS_DEVICE) != 0;
   const bool wantA = (flags & VIML_OUT_RESIDUAL_JACOBIAN) != 0;
   const bool wantHB = (flags & VIML_OUT_HB) != 0, wantS = (flags & VIML_OUT_SCHUR) != 0;
@@ -358,15 +361,19 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
       for (int w = 0; w < W && ok; ++w) ok = lo[w] <= lo[w + 1];
     }
     if (!ok) return fail(ctx, VIML_ERR_INVALID, "window offsets are not a CSR of the factor arrays (offset[0] == 0, non-decreasing, offset[W] == n_factors)");
+  }
+  // packed indices: checked chunk by chunk inside the pipeline below (the host runs ahead of the asynchronous copies and
+  // kernels, so the ~1 ms scan of a 2.3 M-factor batch hides behind the transfers of the previous chunk)
+  auto indices_ok = [&](int64_t pa, int64_t pb, int64_t la, int64_t lb) {
     uint32_t bad = 0;
     const uint32_t uP = (uint32_t)P, uF = (uint32_t)F;
-    for (int64_t k = 0; k < NP; ++k) {
+    for (int64_t k = pa; k < pb; ++k) {
       const uint32_t ix = in->pf_idx[k];
       bad |= (uint32_t)((ix & 0xffu) >= uP) | (uint32_t)(((ix >> 8) & 0xffu) >= uP) | (uint32_t)((ix >> 16) >= uF);
     }
-    for (int64_t k = 0; k < NL; ++k) bad |= (uint32_t)((uint32_t)in->lf_frame[k] >= uP);
-    if (bad) return fail(ctx, VIML_ERR_INVALID, "factor index out of range (pose index >= poses_per_window, feature >= feats_per_window or line frame >= poses_per_window)");
-  }
+    for (int64_t k = la; k < lb; ++k) bad |= (uint32_t)((uint32_t)in->lf_frame[k] >= uP);
+    return bad == 0;
+  };
   // ---- host pointers: chunked pipeline  H2D(c+1) | kernels(c) | D2H(c-1)  on three streams ----
   // Device buffers hold the whole batch at the same absolute positions as the host arrays; a chunk is a range of
   // windows, its kernels run on a "view" (pointers advanced to the first window of the chunk, factor ranges
@@ -423,10 +430,20 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   for (auto& sl : slots) *sl.dev = ctx->out_arena.take<double>(sl.per_window * W + sl.per_pf * NP + sl.per_lf * NL);
 
   cudaStream_t s_in = ctx->copy_stream, s_out = ctx->copy_stream2;
+  cudaEvent_t tv0 = nullptr;
+  if (getenv("VIML_E2E_TIMING")) {
+    cudaEventCreate(&tv0);
+    cudaEventRecord(tv0, s_in);
+  }
   // offsets first (tiny, needed by every chunk); the previous call's work on `st` is already complete (synchronous API)
   VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_poff, in->pf_window_offset, (size_t)(W + 1) * 4, cudaMemcpyHostToDevice, s_in));
   if (NL > 0) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_loff, in->lf_window_offset, (size_t)(W + 1) * 4, cudaMemcpyHostToDevice, s_in));
-  const int nchunk = W >= 512 ? 8 : 1;
+  const int nchunk = W >= 2048 ? 16 : (W >= 512 ? 8 : 1);
+  // small per-window arrays: whole batch, one copy each
+  VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_poses, in->poses, n_pose * 8, cudaMemcpyHostToDevice, s_in));
+  VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_ex, in->ex_pose, n_ex * 8, cudaMemcpyHostToDevice, s_in));
+  if (n_dep) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_dep, in->inv_depth, n_dep * 8, cudaMemcpyHostToDevice, s_in));
+  if (NL > 0) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_frame, in->lf_frame, (size_t)NL * 4, cudaMemcpyHostToDevice, s_in));
   std::vector<cudaEvent_t> ev_in(nchunk), ev_k(nchunk);
   for (int c = 0; c < nchunk; ++c) {
     cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
@@ -440,16 +457,19 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
     const int w0 = (int)((int64_t)W * c / nchunk), w1 = (int)((int64_t)W * (c + 1) / nchunk), Wc = w1 - w0;
     const int64_t pa = in->pf_window_offset[w0], pb = in->pf_window_offset[w1];
     const int64_t la = NL > 0 ? in->lf_window_offset[w0] : 0, lb = NL > 0 ? in->lf_window_offset[w1] : 0;
-    h2d(d_poses + (size_t)w0 * P * 7, in->poses + (size_t)w0 * P * 7, (size_t)Wc * P * 56);
-    h2d(d_ex + (size_t)w0 * 7, in->ex_pose + (size_t)w0 * 7, (size_t)Wc * 56);
-    h2d(d_dep + (size_t)w0 * F, in->inv_depth + (size_t)w0 * F, (size_t)Wc * F * 8);
+    if (!indices_ok(pa, pb, la, lb)) {
+      rc = fail(ctx, VIML_ERR_INVALID, "factor index out of range (pose index >= poses_per_window, feature >= feats_per_window or line frame >= poses_per_window)");
+      break;
+    }
+    // per chunk only the three large arrays (observations, packed indices, line geometry as ONE strided copy of its nine
+    // planes); the small per-window arrays went up for the whole batch before the loop — every copy costs ~10-20 us of
+    // DMA set-up however small it is, and 17 copies per chunk kept the upload stream busy for 6 ms on 125 MB
     h2d(d_idx + pa, in->pf_idx + pa, (size_t)(pb - pa) * 4);
     h2d(d_obs + 4 * pa, in->pf_obs + 4 * pa, (size_t)(pb - pa) * 32);
     if (d_z) h2d(d_z + pa, in->pf_pts_i_z + pa, (size_t)(pb - pa) * 8);
-    if (lb > la) {
-      h2d(d_frame + la, in->lf_frame + la, (size_t)(lb - la) * 4);
-      for (int k = 0; k < 9; ++k) h2d(d_geom + (size_t)k * NL + la, in->lf_geom + (size_t)k * NL + la, (size_t)(lb - la) * 8);
-    }
+    if (lb > la)
+      cudaMemcpy2DAsync(d_geom + la, (size_t)NL * 8, in->lf_geom + la, (size_t)NL * 8, (size_t)(lb - la) * 8, 9,
+                        cudaMemcpyHostToDevice, s_in);
     cudaEventRecord(ev_in[c], s_in);
     cudaStreamWaitEvent(st, ev_in[c], 0);
     // view of windows [w0, w1)
@@ -473,7 +493,27 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
         if (cnt) cudaMemcpyAsync(sl.host + off, *sl.dev + off, cnt * 8, cudaMemcpyDeviceToHost, s_out);
       }
   }
+  const bool e2e_timing = getenv("VIML_E2E_TIMING") != nullptr;
+  timespec ts_q;
+  cudaEvent_t tv[3] = {nullptr, nullptr, nullptr};
+  if (e2e_timing) {
+    clock_gettime(CLOCK_MONOTONIC, &ts_q);
+    for (auto& e : tv) cudaEventCreate(&e);
+    cudaEventRecord(tv[0], s_in), cudaEventRecord(tv[1], st), cudaEventRecord(tv[2], s_out);
+  }
   cudaError_t e1 = cudaStreamSynchronize(s_out), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(s_in);
+  if (e2e_timing) {   // diagnosis: how long the host took to queue the pipeline vs how long the device needed to drain it
+    timespec ts_d;
+    clock_gettime(CLOCK_MONOTONIC, &ts_d);
+    float a = 0, b = 0, c2 = 0;
+    cudaEventElapsedTime(&a, tv0, tv[0]), cudaEventElapsedTime(&b, tv0, tv[1]), cudaEventElapsedTime(&c2, tv0, tv[2]);
+    fprintf(stderr, "[viml e2e] device: uploads done %.3f ms, kernels done %.3f ms, downloads done %.3f ms after the first upload was queued\n", a, b, c2);
+    for (auto& e : tv) cudaEventDestroy(e);
+    cudaEventDestroy(tv0);
+    fprintf(stderr, "[viml e2e] queued after %.3f ms, drained after %.3f ms (%d chunks)\n",
+            (ts_q.tv_sec - ts_begin.tv_sec) * 1e3 + (ts_q.tv_nsec - ts_begin.tv_nsec) * 1e-6,
+            (ts_d.tv_sec - ts_begin.tv_sec) * 1e3 + (ts_d.tv_nsec - ts_begin.tv_nsec) * 1e-6, nchunk);
+  }
   for (int c = 0; c < nchunk; ++c) cudaEventDestroy(ev_in[c]), cudaEventDestroy(ev_k[c]);
   if (rc != VIML_OK) return rc;
   VIML_TRY_CUDA(ctx, e1);

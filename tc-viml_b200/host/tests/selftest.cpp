@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <vector>
 
 #include "oracle/viml_oracle.h"
@@ -463,7 +464,127 @@ static void test_association(const viml_config& cfg) {
   std::printf("association: %d/%zu observations matched\n", matched, obs.size());
 }
 
+// BASELINE.json configs[0] through the drop-in path: ONE EuRoC-shaped window (11 poses, 150 features, ~600 ProjectionFactors,
+// 110 LineProjectionFactors), one evaluation point = LinearizationBatch::PrepareForEvaluation (pack, H2D, kernels, D2H) + one
+// Evaluate per residual block called the way ceres::Solve calls it (copies of the state, all Jacobians), next to the
+// reference's own per-factor CPU Evaluate (oracle port, single thread, like the reference's single process() thread,
+// estimator.cpp:1900).  Prints one JSON object.
+static int bench_cfg1(const viml_config& cfg, int reps) {
+  static double pose[11][7], ex[7], feat[150][1];
+  double base[7];
+  random_pose(base, 1.0, 0.3);
+  for (int i = 0; i < 11; ++i) {
+    std::memcpy(pose[i], base, 56);
+    for (int k = 0; k < 3; ++k) pose[i][k] += 0.05 * i + 0.02 * nrand();
+  }
+  const double ric[7] = {-0.0216, -0.0647, 0.0098, 0.0077, -0.0105, 0.7018, 0.7123};
+  std::memcpy(ex, ric, 56);
+  for (int l = 0; l < 150; ++l) feat[l][0] = 0.15 + 0.3 * urand();
+  viml::Matrix3d K, Ric;
+  K(0, 0) = cfg.fx, K(1, 1) = cfg.fy, K(0, 2) = cfg.cx, K(1, 2) = cfg.cy, K(2, 2) = 1;
+  {
+    const double n = std::sqrt(ex[3] * ex[3] + ex[4] * ex[4] + ex[5] * ex[5] + ex[6] * ex[6]);
+    const double x = ex[3] / n, y = ex[4] / n, z = ex[5] / n, ww = ex[6] / n;
+    const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - ww * z), 2 * (x * z + ww * y), 2 * (x * y + ww * z), 1 - 2 * (x * x + z * z),
+                         2 * (y * z - ww * x), 2 * (x * z - ww * y), 2 * (y * z + ww * x), 1 - 2 * (x * x + y * y)};
+    std::memcpy(Ric.m, R, sizeof(R));
+  }
+  viml::Vector3d Tic(ex[0], ex[1], ex[2]);
+  LinearizationBatch batch;
+  struct PFE { ProjectionFactor* f; int i, j, l; };
+  std::vector<PFE> pfs;
+  std::vector<LineProjectionFactor*> lfs;
+  std::vector<int> lframe;
+  for (int l = 0; l < 150; ++l) {
+    const int i = (int)(urand() * 8) % 8, len = 2 + (int)(urand() * (10 - i)) % (10 - i);   // start_frame < 8, track to frame <= 10
+    for (int j = i + 1; j < i + len && j < 11; ++j) {
+      auto* f = new ProjectionFactor(viml::Vector3d(0.4 * nrand(), 0.3 * nrand(), 1.0), viml::Vector3d(0.4 * nrand(), 0.3 * nrand(), 1.0));
+      batch.AddResidualBlock(f, pose[i], pose[j], ex, feat[l]);
+      pfs.push_back({f, i, j, l});
+    }
+  }
+  for (int p = 0; p < 11; ++p)
+    for (int q = 0; q < 10; ++q) {
+      auto* f = new LineProjectionFactor(viml::Vector3d(pose[p][0] + 3 + nrand(), pose[p][1] + nrand(), pose[p][2] + nrand()),
+                                         viml::Vector3d(pose[p][0] + 3 + nrand(), pose[p][1] + 1 + nrand(), pose[p][2] + nrand()),
+                                         viml::Vector3d(120.0 + 10 * nrand(), -80.0 + 10 * nrand(), 1e4 * nrand()), K, Ric, Tic);
+      batch.AddResidualBlock(f, pose[p]);
+      lfs.push_back(f), lframe.push_back(p);
+    }
+  auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; };
+  double sink = 0.0;
+  auto gpu_point = [&](double* t_prepare) {
+    pose[3][0] += 1e-4;   // a new evaluation point
+    const double t0 = now();
+    batch.PrepareForEvaluation(true, true);
+    const double t1 = now();
+    for (const PFE& e : pfs) {
+      double cp[4][7], r[2], J[4][14];
+      std::memcpy(cp[0], pose[e.i], 56), std::memcpy(cp[1], pose[e.j], 56), std::memcpy(cp[2], ex, 56), cp[3][0] = feat[e.l][0];
+      const double* params[4] = {cp[0], cp[1], cp[2], cp[3]};
+      double* jp[4] = {J[0], J[1], J[2], J[3]};
+      e.f->Evaluate(params, r, jp);
+      sink += r[0] + J[0][0];
+    }
+    for (size_t k = 0; k < lfs.size(); ++k) {
+      double cp[7], r[2], J[14];
+      std::memcpy(cp, pose[lframe[k]], 56);
+      const double* params[1] = {cp};
+      double* jp[1] = {J};
+      lfs[k]->Evaluate(params, r, jp);
+      sink += r[0] + J[0];
+    }
+    *t_prepare += t1 - t0;
+    return now() - t0;
+  };
+  auto cpu_point = [&] {
+    const double t0 = now();
+    for (const PFE& e : pfs) {
+      double r[2], J[4][14];
+      const double* params[4] = {pose[e.i], pose[e.j], ex, feat[e.l]};
+      double* jp[4] = {J[0], J[1], J[2], J[3]};
+      orc_projection_evaluate(e.f->pts_i.data(), e.f->pts_j.data(), cfg.sqrt_info, params, r, jp);
+      sink += r[0] + J[0][0];
+    }
+    for (size_t k = 0; k < lfs.size(); ++k) {
+      double r[2], J[14];
+      const double* params[1] = {pose[lframe[k]]};
+      double* jp[1] = {J};
+      orc_line_evaluate(lfs[k]->pts_start.data(), lfs[k]->pts_end.data(), lfs[k]->line_param.data(), K.m, Ric.m, Tic.data(), params, r, jp);
+      sink += r[0] + J[0];
+    }
+    return now() - t0;
+  };
+  double tp = 0.0, tg = 0.0, tc = 0.0;
+  for (int w = 0; w < 5; ++w) gpu_point(&tp), cpu_point();
+  tp = 0.0;
+  const long served0 = batch.served();
+  for (int r = 0; r < reps; ++r) tg += gpu_point(&tp);
+  const long served = batch.served() - served0;
+  for (int r = 0; r < reps; ++r) tc += cpu_point();
+  const size_t nfac = pfs.size() + lfs.size();
+  std::printf("{\"workload\": \"cfg1: one window, %zu ProjectionFactors + %zu LineProjectionFactors, one evaluation point = "
+              "PrepareForEvaluation + one Evaluate per residual block with copied parameter blocks\", \"evaluation_points\": %d, "
+              "\"gpu_bridge_ms_per_point\": %.4f, \"gpu_prepare_ms_per_point\": %.4f, \"served_from_batch_per_point\": %.1f, "
+              "\"cpu_reference_ms_per_point\": %.4f, \"cpu_threads\": 1, \"gpu_over_cpu\": %.3f, \"sink\": %.3e}\n",
+              pfs.size(), lfs.size(), reps, 1e3 * tg / reps, 1e3 * tp / reps, (double)served / reps, 1e3 * tc / reps, tc / tg, sink);
+  (void)nfac;
+  for (auto& e : pfs) delete e.f;
+  for (auto* f : lfs) delete f;
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && std::strcmp(argv[1], "--bench-cfg1") == 0) {
+    const viml_config cfg = euroc_config();
+    if (viml::Runtime::instance().configure(cfg, 0) != VIML_OK) {
+      std::printf("{\"error\": \"no GPU\"}\n");
+      return 2;
+    }
+    const int rc = bench_cfg1(cfg, argc > 2 ? std::atoi(argv[2]) : 200);
+    viml::Runtime::instance().shutdown();
+    return rc;
+  }
   const bool cpu_only = argc > 1 && std::strcmp(argv[1], "--cpu") == 0;
   test_host_only();
   if (!cpu_only) {

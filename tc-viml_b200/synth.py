@@ -47,7 +47,7 @@ def quat_from_rot(R):
     c1 = (~c0) & (m00 >= m11) & (m00 >= m22)
     c2 = (~c0) & (~c1) & (m11 >= m22)
     c3 = (~c0) & (~c1) & (~c2)
-    with np.errstate(invalid="ignore"):
+    with np.errstate(invalid="ignore", divide="ignore"):
         s = np.sqrt(np.maximum(tr + 1.0, 0)) * 2
         q0 = np.stack([(R[..., 2, 1] - R[..., 1, 2]) / s, (R[..., 0, 2] - R[..., 2, 0]) / s,
                        (R[..., 1, 0] - R[..., 0, 1]) / s, 0.25 * s], -1)
@@ -220,6 +220,75 @@ def _rot_from_quat(q):
                      [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
 
 
+_QCTX = None
+
+
+def _pose_queries(c, p):
+    """The L 2D segments of pose p (own generator seeded by (seed, p): the result does not depend on how poses are
+    distributed over worker processes)."""
+    rng = np.random.Generator(np.random.PCG64([int(c["seed"]), int(p)]))
+    lines, order, cstart, nxc, nyc, cell, reach, pm = (c[k] for k in ("lines", "order", "cstart", "nxc", "nyc", "cell", "reach", "pm"))
+    L, n_true = c["L"], c["n_true"]
+    cx0, cy0 = int(pm[p, 0] / cell), int(pm[p, 1] / cell)
+    sel = []
+    for yy in range(max(cy0 - reach, 0), min(cy0 + reach, nyc - 1) + 1):
+        a = cstart[yy * nxc + max(cx0 - reach, 0)]
+        b = cstart[yy * nxc + min(cx0 + reach, nxc - 1) + 1]
+        sel.append(order[a:b])
+    sel = np.concatenate(sel) if sel else np.zeros(0, dtype=np.int64)
+    uv, front = project_map(c["Rbw"], c["Tbw"], c["cull"][p], c["ex"][p], lines[sel])
+    inside = front & (uv[:, 0] > 1) & (uv[:, 0] < WIDTH - 2) & (uv[:, 1] > 1) & (uv[:, 1] < HEIGHT - 2) & \
+        (uv[:, 2] > 1) & (uv[:, 2] < WIDTH - 2) & (uv[:, 3] > 1) & (uv[:, 3] < HEIGHT - 2)
+    inside &= np.hypot(uv[:, 2] - uv[:, 0], uv[:, 3] - uv[:, 1]) > 15.0
+    vis = np.nonzero(inside)[0]
+    k = min(n_true, len(vis))
+    out = np.empty((L, 4))
+    if k:
+        pick = rng.choice(vis, size=k, replace=False)
+        seg = uv[pick]
+        a0 = rng.uniform(0.0, 0.2, (k, 1))
+        a1 = rng.uniform(0.8, 1.0, (k, 1))
+        s0, e0 = seg[:, :2], seg[:, 2:]
+        out[:k, :2] = s0 + a0 * (e0 - s0)
+        out[:k, 2:] = s0 + a1 * (e0 - s0)
+        out[:k] += rng.standard_normal((k, 4))
+        flip = rng.uniform(size=k) < 0.5
+        out[:k][flip] = out[:k][flip][:, [2, 3, 0, 1]]
+    nclut = L - k
+    u0, v0 = rng.uniform(0, WIDTH, nclut), rng.uniform(0, HEIGHT, nclut)
+    ang, ln = rng.uniform(0, 2 * np.pi, nclut), rng.uniform(100, 400, nclut)
+    out[k:, 0], out[k:, 1] = u0, v0
+    out[k:, 2] = np.clip(u0 + ln * np.cos(ang), 0, WIDTH - 1)
+    out[k:, 3] = np.clip(v0 + ln * np.sin(ang), 0, HEIGHT - 1)
+    return out[rng.permutation(L)]
+
+
+def _pose_range(args):
+    lo, hi = args
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.stack([_pose_queries(_QCTX, p) for p in range(lo, hi)]) if hi > lo else np.empty((0, _QCTX["L"], 4))
+
+
+def _queries_for_poses(c, lo, hi):
+    """Serial for small query sets; large ones (the cfg-3 bench, 4096 poses) are spread over forked worker processes."""
+    global _QCTX
+    _QCTX = c
+    n = hi - lo
+    if n < 512:
+        return _pose_range((lo, hi))
+    import multiprocessing as mp
+    import os
+    nw = max(1, min(32, (os.cpu_count() or 1)))
+    cuts = [lo + (n * k) // (4 * nw) for k in range(4 * nw + 1)]
+    try:
+        with mp.get_context("fork").Pool(nw) as pool:
+            parts = pool.map(_pose_range, list(zip(cuts[:-1], cuts[1:])))
+    except Exception:
+        parts = [_pose_range((lo, hi))]
+    return np.concatenate(parts, 0)
+
+
+
 def make_assoc_queries(lines, n_poses, L=300, n_true=100, seed=0x5EED + 33, altitude=(45.0, 60.0),
                        extent=(2000.0, 2000.0, 30.0), Rbw=RBW, Tbw=TBW, pose_drift=True):
     """n_poses down-looking camera poses on a trajectory over the map, each with L 2D segments:
@@ -263,41 +332,10 @@ def make_assoc_queries(lines, n_poses, L=300, n_true=100, seed=0x5EED + 33, alti
     cid = gy * nxc + gx
     order = np.argsort(cid, kind="stable")
     cstart = np.searchsorted(cid[order], np.arange(nxc * nyc + 1))
-    lines2d = np.empty((n_poses, L, 4))
     reach = int(np.ceil(altitude[1] * np.tan(np.deg2rad(62.0)) / cell)) + 1
-    for p in range(n_poses):
-        cx0, cy0 = int(pm[p, 0] / cell), int(pm[p, 1] / cell)
-        sel = []
-        for yy in range(max(cy0 - reach, 0), min(cy0 + reach, nyc - 1) + 1):
-            a = cstart[yy * nxc + max(cx0 - reach, 0)]
-            b = cstart[yy * nxc + min(cx0 + reach, nxc - 1) + 1]
-            sel.append(order[a:b])
-        sel = np.concatenate(sel) if sel else np.zeros(0, dtype=np.int64)
-        uv, front = project_map(Rbw, Tbw, cull[p], ex[p], lines[sel])
-        inside = front & (uv[:, 0] > 1) & (uv[:, 0] < WIDTH - 2) & (uv[:, 1] > 1) & (uv[:, 1] < HEIGHT - 2) & \
-            (uv[:, 2] > 1) & (uv[:, 2] < WIDTH - 2) & (uv[:, 3] > 1) & (uv[:, 3] < HEIGHT - 2)
-        inside &= np.hypot(uv[:, 2] - uv[:, 0], uv[:, 3] - uv[:, 1]) > 15.0
-        vis = np.nonzero(inside)[0]
-        k = min(n_true, len(vis))
-        out = np.empty((L, 4))
-        if k:
-            pick = rng.choice(vis, size=k, replace=False)
-            seg = uv[pick]
-            a0 = rng.uniform(0.0, 0.2, (k, 1))
-            a1 = rng.uniform(0.8, 1.0, (k, 1))
-            s0, e0 = seg[:, :2], seg[:, 2:]
-            out[:k, :2] = s0 + a0 * (e0 - s0)
-            out[:k, 2:] = s0 + a1 * (e0 - s0)
-            out[:k] += rng.standard_normal((k, 4))
-            flip = rng.uniform(size=k) < 0.5
-            out[:k][flip] = out[:k][flip][:, [2, 3, 0, 1]]
-        nclut = L - k
-        u0, v0 = rng.uniform(0, WIDTH, nclut), rng.uniform(0, HEIGHT, nclut)
-        ang, ln = rng.uniform(0, 2 * np.pi, nclut), rng.uniform(100, 400, nclut)
-        out[k:, 0], out[k:, 1] = u0, v0
-        out[k:, 2] = np.clip(u0 + ln * np.cos(ang), 0, WIDTH - 1)
-        out[k:, 3] = np.clip(v0 + ln * np.sin(ang), 0, HEIGHT - 1)
-        lines2d[p] = out[rng.permutation(L)]
+    ctxd = dict(lines=lines, order=order, cstart=cstart, nxc=nxc, nyc=nyc, cell=cell, reach=reach, pm=pm, cull=cull, ex=ex,
+                Rbw=Rbw, Tbw=Tbw, L=L, n_true=n_true, seed=seed)
+    lines2d = _queries_for_poses(ctxd, 0, n_poses)
     lines2d = lines2d.astype(np.float32).astype(np.float64)
     return (np.ascontiguousarray(cull), np.ascontiguousarray(match), np.ascontiguousarray(ex),
             np.ascontiguousarray(lines2d))
