@@ -15,6 +15,13 @@
  *                             Estimator::LineCorrespondenceInFrame  estimator.cpp:671-885
  *                             (+ CalAngleDist :601-613, CalEulerDist :615-669, Line2D fm.cpp:4-15,:46-71)
  *   viml_set_map           <- lines3d_map ingest                vins_estimator/src/parameters.cpp:50-59, estimator.cpp:54-58
+ *   viml_load_line_map     <- the line_3d.txt reader            vins_estimator/src/parameters.cpp:50-59
+ *   viml_reduced_system    <- the prior and IMU residual blocks of the window entering the normal equations:
+ *                             MarginalizationFactor::Evaluate   marginalization_factor.cpp:335-384
+ *                             IMUFactor::Evaluate               vins_estimator/src/factor/imu_factor.h:19-181
+ *                             (evaluated by their owners; their r / J blocks are inputs here), ThreadsConstructA rule :141-172
+ *   viml_gn_step           <- one solver iteration of ceres::Solve  estimator.cpp:1888-1905 (normal equations, Schur elimination of
+ *                             the landmarks, dense solve, PoseLocalParameterization::Plus  pose_local_parameterization.cpp:3-19)
  *   viml_config            <- the fields Estimator::setParameters reads for this path, estimator.cpp:54-124
  *
  * Conventions
@@ -38,7 +45,7 @@
 extern "C" {
 #endif
 
-#define VIML_ABI_VERSION 1
+#define VIML_ABI_VERSION 2
 
 /* ---- error codes ---------------------------------------------------------------------------- */
 #define VIML_OK 0
@@ -108,6 +115,11 @@ int viml_selftest_division(viml_ctx* ctx, const double* a, const double* b, int6
 /* lines_xyzxyz: N rows of [sx sy sz ex ey ez] exactly as line_3d.txt (parameters.cpp:50-59).
  * Always a HOST pointer.  The map is packed once into six SoA planes in HBM.                    */
 int viml_set_map(viml_ctx* ctx, const double* lines_xyzxyz, int64_t n_lines);
+/* Reads a line_3d.txt prior map like the loop of readParameters (parameters.cpp:50-59): every text line of the file is one map
+ * row of six whitespace-separated doubles, sx sy sz ex ey ez, and is pushed whether or not it parsed (the reference leaves the
+ * fields after a failed extraction uninitialised; here they are 0 — defined where the reference is not).  Installs the map with
+ * viml_set_map; *n_lines (optional) receives the number of rows.  VIML_ERR_INVALID when the file cannot be opened.        */
+int viml_load_line_map(viml_ctx* ctx, const char* path, int64_t* n_lines);
 
 /* ---- linearisation ---------------------------------------------------------------------------
  * A batch of W independent sliding windows.  Factors are grouped by window (CSR offsets); inside a
@@ -168,6 +180,70 @@ typedef struct viml_linearize_out {
 
 int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_linearize_out* out,
                          uint32_t flags);
+
+/* ---- dense-block factors and the reduced system of the whole window ----------------------------------
+ * Cost functions that are NOT evaluated here — the previous prior (MarginalizationFactor) and the IMU factors — enter as
+ * evaluated blocks: factor k has n_k residuals and c_k TANGENT columns (a size-7 pose block contributes its first 6 Jacobian
+ * columns, marginalization_factor.cpp:150-151); col_index maps each local column to a column of the window's tangent vector
+ *     [ pose 0 .. pose P-1 | extrinsic | X extra columns ]     (D = 6(P+1) pose/extrinsic columns, then e.g. 9 per speed-bias block)
+ * Any loss correction has been applied by the owner (the reference passes loss = NULL for both, estimator.cpp:1927, :1939).
+ * The three prefix arrays are CSR offsets over the factors; jacobian is row-major n_k x c_k per factor.
+ *
+ * viml_reduced_system:  Sx = embed(S) + sum_k J_k^T J_k,  gx = embed(g) + sum_k J_k^T r_k   ([W][Dx][Dx], [W][Dx], Dx = D + X),
+ * with S, g the landmark-eliminated system of the window's ProjectionFactors / LineProjectionFactors (viml_linearize_batch,
+ * VIML_OUT_SCHUR; VIML_LOSS_CAUCHY in `flags` applies to those).  dense == NULL gives the embedding alone.               */
+typedef struct viml_dense_factors {
+  int32_t extra_dim;             /* X                                              */
+  int32_t reserved0;
+  int64_t n_factors;             /* ND                                             */
+  const int32_t* window_offset;  /* [W+1] factors of window w                      */
+  const int64_t* row_offset;     /* [ND+1] prefix of n_k   -> residual             */
+  const int64_t* col_offset;     /* [ND+1] prefix of c_k   -> col_index            */
+  const int64_t* jac_offset;     /* [ND+1] prefix of n_k*c_k -> jacobian           */
+  const int32_t* col_index;      /* [sum c_k] in [0, D+X), distinct inside a factor */
+  const double* residual;        /* [sum n_k]                                      */
+  const double* jacobian;        /* [sum n_k*c_k]                                  */
+} viml_dense_factors;
+
+typedef struct viml_reduced_out {
+  double* Sx; /* [W][Dx][Dx] */
+  double* gx; /* [W][Dx]     */
+} viml_reduced_out;
+
+int viml_reduced_system(viml_ctx* ctx, const viml_window_batch* in, const viml_dense_factors* dense,
+                        const viml_reduced_out* out, uint32_t flags);
+
+/* ---- one Gauss-Newton / Levenberg-Marquardt iteration for a batch of windows, device resident -------------------
+ * What one iteration of ceres::Solve(SPARSE_SCHUR) does with the window's problem (estimator.cpp:1888-1905), on the normal
+ * equations this library assembles (b = +J^T r, so the step solves  H dx = -b):
+ *   1. linearise every ProjectionFactor / LineProjectionFactor at the given state, eliminate the landmarks, add the dense-block
+ *      factors:  Sx, gx  (viml_reduced_system);
+ *   2. dx = -(Sx + lambda diag(Sx))^-1 gx   by Cholesky (lambda = 0: Gauss-Newton);  solved[w] = 0 if a pivot is not positive
+ *      (the window's state is then returned unchanged);
+ *   3. landmarks:  d(inv_depth_l) = -(b_l + H_lp[l] . dx_pose) / H_ll[l]   (0 where H_ll <= 1e-8);
+ *   4. update:  p += dp,  q = normalized(q * deltaQ(dtheta))  (PoseLocalParameterization::Plus, pose_local_parameterization.cpp:3-19;
+ *      Utility::deltaQ, utility.h:16-28) for poses and extrinsic; inverse depths and the extra state add their increments;
+ *   5. cost[w] = { f(x), f(x+), model decrease }  with  f = 1/2 sum rho(|r|^2) over the point and line factors (Cauchy when
+ *      VIML_LOSS_CAUCHY, else |r|^2) + 1/2 sum |r_k + J_k dx|^2 over the dense-block factors (their linearisation: re-evaluating
+ *      an IMU factor is its owner's job), model decrease = -gx.dx - 1/2 dx.Sx.dx of the damped-free quadratic model.
+ * The caller decides acceptance (f(x+) < f(x)) and the next lambda.  All pointers follow VIML_PTRS_DEVICE.            */
+typedef struct viml_gn_options {
+  double lambda;   /* Levenberg-Marquardt damping on diag(Sx); 0 = Gauss-Newton */
+  double reserved0;
+} viml_gn_options;
+
+typedef struct viml_gn_out {
+  double* poses;      /* [W][P][7]  updated */
+  double* ex_pose;    /* [W][7]              */
+  double* inv_depth;  /* [W][F]              */
+  double* extra;      /* [W][X] or NULL      */
+  double* dx;         /* [W][Dx] or NULL: the reduced step */
+  double* cost;       /* [W][3]              */
+  int32_t* solved;    /* [W]                 */
+} viml_gn_out;
+
+int viml_gn_step(viml_ctx* ctx, const viml_window_batch* in, const viml_dense_factors* dense, const double* extra_state /* [W][X] or NULL */,
+                 const viml_gn_options* opt, const viml_gn_out* out, uint32_t flags);
 
 /* ---- dense marginalisation (marginalization_factor.cpp:264-293) --------------------------------
  * Per problem k: A [pos][pos] row-major, b [pos], marginalised block = leading m rows, kept n = pos-m.

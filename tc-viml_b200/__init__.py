@@ -25,6 +25,7 @@ ABI_SYMBOLS = (
     "viml_memcpy_d2h", "viml_kernel_launches", "viml_profile_begin", "viml_profile_end", "viml_kernel_name",
     "viml_microbench_fp64", "viml_microbench_dmma", "viml_selftest_division", "viml_set_map", "viml_linearize_batch",
     "viml_marginalize_batch", "viml_line_associate", "viml_assoc_stats", "viml_allreduce_hb",
+    "viml_load_line_map", "viml_reduced_system", "viml_gn_step",
 )
 
 
@@ -72,6 +73,11 @@ def load_library():
     lib.viml_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.viml_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.viml_allreduce_hb.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    lib.viml_load_line_map.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]
+    lib.viml_reduced_system.argtypes = [C.c_void_p, C.POINTER(_abi.WindowBatch), C.POINTER(_abi.DenseFactors),
+                                        C.POINTER(_abi.ReducedOut), C.c_uint32]
+    lib.viml_gn_step.argtypes = [C.c_void_p, C.POINTER(_abi.WindowBatch), C.POINTER(_abi.DenseFactors), C.c_void_p,
+                                 C.POINTER(_abi.GnOptions), C.POINTER(_abi.GnOut), C.c_uint32]
     _LIB = lib
     return lib
 
@@ -181,6 +187,46 @@ class Context:
         lines = np.ascontiguousarray(lines_xyzxyz, dtype=np.float64).reshape(-1, 6)
         self._check(self.lib.viml_set_map(self.h, _abi.ptr(lines), len(lines)))
         self.n_map = len(lines)
+
+    def load_line_map(self, path):
+        """viml_load_line_map: read a line_3d.txt prior map (parameters.cpp:50-59) and install it."""
+        n = C.c_int64()
+        self._check(self.lib.viml_load_line_map(self.h, os.fsencode(path), C.byref(n)))
+        self.n_map = int(n.value)
+        return self.n_map
+
+    def reduced_system(self, batch, dense, flags):
+        """viml_reduced_system with host buffers: (Sx [W,Dx,Dx], gx [W,Dx])."""
+        X = dense.X if dense is not None else 0
+        Dx = batch.D + X
+        Sx, gx = np.full((batch.W, Dx, Dx), np.nan), np.full((batch.W, Dx), np.nan)
+        s = batch.struct()
+        d = dense.struct() if dense is not None else None
+        o = _abi.ReducedOut()
+        o.Sx, o.gx = _abi.ptr(Sx), _abi.ptr(gx)
+        self._check(self.lib.viml_reduced_system(self.h, C.byref(s), C.byref(d) if d is not None else None, C.byref(o),
+                                                 flags & ~PTRS_DEVICE))
+        return Sx, gx
+
+    def gn_step(self, batch, dense, extra, flags, lam=0.0):
+        """viml_gn_step with host buffers: dict(poses, ex_pose, inv_depth, extra, dx, cost, solved)."""
+        X = dense.X if dense is not None else 0
+        W, Dx = batch.W, batch.D + X
+        res = {"poses": np.full_like(batch.poses, np.nan), "ex_pose": np.full_like(batch.ex_pose, np.nan),
+               "inv_depth": np.full_like(batch.inv_depth, np.nan), "extra": np.full((W, X), np.nan),
+               "dx": np.full((W, Dx), np.nan), "cost": np.full((W, 3), np.nan), "solved": np.full(W, -1, dtype=np.int32)}
+        s = batch.struct()
+        d = dense.struct() if dense is not None else None
+        ex = None if extra is None else np.ascontiguousarray(extra, dtype=np.float64)
+        opt = _abi.GnOptions()
+        opt.lambda_ = float(lam)
+        o = _abi.GnOut()
+        for k in ("poses", "ex_pose", "inv_depth", "dx", "cost", "solved"):
+            setattr(o, k, _abi.ptr(res[k]))
+        o.extra = _abi.ptr(res["extra"]) if X > 0 else None
+        self._check(self.lib.viml_gn_step(self.h, C.byref(s), C.byref(d) if d is not None else None, _abi.ptr(ex), C.byref(opt),
+                                          C.byref(o), flags & ~PTRS_DEVICE))
+        return res
 
     def linearize(self, batch, flags, out=None):
         """viml_linearize_batch with host buffers; returns dict of numpy outputs."""

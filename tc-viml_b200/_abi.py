@@ -81,6 +81,59 @@ class AssocOut(C.Structure):
                 ("fov_capacity", C.c_int32), ("reserved0", C.c_int32), ("fov_mask", C.c_void_p)]
 
 
+class DenseFactors(C.Structure):
+    """viml_dense_factors — evaluated residual / Jacobian blocks of the prior and IMU factors (CSR over factors)."""
+
+    _fields_ = [("extra_dim", C.c_int32), ("reserved0", C.c_int32), ("n_factors", C.c_int64),
+                ("window_offset", C.c_void_p), ("row_offset", C.c_void_p), ("col_offset", C.c_void_p), ("jac_offset", C.c_void_p),
+                ("col_index", C.c_void_p), ("residual", C.c_void_p), ("jacobian", C.c_void_p)]
+
+
+class ReducedOut(C.Structure):
+    _fields_ = [("Sx", C.c_void_p), ("gx", C.c_void_p)]
+
+
+class GnOptions(C.Structure):
+    _fields_ = [("lambda_", C.c_double), ("reserved0", C.c_double)]
+
+
+class GnOut(C.Structure):
+    _fields_ = [("poses", C.c_void_p), ("ex_pose", C.c_void_p), ("inv_depth", C.c_void_p), ("extra", C.c_void_p),
+                ("dx", C.c_void_p), ("cost", C.c_void_p), ("solved", C.c_void_p)]
+
+
+class Dense:
+    """Host-side container of one viml_dense_factors: a list of (window, residual [n], jacobian [n, c], col_index [c]) tuples
+    sorted by window."""
+
+    def __init__(self, W, extra_dim, factors):
+        self.W, self.X = W, int(extra_dim)
+        factors = sorted(factors, key=lambda f: f[0])
+        self.factors = factors
+        cnt = np.bincount([f[0] for f in factors], minlength=W) if factors else np.zeros(W, dtype=np.int64)
+        self.window_offset = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+        rows = [len(f[1]) for f in factors]
+        cols = [len(f[3]) for f in factors]
+        self.row_offset = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+        self.col_offset = np.concatenate([[0], np.cumsum(cols)]).astype(np.int64)
+        self.jac_offset = np.concatenate([[0], np.cumsum([r * c for r, c in zip(rows, cols)])]).astype(np.int64)
+        self.col_index = np.ascontiguousarray(np.concatenate([np.asarray(f[3]) for f in factors]) if factors else np.zeros(0), dtype=np.int32)
+        self.residual = np.ascontiguousarray(np.concatenate([np.asarray(f[1], dtype=np.float64) for f in factors]) if factors else np.zeros(0))
+        self.jacobian = np.ascontiguousarray(np.concatenate([np.asarray(f[2], dtype=np.float64).reshape(-1) for f in factors])
+                                             if factors else np.zeros(0))
+
+    def arrays(self):
+        return {k: getattr(self, k) for k in ("window_offset", "row_offset", "col_offset", "jac_offset", "col_index", "residual", "jacobian")}
+
+    def struct(self, arrays=None):
+        a = self.arrays() if arrays is None else arrays
+        s = DenseFactors()
+        s.extra_dim, s.n_factors = self.X, len(self.factors)
+        for k in a:
+            setattr(s, k, ptr(a[k]))
+        return s
+
+
 def ptr(a):
     """Address of a numpy array (host) or an int device pointer; None -> NULL."""
     if a is None:

@@ -75,7 +75,7 @@ struct viml_ctx {
   double* d_tile_sphere = nullptr;  // [n_tiles][4]
   int64_t n_tiles = 0;
   unsigned long long* d_assoc_stats = nullptr;  // {gate tests, gated pairs, overlap-scored, distance-scored} of the last association call
-  DeviceArena in_arena, out_arena, scratch, scratch2, scratch3;
+  DeviceArena in_arena, out_arena, scratch, scratch2, scratch3, gn_in, gn_out;
   void* nccl_lib = nullptr;
   // profiling (viml_profile_begin/end): event pairs per kernel id
   bool brute_cull = false;     // VIML_BRUTE_CULL=1: the literal all-pairs FoV sweep (roofline accounting, cross-check)
@@ -86,7 +86,7 @@ struct viml_ctx {
 
 enum KernelId {
   K_PREP = 0, K_POINTS, K_LINES, K_ASSEMBLE, K_SCHUR, K_CAMPOSE, K_CULL, K_SCAN, K_FILL, K_PROJECT, K_MATCH,
-  K_MARG, K_MICRO, K_PLAN, K_IRREGULAR, K_COUNT
+  K_MARG, K_MICRO, K_PLAN, K_IRREGULAR, K_GN, K_COUNT
 };
 static_assert(K_COUNT <= VIML_NUM_KERNELS, "raise VIML_NUM_KERNELS");
 
@@ -146,8 +146,27 @@ struct LinearizeArgs {  // device pointers only
   uint32_t flags;
 };
 
+struct DenseArgs {  // device pointers only; viml_dense_factors
+  int X;          // extra tangent columns behind the D pose / extrinsic columns
+  int64_t ND;
+  const int32_t* window_offset;
+  const int64_t* row_offset;
+  const int64_t* col_offset;
+  const int64_t* jac_offset;
+  const int32_t* col_index;
+  const double* residual;
+  const double* jacobian;
+};
+
 // linearize_kernels.cu
 int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a);
+int viml_launch_prep(viml_ctx* ctx, const LinearizeArgs& a);   // pose cache of the state in `a` only
+int viml_launch_reduced(viml_ctx* ctx, int W, int D, const DenseArgs& dn, const double* S, const double* g, double* Sx, double* gx);
+int viml_launch_gn_solve(viml_ctx* ctx, int W, int Dx, double lambda, const double* Sx, const double* gx, double* dx, int32_t* solved,
+                         double* cost);
+int viml_launch_gn_update(viml_ctx* ctx, const LinearizeArgs& a, int X, const double* extra_in, const double* dx, const int32_t* solved,
+                          double* o_poses, double* o_ex, double* o_dep, double* o_extra);
+int viml_launch_cost(viml_ctx* ctx, const LinearizeArgs& a, const DenseArgs& dn, const double* dx, int slot, double* cost);
 // schur_kernels.cu
 int viml_launch_schur(viml_ctx* ctx, int W, int F, int D, const double* H_pp, const double* H_lp, const double* H_ll,
                       const double* b_p, const double* b_l, double* S, double* g, double eps);

@@ -1,0 +1,226 @@
+// gn_kernels.cuh — the reduced system of the whole window and one Gauss-Newton / Levenberg-Marquardt iteration on it.
+// Included by linearize_kernels.cu (uses eval_point / eval_line for the cost).
+//
+// Reference: what ceres::Solve(SPARSE_SCHUR) does per iteration with the problem Estimator::OptimizationWithLine builds
+// (estimator.cpp:1677-1905): normal equations of all residual blocks, Schur elimination of the landmarks, a dense solve of
+// the reduced camera system, PoseLocalParameterization::Plus (pose_local_parameterization.cpp:3-19).  The prior and the IMU
+// factors enter as evaluated dense blocks (marginalization_factor.cpp:335-384, imu_factor.h:19-181), accumulated by the
+// ThreadsConstructA rule (marginalization_factor.cpp:141-172): A += J_i^T J_j over the tangent columns, b += J_i^T r.
+#pragma once
+
+namespace gn {
+
+// Sx = embed(S) + sum_k J_k^T J_k,  gx = embed(g) + sum_k J_k^T r_k.  One CTA per window; the window's dense factors are
+// added one after the other (two factors may share columns), every (a, b) column pair of a factor by one thread.
+__global__ void __launch_bounds__(256) reduced_kernel(int D, DenseArgs dn, const double* __restrict__ S, const double* __restrict__ g,
+                                                      double* __restrict__ Sx, double* __restrict__ gx) {
+  const int w = blockIdx.x, tid = threadIdx.x, Dx = D + dn.X;
+  double* __restrict__ A = Sx + (size_t)w * Dx * Dx;
+  double* __restrict__ b = gx + (size_t)w * Dx;
+  const double* __restrict__ Sw = S + (size_t)w * D * D;
+  for (int e = tid; e < Dx * Dx; e += blockDim.x) {
+    const int r = e / Dx, c = e - r * Dx;
+    A[e] = (r < D && c < D) ? Sw[r * D + c] : 0.0;
+  }
+  for (int e = tid; e < Dx; e += blockDim.x) b[e] = e < D ? g[(size_t)w * D + e] : 0.0;
+  if (dn.ND == 0) return;
+  __syncthreads();
+  for (int k = dn.window_offset[w]; k < dn.window_offset[w + 1]; ++k) {
+    const int n = (int)(dn.row_offset[k + 1] - dn.row_offset[k]), c = (int)(dn.col_offset[k + 1] - dn.col_offset[k]);
+    const double* __restrict__ J = dn.jacobian + dn.jac_offset[k];
+    const double* __restrict__ r = dn.residual + dn.row_offset[k];
+    const int32_t* __restrict__ ci = dn.col_index + dn.col_offset[k];
+    for (int e = tid; e < c * c; e += blockDim.x) {
+      const int a = e / c, bb = e - a * c;
+      double v = 0.0;
+      for (int q = 0; q < n; ++q) v = fma(J[(size_t)q * c + a], J[(size_t)q * c + bb], v);
+      A[(size_t)ci[a] * Dx + ci[bb]] += v;
+    }
+    for (int a = tid; a < c; a += blockDim.x) {
+      double v = 0.0;
+      for (int q = 0; q < n; ++q) v = fma(J[(size_t)q * c + a], r[q], v);
+      b[ci[a]] += v;
+    }
+    __syncthreads();
+  }
+}
+
+// dx = -(Sx + lambda diag(Sx))^-1 gx by Cholesky in shared memory (packed lower triangle), one CTA per window.
+// solved[w] = 0 when a pivot is not positive (dx = 0 then).  cost[3w + 2] = -gx.dx - 1/2 dx.Sx.dx (undamped model).
+__global__ void __launch_bounds__(128) solve_kernel(int Dx, double lambda, const double* __restrict__ Sx, const double* __restrict__ gx,
+                                                    double* __restrict__ dx, int32_t* __restrict__ solved, double* __restrict__ cost) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ int s_ok;
+  __shared__ double s_red[4];
+  const int w = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+  double* __restrict__ L = sm;                              // packed: L[i][j] at i(i+1)/2 + j, j <= i
+  double* __restrict__ y = sm + (size_t)Dx * (Dx + 1) / 2;   // right-hand side / solution
+  const double* __restrict__ A = Sx + (size_t)w * Dx * Dx;
+  for (int e = tid; e < Dx * Dx; e += NT) {
+    const int i = e / Dx, j = e - i * Dx;
+    if (j <= i) L[i * (i + 1) / 2 + j] = (i == j) ? A[e] * (1.0 + lambda) : 0.5 * (A[e] + A[(size_t)j * Dx + i]);
+  }
+  for (int e = tid; e < Dx; e += NT) y[e] = -gx[(size_t)w * Dx + e];
+  if (tid == 0) s_ok = 1;
+  __syncthreads();
+  for (int j = 0; j < Dx; ++j) {
+    const double d = L[j * (j + 1) / 2 + j];
+    if (!(d > 0.0) || !isfinite(d)) {   // uniform: every thread reads the same value
+      if (tid == 0) s_ok = 0;
+      break;
+    }
+    const double sd = sqrt(d), inv = 1.0 / sd;
+    __syncthreads();
+    for (int i = j + tid; i < Dx; i += NT) L[i * (i + 1) / 2 + j] = (i == j) ? sd : L[i * (i + 1) / 2 + j] * inv;
+    __syncthreads();
+    for (int i = j + 1 + tid; i < Dx; i += NT) {
+      const double lij = L[i * (i + 1) / 2 + j];
+      double* __restrict__ row = L + i * (i + 1) / 2;
+      for (int k = j + 1; k <= i; ++k) row[k] -= lij * L[k * (k + 1) / 2 + j];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  const bool ok = s_ok != 0;
+  if (ok) {
+    // forward L z = y, backward L^T x = z (column-oriented, one barrier per column)
+    for (int j = 0; j < Dx; ++j) {
+      if (tid == 0) y[j] /= L[j * (j + 1) / 2 + j];
+      __syncthreads();
+      const double yj = y[j];
+      for (int i = j + 1 + tid; i < Dx; i += NT) y[i] -= L[i * (i + 1) / 2 + j] * yj;
+      __syncthreads();
+    }
+    for (int j = Dx - 1; j >= 0; --j) {
+      if (tid == 0) y[j] /= L[j * (j + 1) / 2 + j];
+      __syncthreads();
+      const double yj = y[j];
+      for (int i = tid; i < j; i += NT) y[i] -= L[j * (j + 1) / 2 + i] * yj;
+      __syncthreads();
+    }
+  }
+  // model decrease with the undamped Sx
+  double part = 0.0;
+  for (int i = tid; i < Dx; i += NT) {
+    const double xi = ok ? y[i] : 0.0;
+    double sx = 0.0;
+    if (ok)
+      for (int c = 0; c < Dx; ++c) sx = fma(A[(size_t)i * Dx + c], y[c], sx);
+    part += -gx[(size_t)w * Dx + i] * xi - 0.5 * xi * sx;
+    dx[(size_t)w * Dx + i] = xi;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((tid & 31) == 0) s_red[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int k = 0; k < NT / 32; ++k) t += s_red[k];
+    cost[3 * (size_t)w + 2] = t;
+    solved[w] = ok ? 1 : 0;
+  }
+}
+
+__device__ __forceinline__ void pose_plus(const double* __restrict__ x, const double* __restrict__ d, double* __restrict__ o) {
+  // PoseLocalParameterization::Plus: p = _p + dp; q = (_q * Utility::deltaQ(dtheta)).normalized()
+  o[0] = x[0] + d[0], o[1] = x[1] + d[1], o[2] = x[2] + d[2];
+  const double ax = x[3], ay = x[4], az = x[5], aw = x[6];
+  const double bx = 0.5 * d[3], by = 0.5 * d[4], bz = 0.5 * d[5], bw = 1.0;   // deltaQ: (1, theta/2), not normalised
+  const double w = aw * bw - ax * bx - ay * by - az * bz;
+  const double qx = aw * bx + ax * bw + ay * bz - az * by;
+  const double qy = aw * by + ay * bw + az * bx - ax * bz;
+  const double qz = aw * bz + az * bw + ax * by - ay * bx;
+  const double n = sqrt(qx * qx + qy * qy + qz * qz + w * w);
+  o[3] = qx / n, o[4] = qy / n, o[5] = qz / n, o[6] = w / n;
+}
+
+// New state of every window: poses / extrinsic by Plus, landmarks by back-substitution, extra state by addition.
+__global__ void __launch_bounds__(128) update_kernel(LinearizeArgs A, int X, const double* __restrict__ extra_in, const double* __restrict__ dx,
+                                                     const int32_t* __restrict__ solved, double* __restrict__ o_poses,
+                                                     double* __restrict__ o_ex, double* __restrict__ o_dep, double* __restrict__ o_extra) {
+  const int w = blockIdx.x, tid = threadIdx.x, P = A.P, F = A.F, D = A.D, Dx = D + X;
+  const bool ok = solved[w] != 0;
+  const double* __restrict__ d = dx + (size_t)w * Dx;
+  for (int p = tid; p <= P; p += blockDim.x) {
+    const double* x = p < P ? A.poses + ((size_t)w * P + p) * 7 : A.ex_pose + (size_t)w * 7;
+    double* o = p < P ? o_poses + ((size_t)w * P + p) * 7 : o_ex + (size_t)w * 7;
+    if (ok) {
+      pose_plus(x, d + 6 * p, o);
+    } else {
+      for (int k = 0; k < 7; ++k) o[k] = x[k];
+    }
+  }
+  for (int l = tid; l < F; l += blockDim.x) {
+    const double lam = A.inv_depth[(size_t)w * F + l];
+    double dl = 0.0;
+    const double hll = A.out.H_ll[(size_t)w * F + l];
+    if (ok && hll > 1e-8) {
+      const double* __restrict__ row = A.out.H_lp + ((size_t)w * F + l) * D;
+      double s = A.out.b_l[(size_t)w * F + l];
+      for (int c = 0; c < D; ++c) s = fma(row[c], d[c], s);
+      dl = -s / hll;
+    }
+    o_dep[(size_t)w * F + l] = lam + dl;
+  }
+  if (o_extra)
+    for (int e = tid; e < X; e += blockDim.x) o_extra[(size_t)w * X + e] = (extra_in ? extra_in[(size_t)w * X + e] : 0.0) + (ok ? d[D + e] : 0.0);
+}
+
+// cost[3w + slot] = 1/2 sum rho(|r|^2) over the window's point and line factors at the state of A (pose cache ready)
+// + 1/2 sum |r_k + J_k dx|^2 over its dense-block factors (dx == nullptr: at the linearisation point).
+__global__ void __launch_bounds__(128) cost_kernel(LinearizeArgs A, DenseArgs dn, const double* __restrict__ dx, int slot, double* __restrict__ cost) {
+  __shared__ double s_red[4];
+  const int w = blockIdx.x, tid = threadIdx.x, Dx = A.D + dn.X;
+  const bool cauchy = (A.flags & VIML_LOSS_CAUCHY) != 0;
+  LinearizeArgs R = A;
+  R.flags &= ~VIML_LOSS_CAUCHY;   // raw residuals: rho is applied here, not the Jacobian correction
+  const double a2 = A.cauchy_a * A.cauchy_a;
+  const double* cw = A.cache + (size_t)w * (A.P * kPoseCache + kExCache);
+  double acc = 0.0;
+  for (int64_t k = A.pf_window_offset[w] + tid; k < A.pf_window_offset[w + 1]; k += blockDim.x) {
+    const uint32_t pk = A.pf_idx[k];
+    const int i = pk & 0xff, j = (pk >> 8) & 0xff, f = pk >> 16;
+    if (i >= A.P || j >= A.P || f >= A.F) continue;
+    const double4 ob = reinterpret_cast<const double4*>(A.pf_obs)[k];
+    PointJac J;
+    eval_point(R, cw, i, j, A.inv_depth[(size_t)w * A.F + f], ob.x, ob.y, A.pf_pts_i_z ? A.pf_pts_i_z[k] : 1.0, ob.z, ob.w, J);
+    const double s = J.r[0] * J.r[0] + J.r[1] * J.r[1];
+    acc += cauchy ? a2 * log(1.0 + s / a2) : s;
+  }
+  if (A.NL > 0)
+    for (int64_t k = A.lf_window_offset[w] + tid; k < A.lf_window_offset[w + 1]; k += blockDim.x) {
+      const int frame = A.lf_frame[k];
+      if (frame < 0 || frame >= A.P) continue;
+      double g9[9];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) g9[c] = A.lf_geom[(size_t)c * A.NL_stride + k];
+      LineJac J;
+      eval_line(R, cw, frame, g9, J);
+      const double s = J.r[0] * J.r[0] + J.r[1] * J.r[1];
+      acc += cauchy ? a2 * log(1.0 + s / a2) : s;
+    }
+  if (dn.ND > 0)
+    for (int k = dn.window_offset[w]; k < dn.window_offset[w + 1]; ++k) {
+      const int n = (int)(dn.row_offset[k + 1] - dn.row_offset[k]), c = (int)(dn.col_offset[k + 1] - dn.col_offset[k]);
+      const double* __restrict__ J = dn.jacobian + dn.jac_offset[k];
+      const double* __restrict__ r = dn.residual + dn.row_offset[k];
+      const int32_t* __restrict__ ci = dn.col_index + dn.col_offset[k];
+      for (int q = tid; q < n; q += blockDim.x) {
+        double v = r[q];
+        if (dx)
+          for (int a = 0; a < c; ++a) v = fma(J[(size_t)q * c + a], dx[(size_t)w * Dx + ci[a]], v);
+        acc += v * v;
+      }
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((tid & 31) == 0) s_red[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int k = 0; k < (int)blockDim.x / 32; ++k) t += s_red[k];
+    cost[3 * (size_t)w + slot] = 0.5 * t;
+  }
+}
+
+}  // namespace gn

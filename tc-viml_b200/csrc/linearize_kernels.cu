@@ -434,6 +434,7 @@ __global__ void __launch_bounds__(128) lines_kernel(LinearizeArgs A) {
 }
 
 #include "assemble2.cuh"
+#include "gn_kernels.cuh"
 
 }  // namespace
 
@@ -522,6 +523,46 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
     const double eps = 1e-8;  // MarginalizationInfo::eps (marginalization_factor.h:70)
     viml_launch_schur(ctx, a.W, a.F, a.D, a.out.H_pp, a.out.H_lp, a.out.H_ll, a.out.b_p, a.out.b_l, a.out.S, a.out.g, eps);
   }
+  VIML_TRY_CUDA(ctx, cudaGetLastError());
+  return VIML_OK;
+}
+
+int viml_launch_prep(viml_ctx* ctx, const LinearizeArgs& a) {
+  const int64_t total = (int64_t)a.W * (a.P + 1);
+  LaunchScope ls(ctx, K_PREP);
+  prep_windows_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(a);
+  VIML_TRY_CUDA(ctx, cudaGetLastError());
+  return VIML_OK;
+}
+
+int viml_launch_reduced(viml_ctx* ctx, int W, int D, const DenseArgs& dn, const double* S, const double* g, double* Sx, double* gx) {
+  LaunchScope ls(ctx, K_GN);
+  gn::reduced_kernel<<<W, 256, 0, ctx->stream>>>(D, dn, S, g, Sx, gx);
+  VIML_TRY_CUDA(ctx, cudaGetLastError());
+  return VIML_OK;
+}
+
+int viml_launch_gn_solve(viml_ctx* ctx, int W, int Dx, double lambda, const double* Sx, const double* gx, double* dx, int32_t* solved,
+                         double* cost) {
+  const size_t smem = ((size_t)Dx * (Dx + 1) / 2 + Dx) * sizeof(double);
+  VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(gn::solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchScope ls(ctx, K_GN);
+  gn::solve_kernel<<<W, 128, smem, ctx->stream>>>(Dx, lambda, Sx, gx, dx, solved, cost);
+  VIML_TRY_CUDA(ctx, cudaGetLastError());
+  return VIML_OK;
+}
+
+int viml_launch_gn_update(viml_ctx* ctx, const LinearizeArgs& a, int X, const double* extra_in, const double* dx, const int32_t* solved,
+                          double* o_poses, double* o_ex, double* o_dep, double* o_extra) {
+  LaunchScope ls(ctx, K_GN);
+  gn::update_kernel<<<a.W, 128, 0, ctx->stream>>>(a, X, extra_in, dx, solved, o_poses, o_ex, o_dep, o_extra);
+  VIML_TRY_CUDA(ctx, cudaGetLastError());
+  return VIML_OK;
+}
+
+int viml_launch_cost(viml_ctx* ctx, const LinearizeArgs& a, const DenseArgs& dn, const double* dx, int slot, double* cost) {
+  LaunchScope ls(ctx, K_GN);
+  gn::cost_kernel<<<a.W, 128, 0, ctx->stream>>>(a, dn, dx, slot, cost);
   VIML_TRY_CUDA(ctx, cudaGetLastError());
   return VIML_OK;
 }

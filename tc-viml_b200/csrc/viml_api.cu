@@ -98,6 +98,8 @@ void viml_destroy(viml_ctx* ctx) {
   ctx->scratch.release();
   ctx->scratch2.release();
   ctx->scratch3.release();
+  ctx->gn_in.release();
+  ctx->gn_out.release();
   if (ctx->d_map) cudaFree(ctx->d_map);
   if (ctx->d_map_sorted) cudaFree(ctx->d_map_sorted);
   if (ctx->d_map_orig) cudaFree(ctx->d_map_orig);
@@ -186,7 +188,7 @@ const char* viml_kernel_name(int id) {
   static const char* names[VIML_NUM_KERNELS] = {"prep_windows", "linearize_points", "linearize_lines", "assemble_hb",
                                                 "schur_landmarks", "assoc_cam_pose", "assoc_cull", "assoc_scan",
                                                 "assoc_fill_list", "assoc_project", "assoc_match", "marginalize_dense",
-                                                "microbench", "plan_windows", "assemble_irregular", ""};
+                                                "microbench", "plan_windows", "assemble_irregular", "gn_step"};
   return (id >= 0 && id < VIML_NUM_KERNELS) ? names[id] : "";
 }
 

@@ -19,7 +19,7 @@ def test_header_symbols_exported(pkg):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in viml.h but not exported"
     assert sorted(pkg.ABI_SYMBOLS) == syms
-    assert lib.viml_abi_version() == 1
+    assert lib.viml_abi_version() == 2
 
 
 def test_struct_sizes_match_header(pkg):
@@ -32,6 +32,8 @@ def test_struct_sizes_match_header(pkg):
     assert C.sizeof(abi.MargOut) == 32
     assert C.sizeof(abi.AssocQuery) == 8 + 6 * 8
     assert C.sizeof(abi.AssocOut) == 5 * 8 + 8 + 8
+    assert C.sizeof(abi.DenseFactors) == 8 + 8 + 7 * 8
+    assert C.sizeof(abi.ReducedOut) == 16 and C.sizeof(abi.GnOptions) == 16 and C.sizeof(abi.GnOut) == 7 * 8
 
 
 def test_no_cpu_fallback(pkg, cfg):

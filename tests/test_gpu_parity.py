@@ -271,6 +271,116 @@ def test_huge_window_partition_sums_to_full(pkg, orc, ctx, cfg):
     assert pkg.parity.unit_err("S", accS[None], ref["S"]) < TOL and pkg.parity.unit_err("g", accg[None], ref["g"]) < TOL
 
 
+# ---- whole-window reduced system and the Gauss-Newton step -----------------------------------
+def make_dense(pkg, batch, seed=5):
+    """Per window: one prior-like block over every pose, the extrinsic and the first speed-bias (n = 40 rows) and one IMU-like
+    15-row block per consecutive pose pair (pose i, speed-bias i, pose j, speed-bias j: 15 x 30), as the reference's problem has
+    them (estimator.cpp:1717-1733).  Extra columns: 9 per pose (speed-bias)."""
+    rng = np.random.default_rng(seed)
+    W, P, D = batch.W, batch.P, batch.D
+    X = 9 * P
+    fs = []
+    for w in range(W):
+        cols = np.concatenate([np.arange(D), D + np.arange(9)])
+        J = 30.0 * rng.standard_normal((40, len(cols))) + 0.0
+        J[:len(cols), :] += 200.0 * np.eye(40, len(cols))[:len(cols)] if len(cols) <= 40 else 0.0
+        fs.append((w, 0.05 * rng.standard_normal(40), J, cols))
+        # a strong diagonal prior on every column keeps the reduced system well conditioned (gauge fixed)
+        allc = np.arange(D + X)
+        fs.append((w, 0.01 * rng.standard_normal(len(allc)), np.diag(150.0 + 50.0 * rng.uniform(size=len(allc))), allc))
+        for i in range(P - 1):
+            ci = np.concatenate([6 * i + np.arange(6), D + 9 * i + np.arange(9), 6 * (i + 1) + np.arange(6), D + 9 * (i + 1) + np.arange(9)])
+            fs.append((w, 0.1 * rng.standard_normal(15), 20.0 * rng.standard_normal((15, 30)), ci))
+    return pkg._abi.Dense(W, X, fs)
+
+
+def block_err(got, ref, bounds):
+    """max over windows and (block row, block col) of max|d| / max|ref| with the given block boundaries."""
+    worst = 0.0
+    nb = len(bounds) - 1
+    for i in range(nb):
+        for j in range(nb if got.ndim == 3 else 1):
+            if got.ndim == 3:
+                g, r = got[:, bounds[i]:bounds[i + 1], bounds[j]:bounds[j + 1]], ref[:, bounds[i]:bounds[i + 1], bounds[j]:bounds[j + 1]]
+            else:
+                g, r = got[:, bounds[i]:bounds[i + 1]], ref[:, bounds[i]:bounds[i + 1]]
+            sc = np.abs(r).reshape(len(r), -1).max(axis=1)
+            df = np.abs(g - r).reshape(len(r), -1).max(axis=1)
+            e = np.where(sc > 0, df / np.where(sc > 0, sc, 1.0), np.where(df == 0, 0.0, np.inf))
+            worst = max(worst, float(e.max()))
+    return worst
+
+
+def test_reduced_system_and_gn_step(pkg, orc, ctx, cfg):
+    from oracle import gn_oracle
+    abi, synth = pkg._abi, pkg.synth
+    b = synth.make_windows(12, seed=141)
+    dense = make_dense(pkg, b)
+    P, D, X = b.P, b.D, dense.X
+    bounds = [6 * k for k in range(P + 2)] + [D + 9 * k for k in range(1, P + 1)]
+    flags = abi.LOSS_CAUCHY
+    Sx, gx = ctx.reduced_system(b, dense, flags)
+    rSx, rgx, _ = gn_oracle.reduced_system(cfg, b, dense, flags)
+    assert block_err(Sx, rSx, bounds) < TOL and block_err(gx, rgx, bounds) < TOL
+    # without dense factors: the embedding of S, g
+    S0, g0 = ctx.reduced_system(b, None, flags)
+    r0 = orc.linearize_batch(cfg, b, abi.OUT_SCHUR | abi.LOSS_CAUCHY)
+    assert pkg.parity.unit_err("S", S0, r0["S"]) < TOL and pkg.parity.unit_err("g", g0, r0["g"]) < TOL
+    extra = 0.1 * np.random.default_rng(3).standard_normal((b.W, X))
+    for lam in (0.0, 1e-3):
+        got = ctx.gn_step(b, dense, extra, flags, lam=lam)
+        ref = gn_oracle.gn_step(cfg, b, dense, extra, flags, lam=lam)
+        assert np.array_equal(got["solved"], ref["solved"]) and got["solved"].all()
+        assert block_err(got["dx"], ref["dx"], bounds) < TOL
+        for k in ("poses", "ex_pose"):
+            assert np.abs(got[k] - ref[k]).max() < 1e-9 * max(1.0, np.abs(ref[k]).max()), k
+        # inverse depths / extra state: the increments are what is computed
+        dl_g, dl_r = got["inv_depth"] - b.inv_depth, ref["inv_depth"] - b.inv_depth
+        assert np.abs(dl_g - dl_r).max() < 1e-9 * np.abs(dl_r).max()
+        assert np.abs(got["extra"] - ref["extra"]).max() < 1e-9 * np.abs(ref["extra"]).max()
+        assert np.abs(got["cost"] - ref["cost"]).max(axis=0).max() < 1e-9 * np.abs(ref["cost"]).max()
+        rel = np.abs(got["cost"] - ref["cost"]) / np.maximum(np.abs(ref["cost"]), 1e-300)
+        assert rel.max() < 1e-9, rel.max()
+        # identical accept / reject decisions, and the step does decrease the cost on these windows
+        assert np.array_equal(got["cost"][:, 1] < got["cost"][:, 0], ref["cost"][:, 1] < ref["cost"][:, 0])
+        assert (got["cost"][:, 2] > 0).all()
+    # a few iterations from a perturbed state converge (cost decreases monotonically when every step is accepted)
+    cur = b
+    costs = []
+    ex_state = extra
+    for it in range(3):
+        o = ctx.gn_step(cur, dense, ex_state, flags, lam=1e-4)
+        costs.append(o["cost"][:, 0].sum())
+        cur = abi.Batch(o["poses"], o["ex_pose"], o["inv_depth"], b.pf_window_offset, b.pf_idx, b.pf_obs, b.lf_window_offset, b.lf_frame, b.lf_geom)
+        ex_state = o["extra"]
+    assert costs[1] < costs[0]
+    # a singular system (no dense factors, lambda = 0: gauge freedom) is reported, not solved, and the state comes back unchanged
+    o = ctx.gn_step(b.slice_windows(0, 2), None, None, flags, lam=0.0)
+    r = gn_oracle.gn_step(cfg, b.slice_windows(0, 2), None, None, flags, lam=0.0)
+    assert np.array_equal(o["solved"], r["solved"])
+    for w in range(2):
+        if not o["solved"][w]:
+            assert np.array_equal(o["poses"][w], b.poses[w]) and np.array_equal(o["inv_depth"][w], b.inv_depth[w])
+
+
+def test_load_line_map(pkg, cfg, tmp_path):
+    """viml_load_line_map reads line_3d.txt the way parameters.cpp:50-59 does and gives the same association as viml_set_map."""
+    synth = pkg.synth
+    lines = synth.make_line_map(3000, extent=(120.0, 120.0, 20.0))
+    path = tmp_path / "line_3d.txt"
+    with open(path, "w") as f:
+        for r in lines:
+            f.write(" ".join(repr(float(v)) for v in r) + "\n")
+    cull, match, ex, l2d = synth.make_assoc_queries(lines, 6, L=40, n_true=16, extent=(120.0, 120.0, 20.0))
+    with pkg.Context(cfg) as c1, pkg.Context(cfg) as c2:
+        assert c1.load_line_map(str(path)) == len(lines)
+        c2.set_map(lines)
+        a1, a2 = c1.associate(cull, match, ex, l2d, want_mask=True), c2.associate(cull, match, ex, l2d, want_mask=True)
+        for k in a1:
+            assert np.array_equal(a1[k], a2[k], equal_nan=True), k
+        assert c1.lib.viml_load_line_map(c1.h, b"/nonexistent/line_3d.txt", None) == pkg._abi.VIML_ERR_INVALID
+
+
 # ---- marginalisation ----------------------------------------------------------------------------------
 def test_marginalize_dense(pkg, orc, ctx):
     rng = np.random.default_rng(7)
