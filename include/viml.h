@@ -212,6 +212,10 @@ typedef struct viml_reduced_out {
 
 int viml_reduced_system(viml_ctx* ctx, const viml_window_batch* in, const viml_dense_factors* dense,
                         const viml_reduced_out* out, uint32_t flags);
+/* The same accumulation onto S [W][D][D], g [W][D] the caller already holds (e.g. from viml_linearize_batch with
+ * VIML_OUT_SCHUR): what MarginalizationInfo::marginalize does with its IMU and prior factors after the landmarks are gone. */
+int viml_reduced_from_schur(viml_ctx* ctx, int32_t n_windows, int32_t D, const double* S, const double* g,
+                            const viml_dense_factors* dense, const viml_reduced_out* out, uint32_t flags);
 
 /* ---- one Gauss-Newton / Levenberg-Marquardt iteration for a batch of windows, device resident -------------------
  * What one iteration of ceres::Solve(SPARSE_SCHUR) does with the window's problem (estimator.cpp:1888-1905), on the normal

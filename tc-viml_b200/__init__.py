@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "viml_memcpy_d2h", "viml_kernel_launches", "viml_profile_begin", "viml_profile_end", "viml_kernel_name",
     "viml_microbench_fp64", "viml_microbench_dmma", "viml_selftest_division", "viml_set_map", "viml_linearize_batch",
     "viml_marginalize_batch", "viml_line_associate", "viml_assoc_stats", "viml_allreduce_hb",
-    "viml_load_line_map", "viml_reduced_system", "viml_gn_step",
+    "viml_load_line_map", "viml_reduced_system", "viml_reduced_from_schur", "viml_gn_step",
 )
 
 
@@ -76,6 +76,8 @@ def load_library():
     lib.viml_load_line_map.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]
     lib.viml_reduced_system.argtypes = [C.c_void_p, C.POINTER(_abi.WindowBatch), C.POINTER(_abi.DenseFactors),
                                         C.POINTER(_abi.ReducedOut), C.c_uint32]
+    lib.viml_reduced_from_schur.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(_abi.DenseFactors),
+                                            C.POINTER(_abi.ReducedOut), C.c_uint32]
     lib.viml_gn_step.argtypes = [C.c_void_p, C.POINTER(_abi.WindowBatch), C.POINTER(_abi.DenseFactors), C.c_void_p,
                                  C.POINTER(_abi.GnOptions), C.POINTER(_abi.GnOut), C.c_uint32]
     _LIB = lib

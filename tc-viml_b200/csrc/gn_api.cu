@@ -199,6 +199,59 @@ int viml_reduced_system(viml_ctx* ctx, const viml_window_batch* in, const viml_d
   return run(ctx, in, dense, nullptr, nullptr, out, nullptr, flags);
 }
 
+int viml_reduced_from_schur(viml_ctx* ctx, int32_t W, int32_t D, const double* S, const double* g, const viml_dense_factors* dense,
+                            const viml_reduced_out* out, uint32_t flags) {
+  if (!ctx) return VIML_ERR_INVALID;
+  const int X = dense ? dense->extra_dim : 0, Dx = D + X;
+  const int64_t ND = dense ? dense->n_factors : 0;
+  if (W < 0 || D < 1 || X < 0 || ND < 0 || !S || !g || !out || !out->Sx || !out->gx)
+    return fail(ctx, VIML_ERR_INVALID, "viml_reduced_from_schur: bad arguments");
+  if (ND > 0 && (!dense->window_offset || !dense->row_offset || !dense->col_offset || !dense->jac_offset || !dense->col_index ||
+                 !dense->residual || !dense->jacobian))
+    return fail(ctx, VIML_ERR_INVALID, "dense factors: null array");
+  if (W == 0) return VIML_OK;
+  VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bool dev = (flags & VIML_PTRS_DEVICE) != 0;
+  int64_t n_rows = 0, n_cols = 0, n_jac = 0;
+  if (ND > 0) {
+    if (dev) {
+      int64_t t[3];
+      VIML_TRY_CUDA(ctx, cudaMemcpyAsync(&t[0], dense->row_offset + ND, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      VIML_TRY_CUDA(ctx, cudaMemcpyAsync(&t[1], dense->col_offset + ND, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      VIML_TRY_CUDA(ctx, cudaMemcpyAsync(&t[2], dense->jac_offset + ND, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      VIML_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      n_rows = t[0], n_cols = t[1], n_jac = t[2];
+    } else {
+      n_rows = dense->row_offset[ND], n_cols = dense->col_offset[ND], n_jac = dense->jac_offset[ND];
+      for (int64_t k = 0; k < n_cols; ++k)
+        if (dense->col_index[k] < 0 || dense->col_index[k] >= Dx) return fail(ctx, VIML_ERR_INVALID, "dense factors: col_index out of range");
+    }
+  }
+  Stager st{ctx, dev};
+  const double *dS = nullptr, *dg = nullptr;
+  st.in(S, (size_t)W * D * D, &dS);
+  st.in(g, (size_t)W * D, &dg);
+  DenseArgs dn{};
+  dn.X = X, dn.ND = ND;
+  if (ND > 0) {
+    st.in(dense->window_offset, (size_t)W + 1, &dn.window_offset);
+    st.in(dense->row_offset, (size_t)ND + 1, &dn.row_offset);
+    st.in(dense->col_offset, (size_t)ND + 1, &dn.col_offset);
+    st.in(dense->jac_offset, (size_t)ND + 1, &dn.jac_offset);
+    st.in(dense->col_index, (size_t)n_cols, &dn.col_index);
+    st.in(dense->residual, (size_t)n_rows, &dn.residual);
+    st.in(dense->jacobian, (size_t)n_jac, &dn.jacobian);
+  }
+  double *Sx = nullptr, *gx = nullptr;
+  st.out(out->Sx, (size_t)W * Dx * Dx, &Sx);
+  st.out(out->gx, (size_t)W * Dx, &gx);
+  int rc = st.commit();
+  if (rc != VIML_OK) return rc;
+  rc = viml_launch_reduced(ctx, W, D, dn, dS, dg, Sx, gx);
+  if (rc != VIML_OK) return rc;
+  return st.finish();
+}
+
 int viml_gn_step(viml_ctx* ctx, const viml_window_batch* in, const viml_dense_factors* dense, const double* extra_state,
                  const viml_gn_options* opt, const viml_gn_out* out, uint32_t flags) {
   if (!ctx) return VIML_ERR_INVALID;

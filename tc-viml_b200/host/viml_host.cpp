@@ -521,43 +521,57 @@ void MarginalizationInfo::marginalize() {
   const int L = m - m_dense, pd = m_dense + n;  // dense system after the device eliminated the L landmarks
   auto didx = [&](long a) { const int i = parameter_block_idx[a]; return i < m_dense ? i : i - L; };
   std::vector<double> A((size_t)pd * pd, 0.0), b(pd, 0.0);
-  // (1) point factors: landmark-eliminated S, g from the device, blocks [poses..., extrinsic]
-  if (!S_.empty()) {
-    const int P = (int)gpu_pose_blocks_.size(), D = 6 * (P + 1);
-    std::vector<int> off(P + 1);
-    for (int p = 0; p < P; ++p) off[p] = didx(reinterpret_cast<long>(gpu_pose_blocks_[p]));
-    off[P] = didx(reinterpret_cast<long>(gpu_ex_block_));
-    for (int bi = 0; bi <= P; ++bi)
-      for (int r = 0; r < 6; ++r) {
-        for (int bj = 0; bj <= P; ++bj)
-          for (int c = 0; c < 6; ++c) A[(size_t)(off[bi] + r) * pd + off[bj] + c] += S_[(size_t)(6 * bi + r) * D + 6 * bj + c];
-        b[off[bi] + r] += g_[6 * bi + r];
+  // (1) + (2): the landmark-eliminated S, g of the point factors (device, preMarginalize) and the host-resident cost functions
+  // (IMU, prior) as evaluated dense blocks, accumulated on the device by ThreadsConstructA's rule (:141-172) in ONE call of
+  // viml_reduced_from_schur.  Device column space: [gpu poses | extrinsic | every other block in dense order].
+  {
+    const int P = S_.empty() ? 0 : (int)gpu_pose_blocks_.size();
+    const int D = S_.empty() ? 0 : 6 * (P + 1);
+    std::vector<int> dev_col(pd, -1);   // dense index -> device column
+    if (D) {
+      for (int p = 0; p < P; ++p)
+        for (int r = 0; r < 6; ++r) dev_col[didx(reinterpret_cast<long>(gpu_pose_blocks_[p])) + r] = 6 * p + r;
+      for (int r = 0; r < 6; ++r) dev_col[didx(reinterpret_cast<long>(gpu_ex_block_)) + r] = 6 * P + r;
+    }
+    int X = 0;
+    for (int k = 0; k < pd; ++k)
+      if (dev_col[k] < 0) dev_col[k] = D + X++;
+    std::vector<int32_t> woff(2, 0), col_index;
+    std::vector<int64_t> roff(1, 0), coff(1, 0), joff(1, 0);
+    std::vector<double> res, jac;
+    for (auto it : factors) {
+      if (dynamic_cast<ProjectionFactor*>(it->cost_function)) continue;
+      const std::vector<int32_t>& sizes = it->cost_function->parameter_block_sizes();
+      const int nres = it->cost_function->num_residuals();
+      std::vector<int> cols, src_block, src_col;
+      for (size_t i = 0; i < it->parameter_blocks.size(); i++) {
+        const long ai = reinterpret_cast<long>(it->parameter_blocks[i]);
+        if (is_landmark.count(ai)) die("MarginalizationInfo: a landmark block is shared with a non-projection factor");
+        for (int c = 0; c < localSize(sizes[i]); ++c) cols.push_back(dev_col[didx(ai) + c]), src_block.push_back((int)i), src_col.push_back(c);
       }
-  }
-  // (2) host-resident cost functions (IMU, prior): ThreadsConstructA's rule (:141-172)
-  for (auto it : factors) {
-    if (dynamic_cast<ProjectionFactor*>(it->cost_function)) continue;
-    const std::vector<int32_t>& sizes = it->cost_function->parameter_block_sizes();
-    const int nres = it->cost_function->num_residuals();
-    for (size_t i = 0; i < it->parameter_blocks.size(); i++) {
-      const long ai = reinterpret_cast<long>(it->parameter_blocks[i]);
-      if (is_landmark.count(ai)) die("MarginalizationInfo: a landmark block is shared with a non-projection factor");
-      const int idx_i = didx(ai), size_i = localSize(sizes[i]), gi = sizes[i];
-      for (size_t j = i; j < it->parameter_blocks.size(); j++) {
-        const int idx_j = didx(reinterpret_cast<long>(it->parameter_blocks[j])), size_j = localSize(sizes[j]), gj = sizes[j];
-        for (int r = 0; r < size_i; ++r)
-          for (int c = 0; c < size_j; ++c) {
-            double v = 0.0;
-            for (int q = 0; q < nres; ++q) v += it->jacobians[i][(size_t)q * gi + r] * it->jacobians[j][(size_t)q * gj + c];
-            A[(size_t)(idx_i + r) * pd + idx_j + c] += v;
-            if (i != j) A[(size_t)(idx_j + c) * pd + idx_i + r] = A[(size_t)(idx_i + r) * pd + idx_j + c];
-          }
+      const int nc = (int)cols.size();
+      for (int q = 0; q < nres; ++q) {
+        res.push_back(it->residuals[q]);
+        for (int c = 0; c < nc; ++c) jac.push_back(it->jacobians[src_block[c]][(size_t)q * sizes[src_block[c]] + src_col[c]]);
       }
-      for (int r = 0; r < size_i; ++r) {
-        double v = 0.0;
-        for (int q = 0; q < nres; ++q) v += it->jacobians[i][(size_t)q * gi + r] * it->residuals[q];
-        b[idx_i + r] += v;
-      }
+      col_index.insert(col_index.end(), cols.begin(), cols.end());
+      roff.push_back(roff.back() + nres), coff.push_back(coff.back() + nc), joff.push_back(joff.back() + (int64_t)nres * nc);
+      ++woff[1];
+    }
+    const int Dx = D + X;
+    std::vector<double> S0((size_t)std::max(D, 1) * std::max(D, 1), 0.0), g0(std::max(D, 1), 0.0), Sx((size_t)Dx * Dx), gx(Dx);
+    viml_dense_factors dn{};
+    dn.extra_dim = D ? X : X - 1;   // D == 0: one dummy column keeps the C-ABI's D >= 1
+    dn.n_factors = woff[1];
+    dn.window_offset = woff.data(), dn.row_offset = roff.data(), dn.col_offset = coff.data(), dn.jac_offset = joff.data();
+    dn.col_index = col_index.data(), dn.residual = res.data(), dn.jacobian = jac.data();
+    viml_reduced_out ro{};
+    ro.Sx = Sx.data(), ro.gx = gx.data();
+    last_error = viml_reduced_from_schur(ctx, 1, D ? D : 1, D ? S_.data() : S0.data(), D ? g_.data() : g0.data(), &dn, &ro, 0);
+    check_rc(last_error, "viml_reduced_from_schur");
+    for (int r = 0; r < pd; ++r) {
+      for (int c = 0; c < pd; ++c) A[(size_t)r * pd + c] = Sx[(size_t)dev_col[r] * Dx + dev_col[c]];
+      b[r] = gx[dev_col[r]];
     }
   }
   // (3) dense elimination of the remaining marginalised blocks + square-root factorisation on the device (:264-293)
