@@ -31,7 +31,9 @@ __global__ void __launch_bounds__(SWARPS * 32) schur_dmma_kernel(int F, int D, c
                                                                  const double* __restrict__ H_ll,
                                                                  const double* __restrict__ b_p,
                                                                  const double* __restrict__ b_l, double* __restrict__ S,
-                                                                 double* __restrict__ g, double eps, int ntile) {
+                                                                 double* __restrict__ g, double eps, int ntile,
+                                                                 const int* __restrict__ order, const int* __restrict__ tstart,
+                                                                 const int* __restrict__ span) {
   __shared__ double sR[KC * LDW];   // W[l][row-tile columns]
   __shared__ double sC[KC * LDW];   // W[l][col-tile columns]
   __shared__ double sInv[KC], sB[KC];
@@ -60,18 +62,36 @@ __global__ void __launch_bounds__(SWARPS * 32) schur_dmma_kernel(int F, int D, c
 #pragma unroll
   for (int i = 0; i < MAXT; ++i) acc[i][0] = acc[i][1] = 0.0;
   double gacc = 0.0;  // threads 0..71 of a diagonal tile own g[r0 + tid]
-  for (int l0 = 0; l0 < F; l0 += KC) {
-    const int nl = min(KC, F - l0);
+  // Landmarks that can contribute to this tile.  With the band plan (order != nullptr: landmarks sorted by the first pose
+  // tile they touch, `span` = the widest tile extent of a landmark) a landmark touches row tile ty and column tile tx only if
+  // its first tile lies in [tx - span, ty]; the extrinsic columns (last tile) are touched by every landmark, so for tx = last
+  // the condition is on the rows alone.  Rows outside the range are structural zeros
+  // in these columns: skipping them changes nothing but the work (a 201-pose window: ~10x fewer tile-landmark products).
+  int lb = 0, le = F;
+  const int* __restrict__ ord = nullptr;
+  if (order) {
+    ord = order + (size_t)w * F;
+    const int* ts = tstart + (size_t)w * (ntile + 2);
+    const int sp = span[w], last = ntile - 1;
+    // (the (extrinsic, extrinsic) block and g_ex need every landmark: ex_block_kernel writes them after this kernel)
+    const int lo_t = max(0, (tx == last ? ty : tx) - sp), hi_t = ty;
+    lb = lo_t <= hi_t ? ts[lo_t] : 0;
+    le = lo_t <= hi_t ? ts[hi_t + 1] : 0;
+  }
+  for (int l0 = lb; l0 < le; l0 += KC) {
+    const int nl = min(KC, le - l0);
     __syncthreads();
     for (int e = tid; e < KC * TS; e += SWARPS * 32) {
       const int l = e / TS, c = e % TS;
-      sR[l * LDW + c] = (l < nl && c < nr) ? Hl[(size_t)(l0 + l) * D + r0 + c] : 0.0;
-      if (!diag) sC[l * LDW + c] = (l < nl && c < nc) ? Hl[(size_t)(l0 + l) * D + c0 + c] : 0.0;
+      const size_t row = l < nl ? (size_t)(ord ? ord[l0 + l] : l0 + l) : 0;
+      sR[l * LDW + c] = (l < nl && c < nr) ? Hl[row * D + r0 + c] : 0.0;
+      if (!diag) sC[l * LDW + c] = (l < nl && c < nc) ? Hl[row * D + c0 + c] : 0.0;
     }
     if (tid < KC) {
-      const double L = tid < nl ? H_ll[(size_t)w * F + l0 + tid] : 0.0;
+      const size_t row = tid < nl ? (size_t)(ord ? ord[l0 + tid] : l0 + tid) : 0;
+      const double L = tid < nl ? H_ll[(size_t)w * F + row] : 0.0;
       sInv[tid] = (L > eps) ? 1.0 / L : 0.0;
-      sB[tid] = tid < nl ? b_l[(size_t)w * F + l0 + tid] : 0.0;
+      sB[tid] = tid < nl ? b_l[(size_t)w * F + row] : 0.0;
     }
     __syncthreads();
     const double* cs = diag ? sR : sC;
@@ -110,6 +130,106 @@ __global__ void __launch_bounds__(SWARPS * 32) schur_dmma_kernel(int F, int D, c
       }
     }
   if (diag && tid < nr) g[(size_t)w * D + r0 + tid] = b_p[(size_t)w * D + r0 + tid] - gacc;
+}
+
+// ---- band plan for long windows (D > 2 tiles) ----------------------------------------------------------------------
+// extent_kernel: warp per landmark row, first and last 72-column pose tile with a non-zero entry (the extrinsic's six
+// columns, which every landmark touches, are left out).  order_kernel: landmarks ordered by first tile (stable: warp k
+// compacts the landmarks of key k in index order, so the summation order is fixed), tile start offsets, widest extent.
+__global__ void __launch_bounds__(256) extent_kernel(int F, int D, const double* __restrict__ H_lp, int* __restrict__ tmin,
+                                                     int* __restrict__ tmax, int ntile) {
+  const int w = blockIdx.y, lane = threadIdx.x & 31, l = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (l >= F) return;
+  const double* __restrict__ row = H_lp + ((size_t)w * F + l) * D;
+  int lo = ntile, hi = -1;
+  for (int c = lane; c < D - 6; c += 32)
+    if (row[c] != 0.0) lo = min(lo, c / TS), hi = max(hi, c / TS);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)), hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  if (lane == 0) tmin[(size_t)w * F + l] = lo, tmax[(size_t)w * F + l] = hi;
+}
+
+__global__ void __launch_bounds__(1024) order_kernel(int F, int ntile, const int* __restrict__ tmin, const int* __restrict__ tmax,
+                                                     int* __restrict__ order, int* __restrict__ tstart, int* __restrict__ span) {
+  __shared__ int cnt[34], base[35], s_span;
+  const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int* __restrict__ tm = tmin + (size_t)w * F;
+  const int* __restrict__ tM = tmax + (size_t)w * F;
+  if (tid < 34) cnt[tid] = 0;
+  if (tid == 0) s_span = 0;
+  __syncthreads();
+  int sp = 0;
+  for (int l = tid; l < F; l += blockDim.x) {
+    atomicAdd(&cnt[tm[l]], 1);
+    if (tM[l] >= 0) sp = max(sp, tM[l] - tm[l]);
+  }
+  atomicMax(&s_span, sp);
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int k = 0; k <= ntile; ++k) base[k] = run, run += cnt[k];
+    base[ntile + 1] = run;
+    for (int k = 0; k <= ntile + 1; ++k) tstart[(size_t)w * (ntile + 2) + k] = base[k];
+    span[w] = s_span;
+  }
+  __syncthreads();
+  if (warp <= ntile) {   // keys 0..ntile (ntile = landmarks without any pose entry), one warp per key
+    int pos = base[warp];
+    for (int l0 = 0; l0 < F; l0 += 32) {
+      const int l = l0 + lane;
+      const bool mine = l < F && tm[l] == warp;
+      const unsigned m = __ballot_sync(0xffffffffu, mine);
+      if (mine) order[(size_t)w * F + pos + __popc(m & ((1u << lane) - 1u))] = l;
+      pos += __popc(m);
+    }
+  }
+}
+
+// The one block every landmark contributes to: S[ex, ex] = H_pp[ex, ex] - sum_l w_l w_l^T / L_l, g_ex = b_ex - sum_l w_l b_l / L_l
+// with w_l the six extrinsic entries of landmark row l.  Runs after the band-limited tile kernel and overwrites its partial
+// values for these 42 entries.
+__global__ void __launch_bounds__(256) ex_block_kernel(int F, int D, const double* __restrict__ H_pp, const double* __restrict__ H_lp,
+                                                       const double* __restrict__ H_ll, const double* __restrict__ b_p,
+                                                       const double* __restrict__ b_l, double* __restrict__ S, double* __restrict__ g,
+                                                       double eps) {
+  __shared__ double red[8][42];
+  const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, e0 = D - 6;
+  double acc[42];
+#pragma unroll
+  for (int k = 0; k < 42; ++k) acc[k] = 0.0;
+  for (int l = tid; l < F; l += 256) {
+    const double L = H_ll[(size_t)w * F + l];
+    if (!(L > eps)) continue;
+    const double inv = 1.0 / L, bl = b_l[(size_t)w * F + l];
+    const double* __restrict__ row = H_lp + ((size_t)w * F + l) * D + e0;
+    double v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = row[k];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc[r * 6 + c] = fma(v[r] * inv, v[c], acc[r * 6 + c]);
+      acc[36 + r] = fma(v[r] * inv, bl, acc[36 + r]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 42; ++k) {
+    double t = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) red[warp][k] = t;
+  }
+  __syncthreads();
+  if (tid < 42) {
+    double t = 0.0;
+    for (int q = 0; q < 8; ++q) t += red[q][tid];
+    if (tid < 36) {
+      const int r = e0 + tid / 6, c = e0 + tid % 6;
+      S[(size_t)w * D * D + (size_t)r * D + c] = H_pp[(size_t)w * D * D + (size_t)r * D + c] - t;
+    } else {
+      g[(size_t)w * D + e0 + tid - 36] = b_p[(size_t)w * D + e0 + tid - 36] - t;
+    }
+  }
 }
 
 // ---- D <= 72 (one tile, the sliding-window case): split-K over the 8 warps ------------------------------------
@@ -282,8 +402,32 @@ int viml_launch_schur(viml_ctx* ctx, int W, int F, int D, const double* H_pp, co
     return VIML_OK;
   }
   dim3 grid((unsigned)(ntile * (ntile + 1) / 2), (unsigned)W);
-  LaunchScope ls(ctx, K_SCHUR);
-  schur_dmma_kernel<<<grid, SWARPS * 32, 0, ctx->stream>>>(F, D, H_pp, H_lp, H_ll, b_p, b_l, S, g, eps, ntile);
+  int *order = nullptr, *tstart = nullptr, *span = nullptr;
+  if (ntile >= 3 && ntile <= 31 && F > 0) {   // long window: band plan (a landmark's row is non-zero in a few neighbouring tiles only)
+    auto pad = [](size_t b) { return DeviceArena::padded(b); };
+    VIML_TRY_CUDA(ctx, ctx->scratch2.reserve(3 * pad((size_t)W * F * 4) + pad((size_t)W * (ntile + 2) * 4) + pad((size_t)W * 4)));
+    int* tmin = ctx->scratch2.take<int>((size_t)W * F);
+    int* tmax = ctx->scratch2.take<int>((size_t)W * F);
+    order = ctx->scratch2.take<int>((size_t)W * F);
+    tstart = ctx->scratch2.take<int>((size_t)W * (ntile + 2));
+    span = ctx->scratch2.take<int>((size_t)W);
+    {
+      LaunchScope ls(ctx, K_SCHUR);
+      extent_kernel<<<dim3((unsigned)((F + 7) / 8), (unsigned)W), 256, 0, ctx->stream>>>(F, D, H_lp, tmin, tmax, ntile);
+    }
+    {
+      LaunchScope ls(ctx, K_SCHUR);
+      order_kernel<<<(unsigned)W, 1024, 0, ctx->stream>>>(F, ntile, tmin, tmax, order, tstart, span);
+    }
+  }
+  {
+    LaunchScope ls(ctx, K_SCHUR);
+    schur_dmma_kernel<<<grid, SWARPS * 32, 0, ctx->stream>>>(F, D, H_pp, H_lp, H_ll, b_p, b_l, S, g, eps, ntile, order, tstart, span);
+  }
+  if (order) {
+    LaunchScope ls(ctx, K_SCHUR);
+    ex_block_kernel<<<(unsigned)W, 256, 0, ctx->stream>>>(F, D, H_pp, H_lp, H_ll, b_p, b_l, S, g, eps);
+  }
   return VIML_OK;
 }
 

@@ -24,15 +24,20 @@ def shard_windows(batch, rank, world):
 
 
 def split_huge_window(batch, rank, world):
-    """Rank's share of the factors of a single-window batch (W == 1): landmarks l with l % world == rank,
-    line factors k with k % world == rank.  Poses, extrinsic and inverse depths are replicated."""
+    """Rank's share of the factors of a single-window batch (W == 1): landmarks l with l % world == rank, renumbered densely
+    (local landmark l // world; the rank's inverse-depth array and landmark rows hold F/world entries, not F), line factors k
+    with k % world == rank.  Poses and the extrinsic are replicated."""
     assert batch.W == 1
     feat = (batch.pf_idx >> 16).astype(np.int64)
     keep = (feat % world) == rank
     lkeep = (np.arange(batch.NL) % world) == rank
     z = None if batch.pf_pts_i_z is None else batch.pf_pts_i_z[keep]
-    return Batch(batch.poses, batch.ex_pose, batch.inv_depth,
-                 np.array([0, int(keep.sum())], dtype=np.int32), batch.pf_idx[keep], batch.pf_obs[keep],
+    idx = batch.pf_idx[keep]
+    idx = ((idx & 0xffff) | (((idx >> 16) // world) << 16)).astype(np.uint32)
+    owned = np.arange(rank, batch.F, world)
+    dep = batch.inv_depth[:, owned] if len(owned) else np.zeros((1, 1))
+    return Batch(batch.poses, batch.ex_pose, dep,
+                 np.array([0, int(keep.sum())], dtype=np.int32), idx, batch.pf_obs[keep],
                  np.array([0, int(lkeep.sum())], dtype=np.int32), batch.lf_frame[lkeep], batch.lf_geom[:, lkeep], z)
 
 
