@@ -354,13 +354,14 @@ def main():
     hb = abi.Batch(**{k: p.array for k, p in pins.items()})
     h2d = sum(p.nbytes for p in pins.values())
     e_steps = max(3, min(K, 10))
-    pS = {k: pkg.PinnedArray(shapes[k], np.float64) for k in ("S", "g")}
+    pS = {k: pkg.PinnedArray(shapes[k], np.float64) for k in ("S_packed", "g")}
     hoS = {k: p.array for k, p in pS.items()}
-    e_ms = timed_host(lambda: ctx.linearize(hb, abi.OUT_SCHUR | abi.LOSS_CAUCHY, out=hoS), e_steps)
+    e_ms = timed_host(lambda: ctx.linearize(hb, abi.OUT_SCHUR | abi.S_PACKED | abi.LOSS_CAUCHY, out=hoS), e_steps)
     e2e = {"value": total_factors / (e_ms * 1e-3), "unit": "factors/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(sum(p.nbytes for p in pS.values())), "ms_per_step": e_ms, "steps": e_steps,
-           "api": "viml_linearize_batch(host pointers, VIML_OUT_SCHUR|VIML_LOSS_CAUCHY): evaluate + assemble + landmark Schur, S and g back"}
-    S_host = {k: v.copy() for k, v in hoS.items()}
+           "api": "viml_linearize_batch(host pointers, VIML_OUT_SCHUR|VIML_S_PACKED|VIML_LOSS_CAUCHY): evaluate + assemble + landmark "
+                  "Schur; the upper triangle of S and g back"}
+    S_host = {"S": abi.unpack_upper(hoS["S_packed"], batch.D), "g": hoS["g"].copy()}
     pH = {k: pkg.PinnedArray(shapes[k], np.float64) for k in d_out}
     hoH = {k: p.array for k, p in pH.items()}
     e_ms_hb = timed_host(lambda: ctx.linearize(hb, flags, out=hoH), max(3, e_steps // 2))

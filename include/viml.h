@@ -60,6 +60,8 @@ extern "C" {
 #define VIML_OUT_HB 0x02u                /* mode B: per-window block-structured H = J^T J, b = +J^T r  */
 #define VIML_OUT_SCHUR 0x04u             /* landmark-eliminated S, g per window                        */
 #define VIML_LOSS_CAUCHY 0x10u           /* apply the ResidualBlockInfo::Evaluate loss correction      */
+#define VIML_S_PACKED 0x20u              /* with VIML_OUT_SCHUR: S is written as its upper triangle, [W][D(D+1)/2], row r holds
+                                            columns r..D-1 (entry (r,c) at r*D - r(r-1)/2 + c - r): half the bytes back to the host */
 #define VIML_PTRS_DEVICE 0x100u          /* in/out pointers are device pointers; call is asynchronous  */
 
 typedef struct viml_ctx viml_ctx;

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 from . import _abi, build, parity, shard, synth  # noqa: F401
-from ._abi import (LOSS_CAUCHY, OUT_HB, OUT_RESIDUAL_JACOBIAN, OUT_SCHUR, PTRS_DEVICE, Batch,  # noqa: F401
+from ._abi import (LOSS_CAUCHY, OUT_HB, OUT_RESIDUAL_JACOBIAN, OUT_SCHUR, PTRS_DEVICE, S_PACKED, Batch,  # noqa: F401
                    make_config)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -18,6 +18,7 @@ OUT_RESIDUAL_JACOBIAN = 0x01
 OUT_HB = 0x02
 OUT_SCHUR = 0x04
 LOSS_CAUCHY = 0x10
+S_PACKED = 0x20
 PTRS_DEVICE = 0x100
 
 c_double_p = C.POINTER(C.c_double)
@@ -215,7 +216,7 @@ class Batch:
         return {"pf_residual": (NP, 2), "pf_jac_pose_i": (NP, 14), "pf_jac_pose_j": (NP, 14),
                 "pf_jac_ex": (NP, 14), "pf_jac_feat": (NP, 2), "lf_residual": (NL, 2), "lf_jac_pose": (NL, 14),
                 "H_pp": (W, D, D), "H_lp": (W, F, D), "H_ll": (W, F), "b_p": (W, D), "b_l": (W, F),
-                "S": (W, D, D), "g": (W, D)}
+                "S": (W, D, D), "g": (W, D), "S_packed": (W, D * (D + 1) // 2)}
 
     def alloc_out(self, flags, fill=np.nan):
         """numpy output buffers for the requested modes, NaN-filled so unwritten entries are caught."""
@@ -244,4 +245,16 @@ def out_struct(bufs):
     o = LinearizeOut()
     for n in LIN_OUT_FIELDS:
         setattr(o, n, ptr(bufs.get(n)))
+    if bufs.get("S") is None and bufs.get("S_packed") is not None:   # VIML_S_PACKED: the S pointer receives the upper triangle
+        o.S = ptr(bufs["S_packed"])
     return o
+
+
+def unpack_upper(Sp, D):
+    """[W, D(D+1)/2] upper triangles (VIML_S_PACKED) -> full symmetric [W, D, D]."""
+    W = Sp.shape[0]
+    S = np.zeros((W, D, D))
+    iu = np.triu_indices(D)
+    S[:, iu[0], iu[1]] = Sp
+    S[:, iu[1], iu[0]] = Sp
+    return S

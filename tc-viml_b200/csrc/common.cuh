@@ -75,7 +75,7 @@ struct viml_ctx {
   double* d_tile_sphere = nullptr;  // [n_tiles][4]
   int64_t n_tiles = 0;
   unsigned long long* d_assoc_stats = nullptr;  // {gate tests, gated pairs, overlap-scored, distance-scored} of the last association call
-  DeviceArena in_arena, out_arena, scratch, scratch2, scratch3, gn_in, gn_out;
+  DeviceArena in_arena, out_arena, scratch, scratch2, scratch3, gn_in, gn_out, s_full;
   void* nccl_lib = nullptr;
   // profiling (viml_profile_begin/end): event pairs per kernel id
   bool brute_cull = false;     // VIML_BRUTE_CULL=1: the literal all-pairs FoV sweep (roofline accounting, cross-check)

@@ -433,6 +433,16 @@ __global__ void __launch_bounds__(128) lines_kernel(LinearizeArgs A) {
   if (MODE_B && live) line_atomics(A, w, frame, J);
 }
 
+// VIML_S_PACKED: upper triangle of every window's S, row r = columns r..D-1
+__global__ void __launch_bounds__(256) pack_upper_kernel(int D, const double* __restrict__ S, double* __restrict__ Sp) {
+  const double* __restrict__ s = S + (size_t)blockIdx.x * D * D;
+  double* __restrict__ o = Sp + (size_t)blockIdx.x * ((size_t)D * (D + 1) / 2);
+  for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+    const int r = e / D, c = e - r * D;
+    if (c >= r) o[r * D - (r * (r - 1)) / 2 + c - r] = s[e];
+  }
+}
+
 #include "assemble2.cuh"
 #include "gn_kernels.cuh"
 
@@ -521,7 +531,16 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
   }
   if (a.flags & VIML_OUT_SCHUR) {
     const double eps = 1e-8;  // MarginalizationInfo::eps (marginalization_factor.h:70)
-    viml_launch_schur(ctx, a.W, a.F, a.D, a.out.H_pp, a.out.H_lp, a.out.H_ll, a.out.b_p, a.out.b_l, a.out.S, a.out.g, eps);
+    double* S = a.out.S;
+    if (a.flags & VIML_S_PACKED) {   // full S into scratch, its upper triangle to the caller
+      VIML_TRY_CUDA(ctx, ctx->s_full.reserve(DeviceArena::padded((size_t)a.W * a.D * a.D * 8)));
+      S = ctx->s_full.take<double>((size_t)a.W * a.D * a.D);
+    }
+    viml_launch_schur(ctx, a.W, a.F, a.D, a.out.H_pp, a.out.H_lp, a.out.H_ll, a.out.b_p, a.out.b_l, S, a.out.g, eps);
+    if (a.flags & VIML_S_PACKED) {
+      LaunchScope ls(ctx, K_SCHUR);
+      pack_upper_kernel<<<a.W, 256, 0, st>>>(a.D, S, a.out.S);
+    }
   }
   VIML_TRY_CUDA(ctx, cudaGetLastError());
   return VIML_OK;

@@ -100,6 +100,7 @@ void viml_destroy(viml_ctx* ctx) {
   ctx->scratch3.release();
   ctx->gn_in.release();
   ctx->gn_out.release();
+  ctx->s_full.release();
   if (ctx->d_map) cudaFree(ctx->d_map);
   if (ctx->d_map_sorted) cudaFree(ctx->d_map_sorted);
   if (ctx->d_map_orig) cudaFree(ctx->d_map_orig);
@@ -425,7 +426,7 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
     want(&a.out.b_l, wantHB ? out->b_l : nullptr, (size_t)F, 0, 0, true);
   }
   if (wantS) {
-    want(&a.out.S, out->S, (size_t)D * D, 0, 0, true);
+    want(&a.out.S, out->S, (flags & VIML_S_PACKED) ? (size_t)D * (D + 1) / 2 : (size_t)D * D, 0, 0, true);
     want(&a.out.g, out->g, (size_t)D, 0, 0, true);
   }
   VIML_TRY_CUDA(ctx, ctx->out_arena.reserve(out_bytes));
@@ -440,7 +441,8 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   // offsets first (tiny, needed by every chunk); the previous call's work on `st` is already complete (synchronous API)
   VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_poff, in->pf_window_offset, (size_t)(W + 1) * 4, cudaMemcpyHostToDevice, s_in));
   if (NL > 0) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_loff, in->lf_window_offset, (size_t)(W + 1) * 4, cudaMemcpyHostToDevice, s_in));
-  const int nchunk = W >= 2048 ? 16 : (W >= 512 ? 8 : 1);
+  int nchunk = W >= 512 ? 8 : 1;
+  if (const char* e = getenv("VIML_CHUNKS")) nchunk = std::max(1, std::min(W, atoi(e)));   // tuning hook
   // small per-window arrays: whole batch, one copy each
   VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_poses, in->poses, n_pose * 8, cudaMemcpyHostToDevice, s_in));
   VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_ex, in->ex_pose, n_ex * 8, cudaMemcpyHostToDevice, s_in));
@@ -455,14 +457,12 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   auto h2d = [&](void* d, const void* h, size_t bytes) {
     if (bytes) cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s_in);
   };
-  for (int c = 0; c < nchunk && rc == VIML_OK; ++c) {
-    const int w0 = (int)((int64_t)W * c / nchunk), w1 = (int)((int64_t)W * (c + 1) / nchunk), Wc = w1 - w0;
+  // every upload is queued first (the copies depend on nothing but the caller's arrays), so the upload stream runs at link
+  // speed while the host validates the indices of chunk c and launches its kernels
+  for (int c = 0; c < nchunk; ++c) {
+    const int w0 = (int)((int64_t)W * c / nchunk), w1 = (int)((int64_t)W * (c + 1) / nchunk);
     const int64_t pa = in->pf_window_offset[w0], pb = in->pf_window_offset[w1];
     const int64_t la = NL > 0 ? in->lf_window_offset[w0] : 0, lb = NL > 0 ? in->lf_window_offset[w1] : 0;
-    if (!indices_ok(pa, pb, la, lb)) {
-      rc = fail(ctx, VIML_ERR_INVALID, "factor index out of range (pose index >= poses_per_window, feature >= feats_per_window or line frame >= poses_per_window)");
-      break;
-    }
     // per chunk only the three large arrays (observations, packed indices, line geometry as ONE strided copy of its nine
     // planes); the small per-window arrays went up for the whole batch before the loop — every copy costs ~10-20 us of
     // DMA set-up however small it is, and 17 copies per chunk kept the upload stream busy for 6 ms on 125 MB
@@ -473,6 +473,15 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
       cudaMemcpy2DAsync(d_geom + la, (size_t)NL * 8, in->lf_geom + la, (size_t)NL * 8, (size_t)(lb - la) * 8, 9,
                         cudaMemcpyHostToDevice, s_in);
     cudaEventRecord(ev_in[c], s_in);
+  }
+  for (int c = 0; c < nchunk && rc == VIML_OK; ++c) {
+    const int w0 = (int)((int64_t)W * c / nchunk), w1 = (int)((int64_t)W * (c + 1) / nchunk), Wc = w1 - w0;
+    const int64_t pa = in->pf_window_offset[w0], pb = in->pf_window_offset[w1];
+    const int64_t la = NL > 0 ? in->lf_window_offset[w0] : 0, lb = NL > 0 ? in->lf_window_offset[w1] : 0;
+    if (!indices_ok(pa, pb, la, lb)) {   // bad indices never reach a kernel: this chunk and the following ones are not launched
+      rc = fail(ctx, VIML_ERR_INVALID, "factor index out of range (pose index >= poses_per_window, feature >= feats_per_window or line frame >= poses_per_window)");
+      break;
+    }
     cudaStreamWaitEvent(st, ev_in[c], 0);
     // view of windows [w0, w1)
     LinearizeArgs v = a;

@@ -43,6 +43,21 @@ def test_single_window_cfg1(pkg, orc, ctx, cfg):
             assert np.abs(got["H_pp"] - np.swapaxes(got["H_pp"], 1, 2)).max() <= 1e-9 * np.abs(got["H_pp"]).max()
 
 
+def test_packed_schur_output(pkg, orc, ctx, cfg):
+    """VIML_S_PACKED: the upper triangle of S, bit for bit the entries of the full output (host and device pointers)."""
+    abi = pkg._abi
+    b = pkg.synth.make_windows(20, seed=151)
+    full = ctx.linearize(b, abi.OUT_SCHUR | abi.LOSS_CAUCHY)
+    bufs = {"S_packed": np.full(b.out_shapes()["S_packed"], np.nan), "g": np.full((b.W, b.D), np.nan)}
+    ctx.linearize(b, abi.OUT_SCHUR | abi.S_PACKED | abi.LOSS_CAUCHY, out=bufs)
+    iu = np.triu_indices(b.D)
+    assert pkg.parity.unit_err("S", abi.unpack_upper(bufs["S_packed"], b.D), full["S"]) < 1e-12
+    assert pkg.parity.unit_err("g", bufs["g"], full["g"]) < 1e-12
+    assert not np.isnan(bufs["S_packed"]).any()
+    ref = orc.linearize_batch(cfg, b, abi.OUT_SCHUR | abi.LOSS_CAUCHY)
+    assert pkg.parity.unit_err("S", abi.unpack_upper(bufs["S_packed"], b.D), ref["S"]) < TOL
+
+
 def test_golden_linearize(pkg, orc, ctx, cfg):
     g = np.load(os.path.join(GOLD, "linearize_cfg1.npz"))
     abi = pkg._abi
