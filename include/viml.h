@@ -293,6 +293,8 @@ typedef struct viml_assoc_query {
   const int32_t* n_lines2d;  /* [Pq] or NULL (= L everywhere)       */
   const double* cull_ex_pose;/* [Pq][7] or NULL: extrinsic at frame entry (UpdateLinesInFoV's _Ric/_Tic
                                 argument, estimator.cpp:385); NULL = ex_pose for both                    */
+  const int32_t* fov_slot;   /* with VIML_FOV_CACHED: [Pq] window slot whose cached FoV list pose p is matched against
+                                (NULL = slot p); always a HOST pointer                                       */
 } viml_assoc_query;
 
 /* match_index: MAP index of the chosen 3D line, -1 = none (est.cpp:869-878 / :703-713).
@@ -316,6 +318,33 @@ typedef struct viml_assoc_out {
 
 int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_assoc_out* out,
                         uint32_t flags);
+
+/* ---- FoV cache and sliding-window bookkeeping on the device ------------------------------------------
+ * The reference computes WorldLinesInFOV[i] once, when frame i enters the window (estimator.cpp:342, :385-447), shifts the lists
+ * with the window (estimator.cpp:2148, :2160 MARGIN_OLD; :2218 MARGIN_NEW) and re-matches every observation of every track
+ * against the cached lists under the current poses (estimator.cpp:449-481).  Here the lists stay in HBM as one bit mask per
+ * window slot (VIML_FOV_SLOTS = WINDOW_SIZE + 1):
+ *   viml_fov_update(slot, pose, ex)   UpdateLinesInFoV(slot): cull the map for this frame, keep the result in the slot; *count
+ *                                     (optional) receives the list length.  pose / ex are HOST pointers (7 doubles each).
+ *   viml_fov_slide(marginalize_old)   != 0: slot i <- slot i+1 for i < WINDOW_SIZE, the newest slot keeps its list (:2148, :2160);
+ *                                     == 0: slot WINDOW_SIZE-1 <- slot WINDOW_SIZE (:2218).
+ *   viml_line_associate(..., VIML_FOV_CACHED)   match against the cached lists: cull_poses / cull_ex_pose are not read, no cull
+ *                                     runs; fov_count / fov_index / fov_mask outputs report the cached lists.
+ * A slot that was never updated holds an empty list (every query unmatched, as estimator.cpp:703-713).                  */
+#define VIML_FOV_SLOTS 11
+#define VIML_FOV_CACHED 0x200u
+int viml_fov_update(viml_ctx* ctx, int32_t slot, const double* pose, const double* ex_pose, int32_t* count);
+int viml_fov_slide(viml_ctx* ctx, int32_t marginalize_old);
+
+/* FeatureManager::removeLineOutlier (feature_manager.cpp:494-541) for T line tracks on the device.  Track t owns observations
+ * track_offset[t] .. track_offset[t+1]-1; line_index[k] is the map index of observation k's lineWorld (the matched line, or the
+ * first line of the frame's FoV list for an unmatched observation, estimator.cpp:874; -1 = the zero-length fake line of :709).
+ *   credible_line[k]     = !( (float)|LineVec(first observation) - LineVec(k)| > 0.1 ),  LineVec = PtrEnd - PtrStart of the map row
+ *   credible_matching[t] = !( (count_incredible / n_observations) >= 0.5 )  with the reference's INTEGER division (:524);
+ *                          a track without observations keeps credible_matching = 1.
+ * Pointers follow VIML_PTRS_DEVICE.                                                                                  */
+int viml_track_gate(viml_ctx* ctx, int32_t n_tracks, const int32_t* track_offset, const int32_t* line_index,
+                    uint8_t* credible_line, uint8_t* credible_matching, uint32_t flags);
 /* Work counters of the last viml_line_associate call (synchronises): gate_tests = CalAngleDist evaluations executed (the
  * angular bins a 2D line's window touches; the reference evaluates the whole FoV list per line), gated = pairs that passed the angle gate (what the reference runs CalEulerDist
  * on), overlap_scored = pairs that survived the distance lower bound and ran the overlap half of CalEulerDist,

@@ -26,6 +26,7 @@ ABI_SYMBOLS = (
     "viml_microbench_fp64", "viml_microbench_dmma", "viml_selftest_division", "viml_set_map", "viml_linearize_batch",
     "viml_marginalize_batch", "viml_line_associate", "viml_assoc_stats", "viml_allreduce_hb",
     "viml_load_line_map", "viml_reduced_system", "viml_reduced_from_schur", "viml_gn_step",
+    "viml_fov_update", "viml_fov_slide", "viml_track_gate",
 )
 
 
@@ -73,6 +74,9 @@ def load_library():
     lib.viml_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.viml_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.viml_allreduce_hb.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    lib.viml_fov_update.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+    lib.viml_fov_slide.argtypes = [C.c_void_p, C.c_int32]
+    lib.viml_track_gate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     lib.viml_load_line_map.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]
     lib.viml_reduced_system.argtypes = [C.c_void_p, C.POINTER(_abi.WindowBatch), C.POINTER(_abi.DenseFactors),
                                         C.POINTER(_abi.ReducedOut), C.c_uint32]
@@ -261,9 +265,30 @@ class Context:
         self._check(self.lib.viml_marginalize_batch(self.h, C.byref(i), C.byref(o), 0))
         return res
 
+    def fov_update(self, slot, pose, ex_pose):
+        """viml_fov_update: UpdateLinesInFoV(slot) with the list kept on the device; returns its length."""
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        e = np.ascontiguousarray(ex_pose, dtype=np.float64)
+        n = C.c_int32()
+        self._check(self.lib.viml_fov_update(self.h, int(slot), _abi.ptr(p), _abi.ptr(e), C.byref(n)))
+        return int(n.value)
+
+    def fov_slide(self, marginalize_old):
+        self._check(self.lib.viml_fov_slide(self.h, 1 if marginalize_old else 0))
+
+    def track_gate(self, track_offset, line_index):
+        """viml_track_gate with host buffers: (credible_line [Nobs] bool, credible_matching [T] bool)."""
+        off = np.ascontiguousarray(track_offset, dtype=np.int32)
+        idx = np.ascontiguousarray(line_index, dtype=np.int32)
+        T = len(off) - 1
+        cl, cm = np.full(max(len(idx), 1), 255, dtype=np.uint8), np.full(max(T, 1), 255, dtype=np.uint8)
+        self._check(self.lib.viml_track_gate(self.h, T, _abi.ptr(off), _abi.ptr(idx), _abi.ptr(cl), _abi.ptr(cm), 0))
+        return cl[:len(idx)].astype(bool), cm[:T].astype(bool)
+
     def associate(self, cull_poses, match_poses, ex_pose, lines2d, n_lines2d=None, fov_capacity=0,
-                  want_mask=False, cull_ex_pose=None):
-        """viml_line_associate with host buffers; returns dict of numpy outputs."""
+                  want_mask=False, cull_ex_pose=None, cached=False, fov_slot=None):
+        """viml_line_associate with host buffers; returns dict of numpy outputs.  cached=True matches against the FoV lists
+        kept on the device by fov_update / fov_slide (VIML_FOV_CACHED)."""
         keep = [None if x is None else np.ascontiguousarray(x, dtype=np.float64)
                 for x in (cull_poses, match_poses, ex_pose, lines2d)]
         Pq, L = keep[3].shape[0], keep[3].shape[1]
@@ -274,6 +299,8 @@ class Context:
         q.n_lines2d = _abi.ptr(nl)
         cex = None if cull_ex_pose is None else np.ascontiguousarray(cull_ex_pose, dtype=np.float64)
         q.cull_ex_pose = _abi.ptr(cex)
+        fs = None if fov_slot is None else np.ascontiguousarray(fov_slot, dtype=np.int32)
+        q.fov_slot = _abi.ptr(fs)
         res = {"match_index": np.full((Pq, L), -2, dtype=np.int32),
                "err": np.full((Pq, L, 3), np.nan, dtype=np.float32),
                "projected": np.full((Pq, L, 4), np.nan), "fov_count": np.zeros(Pq, dtype=np.int32)}
@@ -284,7 +311,7 @@ class Context:
         o = _abi.AssocOut()
         o.match_index, o.err, o.projected, o.fov_count = [_abi.ptr(res[k]) for k in ("match_index", "err", "projected", "fov_count")]
         o.fov_index, o.fov_capacity, o.fov_mask = _abi.ptr(res.get("fov_index")), fov_capacity, _abi.ptr(res.get("fov_mask"))
-        self._check(self.lib.viml_line_associate(self.h, C.byref(q), C.byref(o), 0))
+        self._check(self.lib.viml_line_associate(self.h, C.byref(q), C.byref(o), _abi.FOV_CACHED if cached else 0))
         return res
 
     def selftest_division(self, a, b):

@@ -20,6 +20,8 @@ OUT_SCHUR = 0x04
 LOSS_CAUCHY = 0x10
 S_PACKED = 0x20
 PTRS_DEVICE = 0x100
+FOV_CACHED = 0x200
+FOV_SLOTS = 11
 
 c_double_p = C.POINTER(C.c_double)
 c_float_p = C.POINTER(C.c_float)
@@ -73,7 +75,7 @@ class MargOut(C.Structure):
 class AssocQuery(C.Structure):
     _fields_ = [("n_poses", C.c_int32), ("lines_per_pose", C.c_int32),
                 ("cull_poses", C.c_void_p), ("match_poses", C.c_void_p), ("ex_pose", C.c_void_p),
-                ("lines2d", C.c_void_p), ("n_lines2d", C.c_void_p), ("cull_ex_pose", C.c_void_p)]
+                ("lines2d", C.c_void_p), ("n_lines2d", C.c_void_p), ("cull_ex_pose", C.c_void_p), ("fov_slot", C.c_void_p)]
 
 
 class AssocOut(C.Structure):

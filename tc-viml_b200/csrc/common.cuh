@@ -74,6 +74,10 @@ struct viml_ctx {
   int32_t* d_map_orig = nullptr;    // [n_map]
   double* d_tile_sphere = nullptr;  // [n_tiles][4]
   int64_t n_tiles = 0;
+  // FoV cache: one mask row per window slot (viml_fov_update / viml_fov_slide), sized for the current map
+  uint32_t* d_fov_slots = nullptr;     // [VIML_FOV_SLOTS][fov_words]
+  int32_t* d_fov_slot_count = nullptr; // [VIML_FOV_SLOTS]
+  int64_t fov_words = 0;
   unsigned long long* d_assoc_stats = nullptr;  // {gate tests, gated pairs, overlap-scored, distance-scored} of the last association call
   DeviceArena in_arena, out_arena, scratch, scratch2, scratch3, gn_in, gn_out, s_full;
   void* nccl_lib = nullptr;
@@ -198,7 +202,10 @@ struct AssocArgs {  // device pointers only
   uint32_t* fov_mask;   // always valid
   int64_t words;        // ceil(N/32)
   unsigned long long* stats;  // {gate tests, gated, overlap-scored, distance-scored}
+  bool cached;                // VIML_FOV_CACHED: fov_mask / fov_count are given (cached lists), no cull
 };
 // associate_kernels.cu (compiled with -fmad=false)
 int viml_launch_associate(viml_ctx* ctx, const AssocArgs& a);
+int viml_launch_track_gate(viml_ctx* ctx, int n_tracks, const int32_t* track_offset, const int32_t* line_index, uint8_t* credible_line,
+                           uint8_t* credible_matching);
 int viml_launch_divcheck(viml_ctx* ctx, const double* a, const double* b, int64_t n, unsigned long long* mismatches);

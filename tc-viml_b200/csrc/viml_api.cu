@@ -106,6 +106,8 @@ void viml_destroy(viml_ctx* ctx) {
   if (ctx->d_map_orig) cudaFree(ctx->d_map_orig);
   if (ctx->d_tile_sphere) cudaFree(ctx->d_tile_sphere);
   if (ctx->d_assoc_stats) cudaFree(ctx->d_assoc_stats);
+  if (ctx->d_fov_slots) cudaFree(ctx->d_fov_slots);
+  if (ctx->d_fov_slot_count) cudaFree(ctx->d_fov_slot_count);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
@@ -203,6 +205,8 @@ int viml_set_map(viml_ctx* ctx, const double* lines, int64_t n) {
     ptr = nullptr;
   };
   drop(ctx->d_map), drop(ctx->d_map_sorted), drop(ctx->d_map_orig), drop(ctx->d_tile_sphere);
+  drop(ctx->d_fov_slots), drop(ctx->d_fov_slot_count);   // the cached FoV lists index the old map
+  ctx->fov_words = 0;
   ctx->n_map = 0, ctx->n_tiles = 0;
   ctx->map_set = true;
   if (n == 0) return VIML_OK;
@@ -578,8 +582,15 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
   if (!q || !out) return fail(ctx, VIML_ERR_INVALID, "null query or output struct");
   if (!ctx->map_set) return fail(ctx, VIML_ERR_NOMAP, "viml_line_associate before viml_set_map (an empty map is legal, but it must be set)");
   const int Pq = q->n_poses, L = q->lines_per_pose;
-  if (Pq < 0 || L < 0 || !q->cull_poses || !q->ex_pose || (L > 0 && !q->lines2d))
+  const bool cached = (flags & VIML_FOV_CACHED) != 0;
+  if (Pq < 0 || L < 0 || (!cached && !q->cull_poses) || !q->ex_pose || (L > 0 && !q->lines2d))
     return fail(ctx, VIML_ERR_INVALID, "bad association query");
+  if (cached) {
+    if (Pq > VIML_FOV_SLOTS && !q->fov_slot) return fail(ctx, VIML_ERR_INVALID, "VIML_FOV_CACHED: more poses than window slots and no fov_slot map");
+    if (!q->match_poses && !q->cull_poses) return fail(ctx, VIML_ERR_INVALID, "VIML_FOV_CACHED needs match_poses");
+    for (int p = 0; p < Pq && q->fov_slot; ++p)
+      if (q->fov_slot[p] < 0 || q->fov_slot[p] >= VIML_FOV_SLOTS) return fail(ctx, VIML_ERR_INVALID, "fov_slot out of range");
+  }
   if (Pq == 0) return VIML_OK;
   VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -587,6 +598,25 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
   const bool dev = (flags & VIML_PTRS_DEVICE) != 0;
   AssocArgs a{};
   a.Pq = Pq, a.L = L, a.N = N, a.map = ctx->d_map, a.words = words;
+  a.cached = cached;
+  // cached lists: the slots' mask rows and counts gathered into [Pq][words] / [Pq] behind the pose order of this query
+  uint32_t* cmask = nullptr;
+  int32_t* ccount = nullptr;
+  if (cached) {
+    VIML_TRY_CUDA(ctx, ctx->s_full.reserve(DeviceArena::padded((size_t)Pq * words * 4 + 4) + DeviceArena::padded((size_t)Pq * 4)));
+    cmask = ctx->s_full.take<uint32_t>((size_t)Pq * words + 1);
+    ccount = ctx->s_full.take<int32_t>((size_t)Pq);
+    for (int p = 0; p < Pq; ++p) {
+      const int sl = q->fov_slot ? q->fov_slot[p] : p;
+      if (ctx->d_fov_slots && ctx->fov_words == words) {
+        if (words) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(cmask + (size_t)p * words, ctx->d_fov_slots + (size_t)sl * words, (size_t)words * 4, cudaMemcpyDeviceToDevice, st));
+        VIML_TRY_CUDA(ctx, cudaMemcpyAsync(ccount + p, ctx->d_fov_slot_count + sl, 4, cudaMemcpyDeviceToDevice, st));
+      } else {   // no slot was ever updated for this map: empty lists
+        if (words) VIML_TRY_CUDA(ctx, cudaMemsetAsync(cmask + (size_t)p * words, 0, (size_t)words * 4, st));
+        VIML_TRY_CUDA(ctx, cudaMemsetAsync(ccount + p, 0, 4, st));
+      }
+    }
+  }
   if (!ctx->d_assoc_stats) VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_assoc_stats, 32));
   VIML_TRY_CUDA(ctx, cudaMemsetAsync(ctx->d_assoc_stats, 0, 32, st));
   a.stats = ctx->d_assoc_stats;
@@ -599,13 +629,18 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
     if (!out->fov_mask) sb += pad((size_t)Pq * words * 4);
     if (!out->fov_count) sb += pad((size_t)Pq * 4);
     VIML_TRY_CUDA(ctx, ctx->out_arena.reserve(sb));
-    a.cull_poses = q->cull_poses, a.match_poses = q->match_poses ? q->match_poses : q->cull_poses;
+    a.match_poses = q->match_poses ? q->match_poses : q->cull_poses;
+    a.cull_poses = q->cull_poses ? q->cull_poses : a.match_poses;
     a.ex_pose = q->ex_pose, a.lines2d = q->lines2d, a.n_lines2d = q->n_lines2d;
     a.cull_ex_pose = q->cull_ex_pose ? q->cull_ex_pose : q->ex_pose;
     a.match_index = out->match_index, a.err = out->err, a.projected = out->projected;
     a.fov_index = out->fov_index;
     a.fov_mask = out->fov_mask ? out->fov_mask : ctx->out_arena.take<uint32_t>((size_t)Pq * words);
     a.fov_count = out->fov_count ? out->fov_count : ctx->out_arena.take<int32_t>(Pq);
+    if (cached) {
+      if (words) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.fov_mask, cmask, (size_t)Pq * words * 4, cudaMemcpyDeviceToDevice, st));
+      VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.fov_count, ccount, (size_t)Pq * 4, cudaMemcpyDeviceToDevice, st));
+    }
     return viml_launch_associate(ctx, a);
   }
   // Host buffers: poses are independent, so a large query is run as a pipeline of pose chunks -- all uploads are queued
@@ -621,7 +656,7 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
   };
   VIML_TRY_CUDA(ctx, cudaEventRecord(ctx->ev_a, st));   // the copy stream starts after whatever the caller queued before
   VIML_TRY_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_a, 0));
-  a.cull_poses = (const double*)up(q->cull_poses, (size_t)Pq * 56);
+  a.cull_poses = (const double*)up(q->cull_poses ? q->cull_poses : q->match_poses, (size_t)Pq * 56);
   a.match_poses = q->match_poses ? (const double*)up(q->match_poses, (size_t)Pq * 56) : a.cull_poses;
   a.ex_pose = (const double*)up(q->ex_pose, (size_t)Pq * 56);
   a.cull_ex_pose = q->cull_ex_pose ? (const double*)up(q->cull_ex_pose, (size_t)Pq * 56) : a.ex_pose;
@@ -637,6 +672,10 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
   a.fov_count = ctx->out_arena.take<int32_t>(Pq);
   a.fov_index = cap ? ctx->out_arena.take<int32_t>((size_t)Pq * cap) : nullptr;
   a.fov_mask = ctx->out_arena.take<uint32_t>((size_t)Pq * words);
+  if (cached) {
+    if (words) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.fov_mask, cmask, (size_t)Pq * words * 4, cudaMemcpyDeviceToDevice, st));
+    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.fov_count, ccount, (size_t)Pq * 4, cudaMemcpyDeviceToDevice, st));
+  }
   if (out->fov_index && cap)  // entries past fov_count keep the caller's content
     VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.fov_index, out->fov_index, (size_t)Pq * cap * 4, cudaMemcpyHostToDevice, cs));
   if (out->match_index && q->n_lines2d) {  // ragged queries past n_lines2d keep the caller's content
@@ -689,6 +728,103 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
   VIML_TRY_CUDA(ctx, e2);
   VIML_TRY_CUDA(ctx, e3);
   VIML_TRY_CUDA(ctx, cudaGetLastError());
+  return VIML_OK;
+}
+
+// ---- FoV cache ---------------------------------------------------------------------------------------
+static int fov_cache_ready(viml_ctx* ctx) {
+  const int64_t words = (ctx->n_map + 31) / 32;
+  if (ctx->d_fov_slots && ctx->fov_words == words) return VIML_OK;
+  if (ctx->d_fov_slots) cudaFree(ctx->d_fov_slots);
+  ctx->d_fov_slots = nullptr;
+  VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_fov_slots, (size_t)VIML_FOV_SLOTS * std::max<int64_t>(words, 1) * 4));
+  if (!ctx->d_fov_slot_count) VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_fov_slot_count, VIML_FOV_SLOTS * 4));
+  VIML_TRY_CUDA(ctx, cudaMemsetAsync(ctx->d_fov_slots, 0, (size_t)VIML_FOV_SLOTS * std::max<int64_t>(words, 1) * 4, ctx->stream));
+  VIML_TRY_CUDA(ctx, cudaMemsetAsync(ctx->d_fov_slot_count, 0, VIML_FOV_SLOTS * 4, ctx->stream));
+  ctx->fov_words = words;
+  return VIML_OK;
+}
+
+int viml_fov_update(viml_ctx* ctx, int32_t slot, const double* pose, const double* ex_pose, int32_t* count) {
+  if (!ctx) return VIML_ERR_INVALID;
+  if (slot < 0 || slot >= VIML_FOV_SLOTS || !pose || !ex_pose) return fail(ctx, VIML_ERR_INVALID, "viml_fov_update: bad slot or null pose");
+  if (!ctx->map_set) return fail(ctx, VIML_ERR_NOMAP, "viml_fov_update before viml_set_map");
+  VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = fov_cache_ready(ctx);
+  if (rc != VIML_OK) return rc;
+  cudaStream_t st = ctx->stream;
+  VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(2 * DeviceArena::padded(56)));
+  double* dp = ctx->in_arena.take<double>(7);
+  double* de = ctx->in_arena.take<double>(7);
+  VIML_TRY_CUDA(ctx, cudaMemcpyAsync(dp, pose, 56, cudaMemcpyHostToDevice, st));
+  VIML_TRY_CUDA(ctx, cudaMemcpyAsync(de, ex_pose, 56, cudaMemcpyHostToDevice, st));
+  AssocArgs a{};
+  a.Pq = 1, a.L = 0, a.N = ctx->n_map, a.map = ctx->d_map, a.words = ctx->fov_words;
+  a.map_sorted = ctx->d_map_sorted, a.map_orig = ctx->d_map_orig, a.tile_sphere = ctx->d_tile_sphere, a.n_tiles = ctx->n_tiles;
+  if (!ctx->d_assoc_stats) VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_assoc_stats, 32));
+  a.stats = ctx->d_assoc_stats;
+  a.cull_poses = a.match_poses = dp, a.ex_pose = a.cull_ex_pose = de;
+  a.fov_mask = ctx->d_fov_slots + (size_t)slot * ctx->fov_words;
+  a.fov_count = ctx->d_fov_slot_count + slot;
+  rc = viml_launch_associate(ctx, a);
+  if (rc != VIML_OK) return rc;
+  if (count) {
+    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(count, a.fov_count, 4, cudaMemcpyDeviceToHost, st));
+    VIML_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  return VIML_OK;
+}
+
+int viml_fov_slide(viml_ctx* ctx, int32_t marginalize_old) {
+  if (!ctx) return VIML_ERR_INVALID;
+  if (!ctx->map_set) return fail(ctx, VIML_ERR_NOMAP, "viml_fov_slide before viml_set_map");
+  VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int rc = fov_cache_ready(ctx);
+  if (rc != VIML_OK) return rc;
+  cudaStream_t st = ctx->stream;
+  const size_t wb = (size_t)ctx->fov_words * 4;
+  const int last = VIML_FOV_SLOTS - 1;
+  auto row = [&](int s) { return ctx->d_fov_slots + (size_t)s * ctx->fov_words; };
+  if (marginalize_old) {
+    // estimator.cpp:2148 swaps slot i with i+1 for i = 0..WINDOW_SIZE-1 and :2160 then copies slot WINDOW_SIZE-1 into the
+    // newest one: net effect slot i <- old slot i+1 (i < WINDOW_SIZE), newest slot unchanged.  Stream-ordered copies,
+    // ascending, each reading a row that has not been overwritten yet.
+    for (int i = 0; i < last; ++i) {
+      if (wb) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(row(i), row(i + 1), wb, cudaMemcpyDeviceToDevice, st));
+      VIML_TRY_CUDA(ctx, cudaMemcpyAsync(ctx->d_fov_slot_count + i, ctx->d_fov_slot_count + i + 1, 4, cudaMemcpyDeviceToDevice, st));
+    }
+  } else {
+    if (wb) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(row(last - 1), row(last), wb, cudaMemcpyDeviceToDevice, st));   // :2218
+    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(ctx->d_fov_slot_count + last - 1, ctx->d_fov_slot_count + last, 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return VIML_OK;
+}
+
+int viml_track_gate(viml_ctx* ctx, int32_t n_tracks, const int32_t* track_offset, const int32_t* line_index, uint8_t* credible_line,
+                    uint8_t* credible_matching, uint32_t flags) {
+  if (!ctx) return VIML_ERR_INVALID;
+  if (n_tracks < 0 || (n_tracks > 0 && (!track_offset || !credible_matching))) return fail(ctx, VIML_ERR_INVALID, "viml_track_gate: bad arguments");
+  if (!ctx->map_set) return fail(ctx, VIML_ERR_NOMAP, "viml_track_gate before viml_set_map");
+  if (n_tracks == 0) return VIML_OK;
+  VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (flags & VIML_PTRS_DEVICE) return viml_launch_track_gate(ctx, n_tracks, track_offset, line_index, credible_line, credible_matching);
+  const int64_t nobs = track_offset[n_tracks];
+  if (nobs < 0 || (nobs > 0 && (!line_index || !credible_line))) return fail(ctx, VIML_ERR_INVALID, "viml_track_gate: null observation arrays");
+  auto pad = [](size_t b) { return DeviceArena::padded(b); };
+  VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(pad((size_t)(n_tracks + 1) * 4) + pad((size_t)nobs * 4 + 4)));
+  VIML_TRY_CUDA(ctx, ctx->out_arena.reserve(pad((size_t)nobs + 1) + pad((size_t)n_tracks)));
+  int32_t* doff = ctx->in_arena.take<int32_t>((size_t)n_tracks + 1);
+  int32_t* didx = ctx->in_arena.take<int32_t>((size_t)nobs + 1);
+  uint8_t* dcl = ctx->out_arena.take<uint8_t>((size_t)nobs + 1);
+  uint8_t* dcm = ctx->out_arena.take<uint8_t>((size_t)n_tracks);
+  VIML_TRY_CUDA(ctx, cudaMemcpyAsync(doff, track_offset, (size_t)(n_tracks + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (nobs) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(didx, line_index, (size_t)nobs * 4, cudaMemcpyHostToDevice, st));
+  const int rc = viml_launch_track_gate(ctx, n_tracks, doff, didx, dcl, dcm);
+  if (rc != VIML_OK) return rc;
+  if (nobs) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(credible_line, dcl, (size_t)nobs, cudaMemcpyDeviceToHost, st));
+  VIML_TRY_CUDA(ctx, cudaMemcpyAsync(credible_matching, dcm, (size_t)n_tracks, cudaMemcpyDeviceToHost, st));
+  VIML_TRY_CUDA(ctx, cudaStreamSynchronize(st));
   return VIML_OK;
 }
 

@@ -674,13 +674,17 @@ int LineMapAssociator::UpdateLinesInFoV(int i, const double* para_Pose_i, const 
   std::memcpy(cull_pose_[i], para_Pose_i, 56);
   std::memcpy(cull_ex_[i], para_Ex_Pose, 56);
   have_[i] = true;
-  viml_assoc_query q{};
-  q.n_poses = 1, q.lines_per_pose = 0, q.cull_poses = cull_pose_[i], q.ex_pose = cull_ex_[i];
+  // the list stays on the device in window slot i (viml_fov_update); the public WorldLinesInFOV[i] mirror is read back once
   int32_t count = 0;
-  std::vector<int32_t> list(map_.size() + 1);
+  check_rc(viml_fov_update(ctx, i, cull_pose_[i], cull_ex_[i], &count), "viml_fov_update");
+  std::vector<int32_t> list((size_t)count + 1);
+  const int32_t slot = i;
+  viml_assoc_query q{};
+  q.n_poses = 1, q.lines_per_pose = 0, q.match_poses = cull_pose_[i], q.ex_pose = cull_ex_[i], q.fov_slot = &slot;
+  int32_t c2 = 0;
   viml_assoc_out o{};
-  o.fov_count = &count, o.fov_index = list.data(), o.fov_capacity = (int32_t)list.size();
-  check_rc(viml_line_associate(ctx, &q, &o, 0), "viml_line_associate");
+  o.fov_count = &c2, o.fov_index = list.data(), o.fov_capacity = (int32_t)list.size();
+  check_rc(viml_line_associate(ctx, &q, &o, VIML_FOV_CACHED), "viml_line_associate");
   WorldLinesInFOV[i].assign(list.begin(), list.begin() + count);
   return count;
 }
@@ -696,14 +700,11 @@ int LineMapAssociator::updateLinePairInWindow(const double (*para_Pose)[7], cons
   }
   int L = 1;
   for (auto& v : per) L = std::max<int>(L, (int)v.size());
-  std::vector<double> cull((size_t)NPOSE * 7, 0.0), cex((size_t)NPOSE * 7, 0.0), match((size_t)NPOSE * 7), ex((size_t)NPOSE * 7), l2d((size_t)NPOSE * L * 4, 0.0);
+  std::vector<double> match((size_t)NPOSE * 7), ex((size_t)NPOSE * 7), l2d((size_t)NPOSE * L * 4, 0.0);
   std::vector<int32_t> nl(NPOSE);
   for (int f = 0; f < NPOSE; ++f) {
     std::memcpy(&match[7 * f], para_Pose[f], 56);
     std::memcpy(&ex[7 * f], para_Ex_Pose, 56);
-    const bool h = have_[f];
-    std::memcpy(&cull[7 * f], h ? cull_pose_[f] : para_Pose[f], 56);
-    std::memcpy(&cex[7 * f], h ? cull_ex_[f] : para_Ex_Pose, 56);
     nl[f] = (int32_t)per[f].size();
     for (size_t s = 0; s < per[f].size(); ++s) std::memcpy(&l2d[((size_t)f * L + s) * 4], obs[per[f][s]].line, 32);
   }
@@ -711,11 +712,12 @@ int LineMapAssociator::updateLinePairInWindow(const double (*para_Pose)[7], cons
   std::vector<float> err((size_t)NPOSE * L * 3, -1.f);
   std::vector<double> proj((size_t)NPOSE * L * 4, 0.0);
   viml_assoc_query q{};
-  q.n_poses = NPOSE, q.lines_per_pose = L, q.cull_poses = cull.data(), q.match_poses = match.data(), q.ex_pose = ex.data();
-  q.cull_ex_pose = cex.data(), q.lines2d = l2d.data(), q.n_lines2d = nl.data();
+  // against the FoV lists cached on the device when the frames entered (no re-cull): slot f <-> pose f
+  q.n_poses = NPOSE, q.lines_per_pose = L, q.match_poses = match.data(), q.ex_pose = ex.data();
+  q.lines2d = l2d.data(), q.n_lines2d = nl.data();
   viml_assoc_out o{};
   o.match_index = mi.data(), o.err = err.data(), o.projected = proj.data();
-  check_rc(viml_line_associate(ctx, &q, &o, 0), "viml_line_associate");
+  check_rc(viml_line_associate(ctx, &q, &o, VIML_FOV_CACHED), "viml_line_associate");
   out->assign(obs.size(), Match());
   int matched = 0;
   for (int f = 0; f < NPOSE; ++f)
@@ -737,20 +739,22 @@ LineMapAssociator::Match LineMapAssociator::LineCorrespondenceInFrame(int frame_
   viml_ctx* ctx = need_ctx();
   if (!have_[frame_index]) die("LineCorrespondenceInFrame: frame without a FoV list");
   viml_assoc_query q{};
-  q.n_poses = 1, q.lines_per_pose = 1, q.cull_poses = cull_pose_[frame_index], q.cull_ex_pose = cull_ex_[frame_index];
+  const int32_t slot = frame_index;
+  q.n_poses = 1, q.lines_per_pose = 1, q.fov_slot = &slot;
   q.match_poses = para_Pose[frame_index], q.ex_pose = para_Ex_Pose, q.lines2d = detect_line;
   Match mt;
   int32_t mi = -1;
   float err[3] = {-1, -1, -1};
   viml_assoc_out o{};
   o.match_index = &mi, o.err = err, o.projected = mt.projectedLine;
-  check_rc(viml_line_associate(ctx, &q, &o, 0), "viml_line_associate");
+  check_rc(viml_line_associate(ctx, &q, &o, VIML_FOV_CACHED), "viml_line_associate");
   mt.errA = err[0], mt.errD = err[1], mt.overlap = err[2], mt.map_index = mi;
   mt.use_flag = true, mt.credible_line = !(mt.errA == -1);
   return mt;
 }
 
 void LineMapAssociator::slideWindowOld() {  // estimator.cpp:2131-2160: slot i <- slot i+1
+  check_rc(viml_fov_slide(need_ctx(), 1), "viml_fov_slide");
   for (int i = 0; i < kWindowSize; ++i) {
     WorldLinesInFOV[i].swap(WorldLinesInFOV[i + 1]);
     std::memcpy(cull_pose_[i], cull_pose_[i + 1], 56);
@@ -763,14 +767,26 @@ void LineMapAssociator::slideWindowOld() {  // estimator.cpp:2131-2160: slot i <
   have_[kWindowSize] = have_[kWindowSize - 1];
 }
 void LineMapAssociator::slideWindowNew() {  // estimator.cpp:2218: second-newest <- newest
+  check_rc(viml_fov_slide(need_ctx(), 0), "viml_fov_slide");
   WorldLinesInFOV[kWindowSize - 1] = WorldLinesInFOV[kWindowSize];
   std::memcpy(cull_pose_[kWindowSize - 1], cull_pose_[kWindowSize], 56);
   std::memcpy(cull_ex_[kWindowSize - 1], cull_ex_[kWindowSize], 56);
   have_[kWindowSize - 1] = have_[kWindowSize];
 }
 
+void LineMapAssociator::removeLineOutliers(const std::vector<int32_t>& track_offset, const std::vector<int32_t>& line_index,
+                                           std::vector<uint8_t>* credible_line, std::vector<uint8_t>* credible_matching) {
+  // feature_manager.cpp:494-541 for every line track in one device call (viml_track_gate)
+  const int T = (int)track_offset.size() - 1;
+  credible_line->assign(line_index.size(), 1);
+  credible_matching->assign(T > 0 ? T : 0, 1);
+  if (T <= 0) return;
+  check_rc(viml_track_gate(need_ctx(), T, track_offset.data(), line_index.data(), credible_line->data(), credible_matching->data(), 0),
+           "viml_track_gate");
+}
+
 bool LineMapAssociator::removeLineOutlier(const std::vector<viml::Vector3d>& line_vec, std::vector<bool>* credible_line) {
-  // feature_manager.cpp:494-541.  Host bookkeeping (per track <= 11 observations), not a device path.
+  // feature_manager.cpp:494-541 for ONE track on the host (<= 11 observations); removeLineOutliers is the batched device path.
   const int obvers_time = (int)line_vec.size();
   credible_line->assign(obvers_time, true);
   if (obvers_time < 1) return true;

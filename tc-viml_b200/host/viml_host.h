@@ -266,8 +266,8 @@ class LineMapAssociator {
   struct Observation { int frame; double line[4]; };  // one lineFeaturePerFrame: frame = start_frame + k, raw-pixel endpoints
 
   explicit LineMapAssociator(const std::vector<viml::Vector6d>& lines3d_map);  // Estimator::setParameters (estimator.cpp:54-58)
-  // estimator.cpp:385-447; the pose/extrinsic at frame entry are remembered: LineCorrespondenceInFrame matches
-  // against the list that was cached then, under the pose it is given later.
+  // estimator.cpp:385-447; the list is computed once, when the frame enters, and stays ON THE DEVICE in window slot i
+  // (viml_fov_update); LineCorrespondenceInFrame / updateLinePairInWindow match against it under the pose they are given later.
   int UpdateLinesInFoV(int i, const double* para_Pose_i, const double* para_Ex_Pose);
   // estimator.cpp:449-481: re-match every observation of every track with the current poses (one GPU call).
   int updateLinePairInWindow(const double (*para_Pose)[7], const double* para_Ex_Pose,
@@ -280,6 +280,10 @@ class LineMapAssociator {
   void slideWindowNew();
   // feature_manager.cpp:494-541 on one track: line_vec[k] = PtrEnd-PtrStart of the matched map line of observation k.
   static bool removeLineOutlier(const std::vector<viml::Vector3d>& line_vec, std::vector<bool>* credible_line);
+  // the same gate for every track in one device call: track t owns observations track_offset[t] .. track_offset[t+1]-1,
+  // line_index[k] = map index of observation k's lineWorld (-1 = the fake line of estimator.cpp:709)
+  static void removeLineOutliers(const std::vector<int32_t>& track_offset, const std::vector<int32_t>& line_index,
+                                 std::vector<uint8_t>* credible_line, std::vector<uint8_t>* credible_matching);
 
   std::vector<int> WorldLinesInFOV[kWindowSize + 1];
   const std::vector<viml::Vector6d>& map() const { return map_; }

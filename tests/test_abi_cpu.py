@@ -30,7 +30,7 @@ def test_struct_sizes_match_header(pkg):
     assert C.sizeof(abi.LinearizeOut) == 14 * 8
     assert C.sizeof(abi.MargBatch) == 16 + 8 + 16
     assert C.sizeof(abi.MargOut) == 32
-    assert C.sizeof(abi.AssocQuery) == 8 + 6 * 8
+    assert C.sizeof(abi.AssocQuery) == 8 + 7 * 8
     assert C.sizeof(abi.AssocOut) == 5 * 8 + 8 + 8
     assert C.sizeof(abi.DenseFactors) == 8 + 8 + 7 * 8
     assert C.sizeof(abi.ReducedOut) == 16 and C.sizeof(abi.GnOptions) == 16 and C.sizeof(abi.GnOut) == 7 * 8

@@ -378,6 +378,80 @@ def test_reduced_system_and_gn_step(pkg, orc, ctx, cfg):
             assert np.array_equal(o["poses"][w], b.poses[w]) and np.array_equal(o["inv_depth"][w], b.inv_depth[w])
 
 
+def test_fov_cache_and_window_bookkeeping(pkg, orc, cfg):
+    """the per-slot FoV lists live on the device (viml_fov_update), move with the window (viml_fov_slide, both
+    marginalisation flags, estimator.cpp:2148, :2160, :2218) and are matched against under the CURRENT poses (VIML_FOV_CACHED):
+    bit for bit what the oracle gives for the frame-entry cull pose of whatever frame sits in each slot."""
+    abi, synth = pkg._abi, pkg.synth
+    ext = (150.0, 150.0, 20.0)
+    lines = synth.make_line_map(6000, extent=ext)
+    n = 16   # frames of a little sequence; the window holds 11 of them
+    cull, match, ex, l2d = synth.make_assoc_queries(lines, n, L=40, n_true=14, extent=ext, pose_drift=True)
+    with pkg.Context(cfg) as c:
+        c.set_map(lines)
+        frames = list(range(11))            # frame index sitting in each slot
+        for s in range(11):
+            c.fov_update(s, cull[s], ex[s])
+
+        def check(frames):
+            idx = np.array(frames)
+            got = c.associate(None, match[idx], ex[idx], l2d[idx], cached=True, fov_capacity=600, want_mask=True)
+            ref = orc.line_associate(cfg, lines, cull[idx], match[idx], ex[idx], l2d[idx], fov_capacity=600, want_mask=True)
+            check_assoc(got, ref)
+
+        check(frames)
+        nxt = 11
+        for flag_old in (True, False, True, True, False):
+            c.fov_slide(flag_old)
+            if flag_old:
+                frames = frames[1:] + [frames[-1]]
+            else:
+                frames[9] = frames[10]
+            check(frames)
+            cnt = c.fov_update(10, cull[nxt], ex[nxt])    # the next frame enters the newest slot
+            frames[10] = nxt
+            assert cnt == orc.line_associate(cfg, lines, cull[nxt:nxt + 1], None, ex[nxt:nxt + 1], l2d[nxt:nxt + 1])["fov_count"][0]
+            nxt += 1
+            check(frames)
+        # explicit slot map: poses in arbitrary slot order
+        order = [7, 2, 10, 0]
+        idx = np.array([frames[s] for s in order])
+        got = c.associate(None, match[idx], ex[idx], l2d[idx], cached=True, fov_slot=order, want_mask=True)
+        ref = orc.line_associate(cfg, lines, cull[idx], match[idx], ex[idx], l2d[idx], want_mask=True)
+        check_assoc(got, ref)
+        # a new map drops the cache: every slot is empty until updated again
+        c.set_map(lines[:3000])
+        got = c.associate(None, match[:3], ex[:3], l2d[:3], cached=True)
+        assert np.all(got["match_index"] == -1) and np.all(got["fov_count"] == 0)
+
+
+def test_track_gate(pkg, orc, cfg):
+    """FeatureManager::removeLineOutlier on the device against the oracle's restatement (feature_manager.cpp:494-541)."""
+    rng = np.random.default_rng(11)
+    lines = pkg.synth.make_line_map(500, extent=(40.0, 40.0, 10.0))
+    # make near-duplicates so that some LineVec differences fall on both sides of 0.1 m
+    lines[250:] = lines[:250] + rng.normal(0, 0.03, (250, 6))
+    T = 300
+    nobs = rng.integers(0, 12, T)
+    off = np.concatenate([[0], np.cumsum(nobs)]).astype(np.int32)
+    idx = np.empty(off[-1], dtype=np.int32)
+    for t in range(T):
+        base = rng.integers(0, 250)
+        pick = rng.choice([base, base + 250, rng.integers(0, 500), -1], size=nobs[t], p=[0.5, 0.3, 0.15, 0.05])
+        idx[off[t]:off[t + 1]] = pick
+    with pkg.Context(cfg) as c:
+        c.set_map(lines)
+        cl, cm = c.track_gate(off, idx)
+    vec = np.where((idx >= 0)[:, None], lines[np.maximum(idx, 0), 3:] - lines[np.maximum(idx, 0), :3], 0.0)
+    for t in range(T):
+        if nobs[t] == 0:
+            assert cm[t]
+            continue
+        ref_cm, ref_cl = orc.track_gate(vec[off[t]:off[t + 1]])
+        assert bool(cm[t]) == bool(ref_cm), t
+        assert np.array_equal(cl[off[t]:off[t + 1]], np.asarray(ref_cl, dtype=bool)), t
+
+
 def test_load_line_map(pkg, cfg, tmp_path):
     """viml_load_line_map reads line_3d.txt the way parameters.cpp:50-59 does and gives the same association as viml_set_map."""
     synth = pkg.synth
