@@ -336,6 +336,24 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
 int viml_fov_update(viml_ctx* ctx, int32_t slot, const double* pose, const double* ex_pose, int32_t* count);
 int viml_fov_slide(viml_ctx* ctx, int32_t marginalize_old);
 
+/* FeatureManager::triangulate (feature_manager.cpp:440-492) for a batch of point features: feature l of window feat_window[l]
+ * starts in frame start_frame[l] and has observations obs_offset[l] .. obs_offset[l+1]-1 in consecutive frames (points = the
+ * normalised image points x y z of lineFeaturePerFrame / FeaturePerFrame::point).  depth[l] = svd_V[2] / svd_V[3] of the DLT
+ * system in the start camera's frame, INIT_DEPTH when that is below 0.1 (:482-485).  The caller keeps the reference's gates
+ * (used_num >= 2 && start_frame < WINDOW_SIZE - 2, estimated_depth > 0 skipped, :444-449).  Pointers follow VIML_PTRS_DEVICE. */
+typedef struct viml_triangulate_in {
+  int32_t n_windows;
+  int32_t poses_per_window;     /* P                                  */
+  const double* poses;          /* [W][P][7]                          */
+  const double* ex_pose;        /* [W][7]                             */
+  int64_t n_features;           /* NF                                 */
+  const int32_t* feat_window;   /* [NF]                               */
+  const int32_t* start_frame;   /* [NF]                               */
+  const int64_t* obs_offset;    /* [NF+1]                             */
+  const double* points;         /* [obs_offset[NF]][3]                */
+} viml_triangulate_in;
+int viml_triangulate_batch(viml_ctx* ctx, const viml_triangulate_in* in, double init_depth, double* depth, uint32_t flags);
+
 /* FeatureManager::removeLineOutlier (feature_manager.cpp:494-541) for T line tracks on the device.  Track t owns observations
  * track_offset[t] .. track_offset[t+1]-1; line_index[k] is the map index of observation k's lineWorld (the matched line, or the
  * first line of the frame's FoV list for an unmatched observation, estimator.cpp:874; -1 = the zero-length fake line of :709).

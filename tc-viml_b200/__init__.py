@@ -26,7 +26,7 @@ ABI_SYMBOLS = (
     "viml_microbench_fp64", "viml_microbench_dmma", "viml_selftest_division", "viml_set_map", "viml_linearize_batch",
     "viml_marginalize_batch", "viml_line_associate", "viml_assoc_stats", "viml_allreduce_hb",
     "viml_load_line_map", "viml_reduced_system", "viml_reduced_from_schur", "viml_gn_step",
-    "viml_fov_update", "viml_fov_slide", "viml_track_gate",
+    "viml_fov_update", "viml_fov_slide", "viml_track_gate", "viml_triangulate_batch",
 )
 
 
@@ -77,6 +77,7 @@ def load_library():
     lib.viml_fov_update.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
     lib.viml_fov_slide.argtypes = [C.c_void_p, C.c_int32]
     lib.viml_track_gate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.viml_triangulate_batch.argtypes = [C.c_void_p, C.POINTER(_abi.TriangulateIn), C.c_double, C.c_void_p, C.c_uint32]
     lib.viml_load_line_map.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]
     lib.viml_reduced_system.argtypes = [C.c_void_p, C.POINTER(_abi.WindowBatch), C.POINTER(_abi.DenseFactors),
                                         C.POINTER(_abi.ReducedOut), C.c_uint32]
@@ -275,6 +276,19 @@ class Context:
 
     def fov_slide(self, marginalize_old):
         self._check(self.lib.viml_fov_slide(self.h, 1 if marginalize_old else 0))
+
+    def triangulate(self, poses, ex_pose, feat_window, start_frame, obs_offset, points, init_depth=5.0):
+        """viml_triangulate_batch with host buffers: estimated depth per feature."""
+        arrs = [np.ascontiguousarray(poses, dtype=np.float64), np.ascontiguousarray(ex_pose, dtype=np.float64),
+                np.ascontiguousarray(feat_window, dtype=np.int32), np.ascontiguousarray(start_frame, dtype=np.int32),
+                np.ascontiguousarray(obs_offset, dtype=np.int64), np.ascontiguousarray(points, dtype=np.float64)]
+        t = _abi.TriangulateIn()
+        t.n_windows, t.poses_per_window = arrs[0].shape[0], arrs[0].shape[1]
+        t.poses, t.ex_pose, t.feat_window, t.start_frame, t.obs_offset, t.points = [_abi.ptr(a) for a in arrs]
+        t.n_features = len(arrs[2])
+        depth = np.full(len(arrs[2]), np.nan)
+        self._check(self.lib.viml_triangulate_batch(self.h, C.byref(t), float(init_depth), _abi.ptr(depth), 0))
+        return depth
 
     def track_gate(self, track_offset, line_index):
         """viml_track_gate with host buffers: (credible_line [Nobs] bool, credible_matching [T] bool)."""

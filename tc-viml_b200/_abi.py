@@ -92,6 +92,12 @@ class DenseFactors(C.Structure):
                 ("col_index", C.c_void_p), ("residual", C.c_void_p), ("jacobian", C.c_void_p)]
 
 
+class TriangulateIn(C.Structure):
+    _fields_ = [("n_windows", C.c_int32), ("poses_per_window", C.c_int32), ("poses", C.c_void_p), ("ex_pose", C.c_void_p),
+                ("n_features", C.c_int64), ("feat_window", C.c_void_p), ("start_frame", C.c_void_p), ("obs_offset", C.c_void_p),
+                ("points", C.c_void_p)]
+
+
 class ReducedOut(C.Structure):
     _fields_ = [("Sx", C.c_void_p), ("gx", C.c_void_p)]
 

@@ -206,6 +206,9 @@ struct AssocArgs {  // device pointers only
 };
 // associate_kernels.cu (compiled with -fmad=false)
 int viml_launch_associate(viml_ctx* ctx, const AssocArgs& a);
+// triangulate_kernels.cu
+int viml_launch_triangulate(viml_ctx* ctx, int P, int64_t NF, const double* poses, const double* ex, const int32_t* fwin,
+                            const int32_t* start, const int64_t* off, const double* pts, double init_depth, double* depth);
 int viml_launch_track_gate(viml_ctx* ctx, int n_tracks, const int32_t* track_offset, const int32_t* line_index, uint8_t* credible_line,
                            uint8_t* credible_matching);
 int viml_launch_divcheck(viml_ctx* ctx, const double* a, const double* b, int64_t n, unsigned long long* mismatches);

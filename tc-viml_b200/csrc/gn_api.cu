@@ -259,6 +259,45 @@ int viml_gn_step(viml_ctx* ctx, const viml_window_batch* in, const viml_dense_fa
   return run(ctx, in, dense, extra_state, opt, nullptr, out, flags);
 }
 
+int viml_triangulate_batch(viml_ctx* ctx, const viml_triangulate_in* in, double init_depth, double* depth, uint32_t flags) {
+  if (!ctx) return VIML_ERR_INVALID;
+  if (!in || !depth) return fail(ctx, VIML_ERR_INVALID, "viml_triangulate_batch: null arguments");
+  const int W = in->n_windows, P = in->poses_per_window;
+  const int64_t NF = in->n_features;
+  if (W < 0 || P < 1 || NF < 0) return fail(ctx, VIML_ERR_INVALID, "viml_triangulate_batch: sizes out of range");
+  if (NF == 0) return VIML_OK;
+  if (!in->poses || !in->ex_pose || !in->feat_window || !in->start_frame || !in->obs_offset || !in->points)
+    return fail(ctx, VIML_ERR_INVALID, "viml_triangulate_batch: null input array");
+  VIML_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bool dev = (flags & VIML_PTRS_DEVICE) != 0;
+  int64_t nobs = 0;
+  if (dev) {
+    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(&nobs, in->obs_offset + NF, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VIML_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  } else {
+    nobs = in->obs_offset[NF];
+    for (int64_t l = 0; l < NF; ++l)
+      if (in->feat_window[l] < 0 || in->feat_window[l] >= W) return fail(ctx, VIML_ERR_INVALID, "viml_triangulate_batch: feat_window out of range");
+  }
+  Stager st{ctx, dev};
+  const double *dp = nullptr, *de = nullptr, *dpts = nullptr;
+  const int32_t *dw = nullptr, *ds = nullptr;
+  const int64_t* doff = nullptr;
+  st.in(in->poses, (size_t)W * P * 7, &dp);
+  st.in(in->ex_pose, (size_t)W * 7, &de);
+  st.in(in->feat_window, (size_t)NF, &dw);
+  st.in(in->start_frame, (size_t)NF, &ds);
+  st.in(in->obs_offset, (size_t)NF + 1, &doff);
+  st.in(in->points, (size_t)nobs * 3, &dpts);
+  double* dd = nullptr;
+  st.out(depth, (size_t)NF, &dd);
+  int rc = st.commit();
+  if (rc != VIML_OK) return rc;
+  rc = viml_launch_triangulate(ctx, P, NF, dp, de, dw, ds, doff, dpts, init_depth, dd);
+  if (rc != VIML_OK) return rc;
+  return st.finish();
+}
+
 int viml_load_line_map(viml_ctx* ctx, const char* path, int64_t* n_lines) {
   if (!ctx) return VIML_ERR_INVALID;
   if (!path) return fail(ctx, VIML_ERR_INVALID, "null map path");

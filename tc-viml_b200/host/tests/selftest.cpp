@@ -80,7 +80,25 @@ class DenseFactor : public ceres::CostFunction {
   std::vector<std::vector<double>> J;
 };
 
+static void test_ingest() {
+  // estimator_node.cpp:382-413 channel unpacking
+  const int n = 5;
+  float x[n] = {0.1f, -0.2f, 0.3f, 0.0f, 0.5f}, y[n] = {0.2f, 0.1f, -0.4f, 0.3f, 0.0f}, z[n] = {1, 1, 1, 1, 1};
+  float id[n] = {7, 8, 1000003, 12, 0}, u[n] = {100.5f, 200, 300, 400, 500}, v[n] = {50, 60, 70.25f, 80, 90};
+  float vx[n] = {1, 2, 3, 4, 5}, vy[n] = {-1, -2, -3, -4, -5};
+  int32_t fid[n], cam[n];
+  double out[n][7];
+  pack_point_channels(n, PointChannels{x, y, z, id, u, v, vx, vy}, 1, fid, cam, &out[0][0]);
+  CHECK(fid[2] == (int)(1000003.0f + 0.5) && cam[2] == 0 && out[0][3] == (double)100.5f && out[2][4] == (double)70.25f && out[4][6] == -5.0);
+  float lid[2] = {3, 41}, sx[2] = {10.5f, 20}, sy[2] = {30, 40}, ex[2] = {50, 60.75f}, ey[2] = {70, 80};
+  int32_t lfid[2];
+  double l2d[2][4];
+  pack_line_channels(2, LineChannels{lid, sx, sy, ex, ey}, lfid, &l2d[0][0]);
+  CHECK(lfid[1] == 41 && l2d[0][0] == (double)10.5f && l2d[1][2] == (double)60.75f && l2d[1][3] == 80.0);
+}
+
 static void test_host_only() {
+  test_ingest();
   // ceres_compat CauchyLoss == oracle
   for (double a : {1.0, 2.5}) {
     ceres::CauchyLoss loss(a);

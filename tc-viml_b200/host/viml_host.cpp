@@ -661,6 +661,24 @@ bool MarginalizationFactor::Evaluate(double const* const* parameters, double* re
 }
 
 // ---------------------------------------------------------------------------------------------- association
+void pack_point_channels(int n, const PointChannels& c, int num_of_cam, int32_t* feature_id, int32_t* camera_id, double* out) {
+  for (int j = 0; j < n; ++j) {
+    const int v = (int)(c.id[j] + 0.5);                       // estimator_node.cpp:386
+    feature_id[j] = v / num_of_cam, camera_id[j] = v % num_of_cam;
+    double* o = out + 7 * (size_t)j;
+    o[0] = c.x[j], o[1] = c.y[j], o[2] = c.z[j], o[3] = c.u[j], o[4] = c.v[j], o[5] = c.vx[j], o[6] = c.vy[j];
+    if (o[2] != 1.0) die("pack_point_channels: z != 1 (ROS_ASSERT(z == 1), estimator_node.cpp:397)");
+  }
+}
+
+void pack_line_channels(int n, const LineChannels& c, int32_t* feature_id, double* lines2d) {
+  for (int j = 0; j < n; ++j) {
+    feature_id[j] = (int)(c.id[j] / 1);                       // estimator_node.cpp:405
+    double* o = lines2d + 4 * (size_t)j;
+    o[0] = c.sx[j], o[1] = c.sy[j], o[2] = c.ex[j], o[3] = c.ey[j];
+  }
+}
+
 LineMapAssociator::LineMapAssociator(const std::vector<viml::Vector6d>& lines3d_map) : map_(lines3d_map) {
   std::memset(have_, 0, sizeof(have_));
   std::memset(cull_pose_, 0, sizeof(cull_pose_));

@@ -253,6 +253,20 @@ class MarginalizationFactor : public ceres::CostFunction {
   MarginalizationInfo* marginalization_info;
 };
 
+// Ingest of the front-end messages (estimator_node.cpp:382-413): the sensor_msgs::PointCloud of the point tracker and of the line
+// tracker arrive as float32 channel arrays; they are unpacked straight into the SoA layout the C-ABI takes (double precision, the
+// 2D line endpoints as viml_assoc_query::lines2d rows), without the per-feature std::map / Eigen temporaries of the reference.
+struct PointChannels {   // img_msg: points[j] = (x, y, z), channels[0] = id * NUM_OF_CAM + camera, [1..2] = pixel u v, [3..4] = velocity
+  const float *x, *y, *z, *id, *u, *v, *vx, *vy;
+};
+struct LineChannels {    // line_msg: channels[0] = id, channels[1..4] = start x y, end x y (raw pixels)
+  const float *id, *sx, *sy, *ex, *ey;
+};
+// feature_id[j], camera_id[j], xyz_uv_velocity[j][7]  (estimator_node.cpp:384-399; z must be 1, :397)
+void pack_point_channels(int n, const PointChannels& c, int num_of_cam, int32_t* feature_id, int32_t* camera_id, double* xyz_uv_velocity);
+// feature_id[j], lines2d[j][4]  (estimator_node.cpp:403-413)
+void pack_line_channels(int n, const LineChannels& c, int32_t* feature_id, double* lines2d);
+
 // The line-association group of Estimator / FeatureManager.
 class LineMapAssociator {
  public:

@@ -33,6 +33,7 @@ def test_struct_sizes_match_header(pkg):
     assert C.sizeof(abi.AssocQuery) == 8 + 7 * 8
     assert C.sizeof(abi.AssocOut) == 5 * 8 + 8 + 8
     assert C.sizeof(abi.DenseFactors) == 8 + 8 + 7 * 8
+    assert C.sizeof(abi.TriangulateIn) == 8 + 2 * 8 + 8 + 4 * 8
     assert C.sizeof(abi.ReducedOut) == 16 and C.sizeof(abi.GnOptions) == 16 and C.sizeof(abi.GnOut) == 7 * 8
 
 

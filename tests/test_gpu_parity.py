@@ -452,6 +452,60 @@ def test_track_gate(pkg, orc, cfg):
         assert np.array_equal(cl[off[t]:off[t + 1]], np.asarray(ref_cl, dtype=bool)), t
 
 
+def test_triangulate_batch(pkg, ctx, cfg):
+    """FeatureManager::triangulate (feature_manager.cpp:440-492) for a batch: the DLT rows restated with numpy and
+    numpy.linalg.svd standing in for Eigen::JacobiSVD; depth = V[2] / V[3], INIT_DEPTH below 0.1."""
+    synth = pkg.synth
+    b = synth.make_windows(6, seed=161)
+    P = b.P
+
+    def rot(q7):
+        q = q7[3:7] / np.linalg.norm(q7[3:7])
+        return synth._rot_from_quat(q)
+
+    fw, sf, off, pts, ref = [], [], [0], [], []
+    rng = np.random.default_rng(2)
+    for w in range(b.W):
+        k0, k1 = b.pf_window_offset[w], b.pf_window_offset[w + 1]
+        idx = b.pf_idx[k0:k1]
+        feat = idx >> 16
+        for l in np.unique(feat)[:60]:
+            sel = np.nonzero(feat == l)[0]
+            i = int(idx[sel[0]] & 0xff)
+            js = sorted(int((idx[s] >> 8) & 0xff) for s in sel)
+            if js != list(range(i + 1, i + 1 + len(js))):
+                continue
+            obs = [np.array([b.pf_obs[k0 + sel[0], 0], b.pf_obs[k0 + sel[0], 1], 1.0])]
+            for j in js:
+                s = sel[[int((idx[t] >> 8) & 0xff) for t in sel].index(j)]
+                obs.append(np.array([b.pf_obs[k0 + s, 2], b.pf_obs[k0 + s, 3], 1.0]))
+            if rng.uniform() < 0.1:
+                obs = obs[:1]          # a single observation: rank-deficient system, still defined
+            ric, tic = rot(b.ex_pose[w]), b.ex_pose[w, :3]
+            R0 = rot(b.poses[w, i]) @ ric
+            t0 = b.poses[w, i, :3] + rot(b.poses[w, i]) @ tic
+            rows = []
+            for k, p in enumerate(obs):
+                R1 = rot(b.poses[w, i + k]) @ ric
+                t1 = b.poses[w, i + k, :3] + rot(b.poses[w, i + k]) @ tic
+                t, R = R0.T @ (t1 - t0), R0.T @ R1
+                Pm = np.concatenate([R.T, (-R.T @ t)[:, None]], 1)
+                f = p / np.linalg.norm(p)
+                rows += [f[0] * Pm[2] - f[2] * Pm[0], f[1] * Pm[2] - f[2] * Pm[1]]
+            A = np.array(rows)
+            if len(obs) < 2:
+                continue
+            V = np.linalg.svd(A)[2][-1]
+            d = V[2] / V[3]
+            ref.append(5.0 if d < 0.1 else d)
+            fw.append(w), sf.append(i), pts.extend(obs), off.append(off[-1] + len(obs))
+    got = ctx.triangulate(b.poses, b.ex_pose, fw, sf, off, np.array(pts), init_depth=5.0)
+    ref = np.array(ref)
+    assert len(ref) > 200
+    assert np.abs(got - ref).max() < 1e-9 * np.abs(ref).max(), np.abs(got - ref).max()
+    assert np.all(np.abs(got - ref) <= 1e-7 * np.abs(ref))     # per feature (the DLT null vector amplifies rounding by the system's conditioning)
+
+
 def test_load_line_map(pkg, cfg, tmp_path):
     """viml_load_line_map reads line_3d.txt the way parameters.cpp:50-59 does and gives the same association as viml_set_map."""
     synth = pkg.synth
