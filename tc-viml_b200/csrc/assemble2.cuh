@@ -6,7 +6,7 @@
 // leave the SM and there is no CTA-wide phase structure: a window is cut into TASKS that warps execute on their own.
 //
 //   plan_kernel (indices only)   features are ordered by anchor pose; a task is a run of consecutive features
-//       (<= 16 features, ~60 factors); inside a task the factors are ordered by (anchor i, observing frame j) and
+//       (<= 24 features, <= ~110 factors, cut at anchor boundaries); inside a task the factors are ordered by (anchor i, observing frame j) and
 //       every (i, j) SEGMENT is padded to an even length.  The plan is a list of 32-bit slots
 //       (factor id | feature slot | i | j) plus one record per task.
 //   assemble_kernel, one CTA (4 warps) per window, three CTAs per SM.  A warp takes a task and streams its slots
@@ -39,8 +39,8 @@ namespace stream {
 constexpr int PMAX = 12;       // poses per window on the fused path (4-bit i/j, 12-bit observation masks)
 constexpr int FMAXP = 4096;    // features per window the plan kernel's shared tables are sized for
 constexpr int PT = 64;         // plan_kernel threads (warp 0 orders the features, warp 1 the line factors)
-constexpr int TASK_T = 60;     // target point factors per task (two 32-slot chunks with the segment padding)
-constexpr int TASK_F = 16;     // features per task
+constexpr int TASK_T = 110;    // point factors per task at most (+ one feature's worth): an EuRoC anchor group fits
+constexpr int TASK_F = 24;     // features per task
 constexpr int LTASK = 32;      // line slots per line task
 constexpr int AW = 4;          // warps per assemble CTA (3 CTAs x 4 warps per SM = 3 warps per scheduler at <= 168 registers)
 constexpr int LACC_W = 14;     // landmark row: d^T J_i (6) | d^T J_ex (6) | d^T d | d^T r
@@ -57,7 +57,8 @@ struct PlanPtrs {
   int* any_irregular;
 };
 
-__host__ __device__ inline int task_base(int a0_rel, int w, int F) { return a0_rel / 64 + w * (F / TASK_F + 2); }
+// tasks of a window: at most nf/64 cut by the factor limit, F/TASK_F by the feature limit, PMAX+1 by anchor boundaries
+__host__ __device__ inline int task_base(int a0_rel, int w, int F) { return a0_rel / 64 + w * (F / TASK_F + PMAX + 4); }
 
 // ------------------------------------------------------------------------------------------------ plan
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
@@ -148,9 +149,12 @@ __global__ void __launch_bounds__(PT) plan_kernel(LinearizeArgs A, PlanPtrs PL) 
     }
     if (lane == 0) cexcl[F] = (uint32_t)carry;
     __syncwarp();
-    // greedy cut into tasks: as many consecutive features as fit TASK_T factors, at most TASK_F, at least one
+    // greedy cut into tasks: as many consecutive features as fit TASK_T factors, at most TASK_F, at least one — but a task
+    // ends where the anchor changes whenever the rest of the anchor group fits.  A task that holds a WHOLE anchor group is the
+    // only one that ever touches the (anchor, j) blocks of H_pp: it is marked exclusive and stores them without atomics.
     const int tb = task_base(a0r, w, F);
     int pos = 0, t = 0;
+    bool at_group_start = true;
     while (pos < F) {
       const int p = pos + lane;
       const int c = p < F ? (int)(cexcl[p + 1] - cexcl[p]) : 0x10000;
@@ -159,7 +163,18 @@ __global__ void __launch_bounds__(PT) plan_kernel(LinearizeArgs A, PlanPtrs PL) 
       int n = okm == 0xffffffffu ? 32 : __ffs(~okm) - 1;
       n = max(n, 1);
       n = min(n, F - pos);
-      if (lane == 0) PL.tasks[tb + t] = make_int4(2 * (int)cexcl[pos], 0, pos, n);
+      const int an = p < F ? (fanchor[ford[p]] == 0xffu ? P : (int)fanchor[ford[p]]) : -1;
+      const unsigned same = __ballot_sync(0xffffffffu, an == __shfl_sync(0xffffffffu, an, 0));
+      const int na = same == 0xffffffffu ? 33 : __ffs(~same) - 1;   // leading run of the first feature's anchor (33: longer than the view)
+      int excl = 0;
+      if (na <= n) {
+        n = na;
+        excl = at_group_start ? 1 : 0;
+        at_group_start = true;
+      } else {
+        at_group_start = false;
+      }
+      if (lane == 0) PL.tasks[tb + t] = make_int4(2 * (int)cexcl[pos], 0, pos, n | (excl << 16));
       pos += n, ++t;
     }
     if (lane == 0) s_ntasks = t;
@@ -211,7 +226,7 @@ __global__ void __launch_bounds__(PT) plan_kernel(LinearizeArgs A, PlanPtrs PL) 
   for (int t = warp; t < nt; t += PT / 32) {
     int4 tk = PL.tasks[tb + t];
     const int p = tk.z + lane;
-    const bool on = lane < tk.w;
+    const bool on = lane < (tk.w & 0xffff);
     const int l = on ? ford[p] : 0;
     const uint32_t m = on ? fmask[l] : 0u;
     const int an = (on && m) ? (int)fanchor[l] : 0xff;
@@ -361,13 +376,15 @@ __device__ __forceinline__ Dest decode(uint32_t e) {
 }
 template <int ROUNDS>
 __device__ __forceinline__ void scatter(const double* __restrict__ patch, const Dest (&tab)[ROUNDS], double* __restrict__ Hc,
-                                        int mybase) {
+                                        int mybase, bool store_lh = false) {
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
     const int base = __shfl_sync(0xffffffffu, mybase, tab[r].kind);
     if (tab[r].src >= 0) {
-      const double v = patch[tab[r].src];
-      atomicAdd(&Hc[base + tab[r].off], __hiloint2double(__double2hiint(v) ^ (int)tab[r].sign, __double2loint(v)));
+      const double x = patch[tab[r].src];
+      const double v = __hiloint2double(__double2hiint(x) ^ (int)tab[r].sign, __double2loint(x));
+      if (store_lh && tab[r].kind == K_LH) Hc[base + tab[r].off] = v;   // single writer, written once: no read-modify-write
+      else atomicAdd(&Hc[base + tab[r].off], v);
     }
   }
 }
@@ -467,7 +484,8 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
     if (t < ntask) {
       // ================================================================== point task
       const int4 tk = PL.tasks[tb + t];
-      const int n_slots = tk.y, n_feats = tk.w;
+      const int n_slots = tk.y, n_feats = tk.w & 0xffff;
+      const bool excl = (tk.w >> 16) != 0;   // whole anchor group: the (lo, hi) blocks have no other writer
       const uint32_t fi = lane < n_feats ? PL.finfo[(size_t)w * F + tk.z + lane] : 0u;
       {
         double2* z = reinterpret_cast<double2*>(lacc);
@@ -581,7 +599,7 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
             const int mybase = kind_base(kb_rs, kb_cs, kb_isb, lo, hi, NB, boff);
             put_patch(patch, lane, G);
             __syncwarp();
-            scatter<4>(patch, tab_seg, Hc, mybase);
+            scatter<4>(patch, tab_seg, Hc, mybase, excl);
 #pragma unroll
             for (int q = 0; q < 6; ++q) R[q] += G[q], G[q] = 0.0;
             const bool lo_ends = knext == 0xffffffffu || min((int)(knext & 15), (int)((knext >> 4) & 15)) != lo;

@@ -458,7 +458,7 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
   const bool fast = modeB && a.P <= stream::PMAX && a.F <= stream::FMAXP && plan_smem <= 200 * 1024 && !ctx->force_generic;
   stream::PlanPtrs PL{};
   if (fast) {
-    const size_t n_tasks = (size_t)a.NP / 64 + (size_t)a.W * (a.F / stream::TASK_F + 2) + 2;
+    const size_t n_tasks = (size_t)a.NP / 64 + (size_t)a.W * (a.F / stream::TASK_F + stream::PMAX + 4) + 2;
     auto pad = [](size_t b) { return DeviceArena::padded(b); };
     VIML_TRY_CUDA(ctx, ctx->scratch3.reserve(pad((size_t)a.W * 16) + pad(n_tasks * 16) + pad((size_t)a.NP * 8 + 8) +
                                              pad((size_t)a.W * a.F * 4 + 4) + pad((size_t)a.NL * 8 + 8) + pad(4)));
