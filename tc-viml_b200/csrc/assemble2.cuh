@@ -280,8 +280,12 @@ constexpr Tables make_tables() {
   Tables T{};
   int ns = 0, nlo = 0, nli = 0;
   // every (kind, off) in destination order; for each, the (R, C, sign) that feeds it
-  for (int kind = 0; kind < K_NKIND; ++kind)
+  // per-segment table: the blocks that always need the atomic add first (HH, HE, BH = 63 entries = two full rounds), the
+  // (lo, hi) block last (36 entries = rounds 2 and 3, plain stores for an exclusive task)
+  constexpr int kind_order[K_NKIND] = {K_LL, K_LE, K_BL, K_EE, K_BE, K_HH, K_HE, K_BH, K_LH};
+  for (int ko = 0; ko < K_NKIND; ++ko)
     for (int off = 0; off < 36; ++off) {
+      const int kind = kind_order[ko];
       const bool vec = kind >= K_BL;
       if (vec && off >= 6) continue;
       const int dr = vec ? off : off / 6, dc = vec ? 0 : off % 6;
@@ -326,8 +330,12 @@ constexpr Tables make_tables() {
           }
           if (!hit) continue;
           const bool per_segment = kind == K_HH || kind == K_LH || kind == K_HE || kind == K_BH;
-          if (per_segment) T.seg[ns++] = tab_entry(R, C, kind, off, neg);
-          else T.lo[nlo++] = tab_entry(R, C, kind, off, neg);
+          if (per_segment) {
+            if (kind == K_LH && ns < 64) ns = 64;   // the (lo, hi) block starts a round of its own
+            T.seg[ns++] = tab_entry(R, C, kind, off, neg);
+          } else {
+            T.lo[nlo++] = tab_entry(R, C, kind, off, neg);
+          }
         }
     }
   // line factors: columns 0..5 = J, 6 = residual (tile 0 only)
@@ -338,7 +346,8 @@ constexpr Tables make_tables() {
 }
 // read once per CTA with lane-indexed (coalesced) loads: global memory, not __constant__ (divergent constant reads replay)
 __device__ const Tables g_tables = make_tables();
-static_assert(make_tables().seg[98] != 0u && make_tables().seg[99] == 0u, "99 per-segment destinations");
+static_assert(make_tables().seg[62] != 0u && make_tables().seg[63] == 0u && make_tables().seg[99] != 0u && make_tables().seg[100] == 0u,
+              "63 atomic + 36 (lo, hi) per-segment destinations");
 static_assert(make_tables().lo[89] != 0u && make_tables().lo[90] == 0u, "90 per-anchor destinations");
 static_assert(make_tables().line[26] != 0u && make_tables().line[27] == 0u, "27 line destinations");
 
