@@ -1,0 +1,92 @@
+"""ctypes binding of oracle/_ref/libref.so — the REFERENCE's own factor translation units (TEST INFRASTRUCTURE ONLY).
+
+Built by `make -C oracle ref` from the sources under /root/reference (see oracle/Makefile, oracle/ref_wrap.cpp); present in this
+container and, as a prebuilt file, on the GPU box.  available() is False where it was never built."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "_ref", "libref.so")
+_LIB = None
+
+
+def build():
+    """Compile _ref/libref.so when the reference tree is here; a no-op otherwise (the prebuilt file is used as it is)."""
+    if os.path.isdir("/root/reference/vins_estimator/src"):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    return os.path.exists(_PATH)
+
+
+def available():
+    return os.path.exists(_PATH)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(_PATH)
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def projection_evaluate(pts_i, pts_j, sqrt_info, pose_i, pose_j, ex, inv_dep):
+    arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (pose_i, pose_j, ex, np.atleast_1d(inv_dep))]
+    pp = (C.POINTER(C.c_double) * 4)(*[_dp(a) for a in arrs])
+    pi, pj = np.ascontiguousarray(pts_i, dtype=np.float64), np.ascontiguousarray(pts_j, dtype=np.float64)
+    r = np.zeros(2)
+    J = [np.zeros((2, 7)), np.zeros((2, 7)), np.zeros((2, 7)), np.zeros((2, 1))]
+    jp = (C.POINTER(C.c_double) * 4)(*[_dp(j) for j in J])
+    lib().ref_projection_evaluate(_dp(pi), _dp(pj), C.c_double(sqrt_info), pp, _dp(r), jp)
+    return r, J
+
+
+def line_evaluate(ps, pe, abc, K, bcR, bcT, pose):
+    arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (ps, pe, abc, np.asarray(K).reshape(9), np.asarray(bcR).reshape(9), bcT)]
+    pose = np.ascontiguousarray(pose, dtype=np.float64)
+    pp = (C.POINTER(C.c_double) * 1)(_dp(pose))
+    r, J = np.zeros(2), np.zeros((2, 7))
+    jp = (C.POINTER(C.c_double) * 1)(_dp(J))
+    lib().ref_line_evaluate(*[_dp(a) for a in arrs], pp, _dp(r), jp)
+    return r, J
+
+
+def pose_plus(x, delta):
+    x, d = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(delta, dtype=np.float64)
+    o = np.zeros(7)
+    lib().ref_pose_plus(_dp(x), _dp(d), _dp(o))
+    return o
+
+
+def marginalize_old(poses, ex, inv_depth, fj, fl, obs, sqrt_info, cauchy_a=None):
+    """MarginalizationInfo on projection factors (0, j, l) with drop set {0, 3}.  Returns (A [n,n], b [n]) = (J^T J, J^T r) of the
+    reference's linearized_jacobians / linearized_residuals, re-ordered to [pose 1 .. pose P-1, extrinsic] (6 tangent columns
+    each), and m."""
+    poses = np.ascontiguousarray(poses, dtype=np.float64).copy()
+    ex = np.ascontiguousarray(ex, dtype=np.float64).copy()
+    dep = np.ascontiguousarray(inv_depth, dtype=np.float64).copy()
+    fj, fl = np.ascontiguousarray(fj, dtype=np.int32), np.ascontiguousarray(fl, dtype=np.int32)
+    obs = np.ascontiguousarray(obs, dtype=np.float64)
+    P = poses.shape[0]
+    n = 6 * P
+    ko, ki = np.zeros(P, dtype=np.int32), np.zeros(P, dtype=np.int32)
+    lj, lr = np.zeros((n, n)), np.zeros(n)
+    m = C.c_int()
+    code = lib().ref_marginalize_old(P, len(dep), _dp(poses), _dp(ex), _dp(dep), len(fj), fj.ctypes.data_as(C.POINTER(C.c_int)),
+                                     fl.ctypes.data_as(C.POINTER(C.c_int)), _dp(obs), C.c_double(sqrt_info), 0 if cauchy_a is None else 1,
+                                     C.c_double(cauchy_a or 1.0), ko.ctypes.data_as(C.POINTER(C.c_int)), ki.ctypes.data_as(C.POINTER(C.c_int)),
+                                     _dp(lj), _dp(lr), C.byref(m))
+    nn, nkeep = code // 1000, code % 1000
+    assert nn == n and nkeep == P, (nn, nkeep)
+    lj = lj.reshape(-1)[:n * n].reshape(n, n)
+    A, b = lj.T @ lj, lj.T @ lr
+    perm = np.zeros(n, dtype=np.int64)   # canonical column (pose p-1 block, or last block for the extrinsic) -> reference column
+    for blk in range(P):
+        tgt = (ko[blk] - 1) if ko[blk] < P else P - 1
+        perm[6 * tgt:6 * tgt + 6] = ki[blk] + np.arange(6)
+    return A[np.ix_(perm, perm)], b[perm], int(m.value)

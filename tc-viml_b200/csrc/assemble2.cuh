@@ -39,6 +39,7 @@ namespace stream {
 constexpr int PMAX = 12;       // poses per window on the fused path (4-bit i/j, 12-bit observation masks)
 constexpr int FMAXP = 4096;    // features per window the plan kernel's shared tables are sized for
 constexpr int PT = 64;         // plan_kernel threads (warp 0 orders the features, warp 1 the line factors)
+constexpr int PT_MAX = 512;    // ... for windows with many features: more warps write the tasks' slots
 constexpr int TASK_T = 110;    // point factors per task at most (+ one feature's worth): an EuRoC anchor group fits
 constexpr int TASK_F = 24;     // features per task
 constexpr int LTASK = 32;      // line slots per line task
@@ -71,12 +72,12 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 }
 
 // One CTA per window.  Dynamic shared memory: fmask[F] u32 | fanchor[F] u32 | cexcl[F+1] u32 | ford[F] u16 | fid[F*P] u16
-__global__ void __launch_bounds__(PT) plan_kernel(LinearizeArgs A, PlanPtrs PL) {
+__global__ void __launch_bounds__(PT_MAX) plan_kernel(LinearizeArgs A, PlanPtrs PL) {
   extern __shared__ __align__(16) unsigned char plan_raw[];
   __shared__ int gcount[PMAX + 2], grun[PMAX + 2], lcount[PMAX + 1], lrun[PMAX + 1];
   __shared__ int s_bad, s_ntasks, s_nlslots;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, w = blockIdx.x;
-  const int P = A.P, F = A.F;
+  const int P = A.P, F = A.F, NTH = (int)blockDim.x;   // 64 threads for EuRoC-sized windows, PT_MAX for many-feature ones
   uint32_t* fmask = reinterpret_cast<uint32_t*>(plan_raw);
   uint32_t* fanchor = fmask + F;
   uint32_t* cexcl = fanchor + F;
@@ -85,14 +86,14 @@ __global__ void __launch_bounds__(PT) plan_kernel(LinearizeArgs A, PlanPtrs PL) 
   const int a0 = A.pf_window_offset[w], nf = A.pf_window_offset[w + 1] - a0;
   const int b0 = A.NL > 0 ? A.lf_window_offset[w] : 0, nl = A.NL > 0 ? A.lf_window_offset[w + 1] - b0 : 0;
   const int a0r = a0 - (int)A.pf_begin, b0r = b0 - (int)A.lf_begin;
-  for (int f = tid; f < F; f += PT) fmask[f] = 0u, fanchor[f] = 0xffu;
-  for (int e = tid; e < F * P; e += PT) fid[e] = 0xffff;
+  for (int f = tid; f < F; f += NTH) fmask[f] = 0u, fanchor[f] = 0xffu;
+  for (int e = tid; e < F * P; e += NTH) fid[e] = 0xffff;
   if (tid < PMAX + 2) gcount[tid] = 0;
   if (tid < PMAX + 1) lcount[tid] = 0;
   if (tid == 0) s_bad = (nf > 65534 || nl > 65534 || nf < 0 || nl < 0) ? 1 : 0, s_ntasks = 0, s_nlslots = 0;
   __syncthreads();
   const int nfs = s_bad ? 0 : nf;
-  for (int k = tid; k < nfs; k += PT) {
+  for (int k = tid; k < nfs; k += NTH) {
     const uint32_t ix = A.pf_idx[a0 + k];
     const int i = ix & 0xff, j = (ix >> 8) & 0xff, l = ix >> 16;
     if (i >= P || j >= P || l >= F || i == j) {
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(PT) plan_kernel(LinearizeArgs A, PlanPtrs PL) 
   // slots of every task: lane = feature of the task; segments (i, j) in order, padded to even length
   const int tb = task_base(a0r, w, F), nt = s_ntasks;
   uint32_t* sl_w = PL.slots + 2 * (size_t)a0r;
-  for (int t = warp; t < nt; t += PT / 32) {
+  for (int t = warp; t < nt; t += NTH / 32) {
     int4 tk = PL.tasks[tb + t];
     const int p = tk.z + lane;
     const bool on = lane < (tk.w & 0xffff);

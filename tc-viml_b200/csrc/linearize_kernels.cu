@@ -476,7 +476,7 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
     VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(stream::plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem));
     {
       LaunchScope ls(ctx, K_PLAN, ctx->aux_stream);
-      stream::plan_kernel<<<a.W, stream::PT, plan_smem, ctx->aux_stream>>>(a, PL);
+      stream::plan_kernel<<<a.W, a.F > 512 ? stream::PT_MAX : stream::PT, plan_smem, ctx->aux_stream>>>(a, PL);
     }
     VIML_TRY_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
   }

@@ -1,0 +1,111 @@
+"""The oracle against the REFERENCE'S OWN CODE (CPU tests).
+
+oracle/_ref/libref.so is /root/reference/vins_estimator/src/factor/{projection_factor, line_projection_factor,
+pose_local_parameterization, marginalization_factor}.cpp compiled unmodified where they lie (oracle/Makefile `ref`), against the
+Eigen / Ceres / ROS interface stand-ins of oracle/ref_shim/.  tests/golden/ref_factors.npz holds vectors that library produced
+(tests/golden/make_ref_golden.py), so the pin also holds where the reference tree is absent (the GPU box)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+GOLD = os.path.join(ROOT, "tests", "golden", "ref_factors.npz")
+
+
+def _oracle_factors(pkg, orc, g):
+    abi, synth = pkg._abi, pkg.synth
+    cfg = synth.euroc_config(sqrt_info=float(g["pf_sqrt_info"]))
+    W = g["pf_poses"].shape[0]
+    off = np.searchsorted(g["pf_win"], np.arange(W + 1)).astype(np.int32)
+    b = abi.Batch(g["pf_poses"], g["pf_ex"], g["pf_inv_depth"], off, g["pf_idx"], g["pf_obs"])
+    op = orc.linearize_batch(cfg, b, abi.OUT_RESIDUAL_JACOBIAN)
+    loff = np.searchsorted(g["lf_win"], np.arange(W + 1)).astype(np.int32)
+    bl = abi.Batch(g["lf_poses"], g["lf_ex"], np.zeros((W, 1)), np.zeros(W + 1, dtype=np.int32), np.zeros(0, dtype=np.uint32),
+                   np.zeros((0, 4)), loff, g["lf_frame"], g["lf_geom"])
+    ol = orc.linearize_batch(cfg, bl, abi.OUT_RESIDUAL_JACOBIAN)
+    return op, ol
+
+
+def test_oracle_equals_reference_vectors_bit_for_bit(pkg, orc):
+    """ProjectionFactor::Evaluate and LineProjectionFactor::Evaluate: the oracle restatement reproduces the reference's own code
+    bit for bit on 1669 + 330 factors (window 1 has clearly non-unit quaternions)."""
+    g = np.load(GOLD)
+    op, ol = _oracle_factors(pkg, orc, g)
+    N, NL = len(g["pf_idx"]), len(g["lf_frame"])
+    for k, rk in (("pf_residual", "pf_r"), ("pf_jac_pose_i", "pf_Ji"), ("pf_jac_pose_j", "pf_Jj"), ("pf_jac_ex", "pf_Je"), ("pf_jac_feat", "pf_Jl")):
+        assert np.array_equal(op[k].reshape(N, -1), g[rk].reshape(N, -1)), k
+    for k, rk in (("lf_residual", "lf_r"), ("lf_jac_pose", "lf_J")):
+        assert np.array_equal(ol[k].reshape(NL, -1), g[rk].reshape(NL, -1)), k
+
+
+def test_pose_plus_equals_reference(pkg, orc):
+    from oracle import gn_oracle
+    g = np.load(GOLD)
+    for x, d, o in zip(g["plus_x"], g["plus_d"], g["plus_out"]):
+        assert np.abs(gn_oracle.pose_plus(x, d) - o).max() < 1e-15
+
+
+def _oracle_marginalize(pkg, orc, poses, ex, dep, idx, obs, sq, loss):
+    """The oracle's route to the same quantity: dense A, b by the ThreadsConstructA rule, [pose 0, landmarks | kept] ordering,
+    marginalize_dense (eigen pseudo-inverse Schur complement)."""
+    abi, synth = pkg._abi, pkg.synth
+    cfg = synth.euroc_config(sqrt_info=sq, cauchy_a=(loss or 1.0))
+    P, F = poses.shape[0], len(dep)
+    b = abi.Batch(poses[None], ex[None], dep[None], np.array([0, len(idx)], dtype=np.int32), idx, obs)
+    flags = abi.OUT_HB | (abi.LOSS_CAUCHY if loss else 0)
+    A, bb = orc.window_dense(cfg, b, 0, flags)
+    D = b.D
+    perm = np.concatenate([np.arange(6), D + np.arange(F), np.arange(6, D)])
+    A, bb = A[np.ix_(perm, perm)], bb[perm]
+    As, bs, _, _ = orc.marginalize_dense(A, bb, 6 + F)
+    return As, bs
+
+
+def _check_marg(pkg, A, b, As, bs):
+    n = A.shape[0]
+    assert As.shape == (n, n)
+    # per 6x6 block against the block's own scale
+    assert pkg.parity.unit_err("S", As[None], A[None]) < 1e-8, pkg.parity.unit_err("S", As[None], A[None])
+    assert pkg.parity.unit_err("g", bs[None], b[None]) < 1e-8
+
+
+def test_marginalization_equals_reference_vectors(pkg, orc):
+    """MarginalizationInfo::{addResidualBlockInfo, preMarginalize, marginalize} of the reference (pthread ThreadsConstructA, eigen
+    pseudo-inverse, square-root factorisation) on the MARGIN_OLD projection set: J^T J and J^T r of its linearized_jacobians /
+    linearized_residuals against the oracle's dense route.  (1e-8: two eigen-decompositions on each side.)"""
+    g = np.load(GOLD)
+    sq = float(g["pf_sqrt_info"])
+    for w in range(2):
+        k0, k1 = g["marg_off"][w], g["marg_off"][w + 1]
+        for loss, tag in ((None, "noloss"), (1.0, "cauchy")):
+            As, bs = _oracle_marginalize(pkg, orc, g["marg_poses"][w], g["marg_ex"][w], g["marg_inv_depth"][w], g["marg_idx"][k0:k1],
+                                         g["marg_obs"][k0:k1], sq, loss)
+            _check_marg(pkg, g[f"marg{w}_{tag}_A"], g[f"marg{w}_{tag}_b"], As, bs)
+
+
+def test_live_reference_library(pkg, orc):
+    """Where oracle/_ref/libref.so exists (this container; prebuilt on the GPU box): fresh random inputs, not the committed ones."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libref.so not built (reference tree absent)")
+    synth = pkg.synth
+    rng = np.random.default_rng(99)
+    b = synth.make_windows(2, seed=777)
+    sq = 123.0
+    for k in rng.choice(b.NP, 200, replace=False):
+        w = int(np.searchsorted(b.pf_window_offset, k, side="right") - 1)
+        i, j, l = int(b.pf_idx[k] & 0xff), int((b.pf_idx[k] >> 8) & 0xff), int(b.pf_idx[k] >> 16)
+        pi, pj = [b.pf_obs[k, 0], b.pf_obs[k, 1], 1.0], [b.pf_obs[k, 2], b.pf_obs[k, 3], 1.0]
+        r1, J1 = ref.projection_evaluate(pi, pj, sq, b.poses[w, i], b.poses[w, j], b.ex_pose[w], b.inv_depth[w, l])
+        r2, J2 = orc.projection_evaluate(pi, pj, sq, b.poses[w, i], b.poses[w, j], b.ex_pose[w], b.inv_depth[w, l])
+        assert np.array_equal(r1, r2)
+        for a, c in zip(J1, J2):
+            assert np.array_equal(a.reshape(-1), np.asarray(c).reshape(-1))
+    m = synth.make_windows(1, seed=778, P=5, F=25, all_start_zero=True, lines_per_frame=0)
+    idx = m.pf_idx
+    A, bb, mm = ref.marginalize_old(m.poses[0], m.ex_pose[0], m.inv_depth[0], (idx >> 8) & 0xff, idx >> 16, m.pf_obs, sq, 1.0)
+    assert mm == 6 + 25
+    As, bs = _oracle_marginalize(pkg, orc, m.poses[0], m.ex_pose[0], m.inv_depth[0], idx, m.pf_obs, sq, 1.0)
+    _check_marg(pkg, A, bb, As, bs)
