@@ -90,3 +90,30 @@ def marginalize_old(poses, ex, inv_depth, fj, fl, obs, sqrt_info, cauchy_a=None)
         tgt = (ko[blk] - 1) if ko[blk] < P else P - 1
         perm[6 * tgt:6 * tgt + 6] = ki[blk] + np.arange(6)
     return A[np.ix_(perm, perm)], b[perm], int(m.value)
+
+
+def line2d(seg):
+    seg = np.ascontiguousarray(seg, dtype=np.float64)
+    o = np.zeros(7)
+    lib().ref_line2d(_dp(seg), _dp(o))
+    return o
+
+
+def point2flined(seg, p):
+    seg, p = np.ascontiguousarray(seg, dtype=np.float64), np.ascontiguousarray(p, dtype=np.float64)
+    o = np.zeros(2)
+    lib().ref_point2flined(_dp(seg), _dp(p), _dp(o))
+    return o
+
+
+def triangulate(poses, ex, start, off, pts):
+    """FeatureManager::triangulate on one window (the JacobiSVD behind it is the stand-in's one-sided Jacobi: depths agree with
+    any accurate SVD to rounding times conditioning, not bit for bit)."""
+    poses, ex = np.ascontiguousarray(poses, dtype=np.float64), np.ascontiguousarray(ex, dtype=np.float64)
+    start = np.ascontiguousarray(start, dtype=np.int32)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    depth = np.zeros(len(start))
+    lib().ref_triangulate(poses.shape[0], _dp(poses), _dp(ex), len(start), start.ctypes.data_as(C.POINTER(C.c_int)),
+                          off.ctypes.data_as(C.POINTER(C.c_longlong)), _dp(pts), _dp(depth))
+    return depth

@@ -13,9 +13,11 @@
 #include "factor/marginalization_factor.h"
 #include "factor/pose_local_parameterization.h"
 #include "factor/projection_factor.h"
+#include "feature_manager.h"
 
 // globals the reference declares extern in parameters.h and defines in parameters.cpp (not compiled here)
 double INIT_DEPTH = 5.0;
+double MIN_PARALLAX = 10.0 / 460.0;
 
 extern "C" {
 
@@ -83,6 +85,47 @@ int ref_marginalize_old(int P, int F, double* poses, double* ex, double* inv_dep
   delete loss;
   (void)F;
   return n * 1000 + nkeep;
+}
+
+// Line2D::Line2D(Vector4d) (feature_manager.cpp:4-15): out = {A, B, C, A2B2, Length, Direction.x, Direction.y}
+void ref_line2d(const double* seg, double* out) {
+  Line2D l(Eigen::Vector4d(seg[0], seg[1], seg[2], seg[3]));
+  out[0] = l.A, out[1] = l.B, out[2] = l.C, out[3] = l.A2B2, out[4] = l.Length, out[5] = l.Direction(0), out[6] = l.Direction(1);
+}
+
+// Line2D::Point2Flined (feature_manager.cpp:46-71)
+void ref_point2flined(const double* seg, const double* p, double* out) {
+  Line2D l(Eigen::Vector4d(seg[0], seg[1], seg[2], seg[3]));
+  const Eigen::Vector2d r = l.Point2Flined(Eigen::Vector2d(p[0], p[1]));
+  out[0] = r(0), out[1] = r(1);
+}
+
+// FeatureManager::triangulate (feature_manager.cpp:440-492) for NF features of one window: feature l starts in frame start[l] and
+// has observations off[l] .. off[l+1]-1 (normalised points xyz).  poses [P][7] (the estimator's Ps / Rs = normalised quaternion),
+// ex [7].  depth[l] = estimated_depth after the call.
+void ref_triangulate(int P, const double* poses, const double* ex, int NF, const int* start, const long long* off, const double* pts,
+                     double* depth) {
+  std::vector<Eigen::Matrix3d> Rs(P + 1);
+  std::vector<Eigen::Vector3d> Ps(P + 1);
+  for (int p = 0; p < P; ++p) {
+    const double* q = poses + 7 * p;
+    Ps[p] = Eigen::Vector3d(q[0], q[1], q[2]);
+    Rs[p] = Eigen::Quaterniond(q[6], q[3], q[4], q[5]).normalized().toRotationMatrix();   // estimator.cpp double2vector
+  }
+  Eigen::Vector3d tic[1] = {Eigen::Vector3d(ex[0], ex[1], ex[2])};
+  Eigen::Matrix3d ric[1] = {Eigen::Quaterniond(ex[6], ex[3], ex[4], ex[5]).normalized().toRotationMatrix()};
+  FeatureManager fm(Rs.data());
+  for (int l = 0; l < NF; ++l) {
+    fm.feature.push_back(FeaturePerId(l, start[l]));
+    for (long long k = off[l]; k < off[l + 1]; ++k) {
+      Eigen::Matrix<double, 7, 1> v;
+      v << pts[3 * k], pts[3 * k + 1], pts[3 * k + 2], 0, 0, 0, 0;
+      fm.feature.back().feature_per_frame.push_back(FeaturePerFrame(v, 0.0));
+    }
+  }
+  fm.triangulate(Ps.data(), tic, ric);
+  int l = 0;
+  for (auto& it : fm.feature) depth[l++] = it.estimated_depth;
 }
 
 }  // extern "C"

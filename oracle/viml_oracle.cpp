@@ -1024,7 +1024,16 @@ extern "C" int orc_line_associate(const viml_config* cfg, const double* map, int
 }
 
 // a17  FeatureManager::removeLineOutlier / lineDiff — feature_manager.cpp:494-541
-extern "C" int orc_track_gate(int n_obs, const double* line_vec, uint8_t* credible_line) {
+extern "C" void orc_line2d(const double* seg, double* out) {
+  const Line2D l = make_line2d(seg[0], seg[1], seg[2], seg[3]);
+  out[0] = l.A, out[1] = l.B, out[2] = l.C, out[3] = l.A2B2, out[4] = l.Length, out[5] = l.Dx, out[6] = l.Dy;
+}
+void orc_point2flined(const double* seg, const double* p, double* out) {
+  const Line2D l = make_line2d(seg[0], seg[1], seg[2], seg[3]);
+  point2flined(l, p[0], p[1], &out[0], &out[1]);
+}
+
+int orc_track_gate(int n_obs, const double* line_vec, uint8_t* credible_line) {
   if (n_obs < 1) return 1;
   int count = 0;
   for (int k = 0; k < n_obs; ++k) {

@@ -93,6 +93,10 @@ int orc_line_associate(const viml_config* cfg, const double* map_xyzxyz, int64_t
 /* FeatureManager::removeLineOutlier track gate (feature_manager.cpp:494-541) on one track of n_obs
  * observations; line_vec[k][3] = LineVec of the matched map line (oracle definition PtrEnd-PtrStart,
  * SURVEY.md §8a UB policy).  Writes credible_line[k]; returns credible_matching (0/1). */
+/* Line2D::Line2D(Vector4d) (feature_manager.cpp:4-15): out = {A, B, C, A2B2, Length, Direction.x, Direction.y};
+ * Line2D::Point2Flined (feature_manager.cpp:46-71): out = the returned point.  (Exposed for the check against oracle/_ref.) */
+void orc_line2d(const double* seg, double* out);
+void orc_point2flined(const double* seg, const double* p, double* out);
 int orc_track_gate(int n_obs, const double* line_vec, uint8_t* credible_line);
 
 /* c* = min{ c in [0,1] : acos(c) <= angle_th } for the host libm (SURVEY.md §7 "hard parts").

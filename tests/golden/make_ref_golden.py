@@ -60,6 +60,32 @@ for w in range(2):
         A, bb, mm = ref.marginalize_old(m.poses[w], m.ex_pose[w], m.inv_depth[w], (idx >> 8) & 0xff, idx >> 16, m.pf_obs[k0:k1], sq, loss)
         out[f"marg{w}_{tag}_A"], out[f"marg{w}_{tag}_b"], out[f"marg{w}_m"] = A, bb, mm
 out.update(marg_poses=m.poses, marg_ex=m.ex_pose, marg_inv_depth=m.inv_depth, marg_off=m.pf_window_offset, marg_idx=m.pf_idx, marg_obs=m.pf_obs)
+# Line2D::Line2D(Vector4d) and Line2D::Point2Flined (float32-rounded pixel segments, some vertical / degenerate)
+segs = rng.uniform(0, 750, (400, 4)).astype(np.float32).astype(np.float64)
+segs[::40, 2] = segs[::40, 0]                      # vertical: Point2Flined always clamps to an endpoint (feature_manager.cpp:60-66)
+qp = rng.uniform(-50, 800, (400, 2))
+out.update(l2d_seg=segs, l2d_p=qp, l2d_out=np.array([ref.line2d(s_) for s_ in segs]),
+           l2d_foot=np.array([ref.point2flined(s_, p_) for s_, p_ in zip(segs, qp)]))
+# FeatureManager::triangulate: the features of window 0 with consecutive observation frames
+w = 0
+k0, k1 = b.pf_window_offset[w], b.pf_window_offset[w + 1]
+idx = b.pf_idx[k0:k1]
+feat = idx >> 16
+t_start, t_off, t_pts = [], [0], []
+for l in np.unique(feat):
+    sel = np.nonzero(feat == l)[0]
+    i = int(idx[sel[0]] & 0xff)
+    js = sorted(int((idx[s_] >> 8) & 0xff) for s_ in sel)
+    if js != list(range(i + 1, i + 1 + len(js))):
+        continue
+    obs = [[b.pf_obs[k0 + sel[0], 0], b.pf_obs[k0 + sel[0], 1], 1.0]]
+    for j in js:
+        s_ = sel[[int((idx[t] >> 8) & 0xff) for t in sel].index(j)]
+        obs.append([b.pf_obs[k0 + s_, 2], b.pf_obs[k0 + s_, 3], 1.0])
+    t_start.append(i), t_pts.extend(obs), t_off.append(t_off[-1] + len(obs))
+out.update(tri_poses=b.poses[w], tri_ex=b.ex_pose[w], tri_start=np.array(t_start, dtype=np.int32), tri_off=np.array(t_off, dtype=np.int64),
+           tri_pts=np.array(t_pts), tri_depth=ref.triangulate(b.poses[w], b.ex_pose[w], t_start, t_off, np.array(t_pts)))
 path = os.path.join(ROOT, "tests", "golden", "ref_factors.npz")
 np.savez_compressed(path, **out)
-print(f"{path}: {N} ProjectionFactor, {NL} LineProjectionFactor, 64 Plus, 4 marginalisations from the reference's own code")
+print(f"{path}: {N} ProjectionFactor, {NL} LineProjectionFactor, 64 Plus, 4 marginalisations, 400 Line2D / Point2Flined, "
+      f"{len(t_start)} triangulations from the reference's own code")

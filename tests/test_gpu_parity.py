@@ -506,6 +506,15 @@ def test_triangulate_batch(pkg, ctx, cfg):
     assert np.all(np.abs(got - ref) <= 1e-7 * np.abs(ref))     # per feature (the DLT null vector amplifies rounding by the system's conditioning)
 
 
+def test_triangulate_against_reference_vectors(pkg, ctx):
+    """viml_triangulate_batch against depths the reference's own FeatureManager::triangulate produced (tests/golden/ref_factors.npz)."""
+    g = np.load(os.path.join(GOLD, "ref_factors.npz"))
+    got = ctx.triangulate(g["tri_poses"][None], g["tri_ex"][None], np.zeros(len(g["tri_start"]), dtype=np.int32), g["tri_start"], g["tri_off"],
+                          g["tri_pts"], init_depth=5.0)
+    assert np.all(np.abs(got - g["tri_depth"]) <= 1e-7 * np.abs(g["tri_depth"]))
+    assert np.abs(got - g["tri_depth"]).max() < 1e-9 * np.abs(g["tri_depth"]).max()
+
+
 def test_load_line_map(pkg, cfg, tmp_path):
     """viml_load_line_map reads line_3d.txt the way parameters.cpp:50-59 does and gives the same association as viml_set_map."""
     synth = pkg.synth

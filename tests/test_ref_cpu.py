@@ -85,6 +85,49 @@ def test_marginalization_equals_reference_vectors(pkg, orc):
             _check_marg(pkg, g[f"marg{w}_{tag}_A"], g[f"marg{w}_{tag}_b"], As, bs)
 
 
+def test_line2d_and_point2flined_equal_reference_vectors(pkg, orc):
+    """Line2D::Line2D(Vector4d) and Line2D::Point2Flined (feature_manager.cpp:4-15, :46-71), the building blocks of
+    CalAngleDist / CalEulerDist: bit for bit, vertical segments included."""
+    import ctypes as C
+    g = np.load(GOLD)
+    o = orc.lib()
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))   # noqa: E731
+    for seg, p, want, foot in zip(g["l2d_seg"], g["l2d_p"], g["l2d_out"], g["l2d_foot"]):
+        seg, p = np.ascontiguousarray(seg), np.ascontiguousarray(p)
+        a, f = np.zeros(7), np.zeros(2)
+        o.orc_line2d(dp(seg), dp(a))
+        o.orc_point2flined(dp(seg), dp(p), dp(f))
+        assert np.array_equal(a, want) and np.array_equal(f, foot, equal_nan=True)
+
+
+def test_triangulate_reference_vectors_vs_numpy_svd(pkg):
+    """FeatureManager::triangulate of the reference (its JacobiSVD is the stand-in's) against numpy's LAPACK SVD on the same DLT
+    rows: the check that the -m gpu test of viml_triangulate_batch uses a sound expectation."""
+    g = np.load(GOLD)
+    synth = pkg.synth
+
+    def rot(q7):
+        return synth._rot_from_quat(q7[3:7] / np.linalg.norm(q7[3:7]))
+
+    poses, ex = g["tri_poses"], g["tri_ex"]
+    ric, tic = rot(ex), ex[:3]
+    for l in range(len(g["tri_start"])):
+        i = int(g["tri_start"][l])
+        obs = g["tri_pts"][g["tri_off"][l]:g["tri_off"][l + 1]]
+        R0, t0 = rot(poses[i]) @ ric, poses[i, :3] + rot(poses[i]) @ tic
+        rows = []
+        for k, p in enumerate(obs):
+            R1, t1 = rot(poses[i + k]) @ ric, poses[i + k, :3] + rot(poses[i + k]) @ tic
+            t, R = R0.T @ (t1 - t0), R0.T @ R1
+            Pm = np.concatenate([R.T, (-R.T @ t)[:, None]], 1)
+            f = p / np.linalg.norm(p)
+            rows += [f[0] * Pm[2] - f[2] * Pm[0], f[1] * Pm[2] - f[2] * Pm[1]]
+        V = np.linalg.svd(np.array(rows))[2][-1]
+        d = V[2] / V[3]
+        d = 5.0 if d < 0.1 else d
+        assert abs(d - g["tri_depth"][l]) <= 1e-7 * abs(d), (l, d, g["tri_depth"][l])
+
+
 def test_live_reference_library(pkg, orc):
     """Where oracle/_ref/libref.so exists (this container; prebuilt on the GPU box): fresh random inputs, not the committed ones."""
     from oracle import ref
