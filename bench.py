@@ -432,6 +432,61 @@ def main():
                         "gflops": fl / (ps[0] / ps[1] * 1e-3) / 1e9, "shape": f"{batch.W} windows x (D={D}, {F} landmarks)",
                         "step_ms_with_linearize": msS / K, "kernel_ms_per_step": {k: v[0] / K for k, v in profS.items()}}
         free_all(dS)
+    if not args.skip_extras:
+        # ---------------- one device-resident Gauss-Newton / LM iteration on every window (visual factors +
+        # prior / IMU dense blocks): reduced system, Cholesky, landmark back-substitution, state update, cost at both states
+        gW = min(batch.W, 1024)
+        gb = batch.slice_windows(0, gW)
+        dense = synth.make_dense_factors(gb, seed=9 + rank)
+        X, Dx = dense.X, gb.D + dense.X
+        g_in = {k: ctx.to_device(v) for k, v in gb.arrays().items() if v is not None}
+        g_dn = {k: ctx.to_device(v) for k, v in dense.arrays().items()}
+        extra = np.zeros((gW, X))
+        g_ex = ctx.to_device(extra)
+        g_out = {"poses": ctx.device_alloc(gb.poses.nbytes), "ex_pose": ctx.device_alloc(gb.ex_pose.nbytes),
+                 "inv_depth": ctx.device_alloc(gb.inv_depth.nbytes), "extra": ctx.device_alloc(gW * X * 8),
+                 "dx": ctx.device_alloc(gW * Dx * 8), "cost": ctx.device_alloc(gW * 3 * 8), "solved": ctx.device_alloc(gW * 4)}
+        gs, gd = gb.struct(g_in), dense.struct(g_dn)
+        go = abi.GnOut()
+        for k in g_out:
+            setattr(go, k, g_out[k])
+        gopt = abi.GnOptions()
+        gopt.lambda_ = 1e-4
+        gflags = abi.LOSS_CAUCHY | abi.PTRS_DEVICE
+
+        def gn_call():
+            rc = ctx.lib.viml_gn_step(ctx.h, ctypes.byref(gs), ctypes.byref(gd), ctypes.c_void_p(g_ex), ctypes.byref(gopt), ctypes.byref(go), gflags)
+            assert rc == 0, rc
+
+        g_steps = max(3, min(K, 10))
+        msG, profG = timed_device(gn_call, g_steps, 3)
+        out["gn_step"] = {"metric": "gn_iters_per_s", "value": sum_over_ranks(float(gW)) / (msG / g_steps * 1e-3), "unit": "window iterations/s",
+                          "ms_per_step": msG / g_steps, "windows_per_gpu": gW, "reduced_dim": Dx,
+                          "config": f"{gW} cfg-2 windows/GPU, each + {len(dense.factors) // gW} dense-block factors (prior, IMU-like), "
+                                    f"reduced system {Dx} x {Dx}, LM lambda 1e-4, device resident",
+                          "kernel_ms_per_step": {k: v[0] / g_steps for k, v in profG.items()}}
+        if do_cpu:
+            from oracle import gn_oracle
+            orc = ge.load_oracle()
+            ns = 32
+            sb = gb.slice_windows(0, ns)
+            sd = abi.Dense(ns, X, [f for f in dense.factors if f[0] < ns])
+            t0 = time.perf_counter()
+            refg = gn_oracle.gn_step(cfg, sb, sd, extra[:ns], abi.LOSS_CAUCHY, lam=1e-4, nthreads=orc.hardware_threads())
+            dtg = time.perf_counter() - t0
+            got_dx = fetch((gW, Dx), g_out["dx"])[:ns]
+            got_cost = fetch((gW, 3), g_out["cost"])[:ns]
+            sc = np.abs(refg["dx"]).max(axis=1, keepdims=True)
+            e_dx = float((np.abs(got_dx - refg["dx"]) / sc).max())
+            e_c = float((np.abs(got_cost - refg["cost"]) / np.abs(refg["cost"])).max())
+            assert e_dx < 1e-9 and e_c < 1e-9, (e_dx, e_c)
+            out["gn_step"]["cpu_baseline"] = {"value": ns / dtg, "unit": "window iterations/s", "cores": orc.hardware_threads(), "kind": "port",
+                                              "sample": f"{ns} windows: C++ oracle linearisation (all host threads) + numpy Cholesky / update "
+                                                        f"per window ({dtg:.2f} s)"}
+            out["gn_step"]["parity"] = {"parity_checked_windows": ns, "dx_max_rel_err_per_window": e_dx, "cost_max_rel_err": e_c,
+                                        "identical_accept_reject": bool(np.array_equal(got_cost[:, 1] < got_cost[:, 0], refg["cost"][:, 1] < refg["cost"][:, 0]))}
+        free_all(g_in, g_dn, g_out)
+        ctx.device_free(g_ex)
     free_all(d_in, d_out)
 
     if not args.skip_extras:

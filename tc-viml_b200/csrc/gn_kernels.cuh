@@ -47,11 +47,11 @@ __global__ void __launch_bounds__(256) reduced_kernel(int D, DenseArgs dn, const
 
 // dx = -(Sx + lambda diag(Sx))^-1 gx by Cholesky in shared memory (packed lower triangle), one CTA per window.
 // solved[w] = 0 when a pivot is not positive (dx = 0 then).  cost[3w + 2] = -gx.dx - 1/2 dx.Sx.dx (undamped model).
-__global__ void __launch_bounds__(128) solve_kernel(int Dx, double lambda, const double* __restrict__ Sx, const double* __restrict__ gx,
+__global__ void __launch_bounds__(256) solve_kernel(int Dx, double lambda, const double* __restrict__ Sx, const double* __restrict__ gx,
                                                     double* __restrict__ dx, int32_t* __restrict__ solved, double* __restrict__ cost) {
   extern __shared__ __align__(16) double sm[];
   __shared__ int s_ok;
-  __shared__ double s_red[4];
+  __shared__ double s_red[8];
   const int w = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
   double* __restrict__ L = sm;                              // packed: L[i][j] at i(i+1)/2 + j, j <= i
   double* __restrict__ y = sm + (size_t)Dx * (Dx + 1) / 2;   // right-hand side / solution
@@ -73,10 +73,18 @@ __global__ void __launch_bounds__(128) solve_kernel(int Dx, double lambda, const
     __syncthreads();
     for (int i = j + tid; i < Dx; i += NT) L[i * (i + 1) / 2 + j] = (i == j) ? sd : L[i * (i + 1) / 2 + j] * inv;
     __syncthreads();
-    for (int i = j + 1 + tid; i < Dx; i += NT) {
-      const double lij = L[i * (i + 1) / 2 + j];
-      double* __restrict__ row = L + i * (i + 1) / 2;
-      for (int k = j + 1; k <= i; ++k) row[k] -= lij * L[k * (k + 1) / 2 + j];
+    // trailing update L[i][k] -= L[i][j] L[k][j], j < k <= i, as 16 x 16 thread tiles over the (i, k) triangle: every thread
+    // gets the same number of entries whatever its row
+    {
+      const int ti = tid >> 4, tk = tid & 15, n = Dx - j - 1;
+      for (int i0 = 0; i0 < n; i0 += 16) {
+        const int i = j + 1 + i0 + ti;
+        const double lij = i < Dx ? L[i * (i + 1) / 2 + j] : 0.0;
+        for (int k0 = 0; k0 <= i0; k0 += 16) {
+          const int k = j + 1 + k0 + tk;
+          if (i < Dx && k <= i) L[i * (i + 1) / 2 + k] -= lij * L[k * (k + 1) / 2 + j];
+        }
+      }
     }
     __syncthreads();
   }

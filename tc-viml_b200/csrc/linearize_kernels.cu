@@ -566,7 +566,7 @@ int viml_launch_gn_solve(viml_ctx* ctx, int W, int Dx, double lambda, const doub
   const size_t smem = ((size_t)Dx * (Dx + 1) / 2 + Dx) * sizeof(double);
   VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(gn::solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LaunchScope ls(ctx, K_GN);
-  gn::solve_kernel<<<W, 128, smem, ctx->stream>>>(Dx, lambda, Sx, gx, dx, solved, cost);
+  gn::solve_kernel<<<W, 256, smem, ctx->stream>>>(Dx, lambda, Sx, gx, dx, solved, cost);
   VIML_TRY_CUDA(ctx, cudaGetLastError());
   return VIML_OK;
 }

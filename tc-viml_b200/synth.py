@@ -339,3 +339,33 @@ def make_assoc_queries(lines, n_poses, L=300, n_true=100, seed=0x5EED + 33, alti
     lines2d = lines2d.astype(np.float32).astype(np.float64)
     return (np.ascontiguousarray(cull), np.ascontiguousarray(match), np.ascontiguousarray(ex),
             np.ascontiguousarray(lines2d))
+
+
+# ---- dense-block factors of a window (prior + IMU), SURVEY 8f rank 2 ---------------------------------------------
+def make_dense_factors(batch, seed=5):
+    """Per window the dense-block factors the reference's problem carries beside the visual ones (estimator.cpp:1717-1733): the
+    prior of the last marginalisation — n rows over the kept blocks [pose 1 .. P-1, extrinsic, speed-bias 1], n = their tangent size
+    + 1 <= 76 (marginalization_factor.cpp:335-384) — and one IMU block per consecutive pose pair (15 rows over pose i, speed-bias i,
+    pose j, speed-bias j: 15 x 30, imu_factor.h:19-181).  Values are synthetic (a strong diagonal keeps the reduced system well
+    conditioned: the visual factors alone leave the gauge free).  Extra columns: 9 per pose (speed-bias).  Returns a _abi.Dense."""
+    from ._abi import Dense
+    rng = np.random.default_rng(seed)
+    W, P, D = batch.W, batch.P, batch.D
+    X = 9 * P
+    fs = []
+    for w in range(W):
+        cols = np.concatenate([np.arange(6, D), D + 9 + np.arange(9)]) if P > 1 else np.arange(D)
+        n = len(cols) + 1
+        J = 20.0 * rng.standard_normal((n, len(cols)))
+        J[:len(cols)] += np.diag(250.0 + 50.0 * rng.uniform(size=len(cols)))
+        fs.append((w, 0.05 * rng.standard_normal(n), J, cols))
+        for i in range(P - 1):
+            ci = np.concatenate([6 * i + np.arange(6), D + 9 * i + np.arange(9), 6 * (i + 1) + np.arange(6), D + 9 * (i + 1) + np.arange(9)])
+            J = 10.0 * rng.standard_normal((15, 30))
+            J[:, :15] += np.diag(120.0 + 30.0 * rng.uniform(size=15))
+            J[:, 15:] -= np.diag(120.0 + 30.0 * rng.uniform(size=15))
+            fs.append((w, 0.1 * rng.standard_normal(15), J, ci))
+        # the first pose and speed-bias are tied down by the gauge prior a real window carries through its history
+        c0 = np.concatenate([np.arange(6), D + np.arange(9)])
+        fs.append((w, 0.01 * rng.standard_normal(15), np.diag(200.0 + 50.0 * rng.uniform(size=15)), c0))
+    return Dense(W, X, fs)

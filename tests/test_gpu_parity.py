@@ -288,25 +288,7 @@ def test_huge_window_partition_sums_to_full(pkg, orc, ctx, cfg):
 
 # ---- whole-window reduced system and the Gauss-Newton step -----------------------------------
 def make_dense(pkg, batch, seed=5):
-    """Per window: one prior-like block over every pose, the extrinsic and the first speed-bias (n = 40 rows) and one IMU-like
-    15-row block per consecutive pose pair (pose i, speed-bias i, pose j, speed-bias j: 15 x 30), as the reference's problem has
-    them (estimator.cpp:1717-1733).  Extra columns: 9 per pose (speed-bias)."""
-    rng = np.random.default_rng(seed)
-    W, P, D = batch.W, batch.P, batch.D
-    X = 9 * P
-    fs = []
-    for w in range(W):
-        cols = np.concatenate([np.arange(D), D + np.arange(9)])
-        J = 30.0 * rng.standard_normal((40, len(cols))) + 0.0
-        J[:len(cols), :] += 200.0 * np.eye(40, len(cols))[:len(cols)] if len(cols) <= 40 else 0.0
-        fs.append((w, 0.05 * rng.standard_normal(40), J, cols))
-        # a strong diagonal prior on every column keeps the reduced system well conditioned (gauge fixed)
-        allc = np.arange(D + X)
-        fs.append((w, 0.01 * rng.standard_normal(len(allc)), np.diag(150.0 + 50.0 * rng.uniform(size=len(allc))), allc))
-        for i in range(P - 1):
-            ci = np.concatenate([6 * i + np.arange(6), D + 9 * i + np.arange(9), 6 * (i + 1) + np.arange(6), D + 9 * (i + 1) + np.arange(9)])
-            fs.append((w, 0.1 * rng.standard_normal(15), 20.0 * rng.standard_normal((15, 30)), ci))
-    return pkg._abi.Dense(W, X, fs)
+    return pkg.synth.make_dense_factors(batch, seed)
 
 
 def block_err(got, ref, bounds):
