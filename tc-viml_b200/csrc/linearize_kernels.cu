@@ -376,7 +376,9 @@ template <bool MODE_A, bool MODE_B>
 #ifndef VIML_POINTS_MINB
 #define VIML_POINTS_MINB 4
 #endif
-__global__ void __launch_bounds__(128, VIML_POINTS_MINB) points_kernel(LinearizeArgs A) {
+// mode A alone streams (4 CTAs per SM hide the store latency); with the atomic H/b accumulation of the generic path the Jacobians
+// stay live across ~190 atomics and 128 registers spill (70 LDL/STL in round 1): two CTAs per SM, up to 255 registers (at 168 it still spills 100 bytes)
+__global__ void __launch_bounds__(128, MODE_B ? 2 : VIML_POINTS_MINB) points_kernel(LinearizeArgs A) {
   __shared__ double2 stage[MODE_A ? 4 * 7 * 32 : 1];
   const int64_t k_raw = A.pf_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t k_end = A.pf_begin + A.NP;
