@@ -356,11 +356,25 @@ def main():
     e_steps = max(3, min(K, 10))
     pS = {k: pkg.PinnedArray(shapes[k], np.float64) for k in ("S_packed", "g")}
     hoS = {k: p.array for k, p in pS.items()}
-    e_ms = timed_host(lambda: ctx.linearize(hb, abi.OUT_SCHUR | abi.S_PACKED | abi.LOSS_CAUCHY, out=hoS), e_steps)
-    e2e = {"value": total_factors / (e_ms * 1e-3), "unit": "factors/s", "h2d_bytes_per_step": int(h2d),
+    fS = abi.OUT_SCHUR | abi.S_PACKED | abi.LOSS_CAUCHY
+    # observations as the per-feature table (viml.h: feat_obs + pf_obs_j; the anchor observation is not repeated per factor)
+    tab = dict(zip(("feat_obs", "pf_obs_j"), (pkg.pinned_like(a) for a in batch.obs_table())))
+    arr_tab = {k: p.array for k, p in pins.items() if k != "pf_obs"}
+    arr_tab.update({k: p.array for k, p in tab.items()})
+    s_tab, o_S = hb.struct(arr_tab), abi.out_struct(hoS)
+    h2d_tab = sum(p.nbytes for k, p in pins.items() if k != "pf_obs") + sum(p.nbytes for p in tab.values())
+    e_ms = timed_host(lambda: ctx.linearize_raw(s_tab, o_S, fS), e_steps)
+    e2e = {"value": total_factors / (e_ms * 1e-3), "unit": "factors/s", "h2d_bytes_per_step": int(h2d_tab),
            "d2h_bytes_per_step": int(sum(p.nbytes for p in pS.values())), "ms_per_step": e_ms, "steps": e_steps,
-           "api": "viml_linearize_batch(host pointers, VIML_OUT_SCHUR|VIML_S_PACKED|VIML_LOSS_CAUCHY): evaluate + assemble + landmark "
-                  "Schur; the upper triangle of S and g back"}
+           "api": "viml_linearize_batch(host pointers, VIML_OUT_SCHUR|VIML_S_PACKED|VIML_LOSS_CAUCHY), observations as the per-feature "
+                  "table: evaluate + assemble + landmark Schur; the upper triangle of S and g back"}
+    S_tab = hoS["S_packed"].copy()
+    e_ms_pairs = timed_host(lambda: ctx.linearize(hb, fS, out=hoS), e_steps)
+    # same kernels on the same expanded observations: equal up to the summation order of the shared accumulator
+    assert np.abs(S_tab - hoS["S_packed"]).max() <= 1e-12 * np.abs(S_tab).max(), "observation-table and per-factor forms differ"
+    e2e["per_factor_obs_form"] = {"ms_per_step": e_ms_pairs, "value": total_factors / (e_ms_pairs * 1e-3), "h2d_bytes_per_step": int(h2d)}
+    for p in tab.values():
+        p.free()
     S_host = {"S": abi.unpack_upper(hoS["S_packed"], batch.D), "g": hoS["g"].copy()}
     pH = {k: pkg.PinnedArray(shapes[k], np.float64) for k in d_out}
     hoH = {k: p.array for k, p in pH.items()}
@@ -401,7 +415,7 @@ def main():
         assert max(errs.values()) < 1e-9, errs
         out["parity"] = {"parity_checked_windows": nwin, "tolerance": 1e-9,
                          "norm": "per unit: 6x6 block (H_pp, S), 6-vector (b_p, g), landmark row (H_lp), window (H_ll, b_l)",
-                         "max_unit_err": errs, "oracle": "oracle/viml_oracle.cpp (parity unpinned: see DESIGN.md)"}
+                         "max_unit_err": errs, "oracle": "oracle/viml_oracle.cpp (factor evaluation bit for bit equal to the reference's own sources, tests/test_ref_cpu.py)"}
     elif rank == 0:
         out["cpu_baseline"] = None
     del H_dev, S_host

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define VIML_ABI_VERSION 2
+#define VIML_ABI_VERSION 3
 
 /* ---- error codes ---------------------------------------------------------------------------- */
 #define VIML_OK 0
@@ -132,6 +132,12 @@ int viml_load_line_map(viml_ctx* ctx, const char* path, int64_t* n_lines);
  * pf_obs[k] = {pts_i.x, pts_i.y, pts_j.x, pts_j.y}; pts_i.z = pf_pts_i_z[k] or 1.0 when that is NULL
  * (the tracker always publishes z = 1, feature_tracker_node.cpp:121-189; pts_j.z is never read).
  *
+ * Observation table (optional, instead of pf_obs): the reference builds every factor of a feature from the feature's FIRST
+ * observation and the observing frame's own one (pts_i = it_per_id.feature_per_frame[0].point, pts_j = it_per_frame.point;
+ * estimator.cpp:1747-1766, :1961-1982), so pts_i repeats over the factors of a feature.  With pf_obs == NULL the batch carries
+ * feat_obs[w][feat] = {pts_i.x, pts_i.y} once per feature and pf_obs_j[k] = {pts_j.x, pts_j.y} per factor (16 + 16/n_obs bytes per
+ * factor instead of 32); the library expands them on the device, results are identical to the pf_obs form.
+ *
  * Line factor k (LineProjectionFactor, line_projection_factor.h:13-34) couples pose lf_frame[k] only.
  * lf_geom is SoA, nine planes of n_line_factors doubles: P_start.xyz, P_end.xyz (already in VIO world,
  * estimator.cpp:1832-1833), then the detected line's A, B, C (raw-pixel, un-normalised, fm.cpp:11-13).
@@ -154,6 +160,8 @@ typedef struct viml_window_batch {
   const int32_t* lf_window_offset; /* [W+1]                                                     */
   const int32_t* lf_frame;   /* [NL]                                                            */
   const double* lf_geom;     /* [9][NL]                                                         */
+  const double* feat_obs;    /* [W][F][2] or NULL; read only when pf_obs == NULL                */
+  const double* pf_obs_j;    /* [NP][2]   or NULL; read only when pf_obs == NULL                */
 } viml_window_batch;
 
 /* Any pointer may be NULL (= not wanted).  D = 6*(P+1): pose blocks 0..P-1 then the extrinsic.

@@ -202,12 +202,22 @@ class Context:
         self.n_map = int(n.value)
         return self.n_map
 
-    def reduced_system(self, batch, dense, flags):
+    @staticmethod
+    def _batch_struct(batch, obs_table):
+        """viml_window_batch of host arrays; obs_table=True: observations as feat_obs + pf_obs_j, pf_obs NULL."""
+        if not obs_table:
+            return batch.struct(), None
+        arrs = batch.arrays()
+        arrs["pf_obs"] = None
+        arrs["feat_obs"], arrs["pf_obs_j"] = batch.obs_table()
+        return batch.struct(arrs), arrs
+
+    def reduced_system(self, batch, dense, flags, obs_table=False):
         """viml_reduced_system with host buffers: (Sx [W,Dx,Dx], gx [W,Dx])."""
         X = dense.X if dense is not None else 0
         Dx = batch.D + X
         Sx, gx = np.full((batch.W, Dx, Dx), np.nan), np.full((batch.W, Dx), np.nan)
-        s = batch.struct()
+        s, _keep = self._batch_struct(batch, obs_table)
         d = dense.struct() if dense is not None else None
         o = _abi.ReducedOut()
         o.Sx, o.gx = _abi.ptr(Sx), _abi.ptr(gx)
@@ -215,14 +225,14 @@ class Context:
                                                  flags & ~PTRS_DEVICE))
         return Sx, gx
 
-    def gn_step(self, batch, dense, extra, flags, lam=0.0):
+    def gn_step(self, batch, dense, extra, flags, lam=0.0, obs_table=False):
         """viml_gn_step with host buffers: dict(poses, ex_pose, inv_depth, extra, dx, cost, solved)."""
         X = dense.X if dense is not None else 0
         W, Dx = batch.W, batch.D + X
         res = {"poses": np.full_like(batch.poses, np.nan), "ex_pose": np.full_like(batch.ex_pose, np.nan),
                "inv_depth": np.full_like(batch.inv_depth, np.nan), "extra": np.full((W, X), np.nan),
                "dx": np.full((W, Dx), np.nan), "cost": np.full((W, 3), np.nan), "solved": np.full(W, -1, dtype=np.int32)}
-        s = batch.struct()
+        s, _keep = self._batch_struct(batch, obs_table)
         d = dense.struct() if dense is not None else None
         ex = None if extra is None else np.ascontiguousarray(extra, dtype=np.float64)
         opt = _abi.GnOptions()
@@ -235,10 +245,11 @@ class Context:
                                           C.byref(o), flags & ~PTRS_DEVICE))
         return res
 
-    def linearize(self, batch, flags, out=None):
-        """viml_linearize_batch with host buffers; returns dict of numpy outputs."""
+    def linearize(self, batch, flags, out=None, obs_table=False):
+        """viml_linearize_batch with host buffers; returns dict of numpy outputs.  obs_table=True passes the observations as
+        the per-feature table (feat_obs + pf_obs_j) instead of pf_obs."""
         bufs = batch.alloc_out(flags) if out is None else out
-        s = batch.struct()
+        s, _keep = self._batch_struct(batch, obs_table)
         o = _abi.out_struct(bufs)
         self._check(self.lib.viml_linearize_batch(self.h, C.byref(s), C.byref(o), flags & ~PTRS_DEVICE))
         return bufs

@@ -51,6 +51,7 @@ class WindowBatch(C.Structure):
         ("pf_pts_i_z", C.c_void_p),
         ("n_line_factors", C.c_int64),
         ("lf_window_offset", C.c_void_p), ("lf_frame", C.c_void_p), ("lf_geom", C.c_void_p),
+        ("feat_obs", C.c_void_p), ("pf_obs_j", C.c_void_p),
     ]
 
 
@@ -213,11 +214,25 @@ class Batch:
         s.n_windows, s.poses_per_window, s.feats_per_window = self.W, self.P, self.F
         s.poses, s.ex_pose, s.inv_depth = ptr(a["poses"]), ptr(a["ex_pose"]), ptr(a["inv_depth"])
         s.n_point_factors = self.NP
-        s.pf_window_offset, s.pf_idx, s.pf_obs = ptr(a["pf_window_offset"]), ptr(a["pf_idx"]), ptr(a["pf_obs"])
+        s.pf_window_offset, s.pf_idx, s.pf_obs = ptr(a["pf_window_offset"]), ptr(a["pf_idx"]), ptr(a.get("pf_obs"))
+        if a.get("pf_obs") is None:   # observation table instead of per-factor pairs (viml.h, viml_window_batch)
+            s.feat_obs, s.pf_obs_j = ptr(a["feat_obs"]), ptr(a["pf_obs_j"])
         s.pf_pts_i_z = ptr(a.get("pf_pts_i_z"))
         s.n_line_factors = self.NL
         s.lf_window_offset, s.lf_frame, s.lf_geom = ptr(a["lf_window_offset"]), ptr(a["lf_frame"]), ptr(a["lf_geom"])
         return s
+
+    def obs_table(self):
+        """The observation-table form of pf_obs: (feat_obs [W][F][2], pf_obs_j [NP][2]).  Raises when the factors of a feature
+        do not share pts_i (then only the per-factor form describes the batch)."""
+        W, F = self.W, self.F
+        win = np.repeat(np.arange(W, dtype=np.int64), np.diff(self.pf_window_offset))
+        key = win * F + (self.pf_idx >> 16).astype(np.int64)
+        feat_obs = np.zeros((W * F, 2))
+        feat_obs[key] = self.pf_obs[:, :2]          # one of the factors' pts_i per feature ...
+        if not np.array_equal(feat_obs[key], self.pf_obs[:, :2]):   # ... which every other factor must repeat
+            raise ValueError("pts_i differs between the factors of a feature")
+        return feat_obs.reshape(W, F, 2), np.ascontiguousarray(self.pf_obs[:, 2:])
 
     def out_shapes(self):
         W, F, D, NP, NL = self.W, self.F, self.D, self.NP, self.NL

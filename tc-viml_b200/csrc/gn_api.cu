@@ -65,7 +65,7 @@ int check_batch(viml_ctx* ctx, const viml_window_batch* in) {
   if (W < 0 || P < 1 || P > 255 || F < 0 || F > 65535 || in->n_point_factors < 0 || in->n_line_factors < 0)
     return fail(ctx, VIML_ERR_INVALID, "window batch sizes out of range");
   if (W > 0 && (!in->poses || !in->ex_pose || (F > 0 && !in->inv_depth) || !in->pf_window_offset ||
-                (in->n_point_factors > 0 && (!in->pf_idx || !in->pf_obs)) ||
+                (in->n_point_factors > 0 && (!in->pf_idx || (!in->pf_obs && !(in->feat_obs && in->pf_obs_j)))) ||
                 (in->n_line_factors > 0 && (!in->lf_window_offset || !in->lf_frame || !in->lf_geom))))
     return fail(ctx, VIML_ERR_INVALID, "null input array");
   return VIML_OK;
@@ -127,7 +127,15 @@ int run(viml_ctx* ctx, const viml_window_batch* in, const viml_dense_factors* de
   st.in(in->inv_depth, (size_t)W * F, &a.inv_depth);
   st.in(in->pf_window_offset, (size_t)W + 1, &a.pf_window_offset);
   st.in(in->pf_idx, (size_t)NP, &a.pf_idx);
-  st.in(in->pf_obs, (size_t)NP * 4, &a.pf_obs);
+  const bool obs_table = !in->pf_obs && NP > 0;   // observations as a per-feature table (viml.h): expanded on the device
+  const double *d_fobs = nullptr, *d_obsj = nullptr;
+  double* d_obs = nullptr;
+  if (obs_table) {
+    st.in(in->feat_obs, (size_t)W * F * 2, &d_fobs);
+    st.in(in->pf_obs_j, (size_t)NP * 2, &d_obsj);
+  } else {
+    st.in(in->pf_obs, (size_t)NP * 4, &a.pf_obs);
+  }
   st.in(in->pf_pts_i_z, in->pf_pts_i_z ? (size_t)NP : 0, &a.pf_pts_i_z);
   st.in(in->lf_window_offset, NL > 0 ? (size_t)W + 1 : 0, &a.lf_window_offset);
   st.in(in->lf_frame, (size_t)NL, &a.lf_frame);
@@ -150,6 +158,7 @@ int run(viml_ctx* ctx, const viml_window_batch* in, const viml_dense_factors* de
   double *o_poses = nullptr, *o_ex = nullptr, *o_dep = nullptr, *o_extra = nullptr;
   int32_t* solved = nullptr;
   st.out((double*)nullptr, (size_t)W * (P * kPoseCache + kExCache), &cache);
+  if (obs_table) st.out((double*)nullptr, (size_t)NP * 4, &d_obs);
   st.out((double*)nullptr, (size_t)W * D * D, &a.out.H_pp);
   st.out((double*)nullptr, (size_t)W * F * D, &a.out.H_lp);
   st.out((double*)nullptr, (size_t)W * F, &a.out.H_ll);
@@ -171,6 +180,11 @@ int run(viml_ctx* ctx, const viml_window_batch* in, const viml_dense_factors* de
   rc = st.commit();
   if (rc != VIML_OK) return rc;
   a.cache = cache;
+  if (obs_table) {
+    a.pf_obs = d_obs;
+    rc = viml_launch_expand_obs(ctx, a, d_fobs, d_obsj);
+    if (rc != VIML_OK) return rc;
+  }
   rc = viml_launch_linearize(ctx, a);
   if (rc != VIML_OK) return rc;
   rc = viml_launch_reduced(ctx, W, D, dn, a.out.S, a.out.g, Sx, gx);

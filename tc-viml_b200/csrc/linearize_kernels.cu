@@ -37,6 +37,22 @@ __device__ __forceinline__ void mul_AtBt(const double* A, const double* B, doubl
     for (int c = 0; c < 3; ++c) C[3 * r + c] = A[r] * B[3 * c] + A[3 + r] * B[3 * c + 1] + A[6 + r] * B[3 * c + 2];
 }
 
+// Observation table -> per-factor pairs (viml.h, viml_window_batch): one CTA per window; pts_i of a factor is its feature's
+// entry of feat_obs (every factor of a feature is built from feature_per_frame[0].point, estimator.cpp:1747-1766), pts_j its own.
+__global__ void expand_obs_kernel(LinearizeArgs a, const double* __restrict__ feat_obs, const double* __restrict__ pf_obs_j) {
+  const int w = blockIdx.x;
+  const int k0 = a.pf_window_offset[w], k1 = a.pf_window_offset[w + 1];
+  const double2* fo = reinterpret_cast<const double2*>(feat_obs) + (size_t)w * a.F;
+  const double2* oj = reinterpret_cast<const double2*>(pf_obs_j);
+  double4* dst = reinterpret_cast<double4*>(const_cast<double*>(a.pf_obs));
+  for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+    const uint32_t feat = a.pf_idx[k] >> 16;
+    const double2 pi = feat < (uint32_t)a.F ? fo[feat] : make_double2(0.0, 0.0);   // a bad index is dropped later, by the kernels
+    const double2 pj = oj[k];
+    dst[k] = make_double4(pi.x, pi.y, pj.x, pj.y);
+  }
+}
+
 // One thread per pose (and one per window for the extrinsic): fills the cache described in common.cuh.
 __global__ void prep_windows_kernel(LinearizeArgs a) {
   const int stride = a.P * kPoseCache + kExCache;
@@ -544,6 +560,14 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
       pack_upper_kernel<<<a.W, 256, 0, st>>>(a.D, S, a.out.S);
     }
   }
+  VIML_TRY_CUDA(ctx, cudaGetLastError());
+  return VIML_OK;
+}
+
+int viml_launch_expand_obs(viml_ctx* ctx, const LinearizeArgs& a, const double* feat_obs, const double* pf_obs_j) {
+  if (a.NP == 0) return VIML_OK;
+  LaunchScope ls(ctx, K_PREP);
+  expand_obs_kernel<<<a.W, 128, 0, ctx->stream>>>(a, feat_obs, pf_obs_j);
   VIML_TRY_CUDA(ctx, cudaGetLastError());
   return VIML_OK;
 }

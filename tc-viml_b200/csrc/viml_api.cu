@@ -303,8 +303,9 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   if (!(flags & (VIML_OUT_RESIDUAL_JACOBIAN | VIML_OUT_HB | VIML_OUT_SCHUR)))
     return fail(ctx, VIML_ERR_INVALID, "no output mode requested");
   if (W == 0) return VIML_OK;
+  const bool obs_table = !in->pf_obs && in->feat_obs && in->pf_obs_j;   // observations as a per-feature table
   if (!in->poses || !in->ex_pose || (F > 0 && !in->inv_depth) || !in->pf_window_offset ||
-      (NP > 0 && (!in->pf_idx || !in->pf_obs)) || (NL > 0 && (!in->lf_window_offset || !in->lf_frame || !in->lf_geom)))
+      (NP > 0 && (!in->pf_idx || (!in->pf_obs && !obs_table))) || (NL > 0 && (!in->lf_window_offset || !in->lf_frame || !in->lf_geom)))
     return fail(ctx, VIML_ERR_INVALID, "null input array");
   const int D = 6 * (P + 1);
   timespec ts_begin;
@@ -344,6 +345,12 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
     a.pf_pts_i_z = in->pf_pts_i_z;
     a.lf_window_offset = in->lf_window_offset, a.lf_frame = in->lf_frame, a.lf_geom = in->lf_geom;
     a.out = *out;
+    if (obs_table && NP > 0) {
+      VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(DeviceArena::padded((size_t)NP * 32)));
+      a.pf_obs = ctx->in_arena.take<double>((size_t)NP * 4);
+      const int rc = viml_launch_expand_obs(ctx, a, in->feat_obs, in->pf_obs_j);
+      if (rc != VIML_OK) return rc;
+    }
     if (!wantA) a.out.pf_residual = a.out.pf_jac_pose_i = a.out.pf_jac_pose_j = a.out.pf_jac_ex = a.out.pf_jac_feat =
                     a.out.lf_residual = a.out.lf_jac_pose = nullptr;
     if (wantS && !wantHB) {
@@ -389,6 +396,7 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   size_t in_bytes = pad(n_pose * 8) + pad(n_ex * 8) + pad(n_dep * 8) + 2 * pad((size_t)(W + 1) * 4);
   in_bytes += pad((size_t)NP * 4) + pad((size_t)NP * 32) + pad((size_t)NP * 8);
   in_bytes += pad((size_t)NL * 4) + pad((size_t)NL * 72);
+  if (obs_table) in_bytes += pad((size_t)NP * 16) + pad(n_dep * 16);
   VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(in_bytes));
   double* d_poses = ctx->in_arena.take<double>(n_pose);
   double* d_ex = ctx->in_arena.take<double>(n_ex);
@@ -400,6 +408,8 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   int32_t* d_loff = NL > 0 ? ctx->in_arena.take<int32_t>((size_t)W + 1) : nullptr;
   int32_t* d_frame = NL > 0 ? ctx->in_arena.take<int32_t>((size_t)NL) : nullptr;
   double* d_geom = NL > 0 ? ctx->in_arena.take<double>((size_t)NL * 9) : nullptr;
+  double* d_obsj = obs_table ? ctx->in_arena.take<double>((size_t)NP * 2) : nullptr;
+  double* d_fobs = obs_table ? ctx->in_arena.take<double>(n_dep * 2) : nullptr;
   a.poses = d_poses, a.ex_pose = d_ex, a.inv_depth = d_dep, a.pf_window_offset = d_poff, a.pf_idx = d_idx;
   a.pf_obs = d_obs, a.pf_pts_i_z = d_z, a.lf_window_offset = d_loff, a.lf_frame = d_frame, a.lf_geom = d_geom;
 
@@ -471,7 +481,12 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
     // planes); the small per-window arrays went up for the whole batch before the loop — every copy costs ~10-20 us of
     // DMA set-up however small it is, and 17 copies per chunk kept the upload stream busy for 6 ms on 125 MB
     h2d(d_idx + pa, in->pf_idx + pa, (size_t)(pb - pa) * 4);
-    h2d(d_obs + 4 * pa, in->pf_obs + 4 * pa, (size_t)(pb - pa) * 32);
+    if (obs_table) {
+      h2d(d_obsj + 2 * pa, in->pf_obs_j + 2 * pa, (size_t)(pb - pa) * 16);
+      h2d(d_fobs + (size_t)w0 * F * 2, in->feat_obs + (size_t)w0 * F * 2, (size_t)(w1 - w0) * F * 16);
+    } else {
+      h2d(d_obs + 4 * pa, in->pf_obs + 4 * pa, (size_t)(pb - pa) * 32);
+    }
     if (d_z) h2d(d_z + pa, in->pf_pts_i_z + pa, (size_t)(pb - pa) * 8);
     if (lb > la)
       cudaMemcpy2DAsync(d_geom + la, (size_t)NL * 8, in->lf_geom + la, (size_t)NL * 8, (size_t)(lb - la) * 8, 9,
@@ -498,7 +513,8 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
       double** vd = (double**)((char*)&v.out + ((char*)sl.dev - (char*)&a.out));
       *vd = *sl.dev + sl.per_window * w0;   // per-factor arrays stay absolute (indexed by the global factor id)
     }
-    rc = viml_launch_linearize(ctx, v);
+    if (obs_table) rc = viml_launch_expand_obs(ctx, v, d_fobs + (size_t)w0 * F * 2, d_obsj);
+    if (rc == VIML_OK) rc = viml_launch_linearize(ctx, v);
     cudaEventRecord(ev_k[c], st);
     cudaStreamWaitEvent(s_out, ev_k[c], 0);
     for (auto& sl : slots)

@@ -220,6 +220,59 @@ def test_bad_arguments(pkg, ctx, cfg):
     assert lib.viml_linearize_batch(ctx.h, C.byref(s), C.byref(o), abi.OUT_RESIDUAL_JACOBIAN) == abi.VIML_ERR_INVALID
 
 
+def test_observation_table_input(pkg, orc, ctx, cfg):
+    """viml_window_batch.feat_obs / pf_obs_j (pf_obs == NULL): pts_i once per feature, as FeaturePerId stores it
+    (feature_manager.h:65-96; estimator.cpp:1747-1766 builds every factor of a feature from feature_per_frame[0].point).  Same
+    results, bit for bit where the per-factor form is deterministic, through every entry point that takes a window batch."""
+    abi, synth = pkg._abi, pkg.synth
+    b = synth.make_windows(600, seed=171)       # 600 windows: the host pipeline runs in chunks
+    feat_obs, obs_j = b.obs_table()
+    assert feat_obs.shape == (b.W, b.F, 2) and obs_j.shape == (b.NP, 2)
+    flags = abi.OUT_RESIDUAL_JACOBIAN | abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
+    pairs = ctx.linearize(b, flags)
+    table = ctx.linearize(b, flags, obs_table=True)
+    for k, v in pairs.items():
+        assert not np.isnan(table[k]).any(), k
+        if k.startswith(("pf_", "lf_")) or k in ("H_lp", "H_ll", "b_l"):
+            assert np.array_equal(table[k], v), k
+        else:
+            assert pkg.parity.unit_err(k, table[k], v) < 1e-12, k
+    ref = orc.linearize_batch(cfg, b.slice_windows(0, 32), flags, nthreads=8)
+    for k, v in ref.items():
+        n = v.shape[0]
+        assert pkg.parity.unit_err(k, table[k][:n], v) < TOL, k
+    # device pointers
+    small = b.slice_windows(0, 16)
+    fo, oj = small.obs_table()
+    arrs = {k: v for k, v in small.arrays().items() if v is not None and k != "pf_obs"}
+    arrs.update(feat_obs=fo, pf_obs_j=oj)
+    d_in = {k: ctx.to_device(v) for k, v in arrs.items()}
+    want = ctx.linearize(small, abi.OUT_HB | abi.LOSS_CAUCHY)
+    d_out = {k: ctx.device_alloc(v.nbytes) for k, v in want.items()}
+    ctx.linearize_raw(small.struct(d_in), abi.out_struct(d_out), abi.OUT_HB | abi.LOSS_CAUCHY | abi.PTRS_DEVICE)
+    for k, v in want.items():
+        back = np.empty_like(v)
+        ctx.d2h(back, d_out[k])
+        ctx.sync()
+        assert pkg.parity.unit_err(k, back, v) < 1e-12, k
+    for p in list(d_in.values()) + list(d_out.values()):
+        ctx.device_free(p)
+    # the solver entry points take the same batch struct
+    dense = synth.make_dense_factors(small, seed=5)
+    Sx0, gx0 = ctx.reduced_system(small, dense, abi.LOSS_CAUCHY)
+    Sx1, gx1 = ctx.reduced_system(small, dense, abi.LOSS_CAUCHY, obs_table=True)
+    assert np.abs(Sx1 - Sx0).max() <= 1e-12 * np.abs(Sx0).max() and np.abs(gx1 - gx0).max() <= 1e-12 * np.abs(gx0).max()
+    extra = np.zeros((small.W, dense.X))
+    g0 = ctx.gn_step(small, dense, extra, abi.LOSS_CAUCHY, lam=1e-4)
+    g1 = ctx.gn_step(small, dense, extra, abi.LOSS_CAUCHY, lam=1e-4, obs_table=True)
+    assert np.abs(g1["dx"] - g0["dx"]).max() <= 1e-9 * np.abs(g0["dx"]).max()
+    # a batch whose factors do not share pts_i per feature has no table form
+    bad = abi.Batch(b.poses, b.ex_pose, b.inv_depth, b.pf_window_offset, b.pf_idx, b.pf_obs + np.arange(b.NP)[:, None] * 1e-6,
+                    b.lf_window_offset, b.lf_frame, b.lf_geom)
+    with pytest.raises(ValueError):
+        bad.obs_table()
+
+
 def test_device_pointer_mode_matches_host_mode(pkg, ctx, cfg):
     """VIML_PTRS_DEVICE: inputs resident in HBM, asynchronous on the context stream."""
     abi = pkg._abi
