@@ -224,6 +224,7 @@ def main():
     ap.add_argument("--skip-assoc", action="store_true")
     ap.add_argument("--skip-extras", action="store_true", help="only the headline linearise metric")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--only-assoc", action="store_true", help="profiling aid: of the extra objects only `assoc` (implies a small headline)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -420,7 +421,7 @@ def main():
         out["cpu_baseline"] = None
     del H_dev, S_host
 
-    if not args.skip_extras:
+    if not args.skip_extras and not args.only_assoc:
         # ---------------- mode A (per-factor r/J for the Ceres shim)
         flagsA = abi.OUT_RESIDUAL_JACOBIAN | abi.LOSS_CAUCHY
         namesA = ("pf_residual", "pf_jac_pose_i", "pf_jac_pose_j", "pf_jac_ex", "pf_jac_feat", "lf_residual", "lf_jac_pose")
@@ -446,7 +447,7 @@ def main():
                         "gflops": fl / (ps[0] / ps[1] * 1e-3) / 1e9, "shape": f"{batch.W} windows x (D={D}, {F} landmarks)",
                         "step_ms_with_linearize": msS / K, "kernel_ms_per_step": {k: v[0] / K for k, v in profS.items()}}
         free_all(dS)
-    if not args.skip_extras:
+    if not args.skip_extras and not args.only_assoc:
         # ---------------- one device-resident Gauss-Newton / LM iteration on every window (visual factors +
         # prior / IMU dense blocks): reduced system, Cholesky, landmark back-substitution, state update, cost at both states
         gW = min(batch.W, 1024)
@@ -503,7 +504,7 @@ def main():
         ctx.device_free(g_ex)
     free_all(d_in, d_out)
 
-    if not args.skip_extras:
+    if not args.skip_extras and not args.only_assoc:
         # ---------------- cfg 4: marginalisation / Schur stress, 4096 windows x (10 keyframes + 1, 2000 landmarks all starting in
         # frame 0): 256 distinct windows generated, tiled x16 (independent windows; per-window work is what cfg 4 fixes)
         b4s = synth.make_windows(256, seed=0x5EED + 4 + rank, P=11, F=2000, all_start_zero=True, lines_per_frame=0)
@@ -582,7 +583,7 @@ def main():
         out["fp64_peaks"] = dict(zip(("dfma_tflops", "dmul_dadd_tops", "dmma_tflops"), ctx.microbench_fp64()))
 
     # ------------------------------------------------------------------ association (second metric)
-    if not args.skip_assoc and not args.skip_extras:
+    if not args.skip_assoc and (args.only_assoc or not args.skip_extras):
         ext = (2000.0, 2000.0, 30.0)
         lines = synth.make_line_map(args.map_lines, seed=0x5EED + 3, extent=ext)
         Pq, L = args.assoc_poses, 300
@@ -682,7 +683,7 @@ def main():
         free_all(dq, do)
 
     # ------------------------------------------------------------------ one huge window (cfg 5b): partial [S|g] + all-reduce
-    if not args.skip_extras:
+    if not args.skip_extras and not args.only_assoc:
         shard = pkg.shard
         huge = synth.make_windows(1, seed=0x5EED + 5, P=201, F=3000, lines_per_frame=2, max_len=25)
         part = shard.split_huge_window(huge, rank, world)
@@ -723,7 +724,7 @@ def main():
         free_all(dh_in)
 
     # ------------------------------------------------------------------ cfg 1 through the drop-in path (Ceres bridge), rank 0
-    if rank == 0 and not args.skip_extras:
+    if rank == 0 and not args.skip_extras and not args.only_assoc:
         exe = os.path.join(ROOT, "tc-viml_b200", "build", "selftest")
         try:
             r = subprocess.run([exe, "--bench-cfg1", "200"], capture_output=True, text=True, timeout=300,
