@@ -117,3 +117,27 @@ def triangulate(poses, ex, start, off, pts):
     lib().ref_triangulate(poses.shape[0], _dp(poses), _dp(ex), len(start), start.ctypes.data_as(C.POINTER(C.c_int)),
                           off.ctypes.data_as(C.POINTER(C.c_longlong)), _dp(pts), _dp(depth))
     return depth
+
+
+def line_associate(cfg, lines, cull_poses, match_poses, ex_pose, lines2d, n_lines2d=None, fov_capacity=0, nthreads=1, cull_ex_pose=None):
+    """The association sweep through the REFERENCE's own UpdateLinesInFoV / LineCorrespondenceInFrame / CalAngleDist / CalEulerDist
+    (oracle/ref_estimator.cpp): same arguments and result keys as oracle.line_associate (no mask)."""
+    lines = np.ascontiguousarray(lines, dtype=np.float64)
+    Pq, L = lines2d.shape[0], lines2d.shape[1]
+    keep = [np.ascontiguousarray(x, dtype=np.float64) if x is not None else None
+            for x in (cull_poses, match_poses, ex_pose, cull_ex_pose, lines2d)]
+    nl = None if n_lines2d is None else np.ascontiguousarray(n_lines2d, dtype=np.int32)
+    res = {"match_index": np.full((Pq, L), -2, dtype=np.int32), "err": np.full((Pq, L, 3), np.nan, dtype=np.float32),
+           "projected": np.full((Pq, L, 4), np.nan), "fov_count": np.zeros(Pq, dtype=np.int32)}
+    if fov_capacity:
+        res["fov_index"] = np.full((Pq, fov_capacity), -1, dtype=np.int32)
+
+    def p(a, t=C.c_double):
+        return None if a is None else a.ctypes.data_as(C.POINTER(t))
+    f = lib().ref_line_associate
+    f.restype = C.c_int
+    rc = f(C.byref(cfg), p(lines), C.c_int64(len(lines)), C.c_int(Pq), C.c_int(L), p(keep[0]), p(keep[1]), p(keep[2]), p(keep[3]),
+           p(keep[4]), p(nl, C.c_int32), p(res["fov_count"], C.c_int32), p(res.get("fov_index"), C.c_int32), C.c_int(fov_capacity),
+           p(res["match_index"], C.c_int32), p(res["err"], C.c_float), p(res["projected"]), C.c_int(nthreads))
+    assert rc == 0, "a FoV list or a chosen line could not be mapped back to map indices"
+    return res

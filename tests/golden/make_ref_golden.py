@@ -89,3 +89,82 @@ path = os.path.join(ROOT, "tests", "golden", "ref_factors.npz")
 np.savez_compressed(path, **out)
 print(f"{path}: {N} ProjectionFactor, {NL} LineProjectionFactor, 64 Plus, 4 marginalisations, 400 Line2D / Point2Flined, "
       f"{len(t_start)} triangulations from the reference's own code")
+
+# ---- association: the reference's own UpdateLinesInFoV / LineCorrespondenceInFrame / CalAngleDist / CalEulerDist (oracle/ref_estimator.cpp)
+# on queries built ON the thresholds (sub-segments of the projected map lines whose overlap sits within 1e-9 ... 1e-3 of
+# overlap_th, over-long queries, exactly / nearly vertical and (near) zero-length segments, parallel offsets, rotations by about
+# angle_th), duplicated map lines (distance ties), drifting match poses, a frame-entry extrinsic, ragged line counts.
+ext = (150.0, 150.0, 20.0)
+lines = synth.make_line_map(2500, seed=61, extent=ext)
+lines = np.concatenate([lines, lines[:100]])
+Pq, L = 6, 120
+cull, match, ex, l2d = synth.make_assoc_queries(lines, Pq, L=L, n_true=60, seed=62, extent=ext, pose_drift=True)
+arng = np.random.Generator(np.random.PCG64(63))
+aout = {"lines": lines}
+cases = ((0.1745, 0.45, False), (0.18, 0.8, True), (0.3, 0.0, False), (0.1, 1.0, True))
+for c, (ang, ov, extras) in enumerate(cases):
+    cfg = synth.euroc_config(angle_th=ang, overlap_th=ov)
+    base = ref.line_associate(cfg, lines, cull, match, ex, l2d, nthreads=8)
+    q = l2d.copy()
+    for p in range(Pq):
+        segs = base["projected"][p][base["match_index"][p] >= 0]
+        if len(segs) == 0:
+            continue
+        for i in range(L):
+            s = segs[i % len(segs)]
+            S, E = s[:2], s[2:]
+            d = E - S
+            Ls = np.hypot(*d)
+            if not np.isfinite(Ls) or Ls < 1e-6:
+                continue
+            u, n = d / Ls, np.array([-d[1], d[0]]) / Ls
+            eps = (0.0, 1e-9, -1e-9, 1e-6, -1e-6, 1e-4, -1e-4, 1e-3, -1e-3)[arng.integers(9)]
+            f = min(max(ov + eps, 1e-3), 1.0)
+            mode = i % 11
+            mid = 0.5 * (S + E)
+            if mode == 0:
+                a, bb = S, E
+            elif mode == 1:
+                a, bb = S, S + f * Ls * u
+            elif mode == 2:
+                a = S + (1 - f) * Ls * u
+                bb = a + (f * Ls + 40.0) * u * (0.5 if f * Ls + 40.0 > Ls else 1.0)
+            elif mode == 3:
+                e_ = Ls / f - Ls
+                a, bb = S - 0.3 * e_ * u, E + 0.7 * e_ * u
+            elif mode == 4:
+                a, bb = mid - [0, 0.4 * Ls], mid + [0, 0.4 * Ls]
+            elif mode == 5:
+                a, bb = mid - [5e-5, 0.4 * Ls], mid + [5e-5, 0.4 * Ls]
+            elif mode == 6:
+                a, bb = mid, mid + (1e-5 * u if i % 22 == 6 else 0.0)
+            elif mode == 7:
+                a, bb = S + 3 * n, E + 3 * n
+            elif mode == 8:
+                a, bb = E.astype(np.float32), S.astype(np.float32)
+            elif mode == 9:
+                cs, si = np.cos(ang * (1 + eps)), np.sin(ang * (1 + eps))
+                a, bb = S, S + np.array([cs * d[0] - si * d[1], si * d[0] + cs * d[1]])
+            else:
+                continue                                              # keep the synthetic query
+            q[p, i] = [a[0], a[1], bb[0], bb[1]]
+    kw = {}
+    if extras:
+        cex = ex.copy()
+        cex[:, :3] += 0.01 * arng.standard_normal((Pq, 3))
+        kw = dict(cull_ex_pose=cex, n_lines2d=arng.integers(L // 2, L + 1, Pq).astype(np.int32))
+        aout[f"c{c}_cull_ex"], aout[f"c{c}_n_lines2d"] = cex, kw["n_lines2d"]
+    cap = 1024
+    res = ref.line_associate(cfg, lines, cull, match, ex, q, fov_capacity=cap, nthreads=8, **kw)
+    assert res["fov_count"].max() <= cap
+    if "n_lines2d" in kw:                                             # rows beyond a pose's count are not outputs: fixed filler
+        inval = np.arange(L)[None, :] >= kw["n_lines2d"][:, None]
+        res["match_index"][inval], res["err"][inval], res["projected"][inval] = -2, 0, 0
+    aout.update({f"c{c}_angle_th": ang, f"c{c}_overlap_th": ov, f"c{c}_cull": cull, f"c{c}_match": match, f"c{c}_ex": ex,
+                 f"c{c}_lines2d": q, f"c{c}_fov_capacity": cap})
+    aout.update({f"c{c}_{k}": v for k, v in res.items()})
+    print(f"ref_assoc case {c}: angle_th {ang}, overlap_th {ov}: matched {(res['match_index'] >= 0).mean():.2f}, fov median {int(np.median(res['fov_count']))}")
+aout["n_cases"] = len(cases)
+apath = os.path.join(ROOT, "tests", "golden", "ref_assoc.npz")
+np.savez_compressed(apath, **aout)
+print("wrote", apath, os.path.getsize(apath), "bytes")

@@ -1,9 +1,11 @@
 """The oracle against the REFERENCE'S OWN CODE (CPU tests).
 
 oracle/_ref/libref.so is /root/reference/vins_estimator/src/factor/{projection_factor, line_projection_factor,
-pose_local_parameterization, marginalization_factor}.cpp compiled unmodified where they lie (oracle/Makefile `ref`), against the
-Eigen / Ceres / ROS interface stand-ins of oracle/ref_shim/.  tests/golden/ref_factors.npz holds vectors that library produced
-(tests/golden/make_ref_golden.py), so the pin also holds where the reference tree is absent (the GPU box)."""
+pose_local_parameterization, marginalization_factor}.cpp and feature_manager.cpp compiled unmodified where they lie (oracle/Makefile
+`ref`), plus the four association functions of estimator.cpp (UpdateLinesInFoV, CalAngleDist, CalEulerDist,
+LineCorrespondenceInFrame) cut out of that file at build time (oracle/ref_slice.py, oracle/ref_estimator.cpp), against the
+Eigen / Ceres / ROS interface stand-ins of oracle/ref_shim/.  tests/golden/ref_factors.npz and ref_assoc.npz hold vectors that
+library produced (tests/golden/make_ref_golden.py), so the pin also holds where the reference tree is absent."""
 import os
 
 import numpy as np
@@ -152,3 +154,77 @@ def test_live_reference_library(pkg, orc):
     assert mm == 6 + 25
     As, bs = _oracle_marginalize(pkg, orc, m.poses[0], m.ex_pose[0], m.inv_depth[0], idx, m.pf_obs, sq, 1.0)
     _check_marg(pkg, A, bb, As, bs)
+
+
+ASSOC_KEYS = ("match_index", "err", "projected", "fov_count", "fov_index")
+
+
+def _same(a, b, k):
+    if a.dtype.kind == "f":
+        assert np.array_equal(a, b, equal_nan=True), k
+    else:
+        assert np.array_equal(a, b), k
+
+
+def test_association_oracle_equals_reference_vectors(pkg, orc):
+    """tests/golden/ref_assoc.npz: outputs of the reference's own UpdateLinesInFoV + LineCorrespondenceInFrame (+ CalAngleDist,
+    CalEulerDist, Line2D, Point2Flined) on threshold-hugging queries; the oracle reproduces them bit for bit — FoV lists,
+    chosen map index, errA / errD / overlap as float32, projected segment."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_assoc.npz"))
+    for c in range(int(g["n_cases"])):
+        cfg = pkg.synth.euroc_config(angle_th=float(g[f"c{c}_angle_th"]), overlap_th=float(g[f"c{c}_overlap_th"]))
+        cex = g[f"c{c}_cull_ex"] if f"c{c}_cull_ex" in g.files else None
+        nl = g[f"c{c}_n_lines2d"] if f"c{c}_n_lines2d" in g.files else None
+        res = orc.line_associate(cfg, g["lines"], g[f"c{c}_cull"], g[f"c{c}_match"], g[f"c{c}_ex"], g[f"c{c}_lines2d"],
+                                 n_lines2d=nl, fov_capacity=int(g[f"c{c}_fov_capacity"]), nthreads=4, cull_ex_pose=cex)
+        L = g[f"c{c}_lines2d"].shape[1]
+        for k in ASSOC_KEYS:
+            a, b = res[k], g[f"c{c}_{k}"]
+            if nl is not None and k in ("match_index", "err", "projected"):   # rows beyond a pose's own count are not outputs
+                valid = np.arange(L)[None, :] < nl[:, None]
+                a, b = a[valid], b[valid]
+            _same(a, b, (c, k))
+        assert float(g[f"c{c}_overlap_th"]) >= 1.0 or (g[f"c{c}_match_index"] >= 0).mean() > 0.2
+
+
+@pytest.mark.parametrize("name", ["assoc_euroc_v1.npz", "assoc_euroc_v2.npz"])
+def test_association_golden_on_reference_maps_equals_reference_functions(pkg, name):
+    """The committed association fixtures on the reference's real EuRoC line maps were written by the oracle; the reference's own
+    functions give the same lists, indices, errors and projected segments, bit for bit."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libref.so not built (reference tree absent)")
+    g = np.load(os.path.join(ROOT, "tests", "golden", name))
+    c = g["cfg"]
+    cfg = pkg._abi.make_config(fx=c[0], fy=c[1], cx=c[2], cy=c[3], width=int(c[4]), height=int(c[5]), Rbw=g["Rbw"], Tbw=g["Tbw"],
+                               overlap_th=c[6], dist_th=c[7], angle_th=c[8])
+    res = ref.line_associate(cfg, g["lines"], g["cull"], g["match"], g["ex"], g["lines2d"], fov_capacity=g["fov_index"].shape[1], nthreads=8)
+    for k in ASSOC_KEYS:
+        _same(res[k], g[k], k)
+
+
+def test_live_reference_association(pkg, orc):
+    """Fresh random queries through both: drifting match poses, a frame-entry extrinsic that differs from the current one, ragged
+    line counts, duplicated map lines (distance ties are decided by list order)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libref.so not built (reference tree absent)")
+    synth = pkg.synth
+    ext = (150.0, 150.0, 20.0)
+    lines = synth.make_line_map(5000, seed=31, extent=ext)
+    lines = np.concatenate([lines, lines[:300]])
+    cull, match, ex, l2d = synth.make_assoc_queries(lines, 6, L=80, n_true=40, seed=32, extent=ext, pose_drift=True)
+    rng = np.random.default_rng(33)
+    cex = ex.copy()
+    cex[:, :3] += 0.01 * rng.standard_normal((len(ex), 3))
+    nl = rng.integers(0, 81, len(ex)).astype(np.int32)
+    for ang, ov in ((0.1745, 0.45), (0.3, 0.0), (3.2, 0.45)):
+        cfg = synth.euroc_config(angle_th=ang, overlap_th=ov)
+        a = orc.line_associate(cfg, lines, cull, match, ex, l2d, n_lines2d=nl, fov_capacity=4000, nthreads=8, cull_ex_pose=cex)
+        b = ref.line_associate(cfg, lines, cull, match, ex, l2d, n_lines2d=nl, fov_capacity=4000, nthreads=8, cull_ex_pose=cex)
+        valid = np.arange(80)[None, :] < nl[:, None]
+        for k in ASSOC_KEYS:
+            if k in ("match_index", "err", "projected"):
+                _same(a[k][valid], b[k][valid], (ang, k))
+            else:
+                _same(a[k], b[k], (ang, k))
