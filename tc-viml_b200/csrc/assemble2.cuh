@@ -803,7 +803,7 @@ __global__ void __launch_bounds__(128) irregular_kernel(LinearizeArgs A, PlanPtr
         if (A.out.pf_jac_ex) store_jac7(A.out.pf_jac_ex + 14 * k, J.c);
         if (A.out.pf_jac_feat) reinterpret_cast<double2*>(A.out.pf_jac_feat)[k] = make_double2(J.d[0], J.d[1]);
       }
-      point_atomics(A, w, i, j, f, J);
+      point_atomics(A, w, i, j, f, J, true, false);   // lanes diverge here (continue above): no warp reduction
     }
     if (A.NL > 0) {
       const int b0 = A.lf_window_offset[w], b1 = A.lf_window_offset[w + 1];

@@ -351,24 +351,55 @@ __device__ __forceinline__ void atomic_block(double* __restrict__ H, int D, int 
     }
 }
 
-// Generic accumulation of one point factor into the zero-initialised blocks of its window.
-__device__ __forceinline__ void point_atomics(const LinearizeArgs& A, int w, int i, int j, int f, const PointJac& J) {
+// Generic accumulation of one point factor into the zero-initialised blocks of its window.  Every point factor of a window adds
+// to the same extrinsic block and b_ex: when the 32 factors of the warp belong to one window (`warp_window`: always, for one huge
+// window) those 27 sums are reduced over the warp first and lane 0 adds them once — 57 K factors no longer queue on 42 addresses.
+__device__ __forceinline__ void point_atomics(const LinearizeArgs& A, int w, int i, int j, int f, const PointJac& J, bool live,
+                                              bool warp_window) {
   const int D = A.D;
   double* H = A.out.H_pp + (size_t)w * D * D;
   double* bp = A.out.b_p + (size_t)w * D;
-  double* Hl = A.out.H_lp + ((size_t)w * A.F + f) * D;
   const int oi = 6 * i, oj = 6 * j, oe = 6 * A.P;
+  if (warp_window) {
+    double v[27];
+    int n = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = r; c < 6; ++c) v[n++] = live ? J.c[0][r] * J.c[0][c] + J.c[1][r] * J.c[1][c] : 0.0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) v[21 + r] = live ? J.c[0][r] * J.r[0] + J.c[1][r] * J.r[1] : 0.0;
+#pragma unroll
+    for (int e = 0; e < 27; ++e)
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v[e] += __shfl_xor_sync(0xffffffffu, v[e], d);
+    if ((threadIdx.x & 31) == 0) {
+      n = 0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = r; c < 6; ++c) {
+          atomicAdd(H + (size_t)(oe + r) * D + oe + c, v[n]);
+          if (c != r) atomicAdd(H + (size_t)(oe + c) * D + oe + r, v[n]);
+          ++n;
+        }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) atomicAdd(bp + oe + r, v[21 + r]);
+    }
+  }
+  if (!live) return;
+  double* Hl = A.out.H_lp + ((size_t)w * A.F + f) * D;
   atomic_block(H, D, oi, oi, J.a, J.a, true);
   atomic_block(H, D, oi, oj, J.a, J.b, false);
   atomic_block(H, D, oi, oe, J.a, J.c, false);
   atomic_block(H, D, oj, oj, J.b, J.b, true);
   atomic_block(H, D, oj, oe, J.b, J.c, false);
-  atomic_block(H, D, oe, oe, J.c, J.c, true);
+  if (!warp_window) atomic_block(H, D, oe, oe, J.c, J.c, true);
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
     atomicAdd(bp + oi + r, J.a[0][r] * J.r[0] + J.a[1][r] * J.r[1]);
     atomicAdd(bp + oj + r, J.b[0][r] * J.r[0] + J.b[1][r] * J.r[1]);
-    atomicAdd(bp + oe + r, J.c[0][r] * J.r[0] + J.c[1][r] * J.r[1]);
+    if (!warp_window) atomicAdd(bp + oe + r, J.c[0][r] * J.r[0] + J.c[1][r] * J.r[1]);
     atomicAdd(Hl + oi + r, J.a[0][r] * J.d[0] + J.a[1][r] * J.d[1]);
     atomicAdd(Hl + oj + r, J.b[0][r] * J.d[0] + J.b[1][r] * J.d[1]);
     atomicAdd(Hl + oe + r, J.c[0][r] * J.d[0] + J.c[1][r] * J.d[1]);
@@ -421,7 +452,10 @@ __global__ void __launch_bounds__(128, MODE_B ? 2 : VIML_POINTS_MINB) points_ker
     if (A.out.pf_jac_ex) store_jac7_coalesced(st, A.out.pf_jac_ex + 14 * k_warp, J.c, lane, nvalid);
     if (live && A.out.pf_jac_feat) reinterpret_cast<double2*>(A.out.pf_jac_feat)[k] = make_double2(J.d[0], J.d[1]);
   }
-  if (MODE_B && live) point_atomics(A, w, i, j, f, J);
+  if (MODE_B) {
+    const bool warp_window = __all_sync(0xffffffffu, w == __shfl_sync(0xffffffffu, w, 0));
+    point_atomics(A, w, i, j, f, J, live, warp_window);
+  }
 }
 
 template <bool MODE_A, bool MODE_B>
