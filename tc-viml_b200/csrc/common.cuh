@@ -80,6 +80,9 @@ struct viml_ctx {
   int64_t fov_words = 0;
   unsigned long long* d_assoc_stats = nullptr;  // {gate tests, gated pairs, overlap-scored, distance-scored} of the last association call
   DeviceArena in_arena, out_arena, scratch, scratch2, scratch3, gn_in, gn_out, s_full;
+  // pinned staging of the small-batch host path (one H2D, one D2H per call)
+  char *h_stage_in = nullptr, *h_stage_out = nullptr;
+  size_t h_stage_in_cap = 0, h_stage_out_cap = 0;
   void* nccl_lib = nullptr;
   // profiling (viml_profile_begin/end): event pairs per kernel id
   bool brute_cull = false;     // VIML_BRUTE_CULL=1: the literal all-pairs FoV sweep (roofline accounting, cross-check)

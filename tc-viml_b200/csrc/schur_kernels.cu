@@ -48,15 +48,29 @@ __global__ void __launch_bounds__(SWARPS * 32) schur_dmma_kernel(int F, int D, c
   const double* __restrict__ Hl = H_lp + (size_t)w * F * D;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int kq = lane & 3, mq = lane >> 2;
-  // this warp's sub-tiles
+  // this warp's sub-tiles: the valid 8x8 sub-tiles form an nbr x nbc rectangle (its upper triangle on a diagonal tile), dealt
+  // round-robin to the warps in row-major order; the i-th one of this warp is found arithmetically so that the per-warp list
+  // stays in registers (indexing it in a runtime-filled array put it in local memory: 44 LDL in round 1)
   constexpr int MAXT = 11;
+  const int nbr = (nr + 7) >> 3, nbc = (nc + 7) >> 3;
+  const int nsub = diag ? nbr * (nbr + 1) / 2 : nbr * nbc;
   int nt = 0;
-  unsigned char str[MAXT], stc[MAXT];
-  for (int s = 0, k = 0; s < 81; ++s) {
-    const int a = s / 9, b = s % 9;
-    if (diag && a > b) continue;
-    if (8 * a >= nr || 8 * b >= nc) continue;
-    if ((k++ % SWARPS) == warp && nt < MAXT) str[nt] = (unsigned char)a, stc[nt] = (unsigned char)b, ++nt;
+  int str[MAXT], stc[MAXT];
+#pragma unroll
+  for (int i = 0; i < MAXT; ++i) {
+    const int k = warp + i * SWARPS;
+    int a = 0, b = 0;
+    if (k < nsub) {
+      nt = i + 1;
+      if (diag) {
+        int t2 = k;
+        while (t2 >= nbr - a) t2 -= nbr - a, ++a;
+        b = a + t2;
+      } else {
+        a = k / nbc, b = k - a * nbc;
+      }
+    }
+    str[i] = a, stc[i] = b;
   }
   double acc[MAXT][2];
 #pragma unroll

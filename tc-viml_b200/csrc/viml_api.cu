@@ -95,6 +95,8 @@ void viml_destroy(viml_ctx* ctx) {
   drop_prof_events(ctx);
   ctx->in_arena.release();
   ctx->out_arena.release();
+  if (ctx->h_stage_in) cudaFreeHost(ctx->h_stage_in);
+  if (ctx->h_stage_out) cudaFreeHost(ctx->h_stage_out);
   ctx->scratch.release();
   ctx->scratch2.release();
   ctx->scratch3.release();
@@ -445,6 +447,56 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   }
   VIML_TRY_CUDA(ctx, ctx->out_arena.reserve(out_bytes));
   for (auto& sl : slots) *sl.dev = ctx->out_arena.take<double>(sl.per_window * W + sl.per_pf * NP + sl.per_lf * NL);
+
+  // ---- small batches (a live sliding window: BASELINE configs[0]): latency, not bandwidth.  Every cudaMemcpyAsync costs
+  // 5-10 us of driver and DMA set-up whatever its size (more from pageable memory), and this call has ~10 input and up to 14
+  // output arrays: the inputs are gathered into ONE pinned block laid out like the device arena and go up in one copy, the
+  // outputs come back in one copy and are handed out from the pinned block.
+  if (W < 512 && ctx->in_arena.used + ctx->out_arena.used <= ((size_t)4 << 20) && !getenv("VIML_NO_STAGING")) {
+    auto grow = [&](char** buf, size_t* cap, size_t need) -> cudaError_t {
+      if (need <= *cap) return cudaSuccess;
+      if (*buf) cudaFreeHost(*buf);
+      *buf = nullptr, *cap = 0;
+      const cudaError_t e = cudaHostAlloc((void**)buf, need + need / 2 + 4096, cudaHostAllocDefault);
+      if (e == cudaSuccess) *cap = need + need / 2 + 4096;
+      return e;
+    };
+    VIML_TRY_CUDA(ctx, grow(&ctx->h_stage_in, &ctx->h_stage_in_cap, ctx->in_arena.used));
+    VIML_TRY_CUDA(ctx, grow(&ctx->h_stage_out, &ctx->h_stage_out_cap, ctx->out_arena.used));
+    if (!indices_ok(0, NP, 0, NL))
+      return fail(ctx, VIML_ERR_INVALID, "factor index out of range (pose index >= poses_per_window, feature >= feats_per_window or line frame >= poses_per_window)");
+    char* const ibase = ctx->in_arena.base;
+    auto put = [&](const void* dptr, const void* src, size_t bytes) {
+      if (bytes) memcpy(ctx->h_stage_in + ((const char*)dptr - ibase), src, bytes);
+    };
+    put(d_poses, in->poses, n_pose * 8), put(d_ex, in->ex_pose, n_ex * 8), put(d_dep, in->inv_depth, n_dep * 8);
+    put(d_poff, in->pf_window_offset, (size_t)(W + 1) * 4), put(d_idx, in->pf_idx, (size_t)NP * 4);
+    if (obs_table) put(d_obsj, in->pf_obs_j, (size_t)NP * 16), put(d_fobs, in->feat_obs, n_dep * 16);
+    else put(d_obs, in->pf_obs, (size_t)NP * 32);
+    if (d_z) put(d_z, in->pf_pts_i_z, (size_t)NP * 8);
+    if (NL > 0) {
+      put(d_loff, in->lf_window_offset, (size_t)(W + 1) * 4), put(d_frame, in->lf_frame, (size_t)NL * 4);
+      put(d_geom, in->lf_geom, (size_t)NL * 72);
+    }
+    VIML_TRY_CUDA(ctx, cudaMemcpyAsync(ibase, ctx->h_stage_in, ctx->in_arena.used, cudaMemcpyHostToDevice, st));
+    int rc = obs_table ? viml_launch_expand_obs(ctx, a, d_fobs, d_obsj) : VIML_OK;
+    if (rc == VIML_OK) rc = viml_launch_linearize(ctx, a);
+    if (rc != VIML_OK) return rc;
+    // the device range that holds every slot the caller wants
+    char *lo = nullptr, *hi = nullptr;
+    for (auto& sl : slots)
+      if (sl.host) {
+        char* b = (char*)*sl.dev;
+        char* e = b + (sl.per_window * W + sl.per_pf * NP + sl.per_lf * NL) * 8;
+        lo = lo ? std::min(lo, b) : b, hi = hi ? std::max(hi, e) : e;
+      }
+    if (lo) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage_out, lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, st));
+    VIML_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    for (auto& sl : slots)
+      if (sl.host) memcpy(sl.host, ctx->h_stage_out + ((char*)*sl.dev - lo), (sl.per_window * W + sl.per_pf * NP + sl.per_lf * NL) * 8);
+    VIML_TRY_CUDA(ctx, cudaGetLastError());
+    return VIML_OK;
+  }
 
   cudaStream_t s_in = ctx->copy_stream, s_out = ctx->copy_stream2;
   cudaEvent_t tv0 = nullptr;

@@ -273,6 +273,29 @@ def test_observation_table_input(pkg, orc, ctx, cfg):
         bad.obs_table()
 
 
+def test_small_batch_staging_matches_pipeline(pkg, ctx, cfg):
+    """Host-pointer calls on small batches go through one pinned staging block each way (one H2D, one D2H); VIML_NO_STAGING=1
+    sends the same call through the chunked copy pipeline of the large batches.  Same outputs, every mode, both observation forms."""
+    abi = pkg._abi
+    b = pkg.synth.make_windows(12, seed=181)
+    for flags in (abi.OUT_RESIDUAL_JACOBIAN, abi.OUT_SCHUR | abi.LOSS_CAUCHY, abi.OUT_RESIDUAL_JACOBIAN | abi.OUT_SCHUR,
+                  abi.OUT_RESIDUAL_JACOBIAN | abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY):
+        for table in (False, True):
+            staged = ctx.linearize(b, flags, obs_table=table)
+            os.environ["VIML_NO_STAGING"] = "1"
+            try:
+                piped = ctx.linearize(b, flags, obs_table=table)
+            finally:
+                del os.environ["VIML_NO_STAGING"]
+            assert set(staged) == set(piped)
+            for k, v in piped.items():
+                assert not np.isnan(staged[k]).any(), k
+                if k.startswith(("pf_", "lf_")):
+                    assert np.array_equal(staged[k], v), k
+                else:
+                    assert pkg.parity.unit_err(k, staged[k], v) < 1e-12, k
+
+
 def test_device_pointer_mode_matches_host_mode(pkg, ctx, cfg):
     """VIML_PTRS_DEVICE: inputs resident in HBM, asynchronous on the context stream."""
     abi = pkg._abi
