@@ -80,6 +80,7 @@ struct viml_ctx {
   int64_t fov_words = 0;
   unsigned long long* d_assoc_stats = nullptr;  // {gate tests, gated pairs, overlap-scored, distance-scored} of the last association call
   DeviceArena in_arena, out_arena, scratch, scratch2, scratch3, gn_in, gn_out, s_full;
+  bool schur_splitk = false;   // VIML_SCHUR_SPLITK=1: round-1 split-K Schur kernel instead of the TMA-pipelined one
   // pinned staging of the small-batch host path (one H2D, one D2H per call)
   char *h_stage_in = nullptr, *h_stage_out = nullptr;
   size_t h_stage_in_cap = 0, h_stage_out_cap = 0;

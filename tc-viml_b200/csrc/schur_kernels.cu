@@ -402,12 +402,186 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, double a, d
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// ---- sliding-window Schur with a TMA pipeline (D <= 72) ---------------------------------------------------------------------
+// schur_tma_kernel: persistent CTAs of 9 consumer warps + 1 producer warp.  The producer streams the windows' landmark rows
+// through a ring of shared-memory stages with cp.async.bulk (TMA bulk copy, one 8*D-byte row per copy into a stride of 76
+// doubles: conflict-free fragment loads) completing on mbarriers; 1/L and b come from a small pre-pass (schur_inv_kernel,
+// rows padded to whole stages).  The consumers OWN output sub-tiles, so the contraction over the landmarks needs no cross-warp
+// reduction (the split-K kernel above spent half of a 150-landmark window in that epilogue) and no CTA-wide barrier: S is a
+// symmetric 9 x 9 grid of 8x8 tiles, and on the torus every unordered pair of tile indices is (w, (w + d) mod 9) for exactly one
+// w in 0..8 and d in 0..4 — warp w computes those five tiles (one A fragment, five B fragments, five DMMA per step of four
+// landmarks; every warp runs the same code) and writes each with its mirror.  g rides along as a sixth tile whose B operand is
+// b_l in column 0.
+constexpr int kTmaStageL = 32;                         // landmarks per stage
+constexpr int kTmaStageD = kTmaStageL * LDW + 2 * kTmaStageL;   // doubles per stage: rows + 1/L + b
+constexpr int kTmaStages = 4;
+constexpr int kTmaWarps = 9;                           // consumer warps
+constexpr int kTmaThreads = (kTmaWarps + 1) * 32;
+
+__global__ void __launch_bounds__(256) schur_inv_kernel(int W, int F, int Fp, const double* __restrict__ H_ll, const double* __restrict__ b_l,
+                                                        double eps, double* __restrict__ invp, double* __restrict__ bp) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= (int64_t)W * Fp) return;
+  const int w = (int)(e / Fp), l = (int)(e % Fp);
+  double inv = 0.0, b = 0.0;
+  if (l < F) {
+    const double L = H_ll[(size_t)w * F + l];
+    inv = (L > eps) ? 1.0 / L : 0.0;
+    b = b_l[(size_t)w * F + l];
+  }
+  invp[e] = inv, bp[e] = b;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 2) schur_tma_kernel(int W, int F, int Fp, int D, const double* __restrict__ H_pp,
+                                                                   const double* __restrict__ H_lp, const double* __restrict__ invp,
+                                                                   const double* __restrict__ blp, const double* __restrict__ b_p,
+                                                                   double* __restrict__ S, double* __restrict__ g) {
+  extern __shared__ __align__(128) double tsm[];
+  double* stages = tsm;                                             // [kTmaStages][kTmaStageD]
+  uint64_t* full = reinterpret_cast<uint64_t*>(stages + (size_t)kTmaStages * kTmaStageD);
+  uint64_t* empty = full + kTmaStages;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // columns D..75 of a stage row are never written by the copies (a row copy is D doubles) and rows beyond a window's last
+  // landmark keep what the previous user of the stage left: everything starts as zero
+  for (int e = tid; e < kTmaStages * kTmaStageD; e += kTmaThreads) tsm[e] = 0.0;
+  if (tid == 0) {
+    for (int s2 = 0; s2 < kTmaStages; ++s2) mbar_init(&full[s2], 1), mbar_init(&empty[s2], kTmaWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fill (generic proxy) before the bulk copies (async proxy)
+  __syncthreads();
+  const int nchunk = (F + kTmaStageL - 1) / kTmaStageL;
+  uint32_t it = 0;
+  if (warp == kTmaWarps) {   // producer
+    const uint32_t row_bytes = (uint32_t)D * 8u;
+    for (int w = blockIdx.x; w < W; w += gridDim.x) {
+      const double* __restrict__ Hl = H_lp + (size_t)w * F * D;
+      for (int ch = 0; ch < nchunk; ++ch, ++it) {
+        const int stg = it % kTmaStages;
+        double* sw = stages + (size_t)stg * kTmaStageD;
+        const int l0 = ch * kTmaStageL, nl = min(kTmaStageL, F - l0);
+        mbar_wait(&empty[stg], ((it / kTmaStages) & 1) ^ 1);
+        if (lane == 0) mbar_expect_tx(&full[stg], (uint32_t)nl * row_bytes + 2u * kTmaStageL * 8u);
+        __syncwarp();
+        for (int r = lane; r < nl; r += 32) bulk_g2s(sw + r * LDW, Hl + (size_t)(l0 + r) * D, row_bytes, &full[stg]);
+        if (lane == 0) {
+          bulk_g2s(sw + kTmaStageL * LDW, invp + (size_t)w * Fp + l0, kTmaStageL * 8u, &full[stg]);
+          bulk_g2s(sw + kTmaStageL * LDW + kTmaStageL, blp + (size_t)w * Fp + l0, kTmaStageL * 8u, &full[stg]);
+        }
+      }
+    }
+    return;
+  }
+  // consumer warp `warp`: tiles (warp, ct[d]), d = 0..4
+  const int kq = lane & 3, mq = lane >> 2;
+  int coff[5];
+#pragma unroll
+  for (int d = 0; d < 5; ++d) coff[d] = 8 * ((warp + d) % 9);
+  const int r = 8 * warp + mq;
+  for (int w = blockIdx.x; w < W; w += gridDim.x) {
+    // H_pp entries of this warp's tiles and of their mirrors: in flight while the landmarks stream
+    const double* __restrict__ Hp = H_pp + (size_t)w * D * D;
+    double2 hu[5];
+    double hm[5][2];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+      const int c = coff[d] + 2 * kq;
+      const bool in = r < D && c < D;   // D is even: c + 1 < D too
+      hu[d] = in ? *reinterpret_cast<const double2*>(Hp + (size_t)r * D + c) : make_double2(0.0, 0.0);
+      hm[d][0] = (in && d > 0) ? Hp[(size_t)c * D + r] : 0.0;
+      hm[d][1] = (in && d > 0) ? Hp[(size_t)(c + 1) * D + r] : 0.0;
+    }
+    const double bpr = (kq == 0 && r < D) ? b_p[(size_t)w * D + r] : 0.0;
+    double acc[6][2];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) acc[i][0] = acc[i][1] = 0.0;
+    for (int ch = 0; ch < nchunk; ++ch, ++it) {
+      const int stg = it % kTmaStages;
+      const double* sw = stages + (size_t)stg * kTmaStageD;
+      const double* sinv = sw + kTmaStageL * LDW;
+      const double* sb = sinv + kTmaStageL;
+      const int nl = min(kTmaStageL, F - ch * kTmaStageL);
+      mbar_wait(&full[stg], (it / kTmaStages) & 1);
+      const int nk = (nl + 3) >> 2;   // rows nl.. of a last stage hold finite leftovers and meet 1/L = 0 from the padded pre-pass
+#pragma unroll 2
+      for (int k4 = 0; k4 < nk; ++k4) {
+        const int l = 4 * k4 + kq;
+        const double* row = sw + l * LDW + mq;
+        const double fb0 = row[coff[0]];
+        const double fa = fb0 * sinv[l];
+        const double bl = mq == 0 ? sb[l] : 0.0;
+        dmma(acc[0][0], acc[0][1], fa, fb0);
+#pragma unroll
+        for (int d = 1; d < 5; ++d) dmma(acc[d][0], acc[d][1], fa, row[coff[d]]);
+        dmma(acc[5][0], acc[5][1], fa, bl);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stg]);
+    }
+    // S = H_pp - acc on the owned tiles and their mirrors; g = b_p - (sixth tile, column 0)
+    double* __restrict__ So = S + (size_t)w * D * D;
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+      const int c = coff[d] + 2 * kq;
+      if (r < D && c < D) {
+        *reinterpret_cast<double2*>(So + (size_t)r * D + c) = make_double2(hu[d].x - acc[d][0], hu[d].y - acc[d][1]);
+        if (d > 0) {
+          So[(size_t)c * D + r] = hm[d][0] - acc[d][0];
+          So[(size_t)(c + 1) * D + r] = hm[d][1] - acc[d][1];
+        }
+      }
+    }
+    if (kq == 0 && r < D) g[(size_t)w * D + r] = bpr - acc[5][0];
+  }
+}
+
 }  // namespace
 
 int viml_launch_schur(viml_ctx* ctx, int W, int F, int D, const double* H_pp, const double* H_lp, const double* H_ll,
                       const double* b_p, const double* b_l, double* S, double* g, double eps) {
   const int ntile = (D + TS - 1) / TS;
-  if (ntile == 1) {   // sliding-window case: split-K kernel, one CTA per window
+  if (ntile == 1 && F > 0 && !ctx->schur_splitk) {   // sliding-window case: TMA-pipelined kernel, warps own output tiles
+    const int Fp = (F + kTmaStageL - 1) / kTmaStageL * kTmaStageL;
+    VIML_TRY_CUDA(ctx, ctx->scratch2.reserve(2 * DeviceArena::padded((size_t)W * Fp * 8)));
+    double* invp = ctx->scratch2.take<double>((size_t)W * Fp);
+    double* blp = ctx->scratch2.take<double>((size_t)W * Fp);
+    {
+      LaunchScope ls(ctx, K_SCHUR);
+      schur_inv_kernel<<<(unsigned)(((size_t)W * Fp + 255) / 256), 256, 0, ctx->stream>>>(W, F, Fp, H_ll, b_l, eps, invp, blp);
+    }
+    const int smem = kTmaStages * kTmaStageD * (int)sizeof(double) + 2 * kTmaStages * 8;
+    VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(schur_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = W < 2 * ctx->sm_count ? W : 2 * ctx->sm_count;
+    LaunchScope ls(ctx, K_SCHUR);
+    schur_tma_kernel<<<(unsigned)grid, kTmaThreads, smem, ctx->stream>>>(W, F, Fp, D, H_pp, H_lp, invp, blp, b_p, S, g);
+    return VIML_OK;
+  }
+  if (ntile == 1) {   // split-K variant (VIML_SCHUR_SPLITK=1, or no landmarks): one persistent CTA per SM
     LaunchScope ls(ctx, K_SCHUR);
     const int smem = SWARPS * kSplitAcc * (int)sizeof(double);
     if (cudaFuncSetAttribute(schur_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return VIML_ERR_CUDA;
