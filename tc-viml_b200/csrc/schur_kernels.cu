@@ -411,8 +411,8 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, double a, d
 // reduction (the split-K kernel above spent half of a 150-landmark window in that epilogue) and no CTA-wide barrier: S is a
 // symmetric 9 x 9 grid of 8x8 tiles, and on the torus every unordered pair of tile indices is (w, (w + d) mod 9) for exactly one
 // w in 0..8 and d in 0..4 — warp w computes those five tiles (one A fragment, five B fragments, five DMMA per step of four
-// landmarks; every warp runs the same code) and writes each with its mirror.  g rides along as a sixth tile whose B operand is
-// b_l in column 0.
+// landmarks; every warp runs the same code) and writes each with its mirror.  g[8w..8w+7] rides along on the A fragment: one FMA
+// per step and lane, summed over the four k-lanes at the end of the window.
 constexpr int kTmaStageL = 32;                         // landmarks per stage
 constexpr int kTmaStageD = kTmaStageL * LDW + 2 * kTmaStageL;   // doubles per stage: rows + 1/L + b
 constexpr int kTmaStages = 4;
@@ -504,22 +504,24 @@ __global__ void __launch_bounds__(kTmaThreads, 2) schur_tma_kernel(int W, int F,
   for (int d = 0; d < 5; ++d) coff[d] = 8 * ((warp + d) % 9);
   const int r = 8 * warp + mq;
   for (int w = blockIdx.x; w < W; w += gridDim.x) {
-    // H_pp entries of this warp's tiles and of their mirrors: in flight while the landmarks stream
+    // H_pp entries of this warp's tiles and of their mirrors are read in the epilogue; they are pulled into L2 now, while the
+    // landmarks stream (holding them in registers across the loop costs the second CTA per SM)
     const double* __restrict__ Hp = H_pp + (size_t)w * D * D;
-    double2 hu[5];
-    double hm[5][2];
 #pragma unroll
     for (int d = 0; d < 5; ++d) {
       const int c = coff[d] + 2 * kq;
-      const bool in = r < D && c < D;   // D is even: c + 1 < D too
-      hu[d] = in ? *reinterpret_cast<const double2*>(Hp + (size_t)r * D + c) : make_double2(0.0, 0.0);
-      hm[d][0] = (in && d > 0) ? Hp[(size_t)c * D + r] : 0.0;
-      hm[d][1] = (in && d > 0) ? Hp[(size_t)(c + 1) * D + r] : 0.0;
+      if (r < D && c < D) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(Hp + (size_t)r * D + c));
+        if (d > 0) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(Hp + (size_t)c * D + r));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(Hp + (size_t)(c + 1) * D + r));
+        }
+      }
     }
-    const double bpr = (kq == 0 && r < D) ? b_p[(size_t)w * D + r] : 0.0;
-    double acc[6][2];
+    double acc[5][2];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) acc[i][0] = acc[i][1] = 0.0;
+    for (int i = 0; i < 5; ++i) acc[i][0] = acc[i][1] = 0.0;
+    double gacc = 0.0;
     for (int ch = 0; ch < nchunk; ++ch, ++it) {
       const int stg = it % kTmaStages;
       const double* sw = stages + (size_t)stg * kTmaStageD;
@@ -534,17 +536,27 @@ __global__ void __launch_bounds__(kTmaThreads, 2) schur_tma_kernel(int W, int F,
         const double* row = sw + l * LDW + mq;
         const double fb0 = row[coff[0]];
         const double fa = fb0 * sinv[l];
-        const double bl = mq == 0 ? sb[l] : 0.0;
+        gacc = fma(fa, sb[l], gacc);
         dmma(acc[0][0], acc[0][1], fa, fb0);
 #pragma unroll
         for (int d = 1; d < 5; ++d) dmma(acc[d][0], acc[d][1], fa, row[coff[d]]);
-        dmma(acc[5][0], acc[5][1], fa, bl);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stg]);
     }
-    // S = H_pp - acc on the owned tiles and their mirrors; g = b_p - (sixth tile, column 0)
+    // S = H_pp - acc on the owned tiles and their mirrors; g = b_p - sum over the k-lanes
     double* __restrict__ So = S + (size_t)w * D * D;
+    double2 hu[5];
+    double hm[5][2];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+      const int c = coff[d] + 2 * kq;
+      const bool in = r < D && c < D;   // D is even: c + 1 < D too
+      hu[d] = in ? *reinterpret_cast<const double2*>(Hp + (size_t)r * D + c) : make_double2(0.0, 0.0);
+      hm[d][0] = (in && d > 0) ? Hp[(size_t)c * D + r] : 0.0;
+      hm[d][1] = (in && d > 0) ? Hp[(size_t)(c + 1) * D + r] : 0.0;
+    }
+    const double bpr = (kq == 0 && r < D) ? b_p[(size_t)w * D + r] : 0.0;
 #pragma unroll
     for (int d = 0; d < 5; ++d) {
       const int c = coff[d] + 2 * kq;
@@ -556,7 +568,9 @@ __global__ void __launch_bounds__(kTmaThreads, 2) schur_tma_kernel(int W, int F,
         }
       }
     }
-    if (kq == 0 && r < D) g[(size_t)w * D + r] = bpr - acc[5][0];
+    gacc += __shfl_xor_sync(0xffffffffu, gacc, 1);
+    gacc += __shfl_xor_sync(0xffffffffu, gacc, 2);
+    if (kq == 0 && r < D) g[(size_t)w * D + r] = bpr - gacc;
   }
 }
 
