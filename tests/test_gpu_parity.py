@@ -907,6 +907,30 @@ def test_association_sweep_properties_large(pkg, orc, ctx, cfg):
     check_assoc(sub, ref)
 
 
+def test_two_devices_in_one_process(pkg, orc, cfg):
+    """One process, a context on device 0 and one on device 1 (the model viml_create(device) offers): every kernel that needs a
+    per-device attribute (dynamic shared memory of the fused assembly, the Schur and match kernels) must work on the second device
+    too.  Skipped on a single-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    abi, synth = pkg._abi, pkg.synth
+    b = synth.make_windows(24, seed=191)
+    flags = abi.OUT_RESIDUAL_JACOBIAN | abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
+    ref = orc.linearize_batch(cfg, b, flags, nthreads=8)
+    lines = synth.make_line_map(20000, seed=192, extent=(300.0, 300.0, 30.0))
+    cull, match, ex, l2d = synth.make_assoc_queries(lines, 4, L=100, n_true=50, seed=193, extent=(300.0, 300.0, 30.0))
+    aref = orc.line_associate(cfg, lines, cull, match, ex, l2d, nthreads=4)
+    for dev in (0, 1, 0):
+        with pkg.Context(cfg, device=dev) as c:
+            got = c.linearize(b, flags)
+            for k, v in ref.items():
+                assert pkg.parity.unit_err(k, got[k], v) < TOL, (dev, k)
+            c.set_map(lines)
+            a = c.associate(cull, match, ex, l2d)
+            assert np.array_equal(a["match_index"], aref["match_index"]), dev
+
+
 def test_allreduce_hb_two_gpus(pkg, cfg):
     """viml_allreduce_hb (the C++ hosts' all-reduce of partial [S | g]) with raw ncclComm_t handles: one
     process, two contexts on two devices, one thread per device.  Skipped on a single-GPU box."""
