@@ -691,24 +691,26 @@ def main():
         part = shard.split_huge_window(huge, rank, world)
         Dh = huge.D
         dh_in = {k: ctx.to_device(v) for k, v in part.arrays().items() if v is not None}
-        sg = torch.zeros(Dh * Dh + Dh, dtype=torch.float64, device="cuda")
+        # S is symmetric: the partial sums travel as their upper triangle (VIML_S_PACKED), half the all-reduce bytes
+        n_sp = Dh * (Dh + 1) // 2
+        sg = torch.zeros(n_sp + Dh, dtype=torch.float64, device="cuda")
         so = abi.LinearizeOut()
-        so.S, so.g = sg.data_ptr(), sg.data_ptr() + Dh * Dh * 8
+        so.S, so.g = sg.data_ptr(), sg.data_ptr() + n_sp * 8
         sh = part.struct(dh_in)
-        fl = abi.OUT_SCHUR | abi.LOSS_CAUCHY | abi.PTRS_DEVICE
+        fl = abi.OUT_SCHUR | abi.S_PACKED | abi.LOSS_CAUCHY | abi.PTRS_DEVICE
         nccl, comm = (None, None)
         if world > 1:
             nccl, comm = nccl_bootstrap(torch, dist, world, rank)
         via = "none (1 GPU)"
         if world > 1:
-            via = ("viml_allreduce_hb (raw ncclComm_t, ncclAllReduce(sum, f64) of [S|g] on the context stream)" if comm
+            via = ("viml_allreduce_hb (raw ncclComm_t, ncclAllReduce(sum, f64) of [upper triangle of S | g] on the context stream)" if comm
                    else "torch.distributed all_reduce (raw NCCL bootstrap failed)")
 
         def huge_step():
             ctx.linearize_raw(sh, so, fl)
             if world > 1:
                 if comm:
-                    rc = ctx.lib.viml_allreduce_hb(ctx.h, comm, ctypes.c_void_p(sg.data_ptr()), Dh * Dh + Dh)
+                    rc = ctx.lib.viml_allreduce_hb(ctx.h, comm, ctypes.c_void_p(sg.data_ptr()), n_sp + Dh)
                     assert rc == 0, rc
                 else:
                     with torch.cuda.stream(stream):
@@ -718,7 +720,7 @@ def main():
         msH, profH = timed_device(huge_step, h_steps, 3)
         out["huge_window"] = {"factors_per_s": (huge.NP + huge.NL) / (msH / h_steps * 1e-3), "ms_per_step": msH / h_steps,
                               "shape": f"1 window, {huge.P} poses, {huge.F} landmarks, {huge.NP}+{huge.NL} factors, split by landmark over {world} GPU(s)",
-                              "landmarks_per_rank": int(part.F), "allreduce_doubles": int(Dh * Dh + Dh) if world > 1 else 0,
+                              "landmarks_per_rank": int(part.F), "allreduce_doubles": int(n_sp + Dh) if world > 1 else 0,
                               "collective": via, "kernel_ms_per_step": {k: v[0] / h_steps for k, v in profH.items()}}
         if comm:
             ctx.sync()

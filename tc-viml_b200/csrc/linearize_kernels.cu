@@ -485,13 +485,14 @@ __global__ void __launch_bounds__(128) lines_kernel(LinearizeArgs A) {
   if (MODE_B && live) line_atomics(A, w, frame, J);
 }
 
-// VIML_S_PACKED: upper triangle of every window's S, row r = columns r..D-1
+// VIML_S_PACKED: upper triangle of every window's S, row r = columns r..D-1.  grid = (windows, slices of the window's entries):
+// one CTA per window for the sliding-window size, many for a long window (D = 1212: 1.5 M entries)
 __global__ void __launch_bounds__(256) pack_upper_kernel(int D, const double* __restrict__ S, double* __restrict__ Sp) {
   const double* __restrict__ s = S + (size_t)blockIdx.x * D * D;
   double* __restrict__ o = Sp + (size_t)blockIdx.x * ((size_t)D * (D + 1) / 2);
-  for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < D * D; e += gridDim.y * blockDim.x) {
     const int r = e / D, c = e - r * D;
-    if (c >= r) o[r * D - (r * (r - 1)) / 2 + c - r] = s[e];
+    if (c >= r) o[(size_t)r * D - ((size_t)r * (r - 1)) / 2 + c - r] = s[e];
   }
 }
 
@@ -591,7 +592,8 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
     viml_launch_schur(ctx, a.W, a.F, a.D, a.out.H_pp, a.out.H_lp, a.out.H_ll, a.out.b_p, a.out.b_l, S, a.out.g, eps);
     if (a.flags & VIML_S_PACKED) {
       LaunchScope ls(ctx, K_SCHUR);
-      pack_upper_kernel<<<a.W, 256, 0, st>>>(a.D, S, a.out.S);
+      const unsigned slices = (unsigned)std::min<int64_t>(((int64_t)a.D * a.D + 256 * 32 - 1) / (256 * 32), 1024);
+      pack_upper_kernel<<<dim3((unsigned)a.W, slices), 256, 0, st>>>(a.D, S, a.out.S);
     }
   }
   VIML_TRY_CUDA(ctx, cudaGetLastError());

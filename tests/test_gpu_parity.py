@@ -56,6 +56,13 @@ def test_packed_schur_output(pkg, orc, ctx, cfg):
     assert not np.isnan(bufs["S_packed"]).any()
     ref = orc.linearize_batch(cfg, b, abi.OUT_SCHUR | abi.LOSS_CAUCHY)
     assert pkg.parity.unit_err("S", abi.unpack_upper(bufs["S_packed"], b.D), ref["S"]) < TOL
+    # a long window (D = 246: the packing runs on several CTAs per window)
+    h = pkg.synth.make_windows(2, seed=152, P=40, F=400, lines_per_frame=2, max_len=12)
+    fullh = ctx.linearize(h, abi.OUT_SCHUR | abi.LOSS_CAUCHY)
+    bh = {"S_packed": np.full(h.out_shapes()["S_packed"], np.nan), "g": np.full((h.W, h.D), np.nan)}
+    ctx.linearize(h, abi.OUT_SCHUR | abi.S_PACKED | abi.LOSS_CAUCHY, out=bh)
+    assert not np.isnan(bh["S_packed"]).any()
+    assert pkg.parity.unit_err("S", abi.unpack_upper(bh["S_packed"], h.D), fullh["S"]) < 1e-12
 
 
 def test_golden_linearize(pkg, orc, ctx, cfg):
