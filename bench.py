@@ -146,7 +146,7 @@ def run_reference(args):
     cfg = synth.euroc_config()
     nthreads = orc.hardware_threads()
     flags = abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
-    batch = synth.make_windows(args.windows, seed=0x5EED + 2)
+    batch = synth.make_windows(args.windows, seed=0x5EED + 2, f32_obs=True)   # the native arm's rank-0 batch
     steps, warm = args.steps, args.warmup
     bufs = batch.alloc_out(flags, fill=0.0)
     t0 = time.perf_counter()
@@ -308,7 +308,7 @@ def main():
         return a
 
     # ------------------------------------------------------------------ linearise (headline)
-    batch = synth.make_windows(args.windows, seed=0x5EED + 2 + rank)
+    batch = synth.make_windows(args.windows, seed=0x5EED + 2 + rank, f32_obs=True)   # observations as the tracker publishes them (Point32)
     factors = batch.NP + batch.NL
     flags = abi.OUT_HB | abi.LOSS_CAUCHY
     flagsS = abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
@@ -358,8 +358,9 @@ def main():
     pS = {k: pkg.PinnedArray(shapes[k], np.float64) for k in ("S_packed", "g")}
     hoS = {k: p.array for k, p in pS.items()}
     fS = abi.OUT_SCHUR | abi.S_PACKED | abi.LOSS_CAUCHY
-    # observations as the per-feature table (viml.h: feat_obs + pf_obs_j; the anchor observation is not repeated per factor)
-    tab = dict(zip(("feat_obs", "pf_obs_j"), (pkg.pinned_like(a) for a in batch.obs_table())))
+    # observations as the per-feature float32 table (viml.h: feat_obs_f32 + pf_obs_j_f32; the anchor observation is not repeated
+    # per factor and the values travel as the float32 the tracker published; widened on the device, identical results)
+    tab = dict(zip(("feat_obs_f32", "pf_obs_j_f32"), (pkg.pinned_like(a) for a in batch.obs_table(f32=True))))
     arr_tab = {k: p.array for k, p in pins.items() if k != "pf_obs"}
     arr_tab.update({k: p.array for k, p in tab.items()})
     s_tab, o_S = hb.struct(arr_tab), abi.out_struct(hoS)
@@ -368,7 +369,7 @@ def main():
     e2e = {"value": total_factors / (e_ms * 1e-3), "unit": "factors/s", "h2d_bytes_per_step": int(h2d_tab),
            "d2h_bytes_per_step": int(sum(p.nbytes for p in pS.values())), "ms_per_step": e_ms, "steps": e_steps,
            "api": "viml_linearize_batch(host pointers, VIML_OUT_SCHUR|VIML_S_PACKED|VIML_LOSS_CAUCHY), observations as the per-feature "
-                  "table: evaluate + assemble + landmark Schur; the upper triangle of S and g back"}
+                  "float32 table: evaluate + assemble + landmark Schur; the upper triangle of S and g back"}
     S_tab = hoS["S_packed"].copy()
     e_ms_pairs = timed_host(lambda: ctx.linearize(hb, fS, out=hoS), e_steps)
     # same kernels on the same expanded observations: equal up to the summation order of the shared accumulator

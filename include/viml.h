@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define VIML_ABI_VERSION 3
+#define VIML_ABI_VERSION 4
 
 /* ---- error codes ---------------------------------------------------------------------------- */
 #define VIML_OK 0
@@ -137,6 +137,10 @@ int viml_load_line_map(viml_ctx* ctx, const char* path, int64_t* n_lines);
  * estimator.cpp:1747-1766, :1961-1982), so pts_i repeats over the factors of a feature.  With pf_obs == NULL the batch carries
  * feat_obs[w][feat] = {pts_i.x, pts_i.y} once per feature and pf_obs_j[k] = {pts_j.x, pts_j.y} per factor (16 + 16/n_obs bytes per
  * factor instead of 32); the library expands them on the device, results are identical to the pf_obs form.
+ * The tracker publishes these points as geometry_msgs::Point32 (feature_tracker_node.cpp:159-162) and the estimator widens them
+ * (double x = img_msg->points[j].x, estimator_node.cpp:388-390): a caller that still holds the float32 values can pass the table as
+ * feat_obs_f32 / pf_obs_j_f32 instead (same shapes, float; 8 + 8/n_obs bytes per factor).  The device widens them exactly like the
+ * host would: identical results.
  *
  * Line factor k (LineProjectionFactor, line_projection_factor.h:13-34) couples pose lf_frame[k] only.
  * lf_geom is SoA, nine planes of n_line_factors doubles: P_start.xyz, P_end.xyz (already in VIO world,
@@ -162,6 +166,8 @@ typedef struct viml_window_batch {
   const double* lf_geom;     /* [9][NL]                                                         */
   const double* feat_obs;    /* [W][F][2] or NULL; read only when pf_obs == NULL                */
   const double* pf_obs_j;    /* [NP][2]   or NULL; read only when pf_obs == NULL                */
+  const float* feat_obs_f32; /* [W][F][2] or NULL; read only when pf_obs, feat_obs, pf_obs_j are NULL */
+  const float* pf_obs_j_f32; /* [NP][2]   or NULL                                               */
 } viml_window_batch;
 
 /* Any pointer may be NULL (= not wanted).  D = 6*(P+1): pose blocks 0..P-1 then the extrinsic.

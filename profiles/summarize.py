@@ -26,8 +26,8 @@ if os.path.exists(src):
         a[1] += v
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(here, f"launches_{tag}.md"), "w") as f:
-        f.write(f"# ncu launch list summary, round {tag[1:]} (`ncu --metrics gpu__time_duration.sum --clock-control none -c 800 "
-                "python bench.py --steps 2 --warmup 3 --skip-cpu`, see profiles/capture_r1.sh)\n\n"
+        f.write(f"# ncu launch list summary, round {tag[1:]} (`ncu --metrics gpu__time_duration.sum --clock-control none ... "
+                f"python bench.py --steps 2 --warmup 3 --skip-cpu ...`, exact command in profiles/capture_{tag}.sh)\n\n"
                 "Cold-cache, serialised per-launch times: compare SHARES, not absolutes. Raw list: "
                 f"`profiles/launches_{tag}.csv`.\n\n| kernel | launches | total us | avg us | share of captured time |\n|---|---|---|---|---|\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -47,9 +47,17 @@ if os.path.exists(src):
                 pick[name] = sum(top) / len(top)
         if len(pick) == 3:
             tot3 = sum(pick.values())
+            events = ""
+            for bj in (os.path.join(root, "gpurun_out", f"bench_{tag}.json"), os.path.join(here, f"bench_{tag}.json")):
+                if os.path.exists(bj):
+                    km = json.load(open(bj))["roofline"]["kernel_ms_per_step"]
+                    te = sum(km.get(k, 0.0) for k in ("assemble_hb", "plan_windows", "prep_windows"))
+                    events = (". `bench.py` (CUDA events, warm, same command without ncu) reports " + " / ".join(
+                        f"{100 * km.get(k, 0.0) / te:.0f}" for k in ("assemble_hb", "plan_windows", "prep_windows")) +
+                        " % (`roofline.kernel_ms_per_step`; there plan and prep run side by side on two streams and each takes a little longer)")
+                    break
             f.write("\nHeadline step (full-size launches only, mean of the 5 largest of each kernel): " + ", ".join(
-                f"{k} {v:.1f} us = {100 * v / tot3:.1f} %" for k, v in pick.items()) +
-                ". `bench.py` (CUDA events, warm) reports 85 / 11 / 4 % (`roofline.kernel_ms_per_step`; there plan and prep run side by side on two streams and each takes a little longer).\n")
+                f"{k} {v:.1f} us = {100 * v / tot3:.1f} %" for k, v in pick.items()) + events + ".\n")
 
 want = [("gpu__time_duration.sum", "duration"), ("launch__registers_per_thread", "regs/thread"),
         ("launch__grid_size", "grid"), ("launch__block_size", "block"),
@@ -62,7 +70,7 @@ want = [("gpu__time_duration.sum", "duration"), ("launch__registers_per_thread",
         ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
         ("lts__t_sector_hit_rate.pct", "L2 hit %"), ("smsp__inst_executed.sum", "warp instructions"),
         ("smsp__thread_inst_executed_per_inst_executed.ratio", "active threads / instruction")]
-out = [f"# ncu --set full summaries, round {tag[1:]} (one launch per kernel, `--clock-control none`; profiles/capture_r1.sh)\n",
+out = [f"# ncu --set full summaries, round {tag[1:]} (one launch per kernel, `--clock-control none`; profiles/capture_{tag}.sh)\n",
        "Timings under ncu are cold-cache and serialised: they are evidence of WHERE the time goes, never bench values.\n"]
 traffic = {}
 for rep in sorted(glob.glob(os.path.join(root, "gpurun_out", f"full_*_{tag}.ncu-rep"))):
@@ -95,7 +103,7 @@ open(os.path.join(here, f"ncu_summary_{tag}.md"), "w").write("\n".join(out) + "\
 tj = os.path.join(here, "traffic.json")
 old = json.load(open(tj)) if os.path.exists(tj) else {}
 # top-level keys are what bench.py reads for roofline.traffic (library kernel names)
-for lib, k in (("assemble_hb", "assemble_kernel"), ("linearize_points", "points_kernel"), ("schur_landmarks", "schur_splitk_kernel"),
+for lib, k in (("assemble_hb", "assemble_kernel"), ("linearize_points", "points_kernel"), ("schur_landmarks", "schur_tma_kernel"),
                ("assoc_match", "match_kernel"), ("assoc_cull", "cull_tiles_kernel"), ("plan_windows", "plan_kernel")):
     if k in traffic:
         old[lib] = traffic[k]["dram_bytes"]

@@ -209,7 +209,10 @@ class Context:
             return batch.struct(), None
         arrs = batch.arrays()
         arrs["pf_obs"] = None
-        arrs["feat_obs"], arrs["pf_obs_j"] = batch.obs_table()
+        if obs_table == "f32":
+            arrs["feat_obs_f32"], arrs["pf_obs_j_f32"] = batch.obs_table(f32=True)
+        else:
+            arrs["feat_obs"], arrs["pf_obs_j"] = batch.obs_table()
         return batch.struct(arrs), arrs
 
     def reduced_system(self, batch, dense, flags, obs_table=False):
@@ -247,7 +250,7 @@ class Context:
 
     def linearize(self, batch, flags, out=None, obs_table=False):
         """viml_linearize_batch with host buffers; returns dict of numpy outputs.  obs_table=True passes the observations as
-        the per-feature table (feat_obs + pf_obs_j) instead of pf_obs."""
+        the per-feature table (feat_obs + pf_obs_j) instead of pf_obs, obs_table="f32" as the float32 table."""
         bufs = batch.alloc_out(flags) if out is None else out
         s, _keep = self._batch_struct(batch, obs_table)
         o = _abi.out_struct(bufs)

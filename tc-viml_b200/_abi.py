@@ -52,6 +52,7 @@ class WindowBatch(C.Structure):
         ("n_line_factors", C.c_int64),
         ("lf_window_offset", C.c_void_p), ("lf_frame", C.c_void_p), ("lf_geom", C.c_void_p),
         ("feat_obs", C.c_void_p), ("pf_obs_j", C.c_void_p),
+        ("feat_obs_f32", C.c_void_p), ("pf_obs_j_f32", C.c_void_p),
     ]
 
 
@@ -216,15 +217,19 @@ class Batch:
         s.n_point_factors = self.NP
         s.pf_window_offset, s.pf_idx, s.pf_obs = ptr(a["pf_window_offset"]), ptr(a["pf_idx"]), ptr(a.get("pf_obs"))
         if a.get("pf_obs") is None:   # observation table instead of per-factor pairs (viml.h, viml_window_batch)
-            s.feat_obs, s.pf_obs_j = ptr(a["feat_obs"]), ptr(a["pf_obs_j"])
+            if a.get("feat_obs_f32") is not None:
+                s.feat_obs_f32, s.pf_obs_j_f32 = ptr(a["feat_obs_f32"]), ptr(a["pf_obs_j_f32"])
+            else:
+                s.feat_obs, s.pf_obs_j = ptr(a["feat_obs"]), ptr(a["pf_obs_j"])
         s.pf_pts_i_z = ptr(a.get("pf_pts_i_z"))
         s.n_line_factors = self.NL
         s.lf_window_offset, s.lf_frame, s.lf_geom = ptr(a["lf_window_offset"]), ptr(a["lf_frame"]), ptr(a["lf_geom"])
         return s
 
-    def obs_table(self):
+    def obs_table(self, f32=False):
         """The observation-table form of pf_obs: (feat_obs [W][F][2], pf_obs_j [NP][2]).  Raises when the factors of a feature
-        do not share pts_i (then only the per-factor form describes the batch)."""
+        do not share pts_i (then only the per-factor form describes the batch).  f32=True: as float32 arrays, for observations
+        that are float32 values (raises when they are not)."""
         W, F = self.W, self.F
         win = np.repeat(np.arange(W, dtype=np.int64), np.diff(self.pf_window_offset))
         key = win * F + (self.pf_idx >> 16).astype(np.int64)
@@ -232,7 +237,13 @@ class Batch:
         feat_obs[key] = self.pf_obs[:, :2]          # one of the factors' pts_i per feature ...
         if not np.array_equal(feat_obs[key], self.pf_obs[:, :2]):   # ... which every other factor must repeat
             raise ValueError("pts_i differs between the factors of a feature")
-        return feat_obs.reshape(W, F, 2), np.ascontiguousarray(self.pf_obs[:, 2:])
+        feat_obs, obs_j = feat_obs.reshape(W, F, 2), np.ascontiguousarray(self.pf_obs[:, 2:])
+        if f32:
+            f32s = feat_obs.astype(np.float32), obs_j.astype(np.float32)
+            if not (np.array_equal(f32s[0].astype(np.float64), feat_obs) and np.array_equal(f32s[1].astype(np.float64), obs_j)):
+                raise ValueError("observations are not float32 values")
+            return f32s
+        return feat_obs, obs_j
 
     def out_shapes(self):
         W, F, D, NP, NL = self.W, self.F, self.D, self.NP, self.NL

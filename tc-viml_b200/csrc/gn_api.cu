@@ -65,7 +65,7 @@ int check_batch(viml_ctx* ctx, const viml_window_batch* in) {
   if (W < 0 || P < 1 || P > 255 || F < 0 || F > 65535 || in->n_point_factors < 0 || in->n_line_factors < 0)
     return fail(ctx, VIML_ERR_INVALID, "window batch sizes out of range");
   if (W > 0 && (!in->poses || !in->ex_pose || (F > 0 && !in->inv_depth) || !in->pf_window_offset ||
-                (in->n_point_factors > 0 && (!in->pf_idx || (!in->pf_obs && !(in->feat_obs && in->pf_obs_j)))) ||
+                (in->n_point_factors > 0 && (!in->pf_idx || (!in->pf_obs && !(in->feat_obs && in->pf_obs_j) && !(in->feat_obs_f32 && in->pf_obs_j_f32)))) ||
                 (in->n_line_factors > 0 && (!in->lf_window_offset || !in->lf_frame || !in->lf_geom))))
     return fail(ctx, VIML_ERR_INVALID, "null input array");
   return VIML_OK;
@@ -128,9 +128,14 @@ int run(viml_ctx* ctx, const viml_window_batch* in, const viml_dense_factors* de
   st.in(in->pf_window_offset, (size_t)W + 1, &a.pf_window_offset);
   st.in(in->pf_idx, (size_t)NP, &a.pf_idx);
   const bool obs_table = !in->pf_obs && NP > 0;   // observations as a per-feature table (viml.h): expanded on the device
+  const bool obs_f32 = obs_table && !(in->feat_obs && in->pf_obs_j);
   const double *d_fobs = nullptr, *d_obsj = nullptr;
+  const float *d_fobs32 = nullptr, *d_obsj32 = nullptr;
   double* d_obs = nullptr;
-  if (obs_table) {
+  if (obs_f32) {
+    st.in(in->feat_obs_f32, (size_t)W * F * 2, &d_fobs32);
+    st.in(in->pf_obs_j_f32, (size_t)NP * 2, &d_obsj32);
+  } else if (obs_table) {
     st.in(in->feat_obs, (size_t)W * F * 2, &d_fobs);
     st.in(in->pf_obs_j, (size_t)NP * 2, &d_obsj);
   } else {
@@ -182,7 +187,7 @@ int run(viml_ctx* ctx, const viml_window_batch* in, const viml_dense_factors* de
   a.cache = cache;
   if (obs_table) {
     a.pf_obs = d_obs;
-    rc = viml_launch_expand_obs(ctx, a, d_fobs, d_obsj);
+    rc = obs_f32 ? viml_launch_expand_obs(ctx, a, d_fobs32, d_obsj32, true) : viml_launch_expand_obs(ctx, a, d_fobs, d_obsj, false);
     if (rc != VIML_OK) return rc;
   }
   rc = viml_launch_linearize(ctx, a);

@@ -39,17 +39,18 @@ __device__ __forceinline__ void mul_AtBt(const double* A, const double* B, doubl
 
 // Observation table -> per-factor pairs (viml.h, viml_window_batch): one CTA per window; pts_i of a factor is its feature's
 // entry of feat_obs (every factor of a feature is built from feature_per_frame[0].point, estimator.cpp:1747-1766), pts_j its own.
-__global__ void expand_obs_kernel(LinearizeArgs a, const double* __restrict__ feat_obs, const double* __restrict__ pf_obs_j) {
+template <typename T2>   // double2, or float2 (observations the caller still holds as the tracker's float32: widened here, exactly)
+__global__ void expand_obs_kernel(LinearizeArgs a, const T2* __restrict__ feat_obs, const T2* __restrict__ pf_obs_j) {
   const int w = blockIdx.x;
   const int k0 = a.pf_window_offset[w], k1 = a.pf_window_offset[w + 1];
-  const double2* fo = reinterpret_cast<const double2*>(feat_obs) + (size_t)w * a.F;
-  const double2* oj = reinterpret_cast<const double2*>(pf_obs_j);
+  const T2* fo = feat_obs + (size_t)w * a.F;
   double4* dst = reinterpret_cast<double4*>(const_cast<double*>(a.pf_obs));
   for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
     const uint32_t feat = a.pf_idx[k] >> 16;
-    const double2 pi = feat < (uint32_t)a.F ? fo[feat] : make_double2(0.0, 0.0);   // a bad index is dropped later, by the kernels
-    const double2 pj = oj[k];
-    dst[k] = make_double4(pi.x, pi.y, pj.x, pj.y);
+    const T2 pj = pf_obs_j[k];
+    double pix = 0.0, piy = 0.0;   // a bad index is dropped later, by the kernels
+    if (feat < (uint32_t)a.F) pix = (double)fo[feat].x, piy = (double)fo[feat].y;
+    dst[k] = make_double4(pix, piy, (double)pj.x, (double)pj.y);
   }
 }
 
@@ -600,10 +601,11 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
   return VIML_OK;
 }
 
-int viml_launch_expand_obs(viml_ctx* ctx, const LinearizeArgs& a, const double* feat_obs, const double* pf_obs_j) {
+int viml_launch_expand_obs(viml_ctx* ctx, const LinearizeArgs& a, const void* feat_obs, const void* pf_obs_j, bool f32) {
   if (a.NP == 0) return VIML_OK;
   LaunchScope ls(ctx, K_PREP);
-  expand_obs_kernel<<<a.W, 128, 0, ctx->stream>>>(a, feat_obs, pf_obs_j);
+  if (f32) expand_obs_kernel<float2><<<a.W, 128, 0, ctx->stream>>>(a, (const float2*)feat_obs, (const float2*)pf_obs_j);
+  else expand_obs_kernel<double2><<<a.W, 128, 0, ctx->stream>>>(a, (const double2*)feat_obs, (const double2*)pf_obs_j);
   VIML_TRY_CUDA(ctx, cudaGetLastError());
   return VIML_OK;
 }

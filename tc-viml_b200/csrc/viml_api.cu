@@ -306,7 +306,11 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   if (!(flags & (VIML_OUT_RESIDUAL_JACOBIAN | VIML_OUT_HB | VIML_OUT_SCHUR)))
     return fail(ctx, VIML_ERR_INVALID, "no output mode requested");
   if (W == 0) return VIML_OK;
-  const bool obs_table = !in->pf_obs && in->feat_obs && in->pf_obs_j;   // observations as a per-feature table
+  const bool obs_f32 = !in->pf_obs && !(in->feat_obs && in->pf_obs_j) && in->feat_obs_f32 && in->pf_obs_j_f32;
+  const bool obs_table = !in->pf_obs && ((in->feat_obs && in->pf_obs_j) || obs_f32);   // observations as a per-feature table
+  const void* h_fobs = obs_f32 ? (const void*)in->feat_obs_f32 : (const void*)in->feat_obs;
+  const void* h_obsj = obs_f32 ? (const void*)in->pf_obs_j_f32 : (const void*)in->pf_obs_j;
+  const size_t ob = obs_f32 ? 8 : 16;   // bytes of one {x, y}
   if (!in->poses || !in->ex_pose || (F > 0 && !in->inv_depth) || !in->pf_window_offset ||
       (NP > 0 && (!in->pf_idx || (!in->pf_obs && !obs_table))) || (NL > 0 && (!in->lf_window_offset || !in->lf_frame || !in->lf_geom)))
     return fail(ctx, VIML_ERR_INVALID, "null input array");
@@ -351,7 +355,7 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
     if (obs_table && NP > 0) {
       VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(DeviceArena::padded((size_t)NP * 32)));
       a.pf_obs = ctx->in_arena.take<double>((size_t)NP * 4);
-      const int rc = viml_launch_expand_obs(ctx, a, in->feat_obs, in->pf_obs_j);
+      const int rc = viml_launch_expand_obs(ctx, a, h_fobs, h_obsj, obs_f32);
       if (rc != VIML_OK) return rc;
     }
     if (!wantA) a.out.pf_residual = a.out.pf_jac_pose_i = a.out.pf_jac_pose_j = a.out.pf_jac_ex = a.out.pf_jac_feat =
@@ -399,7 +403,7 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   size_t in_bytes = pad(n_pose * 8) + pad(n_ex * 8) + pad(n_dep * 8) + 2 * pad((size_t)(W + 1) * 4);
   in_bytes += pad((size_t)NP * 4) + pad((size_t)NP * 32) + pad((size_t)NP * 8);
   in_bytes += pad((size_t)NL * 4) + pad((size_t)NL * 72);
-  if (obs_table) in_bytes += pad((size_t)NP * 16) + pad(n_dep * 16);
+  if (obs_table) in_bytes += pad((size_t)NP * ob) + pad(n_dep * ob);
   VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(in_bytes));
   double* d_poses = ctx->in_arena.take<double>(n_pose);
   double* d_ex = ctx->in_arena.take<double>(n_ex);
@@ -411,8 +415,8 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   int32_t* d_loff = NL > 0 ? ctx->in_arena.take<int32_t>((size_t)W + 1) : nullptr;
   int32_t* d_frame = NL > 0 ? ctx->in_arena.take<int32_t>((size_t)NL) : nullptr;
   double* d_geom = NL > 0 ? ctx->in_arena.take<double>((size_t)NL * 9) : nullptr;
-  double* d_obsj = obs_table ? ctx->in_arena.take<double>((size_t)NP * 2) : nullptr;
-  double* d_fobs = obs_table ? ctx->in_arena.take<double>(n_dep * 2) : nullptr;
+  char* d_obsj = obs_table ? ctx->in_arena.take<char>((size_t)NP * ob) : nullptr;
+  char* d_fobs = obs_table ? ctx->in_arena.take<char>(n_dep * ob) : nullptr;
   a.poses = d_poses, a.ex_pose = d_ex, a.inv_depth = d_dep, a.pf_window_offset = d_poff, a.pf_idx = d_idx;
   a.pf_obs = d_obs, a.pf_pts_i_z = d_z, a.lf_window_offset = d_loff, a.lf_frame = d_frame, a.lf_geom = d_geom;
 
@@ -472,7 +476,7 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
     };
     put(d_poses, in->poses, n_pose * 8), put(d_ex, in->ex_pose, n_ex * 8), put(d_dep, in->inv_depth, n_dep * 8);
     put(d_poff, in->pf_window_offset, (size_t)(W + 1) * 4), put(d_idx, in->pf_idx, (size_t)NP * 4);
-    if (obs_table) put(d_obsj, in->pf_obs_j, (size_t)NP * 16), put(d_fobs, in->feat_obs, n_dep * 16);
+    if (obs_table) put(d_obsj, h_obsj, (size_t)NP * ob), put(d_fobs, h_fobs, n_dep * ob);
     else put(d_obs, in->pf_obs, (size_t)NP * 32);
     if (d_z) put(d_z, in->pf_pts_i_z, (size_t)NP * 8);
     if (NL > 0) {
@@ -480,7 +484,7 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
       put(d_geom, in->lf_geom, (size_t)NL * 72);
     }
     VIML_TRY_CUDA(ctx, cudaMemcpyAsync(ibase, ctx->h_stage_in, ctx->in_arena.used, cudaMemcpyHostToDevice, st));
-    int rc = obs_table ? viml_launch_expand_obs(ctx, a, d_fobs, d_obsj) : VIML_OK;
+    int rc = obs_table ? viml_launch_expand_obs(ctx, a, d_fobs, d_obsj, obs_f32) : VIML_OK;
     if (rc == VIML_OK) rc = viml_launch_linearize(ctx, a);
     if (rc != VIML_OK) return rc;
     // the device range that holds every slot the caller wants
@@ -535,8 +539,8 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
     // DMA set-up however small it is, and 17 copies per chunk kept the upload stream busy for 6 ms on 125 MB
     h2d(d_idx + pa, in->pf_idx + pa, (size_t)(pb - pa) * 4);
     if (obs_table) {
-      h2d(d_obsj + 2 * pa, in->pf_obs_j + 2 * pa, (size_t)(pb - pa) * 16);
-      h2d(d_fobs + (size_t)w0 * F * 2, in->feat_obs + (size_t)w0 * F * 2, (size_t)(w1 - w0) * F * 16);
+      h2d(d_obsj + ob * pa, (const char*)h_obsj + ob * pa, (size_t)(pb - pa) * ob);
+      h2d(d_fobs + (size_t)w0 * F * ob, (const char*)h_fobs + (size_t)w0 * F * ob, (size_t)(w1 - w0) * F * ob);
     } else {
       h2d(d_obs + 4 * pa, in->pf_obs + 4 * pa, (size_t)(pb - pa) * 32);
     }
@@ -566,7 +570,7 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
       double** vd = (double**)((char*)&v.out + ((char*)sl.dev - (char*)&a.out));
       *vd = *sl.dev + sl.per_window * w0;   // per-factor arrays stay absolute (indexed by the global factor id)
     }
-    if (obs_table) rc = viml_launch_expand_obs(ctx, v, d_fobs + (size_t)w0 * F * 2, d_obsj);
+    if (obs_table) rc = viml_launch_expand_obs(ctx, v, d_fobs + (size_t)w0 * F * ob, d_obsj, obs_f32);
     if (rc == VIML_OK) rc = viml_launch_linearize(ctx, v);
     cudaEventRecord(ev_k[c], st);
     cudaStreamWaitEvent(s_out, ev_k[c], 0);

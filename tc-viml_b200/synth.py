@@ -77,7 +77,7 @@ def pose7(p, R, rng=None, norm_jitter=1e-12):
 
 # ---- sliding windows (cfg 1, 2, 4, 5) ---------------------------------------------------------------
 def make_windows(W, seed=0x5EED, P=11, F=150, lines_per_frame=10, start_max=None, min_len=2,
-                 all_start_zero=False, noise_px=0.5, z_plane=False, max_len=None):
+                 all_start_zero=False, noise_px=0.5, z_plane=False, max_len=None, f32_obs=False):
     """W independent EuRoC-shaped windows.
 
     P poses on a smooth random trajectory, F landmarks 2.5-8 m ahead of their start frame with
@@ -86,6 +86,8 @@ def make_windows(W, seed=0x5EED, P=11, F=150, lines_per_frame=10, start_max=None
     (1+N(0,0.05^2)); state = truth + small perturbation.  Line factors: `lines_per_frame` per pose,
     segments 2-8 m ahead, detected line = projection + N(0,1 px), float32-rounded pixel endpoints.
     all_start_zero=True gives the marginalisation stress shape (every landmark starts in frame 0).
+    f32_obs=True rounds the point observations to float32, which is what the estimator receives (the tracker publishes
+    geometry_msgs::Point32, feature_tracker_node.cpp:159-162; estimator_node.cpp:388-390 widens them).
     """
     rng = np.random.Generator(np.random.PCG64(seed))
     if start_max is None:
@@ -132,6 +134,8 @@ def make_windows(W, seed=0x5EED, P=11, F=150, lines_per_frame=10, start_max=None
     pts_i = pts_all[w_idx, f_idx, i_idx]
     pts_j = pts_all[w_idx, f_idx, j_idx]
     pf_obs = np.concatenate([pts_i, pts_j], -1)
+    if f32_obs:
+        pf_obs = pf_obs.astype(np.float32).astype(np.float64)
     pf_idx = (i_idx | (j_idx << 8) | (f_idx << 16)).astype(np.uint32)
     counts = np.bincount(w_idx, minlength=W)
     pf_off = np.zeros(W + 1, dtype=np.int32)

@@ -273,6 +273,24 @@ def test_observation_table_input(pkg, orc, ctx, cfg):
     g0 = ctx.gn_step(small, dense, extra, abi.LOSS_CAUCHY, lam=1e-4)
     g1 = ctx.gn_step(small, dense, extra, abi.LOSS_CAUCHY, lam=1e-4, obs_table=True)
     assert np.abs(g1["dx"] - g0["dx"]).max() <= 1e-9 * np.abs(g0["dx"]).max()
+    # float32 table: observations that are float32 values (what the tracker publishes) travel as floats, same results bit for bit
+    bf = synth.make_windows(600, seed=171, f32_obs=True)
+    pairs32 = ctx.linearize(bf, flags)
+    table32 = ctx.linearize(bf, flags, obs_table="f32")
+    for k, v in pairs32.items():
+        if k.startswith(("pf_", "lf_")) or k in ("H_lp", "H_ll", "b_l"):
+            assert np.array_equal(table32[k], v), k
+        else:
+            assert pkg.parity.unit_err(k, table32[k], v) < 1e-12, k
+    s32 = bf.slice_windows(0, 8)           # the small-batch staging path and the solver entry point
+    a32, b32 = ctx.linearize(s32, flags), ctx.linearize(s32, flags, obs_table="f32")
+    assert np.array_equal(a32["pf_jac_pose_i"], b32["pf_jac_pose_i"]) and pkg.parity.unit_err("S", b32["S"], a32["S"]) < 1e-12
+    d32 = synth.make_dense_factors(s32, seed=5)
+    Sa, ga = ctx.reduced_system(s32, d32, abi.LOSS_CAUCHY)
+    Sb, gb = ctx.reduced_system(s32, d32, abi.LOSS_CAUCHY, obs_table="f32")
+    assert np.abs(Sb - Sa).max() <= 1e-12 * np.abs(Sa).max() and np.abs(gb - ga).max() <= 1e-12 * np.abs(ga).max()
+    with pytest.raises(ValueError):
+        b.obs_table(f32=True)              # b's observations are full doubles
     # a batch whose factors do not share pts_i per feature has no table form
     bad = abi.Batch(b.poses, b.ex_pose, b.inv_depth, b.pf_window_offset, b.pf_idx, b.pf_obs + np.arange(b.NP)[:, None] * 1e-6,
                     b.lf_window_offset, b.lf_frame, b.lf_geom)
