@@ -45,6 +45,189 @@ __global__ void __launch_bounds__(256) reduced_kernel(int D, DenseArgs dn, const
   }
 }
 
+// ---- tiled Cholesky solve ---------------------------------------------------------------------------------------------------------
+// solve_tiled_kernel: (Sx + lambda diag Sx) dx = -gx, one CTA (8 warps) per window, the matrix held in shared memory as the lower
+// triangle of 8 x 8 tiles (tile (I, J), J <= I, at (I (I + 1) / 2 + J) * 64; Dx padded to a multiple of 8 with an identity
+// diagonal).  Right-looking blocked factorisation: per tile column K (1) warp 0 factors the diagonal tile, (2) one thread per row
+// solves the panel rows against it, (3) the trailing tiles take A[I][J] -= L[I][K] L[J][K]^T as two DMMA steps each, dealt
+// round-robin to the warps.  22 tile columns and ~66 barriers for Dx = 171 instead of 171 columns and ~510 barriers in
+// solve_kernel below, and the O(n^3) part runs on the FP64 tensor pipe.  Forward / backward substitution tile by tile.
+constexpr int kTile = 8;
+__device__ __forceinline__ int tile_at(int I, int J) { return (I * (I + 1) / 2 + J) * 64; }
+
+__global__ void __launch_bounds__(256) solve_tiled_kernel(int Dx, double lambda, const double* __restrict__ Sx, const double* __restrict__ gx,
+                                                          double* __restrict__ dx, int32_t* __restrict__ solved, double* __restrict__ cost) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ int s_ok;
+  __shared__ double s_red[8], s_dinv[kTile];
+  const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NB = (Dx + kTile - 1) / kTile, Dp = NB * kTile;
+  double* __restrict__ L = sm;                                   // NB (NB + 1) / 2 tiles
+  double* __restrict__ y = sm + (size_t)NB * (NB + 1) / 2 * 64;  // [Dp]
+  const double* __restrict__ A = Sx + (size_t)w * Dx * Dx;
+  // (A + A^T) / 2 into the tiles with row-wise (coalesced) reads only: the lower entries first, then every upper entry adds its
+  // half to its mirror (one writer per entry in either pass)
+  for (int e = tid; e < Dp * Dp; e += 256) {   // padding rows: identity; everything else starts at zero
+    const int i = e / Dp, j = e - i * Dp;
+    if (j <= i) L[tile_at(i >> 3, j >> 3) + (i & 7) * 8 + (j & 7)] = (i >= Dx && i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  // four independent loads in flight per thread and pass (8 warps per SM: the load latency is otherwise exposed)
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int e0 = tid; e0 < Dx * Dx; e0 += 4 * 256) {
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = e0 + u * 256 < Dx * Dx ? A[e0 + u * 256] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * 256;
+        if (e >= Dx * Dx) break;
+        const int i = e / Dx, j = e - i * Dx;
+        if (pass == 0 && j <= i) L[tile_at(i >> 3, j >> 3) + (i & 7) * 8 + (j & 7)] = (i == j) ? v[u] * (1.0 + lambda) : 0.5 * v[u];
+        if (pass == 1 && j > i) L[tile_at(j >> 3, i >> 3) + (j & 7) * 8 + (i & 7)] += 0.5 * v[u];
+      }
+    }
+    __syncthreads();
+  }
+  // the strictly upper part of the diagonal tiles is never read as data but is multiplied in the DMMA steps: zero it
+  for (int e = tid; e < NB * 64; e += 256) {
+    const int I = e >> 6, r = (e >> 3) & 7, c = e & 7;
+    if (c > r) L[tile_at(I, I) + r * 8 + c] = 0.0;
+  }
+  for (int e = tid; e < Dp; e += 256) y[e] = e < Dx ? -gx[(size_t)w * Dx + e] : 0.0;
+  if (tid == 0) s_ok = 1;
+  __syncthreads();
+  const int kq = lane & 3, mq = lane >> 2;
+  for (int K = 0; K < NB; ++K) {
+    double* __restrict__ Dk = L + tile_at(K, K);
+    if (warp == 0) {   // 8 x 8 Cholesky of the diagonal tile: lane = (row r, column c) pairs, column by column
+      for (int j = 0; j < kTile; ++j) {
+        const double d = Dk[j * 8 + j];
+        const bool good = d > 0.0 && isfinite(d);
+        const double sd = good ? sqrt(d) : 1.0, inv = good ? rsqrt(d) : 1.0;
+        __syncwarp();
+        if (!good && lane == 0) s_ok = 0;
+        if (lane < kTile && lane >= j) Dk[lane * 8 + j] = (lane == j) ? sd : Dk[lane * 8 + j] * inv;
+        if (lane == 0) s_dinv[j] = inv;
+        __syncwarp();
+        // trailing part of the tile: entry (r, c), j < c <= r
+        for (int e = lane; e < 64; e += 32) {
+          const int r = e >> 3, c = e & 7;
+          if (c > j && r >= c) Dk[r * 8 + c] -= Dk[r * 8 + j] * Dk[c * 8 + j];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (!s_ok) break;   // uniform
+    // panel: row `row` of the tiles below the diagonal one solves x L_KK^T = a (forward substitution over the 8 columns)
+    const int nrows = (NB - K - 1) * kTile;
+    if (tid < nrows) {
+      double* __restrict__ a = L + tile_at(K + 1 + (tid >> 3), K) + (tid & 7) * 8;
+      double x[kTile];
+#pragma unroll
+      for (int c = 0; c < kTile; ++c) {
+        double v = a[c];
+#pragma unroll
+        for (int k = 0; k < c; ++k) v -= x[k] * Dk[c * 8 + k];
+        x[c] = v * s_dinv[c];
+      }
+#pragma unroll
+      for (int c = 0; c < kTile; ++c) a[c] = x[c];
+    }
+    __syncthreads();
+    // trailing update on the tensor pipe: tile (I, J), K < J <= I, dealt round-robin to the warps
+    {
+      const int m = NB - K - 1;
+      int t = warp, I = 0, J = 0;          // t-th tile of the m x m lower triangle (row-major): advance (I, J) incrementally
+      while (t >= I + 1 && I < m) t -= I + 1, ++I;
+      J = t;
+      while (I < m) {
+        const double* __restrict__ Li = L + tile_at(K + 1 + I, K);
+        const double* __restrict__ Lj = L + tile_at(K + 1 + J, K);
+        double2* cptr = reinterpret_cast<double2*>(L + tile_at(K + 1 + I, K + 1 + J) + mq * 8 + 2 * kq);
+        double2 c = *cptr;
+        stream::dmma(c.x, c.y, -Li[mq * 8 + kq], Lj[mq * 8 + kq]);
+        stream::dmma(c.x, c.y, -Li[mq * 8 + 4 + kq], Lj[mq * 8 + 4 + kq]);
+        *cptr = c;
+        J += 8;                               // the next tile of this warp: 8 further in row-major order
+        while (I < m && J > I) J -= I + 1, ++I;
+      }
+    }
+    __syncthreads();
+  }
+  const bool ok = s_ok != 0;
+  if (ok) {
+    // forward L z = y: diagonal tile by warp 0 (serial over its 8 rows), then one thread per row below
+    for (int K = 0; K < NB; ++K) {
+      const double* __restrict__ Dk = L + tile_at(K, K);
+      if (tid == 0) {
+#pragma unroll
+        for (int r = 0; r < kTile; ++r) {
+          double v = y[K * 8 + r];
+          for (int k = 0; k < r; ++k) v -= Dk[r * 8 + k] * y[K * 8 + k];
+          y[K * 8 + r] = v / Dk[r * 8 + r];
+        }
+      }
+      __syncthreads();
+      const int nrows = (NB - K - 1) * kTile;
+      if (tid < nrows) {
+        const double* __restrict__ a = L + tile_at(K + 1 + (tid >> 3), K) + (tid & 7) * 8;
+        double v = y[(K + 1) * 8 + tid];
+#pragma unroll
+        for (int c = 0; c < kTile; ++c) v -= a[c] * y[K * 8 + c];
+        y[(K + 1) * 8 + tid] = v;
+      }
+      __syncthreads();
+    }
+    // backward L^T x = z: diagonal tile, then every entry above takes its share of this tile row
+    for (int K = NB - 1; K >= 0; --K) {
+      const double* __restrict__ Dk = L + tile_at(K, K);
+      if (tid == 0) {
+#pragma unroll
+        for (int r = kTile - 1; r >= 0; --r) {
+          double v = y[K * 8 + r];
+          for (int k = r + 1; k < kTile; ++k) v -= Dk[k * 8 + r] * y[K * 8 + k];
+          y[K * 8 + r] = v / Dk[r * 8 + r];
+        }
+      }
+      __syncthreads();
+      if (tid < K * kTile) {   // y[8 J + c] -= sum_r L[K][J][r][c] y[8 K + r]
+        const double* __restrict__ a = L + tile_at(K, tid >> 3) + (tid & 7);
+        double v = y[tid];
+#pragma unroll
+        for (int r = 0; r < kTile; ++r) v -= a[r * 8] * y[K * 8 + r];
+        y[tid] = v;
+      }
+      __syncthreads();
+    }
+  }
+  // model decrease with the undamped Sx: -g.x - x.Sx x / 2; a warp per row of Sx (coalesced), lanes over the columns
+  double part = 0.0;
+  for (int i = warp; i < Dx; i += 8) {
+    double sx = 0.0;
+    if (ok)
+      for (int c = lane; c < Dx; c += 32) sx = fma(A[(size_t)i * Dx + c], y[c], sx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    const double xi = ok ? y[i] : 0.0;
+    if (lane == 0) {
+      part += -gx[(size_t)w * Dx + i] * xi - 0.5 * xi * sx;
+      dx[(size_t)w * Dx + i] = xi;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) s_red[warp] = part;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += s_red[k];
+    cost[3 * (size_t)w + 2] = t;
+    solved[w] = ok ? 1 : 0;
+  }
+}
+
 // dx = -(Sx + lambda diag(Sx))^-1 gx by Cholesky in shared memory (packed lower triangle), one CTA per window.
 // solved[w] = 0 when a pivot is not positive (dx = 0 then).  cost[3w + 2] = -gx.dx - 1/2 dx.Sx.dx (undamped model).
 __global__ void __launch_bounds__(256) solve_kernel(int Dx, double lambda, const double* __restrict__ Sx, const double* __restrict__ gx,

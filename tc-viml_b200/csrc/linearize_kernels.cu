@@ -627,9 +627,17 @@ int viml_launch_reduced(viml_ctx* ctx, int W, int D, const DenseArgs& dn, const 
 
 int viml_launch_gn_solve(viml_ctx* ctx, int W, int Dx, double lambda, const double* Sx, const double* gx, double* dx, int32_t* solved,
                          double* cost) {
+  const int NB = (Dx + 7) / 8;
+  const size_t smem_t = ((size_t)NB * (NB + 1) / 2 * 64 + (size_t)NB * 8) * sizeof(double);
+  LaunchScope ls(ctx, K_GN);
+  if (smem_t <= 220 * 1024 && Dx <= 256 - 8 && !getenv("VIML_GN_UNBLOCKED")) {   // tiled factorisation on the tensor pipe
+    VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(gn::solve_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+    gn::solve_tiled_kernel<<<W, 256, smem_t, ctx->stream>>>(Dx, lambda, Sx, gx, dx, solved, cost);
+    VIML_TRY_CUDA(ctx, cudaGetLastError());
+    return VIML_OK;
+  }
   const size_t smem = ((size_t)Dx * (Dx + 1) / 2 + Dx) * sizeof(double);
   VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(gn::solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  LaunchScope ls(ctx, K_GN);
   gn::solve_kernel<<<W, 256, smem, ctx->stream>>>(Dx, lambda, Sx, gx, dx, solved, cost);
   VIML_TRY_CUDA(ctx, cudaGetLastError());
   return VIML_OK;
