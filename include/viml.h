@@ -22,6 +22,11 @@
  *                             (evaluated by their owners; their r / J blocks are inputs here), ThreadsConstructA rule :141-172
  *   viml_gn_step           <- one solver iteration of ceres::Solve  estimator.cpp:1888-1905 (normal equations, Schur elimination of
  *                             the landmarks, dense solve, PoseLocalParameterization::Plus  pose_local_parameterization.cpp:3-19)
+ *   viml_fov_update / viml_fov_slide / VIML_FOV_CACHED
+ *                          <- the per-slot FoV lists the estimator keeps between frames: UpdateLinesInFoV at frame entry
+ *                             (estimator.cpp:342) and their shifts in slideWindowWithLinesFoV (estimator.cpp:2148, :2160, :2218)
+ *   viml_track_gate        <- FeatureManager::removeLineOutlier + lineDiff  vins_estimator/src/feature_manager.cpp:494-541
+ *   viml_triangulate_batch <- FeatureManager::triangulate       feature_manager.cpp:440-492
  *   viml_config            <- the fields Estimator::setParameters reads for this path, estimator.cpp:54-124
  *
  * Conventions

@@ -541,7 +541,7 @@ int viml_launch_linearize(viml_ctx* ctx, const LinearizeArgs& a) {
   }
   if (fast) {
     VIML_TRY_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
-    // one CTA per window, two CTAs per SM; every H/b entry is written exactly once (no memset)
+    // one CTA (4 warps) per window, three CTAs per SM; every H/b entry is written exactly once (no memset)
     const int NB = a.P + 1, nblk = NB * (NB + 1) / 2;
     const size_t smem = ((size_t)((nblk * 36 + a.D + 1) & ~1) + (size_t)a.P * kPoseCache + kExCache + (size_t)stream::AW * stream::WORK_D) * 8;
     const int use_tma = ((((uintptr_t)a.out.H_pp) | ((uintptr_t)a.out.b_p)) & 15) == 0 ? 1 : 0;

@@ -8,9 +8,11 @@
 // It is a SYRK: D x D output, contraction over the F landmarks — the one GEMM-shaped piece of the hot path
 // (2 D^2 F flop over D F 8 bytes, ~18 flop/B at D = 72), so it goes to the FP64 tensor pipe.  tcgen05 has no
 // FP64 kind; on sm_100a the FP64 MMA is still mma.sync (DMMA in SASS).
-// One CTA per (72 x 72 output tile, window); 8 warps share the 81 8x8 sub-tiles (45 when the tile is on the
-// diagonal: only the upper triangle is computed and mirrored).  W is staged through shared memory in chunks
-// of 32 landmarks with a row stride of 76 doubles (conflict-free fragment loads).
+// Three kernels: schur_tma_kernel (D <= 72, the sliding window: TMA + mbarrier producer/consumer pipeline, warps own output tiles;
+// the default), schur_splitk_kernel (its round-1 predecessor, VIML_SCHUR_SPLITK=1) and schur_dmma_kernel (D > 72: one CTA per
+// (72 x 72 output tile, window), 8 warps share the 81 8x8 sub-tiles — 45 on the diagonal, where only the upper triangle is computed
+// and mirrored; W staged through shared memory in chunks of 32 landmarks with a row stride of 76 doubles, conflict-free fragment
+// loads; with the band plan of extent_kernel / order_kernel a tile only visits the landmarks that touch it).
 #include "common.cuh"
 
 namespace {
