@@ -11,10 +11,16 @@
 namespace gn {
 
 // Sx = embed(S) + sum_k J_k^T J_k,  gx = embed(g) + sum_k J_k^T r_k.  One CTA per window; the window's dense factors are
-// added one after the other (two factors may share columns), every (a, b) column pair of a factor by one thread.
+// added one after the other (two factors may share columns).  A factor's Jacobian (n x c, row-major) is staged in shared memory
+// with a row stride of c_pad + 4 doubles (conflict-free fragment loads) and J^T J is formed as 8 x 8 tiles on the FP64 tensor pipe:
+// the upper-triangle tiles dealt round-robin to the warps, ceil(n / 4) DMMA steps each, scattered through the factor's column map
+// with their mirrors.  A factor that does not fit the staging area (cap doubles) takes the entry-by-entry loop.
+constexpr int kReducedStage = 12288;   // doubles of dynamic shared memory (96 KB): a 76 x 75 prior needs 76 x 84
+
 __global__ void __launch_bounds__(256) reduced_kernel(int D, DenseArgs dn, const double* __restrict__ S, const double* __restrict__ g,
                                                       double* __restrict__ Sx, double* __restrict__ gx) {
-  const int w = blockIdx.x, tid = threadIdx.x, Dx = D + dn.X;
+  extern __shared__ __align__(16) double sJ[];
+  const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, Dx = D + dn.X;
   double* __restrict__ A = Sx + (size_t)w * Dx * Dx;
   double* __restrict__ b = gx + (size_t)w * Dx;
   const double* __restrict__ Sw = S + (size_t)w * D * D;
@@ -25,21 +31,60 @@ __global__ void __launch_bounds__(256) reduced_kernel(int D, DenseArgs dn, const
   for (int e = tid; e < Dx; e += blockDim.x) b[e] = e < D ? g[(size_t)w * D + e] : 0.0;
   if (dn.ND == 0) return;
   __syncthreads();
+  const int kq = lane & 3, mq = lane >> 2;
   for (int k = dn.window_offset[w]; k < dn.window_offset[w + 1]; ++k) {
     const int n = (int)(dn.row_offset[k + 1] - dn.row_offset[k]), c = (int)(dn.col_offset[k + 1] - dn.col_offset[k]);
     const double* __restrict__ J = dn.jacobian + dn.jac_offset[k];
     const double* __restrict__ r = dn.residual + dn.row_offset[k];
     const int32_t* __restrict__ ci = dn.col_index + dn.col_offset[k];
-    for (int e = tid; e < c * c; e += blockDim.x) {
-      const int a = e / c, bb = e - a * c;
-      double v = 0.0;
-      for (int q = 0; q < n; ++q) v = fma(J[(size_t)q * c + a], J[(size_t)q * c + bb], v);
-      A[(size_t)ci[a] * Dx + ci[bb]] += v;
-    }
-    for (int a = tid; a < c; a += blockDim.x) {
-      double v = 0.0;
-      for (int q = 0; q < n; ++q) v = fma(J[(size_t)q * c + a], r[q], v);
-      b[ci[a]] += v;
+    const int np = (n + 3) & ~3, cp = (c + 7) & ~7, ld = cp + 4;
+    if (np * ld + np <= kReducedStage) {
+      double* __restrict__ sr = sJ + np * ld;   // the residual behind the Jacobian
+      for (int e = tid; e < np * ld; e += 256) {
+        const int q = e / ld, a = e - q * ld;
+        sJ[e] = (q < n && a < c) ? J[(size_t)q * c + a] : 0.0;
+      }
+      for (int q = tid; q < np; q += 256) sr[q] = q < n ? r[q] : 0.0;
+      __syncthreads();
+      const int nt = cp >> 3, ntile = nt * (nt + 1) / 2;
+      for (int t = warp; t < ntile; t += 8) {      // t-th tile of the upper triangle, row-major: row ta holds nt - ta tiles
+        int rem = t, ta = 0;
+        while (rem >= nt - ta) rem -= nt - ta, ++ta;
+        const int tb = ta + rem;
+        double c0 = 0.0, c1 = 0.0;
+        const double* __restrict__ pa = sJ + kq * ld + 8 * ta + mq;
+        const double* __restrict__ pb = sJ + kq * ld + 8 * tb + mq;
+        for (int s4 = 0; s4 < np; s4 += 4) stream::dmma(c0, c1, pa[s4 * ld], pb[s4 * ld]);
+        const int a = 8 * ta + mq, bb = 8 * tb + 2 * kq;
+        if (a < c) {
+          const size_t ra = (size_t)ci[a] * Dx;
+          if (bb < c) {
+            A[ra + ci[bb]] += c0;
+            if (ta != tb) A[(size_t)ci[bb] * Dx + ci[a]] += c0;
+          }
+          if (bb + 1 < c) {
+            A[ra + ci[bb + 1]] += c1;
+            if (ta != tb) A[(size_t)ci[bb + 1] * Dx + ci[a]] += c1;
+          }
+        }
+      }
+      for (int a = tid; a < c; a += 256) {
+        double v = 0.0;
+        for (int q = 0; q < n; ++q) v = fma(sJ[q * ld + a], sr[q], v);
+        b[ci[a]] += v;
+      }
+    } else {
+      for (int e = tid; e < c * c; e += blockDim.x) {
+        const int a = e / c, bb = e - a * c;
+        double v = 0.0;
+        for (int q = 0; q < n; ++q) v = fma(J[(size_t)q * c + a], J[(size_t)q * c + bb], v);
+        A[(size_t)ci[a] * Dx + ci[bb]] += v;
+      }
+      for (int a = tid; a < c; a += blockDim.x) {
+        double v = 0.0;
+        for (int q = 0; q < n; ++q) v = fma(J[(size_t)q * c + a], r[q], v);
+        b[ci[a]] += v;
+      }
     }
     __syncthreads();
   }

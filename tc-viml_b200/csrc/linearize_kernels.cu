@@ -620,7 +620,9 @@ int viml_launch_prep(viml_ctx* ctx, const LinearizeArgs& a) {
 
 int viml_launch_reduced(viml_ctx* ctx, int W, int D, const DenseArgs& dn, const double* S, const double* g, double* Sx, double* gx) {
   LaunchScope ls(ctx, K_GN);
-  gn::reduced_kernel<<<W, 256, 0, ctx->stream>>>(D, dn, S, g, Sx, gx);
+  const int smem = gn::kReducedStage * (int)sizeof(double);
+  VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(gn::reduced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  gn::reduced_kernel<<<W, 256, smem, ctx->stream>>>(D, dn, S, g, Sx, gx);
   VIML_TRY_CUDA(ctx, cudaGetLastError());
   return VIML_OK;
 }
