@@ -1,3 +1,6 @@
+"""Times the solver-iteration kernels (K_GN event pairs) of viml_gn_step on 1024 EuRoC-shaped windows with the realistic dense-factor
+set, tiled Cholesky vs the column-by-column kernel (VIML_GN_UNBLOCKED=1), and prints the difference of the two steps.
+usage (on a GPU box, from the repo root): python profiles/gn_time.py"""
 import importlib, sys, time, json, os
 sys.path.insert(0, ".")
 import numpy as np
