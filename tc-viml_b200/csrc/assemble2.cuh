@@ -75,7 +75,7 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 __global__ void __launch_bounds__(PT_MAX) plan_kernel(LinearizeArgs A, PlanPtrs PL) {
   extern __shared__ __align__(16) unsigned char plan_raw[];
   __shared__ int gcount[PMAX + 2], grun[PMAX + 2], lcount[PMAX + 1], lrun[PMAX + 1];
-  __shared__ int s_bad, s_ntasks, s_nlslots;
+  __shared__ int s_bad, s_big, s_ntasks, s_nlslots;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, w = blockIdx.x;
   const int P = A.P, F = A.F, NTH = (int)blockDim.x;   // 64 threads for EuRoC-sized windows, PT_MAX for many-feature ones
   uint32_t* fmask = reinterpret_cast<uint32_t*>(plan_raw);
@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(PT_MAX) plan_kernel(LinearizeArgs A, PlanPtrs 
   for (int e = tid; e < F * P; e += NTH) fid[e] = 0xffff;
   if (tid < PMAX + 2) gcount[tid] = 0;
   if (tid < PMAX + 1) lcount[tid] = 0;
-  if (tid == 0) s_bad = (nf > 65534 || nl > 65534 || nf < 0 || nl < 0) ? 1 : 0, s_ntasks = 0, s_nlslots = 0;
+  if (tid == 0) s_bad = s_big = (nf > 65534 || nl > 65534 || nf < 0 || nl < 0) ? 1 : 0, s_ntasks = 0, s_nlslots = 0;
   __syncthreads();
-  const int nfs = s_bad ? 0 : nf;
+  const int nfs = s_big ? 0 : nf;   // (s_bad itself is written by the loop below: not read before the next barrier)
   for (int k = tid; k < nfs; k += NTH) {
     const uint32_t ix = A.pf_idx[a0 + k];
     const int i = ix & 0xff, j = (ix >> 8) & 0xff, l = ix >> 16;

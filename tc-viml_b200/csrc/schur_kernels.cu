@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(kTmaThreads, 2) schur_tma_kernel(int W, int F,
   // landmark keep what the previous user of the stage left: everything starts as zero
   for (int e = tid; e < kTmaStages * kTmaStageD; e += kTmaThreads) tsm[e] = 0.0;
   if (tid == 0) {
-    for (int s2 = 0; s2 < kTmaStages; ++s2) mbar_init(&full[s2], 1), mbar_init(&empty[s2], kTmaWarps);
+    for (int s2 = 0; s2 < kTmaStages; ++s2) mbar_init(&full[s2], 32), mbar_init(&empty[s2], kTmaWarps * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fill (generic proxy) before the bulk copies (async proxy)
@@ -488,8 +488,10 @@ __global__ void __launch_bounds__(kTmaThreads, 2) schur_tma_kernel(int W, int F,
         double* sw = stages + (size_t)stg * kTmaStageD;
         const int l0 = ch * kTmaStageL, nl = min(kTmaStageL, F - l0);
         mbar_wait(&empty[stg], ((it / kTmaStages) & 1) ^ 1);
-        if (lane == 0) mbar_expect_tx(&full[stg], (uint32_t)nl * row_bytes + 2u * kTmaStageL * 8u);
-        __syncwarp();
+        // every producer lane arrives with the byte count of its own copies, then issues them (the stage's full barrier counts
+        // 32 arrivals): the canonical arrive.expect_tx + copy pair per issuing thread
+        const int my_rows = lane < nl ? (nl - lane + 31) / 32 : 0;
+        mbar_expect_tx(&full[stg], (uint32_t)my_rows * row_bytes + (lane == 0 ? 2u * kTmaStageL * 8u : 0u));
         for (int r = lane; r < nl; r += 32) bulk_g2s(sw + r * LDW, Hl + (size_t)(l0 + r) * D, row_bytes, &full[stg]);
         if (lane == 0) {
           bulk_g2s(sw + kTmaStageL * LDW, invp + (size_t)w * Fp + l0, kTmaStageL * 8u, &full[stg]);
@@ -543,8 +545,7 @@ __global__ void __launch_bounds__(kTmaThreads, 2) schur_tma_kernel(int W, int F,
 #pragma unroll
         for (int d = 1; d < 5; ++d) dmma(acc[d][0], acc[d][1], fa, row[coff[d]]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[stg]);
+      mbar_arrive(&empty[stg]);   // every consumer thread releases the stage itself (288 arrivals per phase)
     }
     // S = H_pp - acc on the owned tiles and their mirrors; g = b_p - sum over the k-lanes
     double* __restrict__ So = S + (size_t)w * D * D;
