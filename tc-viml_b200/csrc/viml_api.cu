@@ -512,8 +512,10 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   // offsets first (tiny, needed by every chunk); the previous call's work on `st` is already complete (synchronous API)
   VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_poff, in->pf_window_offset, (size_t)(W + 1) * 4, cudaMemcpyHostToDevice, s_in));
   if (NL > 0) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_loff, in->lf_window_offset, (size_t)(W + 1) * 4, cudaMemcpyHostToDevice, s_in));
-  int nchunk = W >= 512 ? 8 : 1;
+  int nchunk = W >= 512 ? 4 : 1;   // measured on the 4096-window batch with the float32 table (75 MB up, 88 MB down): 2, 3, 4, 5, 6, 8, 12, 16 chunks -> 2.96, 2.81, 2.67, 2.75, 2.70, 2.79, 2.93, 2.96 ms
   if (const char* e = getenv("VIML_CHUNKS")) nchunk = std::max(1, std::min(W, atoi(e)));   // tuning hook
+  std::vector<int> wb(nchunk + 1, 0);   // uniform chunks (a ramp with small first / last chunks was measured: no gain)
+  for (int c = 0; c <= nchunk; ++c) wb[c] = (int)((int64_t)W * c / nchunk);
   // small per-window arrays: whole batch, one copy each
   VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_poses, in->poses, n_pose * 8, cudaMemcpyHostToDevice, s_in));
   VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_ex, in->ex_pose, n_ex * 8, cudaMemcpyHostToDevice, s_in));
@@ -531,7 +533,7 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   // every upload is queued first (the copies depend on nothing but the caller's arrays), so the upload stream runs at link
   // speed while the host validates the indices of chunk c and launches its kernels
   for (int c = 0; c < nchunk; ++c) {
-    const int w0 = (int)((int64_t)W * c / nchunk), w1 = (int)((int64_t)W * (c + 1) / nchunk);
+    const int w0 = wb[c], w1 = wb[c + 1];
     const int64_t pa = in->pf_window_offset[w0], pb = in->pf_window_offset[w1];
     const int64_t la = NL > 0 ? in->lf_window_offset[w0] : 0, lb = NL > 0 ? in->lf_window_offset[w1] : 0;
     // per chunk only the three large arrays (observations, packed indices, line geometry as ONE strided copy of its nine
@@ -551,7 +553,7 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
     cudaEventRecord(ev_in[c], s_in);
   }
   for (int c = 0; c < nchunk && rc == VIML_OK; ++c) {
-    const int w0 = (int)((int64_t)W * c / nchunk), w1 = (int)((int64_t)W * (c + 1) / nchunk), Wc = w1 - w0;
+    const int w0 = wb[c], w1 = wb[c + 1], Wc = w1 - w0;
     const int64_t pa = in->pf_window_offset[w0], pb = in->pf_window_offset[w1];
     const int64_t la = NL > 0 ? in->lf_window_offset[w0] : 0, lb = NL > 0 ? in->lf_window_offset[w1] : 0;
     if (!indices_ok(pa, pb, la, lb)) {   // bad indices never reach a kernel: this chunk and the following ones are not launched
@@ -570,8 +572,8 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
       double** vd = (double**)((char*)&v.out + ((char*)sl.dev - (char*)&a.out));
       *vd = *sl.dev + sl.per_window * w0;   // per-factor arrays stay absolute (indexed by the global factor id)
     }
-    if (obs_table) rc = viml_launch_expand_obs(ctx, v, d_fobs + (size_t)w0 * F * ob, d_obsj, obs_f32);
-    if (rc == VIML_OK) rc = viml_launch_linearize(ctx, v);
+    if (Wc > 0 && obs_table) rc = viml_launch_expand_obs(ctx, v, d_fobs + (size_t)w0 * F * ob, d_obsj, obs_f32);
+    if (Wc > 0 && rc == VIML_OK) rc = viml_launch_linearize(ctx, v);
     cudaEventRecord(ev_k[c], st);
     cudaStreamWaitEvent(s_out, ev_k[c], 0);
     for (auto& sl : slots)
