@@ -146,7 +146,7 @@ def run_reference(args):
     cfg = synth.euroc_config()
     nthreads = orc.hardware_threads()
     flags = abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
-    batch = synth.make_windows(args.windows, seed=0x5EED + 2, f32_obs=True)   # the native arm's rank-0 batch
+    batch, _ = synth.with_line_map(synth.make_windows(args.windows, seed=0x5EED + 2, f32_obs=True), cfg)   # the native arm's rank-0 batch
     steps, warm = args.steps, args.warmup
     bufs = batch.alloc_out(flags, fill=0.0)
     t0 = time.perf_counter()
@@ -308,7 +308,8 @@ def main():
         return a
 
     # ------------------------------------------------------------------ linearise (headline)
-    batch = synth.make_windows(args.windows, seed=0x5EED + 2 + rank, f32_obs=True)   # observations as the tracker publishes them (Point32)
+    # observations as the tracker publishes them (Point32); line factors tied to a prior map (one map line per factor)
+    batch, line_map = synth.with_line_map(synth.make_windows(args.windows, seed=0x5EED + 2 + rank, f32_obs=True), cfg)
     factors = batch.NP + batch.NL
     flags = abi.OUT_HB | abi.LOSS_CAUCHY
     flagsS = abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
@@ -361,19 +362,23 @@ def main():
     # observations as the per-feature float32 table (viml.h: feat_obs_f32 + pf_obs_j_f32; the anchor observation is not repeated
     # per factor and the values travel as the float32 the tracker published; widened on the device, identical results)
     tab = dict(zip(("feat_obs_f32", "pf_obs_j_f32"), (pkg.pinned_like(a) for a in batch.obs_table(f32=True))))
-    arr_tab = {k: p.array for k, p in pins.items() if k != "pf_obs"}
+    # line factors as the table (viml.h: lf_map_index + lf_seg2d_f32): the matched map line and the detected 2D segment, the
+    # nine geometry values are formed on the device from the map installed with viml_set_map
+    tab["lf_map_index"], tab["lf_seg2d_f32"] = pkg.pinned_like(batch.lf_map_index), pkg.pinned_like(batch.lf_seg2d)
+    ctx.set_map(line_map)
+    arr_tab = {k: p.array for k, p in pins.items() if k not in ("pf_obs", "lf_geom")}
     arr_tab.update({k: p.array for k, p in tab.items()})
     s_tab, o_S = hb.struct(arr_tab), abi.out_struct(hoS)
-    h2d_tab = sum(p.nbytes for k, p in pins.items() if k != "pf_obs") + sum(p.nbytes for p in tab.values())
+    h2d_tab = sum(p.nbytes for k, p in pins.items() if k not in ("pf_obs", "lf_geom")) + sum(p.nbytes for p in tab.values())
     e_ms = timed_host(lambda: ctx.linearize_raw(s_tab, o_S, fS), e_steps)
     e2e = {"value": total_factors / (e_ms * 1e-3), "unit": "factors/s", "h2d_bytes_per_step": int(h2d_tab),
            "d2h_bytes_per_step": int(sum(p.nbytes for p in pS.values())), "ms_per_step": e_ms, "steps": e_steps,
            "api": "viml_linearize_batch(host pointers, VIML_OUT_SCHUR|VIML_S_PACKED|VIML_LOSS_CAUCHY), observations as the per-feature "
-                  "float32 table: evaluate + assemble + landmark Schur; the upper triangle of S and g back"}
+                  "float32 table, line factors as (map line, 2D segment): evaluate + assemble + landmark Schur; the upper triangle of S and g back"}
     S_tab = hoS["S_packed"].copy()
     e_ms_pairs = timed_host(lambda: ctx.linearize(hb, fS, out=hoS), e_steps)
     # same kernels on the same expanded observations: equal up to the summation order of the shared accumulator
-    assert np.abs(S_tab - hoS["S_packed"]).max() <= 1e-12 * np.abs(S_tab).max(), "observation-table and per-factor forms differ"
+    assert np.abs(S_tab - hoS["S_packed"]).max() <= 1e-12 * np.abs(S_tab).max(), "table and per-factor input forms differ"
     e2e["per_factor_obs_form"] = {"ms_per_step": e_ms_pairs, "value": total_factors / (e_ms_pairs * 1e-3), "h2d_bytes_per_step": int(h2d)}
     for p in tab.values():
         p.free()

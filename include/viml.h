@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define VIML_ABI_VERSION 4
+#define VIML_ABI_VERSION 5
 
 /* ---- error codes ---------------------------------------------------------------------------- */
 #define VIML_OK 0
@@ -151,7 +151,15 @@ int viml_load_line_map(viml_ctx* ctx, const char* path, int64_t* n_lines);
  * lf_geom is SoA, nine planes of n_line_factors doubles: P_start.xyz, P_end.xyz (already in VIO world,
  * estimator.cpp:1832-1833), then the detected line's A, B, C (raw-pixel, un-normalised, fm.cpp:11-13).
  * Its K is viml_config's; its b_c_R/b_c_T are the window's extrinsic, rotation normalised
- * (estimator.cpp:1777-1781).                                                                      */
+ * (estimator.cpp:1777-1781).
+ *
+ * Line table (optional, instead of lf_geom): the estimator builds a line factor from the matched MAP line and the detected 2D
+ * segment — ptr_start = Rbw * lineWorld.PtrStart + Tbw, ptr_end likewise (estimator.cpp:1832-1833), line_param = (A, B, C) of
+ * Line2D(Vector4d) on the float32 channel endpoints (feature_manager.cpp:11-13, estimator_node.cpp:406-410).  With lf_geom == NULL
+ * the batch carries lf_map_index[k] (index into the map installed by viml_set_map) and lf_seg2d_f32[k] = {sx, sy, ex, ey}: 20 bytes
+ * per line factor instead of 72.  The device forms the nine lf_geom values with the reference's operation order (no fused
+ * multiply-add): identical results.  Needs a map (VIML_ERR_NOMAP otherwise); an index outside the map is VIML_ERR_INVALID on the
+ * host-pointer path and is clamped on the device-pointer path.                                        */
 typedef struct viml_window_batch {
   int32_t n_windows;         /* W                                                               */
   int32_t poses_per_window;  /* P  (WINDOW_SIZE+1 = 11; up to 255)                              */
@@ -173,6 +181,8 @@ typedef struct viml_window_batch {
   const double* pf_obs_j;    /* [NP][2]   or NULL; read only when pf_obs == NULL                */
   const float* feat_obs_f32; /* [W][F][2] or NULL; read only when pf_obs, feat_obs, pf_obs_j are NULL */
   const float* pf_obs_j_f32; /* [NP][2]   or NULL                                               */
+  const int32_t* lf_map_index; /* [NL]    or NULL; read only when lf_geom == NULL               */
+  const float* lf_seg2d_f32;   /* [NL][4] or NULL                                               */
 } viml_window_batch;
 
 /* Any pointer may be NULL (= not wanted).  D = 6*(P+1): pose blocks 0..P-1 then the extrinsic.

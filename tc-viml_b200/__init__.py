@@ -203,24 +203,30 @@ class Context:
         return self.n_map
 
     @staticmethod
-    def _batch_struct(batch, obs_table):
-        """viml_window_batch of host arrays; obs_table=True: observations as feat_obs + pf_obs_j, pf_obs NULL."""
-        if not obs_table:
+    def _batch_struct(batch, obs_table, line_table=False):
+        """viml_window_batch of host arrays; obs_table=True / "f32": observations as feat_obs + pf_obs_j (pf_obs NULL);
+        line_table=True: line factors as lf_map_index + lf_seg2d_f32 (lf_geom NULL; the map must be set)."""
+        if not obs_table and not line_table:
             return batch.struct(), None
         arrs = batch.arrays()
-        arrs["pf_obs"] = None
-        if obs_table == "f32":
-            arrs["feat_obs_f32"], arrs["pf_obs_j_f32"] = batch.obs_table(f32=True)
-        else:
-            arrs["feat_obs"], arrs["pf_obs_j"] = batch.obs_table()
+        if obs_table:
+            arrs["pf_obs"] = None
+            if obs_table == "f32":
+                arrs["feat_obs_f32"], arrs["pf_obs_j_f32"] = batch.obs_table(f32=True)
+            else:
+                arrs["feat_obs"], arrs["pf_obs_j"] = batch.obs_table()
+        if line_table:
+            assert batch.lf_map_index is not None and batch.lf_seg2d is not None, "batch has no line table (synth.with_line_map)"
+            arrs["lf_geom"] = None
+            arrs["lf_map_index"], arrs["lf_seg2d_f32"] = batch.lf_map_index, batch.lf_seg2d
         return batch.struct(arrs), arrs
 
-    def reduced_system(self, batch, dense, flags, obs_table=False):
+    def reduced_system(self, batch, dense, flags, obs_table=False, line_table=False):
         """viml_reduced_system with host buffers: (Sx [W,Dx,Dx], gx [W,Dx])."""
         X = dense.X if dense is not None else 0
         Dx = batch.D + X
         Sx, gx = np.full((batch.W, Dx, Dx), np.nan), np.full((batch.W, Dx), np.nan)
-        s, _keep = self._batch_struct(batch, obs_table)
+        s, _keep = self._batch_struct(batch, obs_table, line_table)
         d = dense.struct() if dense is not None else None
         o = _abi.ReducedOut()
         o.Sx, o.gx = _abi.ptr(Sx), _abi.ptr(gx)
@@ -228,14 +234,14 @@ class Context:
                                                  flags & ~PTRS_DEVICE))
         return Sx, gx
 
-    def gn_step(self, batch, dense, extra, flags, lam=0.0, obs_table=False):
+    def gn_step(self, batch, dense, extra, flags, lam=0.0, obs_table=False, line_table=False):
         """viml_gn_step with host buffers: dict(poses, ex_pose, inv_depth, extra, dx, cost, solved)."""
         X = dense.X if dense is not None else 0
         W, Dx = batch.W, batch.D + X
         res = {"poses": np.full_like(batch.poses, np.nan), "ex_pose": np.full_like(batch.ex_pose, np.nan),
                "inv_depth": np.full_like(batch.inv_depth, np.nan), "extra": np.full((W, X), np.nan),
                "dx": np.full((W, Dx), np.nan), "cost": np.full((W, 3), np.nan), "solved": np.full(W, -1, dtype=np.int32)}
-        s, _keep = self._batch_struct(batch, obs_table)
+        s, _keep = self._batch_struct(batch, obs_table, line_table)
         d = dense.struct() if dense is not None else None
         ex = None if extra is None else np.ascontiguousarray(extra, dtype=np.float64)
         opt = _abi.GnOptions()
@@ -248,11 +254,11 @@ class Context:
                                           C.byref(o), flags & ~PTRS_DEVICE))
         return res
 
-    def linearize(self, batch, flags, out=None, obs_table=False):
+    def linearize(self, batch, flags, out=None, obs_table=False, line_table=False):
         """viml_linearize_batch with host buffers; returns dict of numpy outputs.  obs_table=True passes the observations as
         the per-feature table (feat_obs + pf_obs_j) instead of pf_obs, obs_table="f32" as the float32 table."""
         bufs = batch.alloc_out(flags) if out is None else out
-        s, _keep = self._batch_struct(batch, obs_table)
+        s, _keep = self._batch_struct(batch, obs_table, line_table)
         o = _abi.out_struct(bufs)
         self._check(self.lib.viml_linearize_batch(self.h, C.byref(s), C.byref(o), flags & ~PTRS_DEVICE))
         return bufs

@@ -53,6 +53,7 @@ class WindowBatch(C.Structure):
         ("lf_window_offset", C.c_void_p), ("lf_frame", C.c_void_p), ("lf_geom", C.c_void_p),
         ("feat_obs", C.c_void_p), ("pf_obs_j", C.c_void_p),
         ("feat_obs_f32", C.c_void_p), ("pf_obs_j_f32", C.c_void_p),
+        ("lf_map_index", C.c_void_p), ("lf_seg2d_f32", C.c_void_p),
     ]
 
 
@@ -178,7 +179,7 @@ class Batch:
     """Host-side container of one viml_window_batch (numpy arrays, SoA as in viml.h)."""
 
     def __init__(self, poses, ex_pose, inv_depth, pf_window_offset, pf_idx, pf_obs,
-                 lf_window_offset=None, lf_frame=None, lf_geom=None, pf_pts_i_z=None):
+                 lf_window_offset=None, lf_frame=None, lf_geom=None, pf_pts_i_z=None, lf_seg2d=None, lf_map_index=None):
         self.poses = np.ascontiguousarray(poses, dtype=np.float64)
         self.ex_pose = np.ascontiguousarray(ex_pose, dtype=np.float64)
         self.inv_depth = np.ascontiguousarray(inv_depth, dtype=np.float64)
@@ -194,6 +195,9 @@ class Batch:
         self.lf_window_offset = np.ascontiguousarray(lf_window_offset, dtype=np.int32)
         self.lf_frame = np.ascontiguousarray(lf_frame, dtype=np.int32)
         self.lf_geom = np.ascontiguousarray(lf_geom, dtype=np.float64).reshape(9, -1)
+        # optional line-table form of lf_geom (viml.h): the detected 2D segments as float32 and the map line of every factor
+        self.lf_seg2d = None if lf_seg2d is None else np.ascontiguousarray(lf_seg2d, dtype=np.float32).reshape(-1, 4)
+        self.lf_map_index = None if lf_map_index is None else np.ascontiguousarray(lf_map_index, dtype=np.int32)
         assert self.poses.ndim == 3 and self.poses.shape[2] == 7
         assert self.ex_pose.shape == (W, 7) and self.inv_depth.shape[0] == W
         assert self.pf_window_offset.shape == (W + 1,) and self.lf_window_offset.shape == (W + 1,)
@@ -223,7 +227,9 @@ class Batch:
                 s.feat_obs, s.pf_obs_j = ptr(a["feat_obs"]), ptr(a["pf_obs_j"])
         s.pf_pts_i_z = ptr(a.get("pf_pts_i_z"))
         s.n_line_factors = self.NL
-        s.lf_window_offset, s.lf_frame, s.lf_geom = ptr(a["lf_window_offset"]), ptr(a["lf_frame"]), ptr(a["lf_geom"])
+        s.lf_window_offset, s.lf_frame, s.lf_geom = ptr(a["lf_window_offset"]), ptr(a["lf_frame"]), ptr(a.get("lf_geom"))
+        if a.get("lf_geom") is None and self.NL > 0:   # line table instead of the nine geometry planes
+            s.lf_map_index, s.lf_seg2d_f32 = ptr(a["lf_map_index"]), ptr(a["lf_seg2d_f32"])
         return s
 
     def obs_table(self, f32=False):
@@ -272,7 +278,9 @@ class Batch:
         return Batch(self.poses[lo:hi], self.ex_pose[lo:hi], self.inv_depth[lo:hi],
                      self.pf_window_offset[lo:hi + 1] - p0, self.pf_idx[p0:p1], self.pf_obs[p0:p1],
                      self.lf_window_offset[lo:hi + 1] - l0, self.lf_frame[l0:l1], self.lf_geom[:, l0:l1],
-                     None if self.pf_pts_i_z is None else self.pf_pts_i_z[p0:p1])
+                     None if self.pf_pts_i_z is None else self.pf_pts_i_z[p0:p1],
+                     None if self.lf_seg2d is None else self.lf_seg2d[l0:l1],
+                     None if self.lf_map_index is None else self.lf_map_index[l0:l1])
 
 
 def out_struct(bufs):

@@ -66,7 +66,7 @@ int check_batch(viml_ctx* ctx, const viml_window_batch* in) {
     return fail(ctx, VIML_ERR_INVALID, "window batch sizes out of range");
   if (W > 0 && (!in->poses || !in->ex_pose || (F > 0 && !in->inv_depth) || !in->pf_window_offset ||
                 (in->n_point_factors > 0 && (!in->pf_idx || (!in->pf_obs && !(in->feat_obs && in->pf_obs_j) && !(in->feat_obs_f32 && in->pf_obs_j_f32)))) ||
-                (in->n_line_factors > 0 && (!in->lf_window_offset || !in->lf_frame || !in->lf_geom))))
+                (in->n_line_factors > 0 && (!in->lf_window_offset || !in->lf_frame || (!in->lf_geom && !(in->lf_map_index && in->lf_seg2d_f32))))))
     return fail(ctx, VIML_ERR_INVALID, "null input array");
   return VIML_OK;
 }
@@ -144,7 +144,19 @@ int run(viml_ctx* ctx, const viml_window_batch* in, const viml_dense_factors* de
   st.in(in->pf_pts_i_z, in->pf_pts_i_z ? (size_t)NP : 0, &a.pf_pts_i_z);
   st.in(in->lf_window_offset, NL > 0 ? (size_t)W + 1 : 0, &a.lf_window_offset);
   st.in(in->lf_frame, (size_t)NL, &a.lf_frame);
-  st.in(in->lf_geom, (size_t)NL * 9, &a.lf_geom);
+  const bool line_table = NL > 0 && !in->lf_geom;   // line factors as (map line, 2D segment): expanded on the device
+  const int32_t* d_lidx = nullptr;
+  const float* d_lseg = nullptr;
+  double* d_geom = nullptr;
+  if (line_table) {
+    if (!dev)
+      for (int64_t k = 0; k < NL; ++k)
+        if (in->lf_map_index[k] < 0 || in->lf_map_index[k] >= ctx->n_map) return fail(ctx, VIML_ERR_INVALID, "line factor: map index outside the map");
+    st.in(in->lf_map_index, (size_t)NL, &d_lidx);
+    st.in(in->lf_seg2d_f32, (size_t)NL * 4, &d_lseg);
+  } else {
+    st.in(in->lf_geom, (size_t)NL * 9, &a.lf_geom);
+  }
   const double* d_extra = nullptr;
   st.in(extra_state, extra_state ? (size_t)W * X : 0, &d_extra);
   DenseArgs dn{};
@@ -164,6 +176,7 @@ int run(viml_ctx* ctx, const viml_window_batch* in, const viml_dense_factors* de
   int32_t* solved = nullptr;
   st.out((double*)nullptr, (size_t)W * (P * kPoseCache + kExCache), &cache);
   if (obs_table) st.out((double*)nullptr, (size_t)NP * 4, &d_obs);
+  if (line_table) st.out((double*)nullptr, (size_t)NL * 9, &d_geom);
   st.out((double*)nullptr, (size_t)W * D * D, &a.out.H_pp);
   st.out((double*)nullptr, (size_t)W * F * D, &a.out.H_lp);
   st.out((double*)nullptr, (size_t)W * F, &a.out.H_ll);
@@ -188,6 +201,11 @@ int run(viml_ctx* ctx, const viml_window_batch* in, const viml_dense_factors* de
   if (obs_table) {
     a.pf_obs = d_obs;
     rc = obs_f32 ? viml_launch_expand_obs(ctx, a, d_fobs32, d_obsj32, true) : viml_launch_expand_obs(ctx, a, d_fobs, d_obsj, false);
+    if (rc != VIML_OK) return rc;
+  }
+  if (line_table) {
+    a.lf_geom = d_geom;
+    rc = viml_launch_expand_lines(ctx, a, d_lidx, d_lseg);
     if (rc != VIML_OK) return rc;
   }
   rc = viml_launch_linearize(ctx, a);

@@ -54,6 +54,33 @@ __global__ void expand_obs_kernel(LinearizeArgs a, const T2* __restrict__ feat_o
   }
 }
 
+// Line table -> lf_geom (viml.h, viml_window_batch): ptr = Rbw * map line end point + Tbw as Eigen evaluates it (row dot product
+// left to right, then the translation; estimator.cpp:1832-1833) and (A, B, C) of Line2D(Vector4d) on the widened float32 end points
+// (feature_manager.cpp:11-13).  Explicit round-to-nearest multiplies and adds: this file is compiled with FMA contraction.
+struct MapFrame { double R[9], T[3]; };
+__global__ void expand_lines_kernel(LinearizeArgs a, const double* __restrict__ map, int64_t N, MapFrame mf,
+                                    const int32_t* __restrict__ idx, const float4* __restrict__ seg) {
+  const int64_t k = a.lf_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= a.lf_begin + a.NL) return;
+  double* __restrict__ g = const_cast<double*>(a.lf_geom);
+  int64_t j = idx[k];
+  j = j < 0 ? 0 : (j >= N ? N - 1 : j);   // validated on the host-pointer path; clamped here for device-pointer callers
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const double x = map[(3 * e) * N + j], y = map[(3 * e + 1) * N + j], z = map[(3 * e + 2) * N + j];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double d = __dadd_rn(__dadd_rn(__dmul_rn(mf.R[3 * r], x), __dmul_rn(mf.R[3 * r + 1], y)), __dmul_rn(mf.R[3 * r + 2], z));
+      g[(size_t)(3 * e + r) * a.NL_stride + k] = __dadd_rn(d, mf.T[r]);
+    }
+  }
+  const float4 s = seg[k];
+  const double sx = s.x, sy = s.y, ex = s.z, ey = s.w;
+  g[(size_t)6 * a.NL_stride + k] = __dsub_rn(ey, sy);
+  g[(size_t)7 * a.NL_stride + k] = __dsub_rn(sx, ex);
+  g[(size_t)8 * a.NL_stride + k] = __dsub_rn(__dmul_rn(ex, sy), __dmul_rn(sx, ey));
+}
+
 // One thread per pose (and one per window for the extrinsic): fills the cache described in common.cuh.
 __global__ void prep_windows_kernel(LinearizeArgs a) {
   const int stride = a.P * kPoseCache + kExCache;
@@ -606,6 +633,22 @@ int viml_launch_expand_obs(viml_ctx* ctx, const LinearizeArgs& a, const void* fe
   LaunchScope ls(ctx, K_PREP);
   if (f32) expand_obs_kernel<float2><<<a.W, 128, 0, ctx->stream>>>(a, (const float2*)feat_obs, (const float2*)pf_obs_j);
   else expand_obs_kernel<double2><<<a.W, 128, 0, ctx->stream>>>(a, (const double2*)feat_obs, (const double2*)pf_obs_j);
+  VIML_TRY_CUDA(ctx, cudaGetLastError());
+  return VIML_OK;
+}
+
+int viml_launch_expand_lines(viml_ctx* ctx, const LinearizeArgs& a, const int32_t* lf_map_index, const float* lf_seg2d) {
+  if (a.NL == 0) return VIML_OK;
+  if (!ctx->map_set || ctx->n_map <= 0) {
+    ctx->err = "line factors given by map index need a map (viml_set_map)";
+    return VIML_ERR_NOMAP;
+  }
+  MapFrame mf;
+  for (int k = 0; k < 9; ++k) mf.R[k] = ctx->cfg.Rbw[k];
+  for (int k = 0; k < 3; ++k) mf.T[k] = ctx->cfg.Tbw[k];
+  LaunchScope ls(ctx, K_PREP);
+  expand_lines_kernel<<<(unsigned)((a.NL + 127) / 128), 128, 0, ctx->stream>>>(a, ctx->d_map, ctx->n_map, mf, lf_map_index,
+                                                                             reinterpret_cast<const float4*>(lf_seg2d));
   VIML_TRY_CUDA(ctx, cudaGetLastError());
   return VIML_OK;
 }

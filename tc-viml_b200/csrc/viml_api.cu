@@ -311,9 +311,13 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   const void* h_fobs = obs_f32 ? (const void*)in->feat_obs_f32 : (const void*)in->feat_obs;
   const void* h_obsj = obs_f32 ? (const void*)in->pf_obs_j_f32 : (const void*)in->pf_obs_j;
   const size_t ob = obs_f32 ? 8 : 16;   // bytes of one {x, y}
+  const bool line_table = NL > 0 && !in->lf_geom && in->lf_map_index && in->lf_seg2d_f32;   // line factors as (map line, 2D segment)
   if (!in->poses || !in->ex_pose || (F > 0 && !in->inv_depth) || !in->pf_window_offset ||
-      (NP > 0 && (!in->pf_idx || (!in->pf_obs && !obs_table))) || (NL > 0 && (!in->lf_window_offset || !in->lf_frame || !in->lf_geom)))
+      (NP > 0 && (!in->pf_idx || (!in->pf_obs && !obs_table))) ||
+      (NL > 0 && (!in->lf_window_offset || !in->lf_frame || (!in->lf_geom && !line_table))))
     return fail(ctx, VIML_ERR_INVALID, "null input array");
+  if (line_table && (!ctx->map_set || ctx->n_map <= 0))
+    return fail(ctx, VIML_ERR_NOMAP, "line factors given by map index need a map (viml_set_map)");
   const int D = 6 * (P + 1);
   timespec ts_begin;
   clock_gettime(CLOCK_MONOTONIC, &ts_begin);
@@ -352,11 +356,18 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
     a.pf_pts_i_z = in->pf_pts_i_z;
     a.lf_window_offset = in->lf_window_offset, a.lf_frame = in->lf_frame, a.lf_geom = in->lf_geom;
     a.out = *out;
-    if (obs_table && NP > 0) {
-      VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(DeviceArena::padded((size_t)NP * 32)));
-      a.pf_obs = ctx->in_arena.take<double>((size_t)NP * 4);
-      const int rc = viml_launch_expand_obs(ctx, a, h_fobs, h_obsj, obs_f32);
-      if (rc != VIML_OK) return rc;
+    if ((obs_table && NP > 0) || line_table) {
+      VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(DeviceArena::padded((size_t)NP * 32) + DeviceArena::padded((size_t)NL * 72)));
+      if (obs_table && NP > 0) {
+        a.pf_obs = ctx->in_arena.take<double>((size_t)NP * 4);
+        const int rc = viml_launch_expand_obs(ctx, a, h_fobs, h_obsj, obs_f32);
+        if (rc != VIML_OK) return rc;
+      }
+      if (line_table) {
+        a.lf_geom = ctx->in_arena.take<double>((size_t)NL * 9);
+        const int rc = viml_launch_expand_lines(ctx, a, in->lf_map_index, in->lf_seg2d_f32);
+        if (rc != VIML_OK) return rc;
+      }
     }
     if (!wantA) a.out.pf_residual = a.out.pf_jac_pose_i = a.out.pf_jac_pose_j = a.out.pf_jac_ex = a.out.pf_jac_feat =
                     a.out.lf_residual = a.out.lf_jac_pose = nullptr;
@@ -393,6 +404,8 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
       bad |= (uint32_t)((ix & 0xffu) >= uP) | (uint32_t)(((ix >> 8) & 0xffu) >= uP) | (uint32_t)((ix >> 16) >= uF);
     }
     for (int64_t k = la; k < lb; ++k) bad |= (uint32_t)((uint32_t)in->lf_frame[k] >= uP);
+    if (line_table)
+      for (int64_t k = la; k < lb; ++k) bad |= (uint32_t)((uint64_t)(int64_t)in->lf_map_index[k] >= (uint64_t)ctx->n_map);
     return bad == 0;
   };
   // ---- host pointers: chunked pipeline  H2D(c+1) | kernels(c) | D2H(c-1)  on three streams ----
@@ -404,6 +417,7 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   in_bytes += pad((size_t)NP * 4) + pad((size_t)NP * 32) + pad((size_t)NP * 8);
   in_bytes += pad((size_t)NL * 4) + pad((size_t)NL * 72);
   if (obs_table) in_bytes += pad((size_t)NP * ob) + pad(n_dep * ob);
+  if (line_table) in_bytes += pad((size_t)NL * 4) + pad((size_t)NL * 16);
   VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(in_bytes));
   double* d_poses = ctx->in_arena.take<double>(n_pose);
   double* d_ex = ctx->in_arena.take<double>(n_ex);
@@ -417,6 +431,8 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   double* d_geom = NL > 0 ? ctx->in_arena.take<double>((size_t)NL * 9) : nullptr;
   char* d_obsj = obs_table ? ctx->in_arena.take<char>((size_t)NP * ob) : nullptr;
   char* d_fobs = obs_table ? ctx->in_arena.take<char>(n_dep * ob) : nullptr;
+  int32_t* d_lidx = line_table ? ctx->in_arena.take<int32_t>((size_t)NL) : nullptr;
+  float* d_lseg = line_table ? ctx->in_arena.take<float>((size_t)NL * 4) : nullptr;
   a.poses = d_poses, a.ex_pose = d_ex, a.inv_depth = d_dep, a.pf_window_offset = d_poff, a.pf_idx = d_idx;
   a.pf_obs = d_obs, a.pf_pts_i_z = d_z, a.lf_window_offset = d_loff, a.lf_frame = d_frame, a.lf_geom = d_geom;
 
@@ -469,7 +485,7 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
     VIML_TRY_CUDA(ctx, grow(&ctx->h_stage_in, &ctx->h_stage_in_cap, ctx->in_arena.used));
     VIML_TRY_CUDA(ctx, grow(&ctx->h_stage_out, &ctx->h_stage_out_cap, ctx->out_arena.used));
     if (!indices_ok(0, NP, 0, NL))
-      return fail(ctx, VIML_ERR_INVALID, "factor index out of range (pose index >= poses_per_window, feature >= feats_per_window or line frame >= poses_per_window)");
+      return fail(ctx, VIML_ERR_INVALID, "factor index out of range (pose index >= poses_per_window, feature >= feats_per_window, line frame >= poses_per_window or map index outside the map)");
     char* const ibase = ctx->in_arena.base;
     auto put = [&](const void* dptr, const void* src, size_t bytes) {
       if (bytes) memcpy(ctx->h_stage_in + ((const char*)dptr - ibase), src, bytes);
@@ -481,10 +497,12 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
     if (d_z) put(d_z, in->pf_pts_i_z, (size_t)NP * 8);
     if (NL > 0) {
       put(d_loff, in->lf_window_offset, (size_t)(W + 1) * 4), put(d_frame, in->lf_frame, (size_t)NL * 4);
-      put(d_geom, in->lf_geom, (size_t)NL * 72);
+      if (line_table) put(d_lidx, in->lf_map_index, (size_t)NL * 4), put(d_lseg, in->lf_seg2d_f32, (size_t)NL * 16);
+      else put(d_geom, in->lf_geom, (size_t)NL * 72);
     }
     VIML_TRY_CUDA(ctx, cudaMemcpyAsync(ibase, ctx->h_stage_in, ctx->in_arena.used, cudaMemcpyHostToDevice, st));
     int rc = obs_table ? viml_launch_expand_obs(ctx, a, d_fobs, d_obsj, obs_f32) : VIML_OK;
+    if (rc == VIML_OK && line_table) rc = viml_launch_expand_lines(ctx, a, d_lidx, d_lseg);
     if (rc == VIML_OK) rc = viml_launch_linearize(ctx, a);
     if (rc != VIML_OK) return rc;
     // the device range that holds every slot the caller wants
@@ -547,9 +565,13 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
       h2d(d_obs + 4 * pa, in->pf_obs + 4 * pa, (size_t)(pb - pa) * 32);
     }
     if (d_z) h2d(d_z + pa, in->pf_pts_i_z + pa, (size_t)(pb - pa) * 8);
-    if (lb > la)
+    if (lb > la && line_table) {
+      h2d(d_lidx + la, in->lf_map_index + la, (size_t)(lb - la) * 4);
+      h2d(d_lseg + 4 * la, in->lf_seg2d_f32 + 4 * la, (size_t)(lb - la) * 16);
+    } else if (lb > la) {
       cudaMemcpy2DAsync(d_geom + la, (size_t)NL * 8, in->lf_geom + la, (size_t)NL * 8, (size_t)(lb - la) * 8, 9,
                         cudaMemcpyHostToDevice, s_in);
+    }
     cudaEventRecord(ev_in[c], s_in);
   }
   for (int c = 0; c < nchunk && rc == VIML_OK; ++c) {
@@ -557,7 +579,7 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
     const int64_t pa = in->pf_window_offset[w0], pb = in->pf_window_offset[w1];
     const int64_t la = NL > 0 ? in->lf_window_offset[w0] : 0, lb = NL > 0 ? in->lf_window_offset[w1] : 0;
     if (!indices_ok(pa, pb, la, lb)) {   // bad indices never reach a kernel: this chunk and the following ones are not launched
-      rc = fail(ctx, VIML_ERR_INVALID, "factor index out of range (pose index >= poses_per_window, feature >= feats_per_window or line frame >= poses_per_window)");
+      rc = fail(ctx, VIML_ERR_INVALID, "factor index out of range (pose index >= poses_per_window, feature >= feats_per_window, line frame >= poses_per_window or map index outside the map)");
       break;
     }
     cudaStreamWaitEvent(st, ev_in[c], 0);
@@ -573,6 +595,7 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
       *vd = *sl.dev + sl.per_window * w0;   // per-factor arrays stay absolute (indexed by the global factor id)
     }
     if (Wc > 0 && obs_table) rc = viml_launch_expand_obs(ctx, v, d_fobs + (size_t)w0 * F * ob, d_obsj, obs_f32);
+    if (Wc > 0 && rc == VIML_OK && line_table) rc = viml_launch_expand_lines(ctx, v, d_lidx, d_lseg);
     if (Wc > 0 && rc == VIML_OK) rc = viml_launch_linearize(ctx, v);
     cudaEventRecord(ev_k[c], st);
     cudaStreamWaitEvent(s_out, ev_k[c], 0);

@@ -175,9 +175,34 @@ def make_windows(W, seed=0x5EED, P=11, F=150, lines_per_frame=10, start_max=None
         lf_geom = np.stack([Pw0[..., 0], Pw0[..., 1], Pw0[..., 2], Pw1[..., 0], Pw1[..., 1], Pw1[..., 2],
                             A, B, Cc], 0).reshape(9, -1)
         lf_off = (np.arange(W + 1) * (P * NLf)).astype(np.int32)
+        lf_seg2d = det.reshape(-1, 4).astype(np.float32)
     else:
-        lf_frame, lf_geom, lf_off = None, None, None
-    return Batch(poses, ex, inv_depth, pf_off, pf_idx, pf_obs, lf_off, lf_frame, lf_geom)
+        lf_frame, lf_geom, lf_off, lf_seg2d = None, None, None, None
+    return Batch(poses, ex, inv_depth, pf_off, pf_idx, pf_obs, lf_off, lf_frame, lf_geom, lf_seg2d=lf_seg2d)
+
+
+def with_line_map(batch, cfg):
+    """(batch2, line_map): the same batch with its line factors tied to a prior map, the way the estimator builds them
+    (estimator.cpp:1831-1835: ptr = Rbw * lineWorld.Ptr + Tbw).  line_map [NL][6] holds one map line per factor in the MAP frame;
+    batch2.lf_geom[0:6] is fl(Rbw p + Tbw) with the reference's operation order (row dot product left to right, then the
+    translation; no fused multiply-add), batch2.lf_map_index = arange(NL).  The nine planes of batch2.lf_geom are then exactly what
+    the line table (lf_map_index + lf_seg2d) expands to on the device."""
+    R = np.array([cfg.Rbw[k] for k in range(9)]).reshape(3, 3)
+    T = np.array([cfg.Tbw[k] for k in range(3)])
+    Pw = batch.lf_geom[:6].T
+    pm = np.concatenate([(Pw[:, :3] - T) @ R, (Pw[:, 3:] - T) @ R], 1)      # R^T (p - T): any map point near it will do
+
+    def fwd(p):
+        return ((R[:, 0] * p[:, 0:1] + R[:, 1] * p[:, 1:2]) + R[:, 2] * p[:, 2:3]) + T
+
+    geom = batch.lf_geom.copy()
+    geom[0:3], geom[3:6] = fwd(pm[:, :3]).T, fwd(pm[:, 3:]).T
+    s = batch.lf_seg2d.astype(np.float64)
+    abc = np.stack([s[:, 3] - s[:, 1], s[:, 0] - s[:, 2], s[:, 2] * s[:, 1] - s[:, 0] * s[:, 3]], 0)   # feature_manager.cpp:11-13
+    assert np.array_equal(abc, geom[6:9]), "lf_seg2d does not reproduce the A, B, C planes"
+    b2 = Batch(batch.poses, batch.ex_pose, batch.inv_depth, batch.pf_window_offset, batch.pf_idx, batch.pf_obs, batch.lf_window_offset,
+               batch.lf_frame, geom, batch.pf_pts_i_z, batch.lf_seg2d, np.arange(batch.NL, dtype=np.int32))
+    return b2, pm
 
 
 # ---- prior line map + association queries (cfg 3) --------------------------------------------------

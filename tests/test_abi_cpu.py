@@ -19,14 +19,14 @@ def test_header_symbols_exported(pkg):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in viml.h but not exported"
     assert sorted(pkg.ABI_SYMBOLS) == syms
-    assert lib.viml_abi_version() == 4
+    assert lib.viml_abi_version() == 5
 
 
 def test_struct_sizes_match_header(pkg):
     # sizes implied by the C declarations (LP64): catches drift between viml.h and the ctypes mirror
     abi = pkg._abi
     assert C.sizeof(abi.Config) == 4 * 8 + 2 * 4 + 12 * 8 + 5 * 8
-    assert C.sizeof(abi.WindowBatch) == 16 + 3 * 8 + 8 + 4 * 8 + 8 + 3 * 8 + 4 * 8
+    assert C.sizeof(abi.WindowBatch) == 16 + 3 * 8 + 8 + 4 * 8 + 8 + 3 * 8 + 6 * 8
     assert C.sizeof(abi.LinearizeOut) == 14 * 8
     assert C.sizeof(abi.MargBatch) == 16 + 8 + 16
     assert C.sizeof(abi.MargOut) == 32

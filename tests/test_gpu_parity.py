@@ -298,6 +298,61 @@ def test_observation_table_input(pkg, orc, ctx, cfg):
         bad.obs_table()
 
 
+def test_line_table_input(pkg, orc, cfg):
+    """viml_window_batch.lf_map_index / lf_seg2d_f32 (lf_geom == NULL): a line factor given by its map line and the detected 2D segment,
+    as the estimator builds it (estimator.cpp:1831-1835, feature_manager.cpp:11-13).  The device expands them with the reference's
+    operation order: same outputs as the nine-plane form, bit for bit on the per-factor line outputs, through the chunked pipeline,
+    the small-batch staging, device pointers and the solver entry point; errors without a map or with an index outside it."""
+    abi, synth = pkg._abi, pkg.synth
+    b0 = synth.make_windows(600, seed=201, f32_obs=True)
+    b, lmap = synth.with_line_map(b0, cfg)
+    flags = abi.OUT_RESIDUAL_JACOBIAN | abi.OUT_HB | abi.OUT_SCHUR | abi.LOSS_CAUCHY
+    with pkg.Context(cfg) as c:
+        with pytest.raises(pkg.VimlError):
+            c.linearize(b.slice_windows(0, 4), flags, line_table=True)          # no map yet
+        c.set_map(lmap)
+        planes = c.linearize(b, flags)
+        table = c.linearize(b, flags, obs_table="f32", line_table=True)
+        for k, v in planes.items():
+            assert not np.isnan(table[k]).any(), k
+            if k.startswith(("pf_", "lf_")) or k in ("H_lp", "H_ll", "b_l"):
+                assert np.array_equal(table[k], v), k
+            else:
+                assert pkg.parity.unit_err(k, table[k], v) < 1e-12, k
+        ref = orc.linearize_batch(cfg, b.slice_windows(0, 16), flags, nthreads=8)
+        for k, v in ref.items():
+            assert pkg.parity.unit_err(k, table[k][:v.shape[0]], v) < TOL, k
+        small = b.slice_windows(590, 600)                                       # staging path; map indices are absolute
+        s_pl, s_tb = c.linearize(small, flags), c.linearize(small, flags, line_table=True)
+        assert np.array_equal(s_tb["lf_jac_pose"], s_pl["lf_jac_pose"]) and np.array_equal(s_tb["lf_residual"], s_pl["lf_residual"])
+        assert pkg.parity.unit_err("S", s_tb["S"], s_pl["S"]) < 1e-12
+        # device pointers
+        arrs = {k: v for k, v in small.arrays().items() if v is not None and k != "lf_geom"}
+        arrs.update(lf_map_index=small.lf_map_index, lf_seg2d_f32=small.lf_seg2d)
+        d_in = {k: c.to_device(v) for k, v in arrs.items()}
+        want = {k: s_pl[k] for k in ("H_pp", "H_lp", "H_ll", "b_p", "b_l")}
+        d_out = {k: c.device_alloc(v.nbytes) for k, v in want.items()}
+        c.linearize_raw(small.struct(d_in), abi.out_struct(d_out), abi.OUT_HB | abi.LOSS_CAUCHY | abi.PTRS_DEVICE)
+        for k, v in want.items():
+            back = np.empty_like(v)
+            c.d2h(back, d_out[k])
+            c.sync()
+            assert pkg.parity.unit_err(k, back, v) < 1e-12, k
+        for p in list(d_in.values()) + list(d_out.values()):
+            c.device_free(p)
+        # solver entry point
+        dense = synth.make_dense_factors(small, seed=5)
+        Sa, ga = c.reduced_system(small, dense, abi.LOSS_CAUCHY)
+        Sb, gb = c.reduced_system(small, dense, abi.LOSS_CAUCHY, line_table=True)
+        assert np.abs(Sb - Sa).max() <= 1e-12 * np.abs(Sa).max() and np.abs(gb - ga).max() <= 1e-12 * np.abs(ga).max()
+        # an index outside the map
+        bad = small.slice_windows(0, 10)
+        bad.lf_map_index = bad.lf_map_index.copy()
+        bad.lf_map_index[3] = len(lmap)
+        with pytest.raises(pkg.VimlError):
+            c.linearize(bad, flags, line_table=True)
+
+
 def test_small_batch_staging_matches_pipeline(pkg, ctx, cfg):
     """Host-pointer calls on small batches go through one pinned staging block each way (one H2D, one D2H); VIML_NO_STAGING=1
     sends the same call through the chunked copy pipeline of the large batches.  Same outputs, every mode, both observation forms."""
