@@ -21,6 +21,9 @@ with pkg.Context(cfg) as ctx:
     ctx.linearize(synth.make_windows(2, seed=4), abi.OUT_RESIDUAL_JACOBIAN)             # mode A kernels
     b = synth.make_windows(600, seed=5, f32_obs=True)                                    # chunked host pipeline + float32 observation table
     ctx.linearize(b, abi.OUT_SCHUR | abi.S_PACKED | abi.LOSS_CAUCHY, obs_table="f32")
+    bl, lmap = synth.with_line_map(synth.make_windows(5, seed=10, f32_obs=True), cfg)      # line table: expanded from the map in HBM
+    ctx.set_map(lmap)
+    ctx.linearize(bl, allf, obs_table="f32", line_table=True)
     irr = synth.make_windows(3, seed=6)
     idx = irr.pf_idx.copy()
     idx[1] = (idx[1] & 0xffff0000) | 0x0101                                              # i == j: the window goes to irregular_kernel
