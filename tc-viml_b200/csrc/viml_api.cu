@@ -532,8 +532,22 @@ int viml_linearize_batch(viml_ctx* ctx, const viml_window_batch* in, const viml_
   if (NL > 0) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_loff, in->lf_window_offset, (size_t)(W + 1) * 4, cudaMemcpyHostToDevice, s_in));
   int nchunk = W >= 512 ? 4 : 1;   // measured on the 4096-window batch with the float32 table (75 MB up, 88 MB down): 2, 3, 4, 5, 6, 8, 12, 16 chunks -> 2.96, 2.81, 2.67, 2.75, 2.70, 2.79, 2.93, 2.96 ms
   if (const char* e = getenv("VIML_CHUNKS")) nchunk = std::max(1, std::min(W, atoi(e)));   // tuning hook
-  std::vector<int> wb(nchunk + 1, 0);   // uniform chunks (a ramp with small first / last chunks was measured: no gain)
-  for (int c = 0; c <= nchunk; ++c) wb[c] = (int)((int64_t)W * c / nchunk);
+  std::vector<int> wt(nchunk, 1);       // relative chunk sizes
+  if (const char* e = getenv("VIML_CHUNK_WEIGHTS")) {   // tuning hook: e.g. "1,2,4,4,5" (also sets the chunk count)
+    std::vector<int> v;
+    for (const char* q = e; *q;) {
+      v.push_back(std::max(1, atoi(q)));
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+    if (!v.empty() && (int)v.size() <= W) wt = v, nchunk = (int)v.size();
+  }
+  std::vector<int> wb(nchunk + 1, 0);
+  {
+    int64_t tot = 0, run = 0;
+    for (int x : wt) tot += x;
+    for (int c = 0; c < nchunk; ++c) run += wt[c], wb[c + 1] = (int)((int64_t)W * run / tot);
+  }
   // small per-window arrays: whole batch, one copy each
   VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_poses, in->poses, n_pose * 8, cudaMemcpyHostToDevice, s_in));
   VIML_TRY_CUDA(ctx, cudaMemcpyAsync(d_ex, in->ex_pose, n_ex * 8, cudaMemcpyHostToDevice, s_in));
