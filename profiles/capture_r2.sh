@@ -10,8 +10,8 @@ for k in assemble_kernel plan_kernel schur_dmma_kernel reduced_kernel solve_tile
   ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o gpurun_out/full_${k}_r2 \
       python bench.py --steps 1 --warmup 3 --skip-cpu --skip-assoc > /dev/null 2>&1
 done
-# the sliding-window Schur kernel first runs on the 512-window chunks of the e2e legs (80 launches with these flags): skip them
-ncu --set full --clock-control none --import-source on -k regex:schur_tma_kernel --launch-skip 80 -c 1 -f -o gpurun_out/full_schur_tma_kernel_r2 \
+# the sliding-window Schur kernel first runs on the 512-window chunks of the e2e legs (40 launches with these flags: 2 warm-up + 3 timed calls x 4 chunks, twice): skip them
+ncu --set full --clock-control none --import-source on -k regex:schur_tma_kernel --launch-skip 40 -c 1 -f -o gpurun_out/full_schur_tma_kernel_r2 \
     python bench.py --steps 1 --warmup 3 --skip-cpu --skip-assoc > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:match_kernel -c 1 -f -o gpurun_out/full_match_kernel_r2 \
     python bench.py --steps 1 --warmup 3 --skip-cpu --only-assoc --windows 64 > /dev/null 2>&1
