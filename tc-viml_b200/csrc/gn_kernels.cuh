@@ -143,29 +143,30 @@ __global__ void __launch_bounds__(256) solve_tiled_kernel(int Dx, double lambda,
   if (tid == 0) s_ok = 1;
   __syncthreads();
   const int kq = lane & 3, mq = lane >> 2;
-  for (int K = 0; K < NB; ++K) {
-    double* __restrict__ Dk = L + tile_at(K, K);
-    if (warp == 0) {   // 8 x 8 Cholesky of the diagonal tile: lane = (row r, column c) pairs, column by column
-      for (int j = 0; j < kTile; ++j) {
-        const double d = Dk[j * 8 + j];
-        const bool good = d > 0.0 && isfinite(d);
-        const double sd = good ? sqrt(d) : 1.0, inv = good ? rsqrt(d) : 1.0;
-        __syncwarp();
-        if (!good && lane == 0) s_ok = 0;
-        if (lane < kTile && lane >= j) Dk[lane * 8 + j] = (lane == j) ? sd : Dk[lane * 8 + j] * inv;
-        if (lane == 0) s_dinv[j] = inv;
-        __syncwarp();
-        // trailing part of the tile: entry (r, c), j < c <= r
-        for (int e = lane; e < 64; e += 32) {
-          const int r = e >> 3, c = e & 7;
-          if (c > j && r >= c) Dk[r * 8 + c] -= Dk[r * 8 + j] * Dk[c * 8 + j];
-        }
-        __syncwarp();
+  // 8 x 8 Cholesky of a diagonal tile by one warp: column by column, lane = row for the scaling, lanes over the 64 entries for
+  // the update; leaves 1 / L[j][j] in s_dinv.  Clears s_ok on a non-positive pivot.
+  auto factor_diag = [&](double* __restrict__ Dk) {
+    for (int j = 0; j < kTile; ++j) {
+      const double d = Dk[j * 8 + j];
+      const bool good = d > 0.0 && isfinite(d);
+      const double sd = good ? sqrt(d) : 1.0, inv = good ? rsqrt(d) : 1.0;
+      __syncwarp();
+      if (!good && lane == 0) s_ok = 0;
+      if (lane < kTile && lane >= j) Dk[lane * 8 + j] = (lane == j) ? sd : Dk[lane * 8 + j] * inv;
+      if (lane == 0) s_dinv[j] = inv;
+      __syncwarp();
+      for (int e = lane; e < 64; e += 32) {
+        const int r = e >> 3, c = e & 7;
+        if (c > j && r >= c) Dk[r * 8 + c] -= Dk[r * 8 + j] * Dk[c * 8 + j];
       }
+      __syncwarp();
     }
-    __syncthreads();
-    if (!s_ok) break;   // uniform
-    // panel: row `row` of the tiles below the diagonal one solves x L_KK^T = a (forward substitution over the 8 columns)
+  };
+  if (warp == 0) factor_diag(L + tile_at(0, 0));
+  __syncthreads();
+  for (int K = 0; K < NB && s_ok; ++K) {   // s_ok is only written between the barriers below: uniform
+    const double* __restrict__ Dk = L + tile_at(K, K);
+    // panel: row `tid` of the tiles below the diagonal one solves x L_KK^T = a (forward substitution over the 8 columns)
     const int nrows = (NB - K - 1) * kTile;
     if (tid < nrows) {
       double* __restrict__ a = L + tile_at(K + 1 + (tid >> 3), K) + (tid & 7) * 8;
@@ -181,13 +182,12 @@ __global__ void __launch_bounds__(256) solve_tiled_kernel(int Dx, double lambda,
       for (int c = 0; c < kTile; ++c) a[c] = x[c];
     }
     __syncthreads();
-    // trailing update on the tensor pipe: tile (I, J), K < J <= I, dealt round-robin to the warps
+    // trailing update on the tensor pipe: tile (I, J), K < J <= I, of the m x m lower triangle (row-major index t).  Warp 0 takes
+    // tile 0 — the next diagonal tile — and factors it at once (look-ahead: the serial 8-column factorisation runs beside the
+    // other warps' tiles instead of in front of a barrier); warps 1..7 share the rest.
     {
       const int m = NB - K - 1;
-      int t = warp, I = 0, J = 0;          // t-th tile of the m x m lower triangle (row-major): advance (I, J) incrementally
-      while (t >= I + 1 && I < m) t -= I + 1, ++I;
-      J = t;
-      while (I < m) {
+      auto update = [&](int I, int J) {
         const double* __restrict__ Li = L + tile_at(K + 1 + I, K);
         const double* __restrict__ Lj = L + tile_at(K + 1 + J, K);
         double2* cptr = reinterpret_cast<double2*>(L + tile_at(K + 1 + I, K + 1 + J) + mq * 8 + 2 * kq);
@@ -195,8 +195,22 @@ __global__ void __launch_bounds__(256) solve_tiled_kernel(int Dx, double lambda,
         stream::dmma(c.x, c.y, -Li[mq * 8 + kq], Lj[mq * 8 + kq]);
         stream::dmma(c.x, c.y, -Li[mq * 8 + 4 + kq], Lj[mq * 8 + 4 + kq]);
         *cptr = c;
-        J += 8;                               // the next tile of this warp: 8 further in row-major order
-        while (I < m && J > I) J -= I + 1, ++I;
+      };
+      if (warp == 0) {
+        if (m > 0) {
+          update(0, 0);
+          __syncwarp();
+          factor_diag(L + tile_at(K + 1, K + 1));
+        }
+      } else {
+        int t = warp, I = 0;                 // tiles 1, 2, ...: t = 1 + (warp - 1), step 7
+        while (I < m && t >= I + 1) t -= I + 1, ++I;
+        int J = t;
+        while (I < m) {
+          update(I, J);
+          J += 7;
+          while (I < m && J > I) J -= I + 1, ++I;
+        }
       }
     }
     __syncthreads();
