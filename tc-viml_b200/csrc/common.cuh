@@ -174,6 +174,8 @@ int viml_launch_expand_obs(viml_ctx* ctx, const LinearizeArgs& a, const void* fe
 // line table -> the nine lf_geom planes for the line-factor range of `a` (a.lf_geom is the destination, absolute factor ids)
 int viml_launch_expand_lines(viml_ctx* ctx, const LinearizeArgs& a, const int32_t* lf_map_index, const float* lf_seg2d);
 int viml_launch_reduced(viml_ctx* ctx, int W, int D, const DenseArgs& dn, const double* S, const double* g, double* Sx, double* gx);
+int viml_launch_gn_reduced_solve(viml_ctx* ctx, int W, int D, const DenseArgs& dn, const double* S, const double* g, double lambda,
+                                 double* dx, int32_t* solved, double* cost);
 int viml_launch_gn_solve(viml_ctx* ctx, int W, int Dx, double lambda, const double* Sx, const double* gx, double* dx, int32_t* solved,
                          double* cost);
 int viml_launch_gn_update(viml_ctx* ctx, const LinearizeArgs& a, int X, const double* extra_in, const double* dx, const int32_t* solved,

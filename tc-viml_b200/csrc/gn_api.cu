@@ -210,11 +210,25 @@ int run(viml_ctx* ctx, const viml_window_batch* in, const viml_dense_factors* de
   }
   rc = viml_launch_linearize(ctx, a);
   if (rc != VIML_OK) return rc;
-  rc = viml_launch_reduced(ctx, W, D, dn, a.out.S, a.out.g, Sx, gx);
-  if (rc != VIML_OK) return rc;
-  if (step) {
+  // a step that does not have to hand Sx / gx to the caller builds and solves the reduced system in one kernel
+  bool fused = false;
+  if (step && !(rout && (rout->Sx || rout->gx))) {
     rc = viml_launch_cost(ctx, a, dn, nullptr, 0, cost);
-    if (rc == VIML_OK) rc = viml_launch_gn_solve(ctx, W, Dx, opt ? opt->lambda : 0.0, Sx, gx, dxv, solved, cost);
+    if (rc != VIML_OK) return rc;
+    rc = viml_launch_gn_reduced_solve(ctx, W, D, dn, a.out.S, a.out.g, opt ? opt->lambda : 0.0, dxv, solved, cost);
+    if (rc == VIML_OK) fused = true;
+    else if (rc != VIML_ERR_UNSUPPORTED) return rc;
+  }
+  if (!fused) {
+    rc = viml_launch_reduced(ctx, W, D, dn, a.out.S, a.out.g, Sx, gx);
+    if (rc != VIML_OK) return rc;
+  }
+  if (step) {
+    rc = VIML_OK;
+    if (!fused) {
+      rc = viml_launch_cost(ctx, a, dn, nullptr, 0, cost);
+      if (rc == VIML_OK) rc = viml_launch_gn_solve(ctx, W, Dx, opt ? opt->lambda : 0.0, Sx, gx, dxv, solved, cost);
+    }
     if (rc == VIML_OK) rc = viml_launch_gn_update(ctx, a, X, d_extra, dxv, solved, o_poses, o_ex, o_dep, o_extra);
     if (rc != VIML_OK) return rc;
     LinearizeArgs a2 = a;

@@ -95,13 +95,20 @@ __global__ void __launch_bounds__(256) reduced_kernel(int D, DenseArgs dn, const
 // triangle of 8 x 8 tiles (tile (I, J), J <= I, at (I (I + 1) / 2 + J) * 64; Dx padded to a multiple of 8 with an identity
 // diagonal).  Right-looking blocked factorisation: per tile column K (1) warp 0 factors the diagonal tile, (2) one thread per row
 // solves the panel rows against it, (3) the trailing tiles take A[I][J] -= L[I][K] L[J][K]^T as two DMMA steps each, dealt
-// round-robin to the warps.  22 tile columns and ~66 barriers for Dx = 171 instead of 171 columns and ~510 barriers in
-// solve_kernel below, and the O(n^3) part runs on the FP64 tensor pipe.  Forward / backward substitution tile by tile.
+// round-robin to warps 1..7 while warp 0 updates and factors the next diagonal tile (look-ahead).  22 tile columns and ~44 barriers
+// for Dx = 171 instead of 171 columns and ~510 barriers in solve_kernel below, and the O(n^3) part runs on the FP64 tensor pipe.
+// Forward / backward substitution tile by tile.
+// FUSED: the matrix is not read from Sx but built in place — embed(S) plus the window's dense-block factors (J^T J as DMMA tiles
+// from a staged Jacobian, like reduced_kernel) — so that Sx never makes its 234 KB round trip through HBM; the model decrease then
+// uses A x = -g:  x^T Sx x = -g.x - lambda sum d_i x_i^2  with d the undamped diagonal.
+constexpr int kFusedStage = 6656;   // doubles for a staged dense-factor Jacobian + residual in the fused kernel (a 76 x 75 prior: 6460)
 constexpr int kTile = 8;
 __device__ __forceinline__ int tile_at(int I, int J) { return (I * (I + 1) / 2 + J) * 64; }
 
+template <bool FUSED>
 __global__ void __launch_bounds__(256) solve_tiled_kernel(int Dx, double lambda, const double* __restrict__ Sx, const double* __restrict__ gx,
-                                                          double* __restrict__ dx, int32_t* __restrict__ solved, double* __restrict__ cost) {
+                                                          double* __restrict__ dx, int32_t* __restrict__ solved, double* __restrict__ cost,
+                                                          int D, DenseArgs dn, const double* __restrict__ S, const double* __restrict__ g) {
   extern __shared__ __align__(16) double sm[];
   __shared__ int s_ok;
   __shared__ double s_red[8], s_dinv[kTile];
@@ -109,40 +116,124 @@ __global__ void __launch_bounds__(256) solve_tiled_kernel(int Dx, double lambda,
   const int NB = (Dx + kTile - 1) / kTile, Dp = NB * kTile;
   double* __restrict__ L = sm;                                   // NB (NB + 1) / 2 tiles
   double* __restrict__ y = sm + (size_t)NB * (NB + 1) / 2 * 64;  // [Dp]
-  const double* __restrict__ A = Sx + (size_t)w * Dx * Dx;
-  // (A + A^T) / 2 into the tiles with row-wise (coalesced) reads only: the lower entries first, then every upper entry adds its
-  // half to its mirror (one writer per entry in either pass)
+  double* __restrict__ gv = y + Dp;                              // FUSED: [Dp] the right-hand side's g, [Dp] the undamped diagonal,
+  double* __restrict__ dv = gv + Dp;                             //        then the Jacobian stage
+  double* __restrict__ sJ = dv + Dp;
+  const double* __restrict__ A = FUSED ? nullptr : Sx + (size_t)w * Dx * Dx;
   for (int e = tid; e < Dp * Dp; e += 256) {   // padding rows: identity; everything else starts at zero
     const int i = e / Dp, j = e - i * Dp;
     if (j <= i) L[tile_at(i >> 3, j >> 3) + (i & 7) * 8 + (j & 7)] = (i >= Dx && i == j) ? 1.0 : 0.0;
   }
   __syncthreads();
-  // four independent loads in flight per thread and pass (8 warps per SM: the load latency is otherwise exposed)
-  for (int pass = 0; pass < 2; ++pass) {
-    for (int e0 = tid; e0 < Dx * Dx; e0 += 4 * 256) {
+  const int kq = lane & 3, mq = lane >> 2;
+  if (FUSED) {
+    // embed(S): the landmark Schur complement of the window is exactly symmetric (every tile is written with its mirror)
+    const double* __restrict__ Sw = S + (size_t)w * D * D;
+    for (int e0 = tid; e0 < D * D; e0 += 4 * 256) {
       double v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = e0 + u * 256 < Dx * Dx ? A[e0 + u * 256] : 0.0;
+      for (int u = 0; u < 4; ++u) v[u] = e0 + u * 256 < D * D ? Sw[e0 + u * 256] : 0.0;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int e = e0 + u * 256;
-        if (e >= Dx * Dx) break;
-        const int i = e / Dx, j = e - i * Dx;
-        if (pass == 0 && j <= i) L[tile_at(i >> 3, j >> 3) + (i & 7) * 8 + (j & 7)] = (i == j) ? v[u] * (1.0 + lambda) : 0.5 * v[u];
-        if (pass == 1 && j > i) L[tile_at(j >> 3, i >> 3) + (j & 7) * 8 + (i & 7)] += 0.5 * v[u];
+        if (e >= D * D) break;
+        const int i = e / D, j = e - i * D;
+        if (j <= i) L[tile_at(i >> 3, j >> 3) + (i & 7) * 8 + (j & 7)] = v[u];
       }
     }
+    for (int e = tid; e < Dp; e += 256) gv[e] = e < D ? g[(size_t)w * D + e] : 0.0;
     __syncthreads();
+    for (int k = dn.ND ? dn.window_offset[w] : 0; k < (dn.ND ? dn.window_offset[w + 1] : 0); ++k) {
+      const int n = (int)(dn.row_offset[k + 1] - dn.row_offset[k]), c = (int)(dn.col_offset[k + 1] - dn.col_offset[k]);
+      const double* __restrict__ J = dn.jacobian + dn.jac_offset[k];
+      const double* __restrict__ r = dn.residual + dn.row_offset[k];
+      const int32_t* __restrict__ ci = dn.col_index + dn.col_offset[k];
+      const int np = (n + 3) & ~3, cp = (c + 7) & ~7, ld = cp + 4;
+      auto lower = [&](int gi, int gj) -> double& {
+        const int hi = max(gi, gj), lo = min(gi, gj);
+        return L[tile_at(hi >> 3, lo >> 3) + (hi & 7) * 8 + (lo & 7)];
+      };
+      if (np * ld + np <= kFusedStage) {
+        double* __restrict__ sr = sJ + np * ld;
+        for (int e = tid; e < np * ld; e += 256) {
+          const int q = e / ld, a = e - q * ld;
+          sJ[e] = (q < n && a < c) ? J[(size_t)q * c + a] : 0.0;
+        }
+        for (int q = tid; q < np; q += 256) sr[q] = q < n ? r[q] : 0.0;
+        __syncthreads();
+        const int nt = cp >> 3, ntile = nt * (nt + 1) / 2;
+        for (int t = warp; t < ntile; t += 8) {
+          int rem = t, ta = 0;
+          while (rem >= nt - ta) rem -= nt - ta, ++ta;
+          const int tb = ta + rem;
+          double c0 = 0.0, c1 = 0.0;
+          const double* __restrict__ pa = sJ + kq * ld + 8 * ta + mq;
+          const double* __restrict__ pb = sJ + kq * ld + 8 * tb + mq;
+          for (int s4 = 0; s4 < np; s4 += 4) stream::dmma(c0, c1, pa[s4 * ld], pb[s4 * ld]);
+          // entry (a, b) and its mirror land on the same lower-triangle slot: off-diagonal tiles add once, a diagonal tile
+          // (which holds both) adds the a >= b half
+          const int a = 8 * ta + mq, bb = 8 * tb + 2 * kq;
+          if (a < c) {
+            if (bb < c && (ta != tb || a >= bb)) lower(ci[a], ci[bb]) += c0;
+            if (bb + 1 < c && (ta != tb || a >= bb + 1)) lower(ci[a], ci[bb + 1]) += c1;
+          }
+        }
+        for (int a = tid; a < c; a += 256) {
+          double v = 0.0;
+          for (int q = 0; q < n; ++q) v = fma(sJ[q * ld + a], sr[q], v);
+          gv[ci[a]] += v;
+        }
+      } else {
+        for (int e = tid; e < c * c; e += 256) {
+          const int a = e / c, bb = e - a * c;
+          if (a < bb) continue;
+          double v = 0.0;
+          for (int q = 0; q < n; ++q) v = fma(J[(size_t)q * c + a], J[(size_t)q * c + bb], v);
+          lower(ci[a], ci[bb]) += v;
+        }
+        for (int a = tid; a < c; a += 256) {
+          double v = 0.0;
+          for (int q = 0; q < n; ++q) v = fma(J[(size_t)q * c + a], r[q], v);
+          gv[ci[a]] += v;
+        }
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < Dp; i += 256) {
+      double& d = L[tile_at(i >> 3, i >> 3) + (i & 7) * 8 + (i & 7)];
+      dv[i] = d;
+      if (i < Dx) d *= 1.0 + lambda;
+      y[i] = -gv[i];
+    }
+  } else {
+    // (A + A^T) / 2 into the tiles with row-wise (coalesced) reads only: the lower entries first, then every upper entry adds
+    // its half to its mirror (one writer per entry in either pass); four independent loads in flight per thread and pass
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int e0 = tid; e0 < Dx * Dx; e0 += 4 * 256) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = e0 + u * 256 < Dx * Dx ? A[e0 + u * 256] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * 256;
+          if (e >= Dx * Dx) break;
+          const int i = e / Dx, j = e - i * Dx;
+          if (pass == 0 && j <= i) L[tile_at(i >> 3, j >> 3) + (i & 7) * 8 + (j & 7)] = (i == j) ? v[u] * (1.0 + lambda) : 0.5 * v[u];
+          if (pass == 1 && j > i) L[tile_at(j >> 3, i >> 3) + (j & 7) * 8 + (i & 7)] += 0.5 * v[u];
+        }
+      }
+      __syncthreads();
+    }
+    for (int e = tid; e < Dp; e += 256) y[e] = e < Dx ? -gx[(size_t)w * Dx + e] : 0.0;
   }
+  __syncthreads();
   // the strictly upper part of the diagonal tiles is never read as data but is multiplied in the DMMA steps: zero it
   for (int e = tid; e < NB * 64; e += 256) {
     const int I = e >> 6, r = (e >> 3) & 7, c = e & 7;
     if (c > r) L[tile_at(I, I) + r * 8 + c] = 0.0;
   }
-  for (int e = tid; e < Dp; e += 256) y[e] = e < Dx ? -gx[(size_t)w * Dx + e] : 0.0;
   if (tid == 0) s_ok = 1;
   __syncthreads();
-  const int kq = lane & 3, mq = lane >> 2;
   // 8 x 8 Cholesky of a diagonal tile by one warp: column by column, lane = row for the scaling, lanes over the 64 entries for
   // the update; leaves 1 / L[j][j] in s_dinv.  Clears s_ok on a non-positive pivot.
   auto factor_diag = [&](double* __restrict__ Dk) {
@@ -261,18 +352,26 @@ __global__ void __launch_bounds__(256) solve_tiled_kernel(int Dx, double lambda,
       __syncthreads();
     }
   }
-  // model decrease with the undamped Sx: -g.x - x.Sx x / 2; a warp per row of Sx (coalesced), lanes over the columns
+  // model decrease with the undamped Sx: -g.x - x.Sx x / 2
   double part = 0.0;
-  for (int i = warp; i < Dx; i += 8) {
-    double sx = 0.0;
-    if (ok)
-      for (int c = lane; c < Dx; c += 32) sx = fma(A[(size_t)i * Dx + c], y[c], sx);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
-    const double xi = ok ? y[i] : 0.0;
-    if (lane == 0) {
-      part += -gx[(size_t)w * Dx + i] * xi - 0.5 * xi * sx;
+  if (FUSED) {   // (Sx + lambda diag d) x = -g  =>  x.Sx x = -g.x - lambda sum d_i x_i^2
+    for (int i = tid; i < Dx; i += 256) {
+      const double xi = ok ? y[i] : 0.0;
+      part += -0.5 * gv[i] * xi + 0.5 * lambda * dv[i] * xi * xi;
       dx[(size_t)w * Dx + i] = xi;
+    }
+  } else {       // a warp per row of Sx (coalesced), lanes over the columns
+    for (int i = warp; i < Dx; i += 8) {
+      double sx = 0.0;
+      if (ok)
+        for (int c = lane; c < Dx; c += 32) sx = fma(A[(size_t)i * Dx + c], y[c], sx);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      const double xi = ok ? y[i] : 0.0;
+      if (lane == 0) {
+        part += -gx[(size_t)w * Dx + i] * xi - 0.5 * xi * sx;
+        dx[(size_t)w * Dx + i] = xi;
+      }
     }
   }
 #pragma unroll

@@ -676,14 +676,28 @@ int viml_launch_gn_solve(viml_ctx* ctx, int W, int Dx, double lambda, const doub
   const size_t smem_t = ((size_t)NB * (NB + 1) / 2 * 64 + (size_t)NB * 8) * sizeof(double);
   LaunchScope ls(ctx, K_GN);
   if (smem_t <= 220 * 1024 && Dx <= 256 - 8 && !getenv("VIML_GN_UNBLOCKED")) {   // tiled factorisation on the tensor pipe
-    VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(gn::solve_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-    gn::solve_tiled_kernel<<<W, 256, smem_t, ctx->stream>>>(Dx, lambda, Sx, gx, dx, solved, cost);
+    VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(gn::solve_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+    gn::solve_tiled_kernel<false><<<W, 256, smem_t, ctx->stream>>>(Dx, lambda, Sx, gx, dx, solved, cost, 0, DenseArgs{}, nullptr, nullptr);
     VIML_TRY_CUDA(ctx, cudaGetLastError());
     return VIML_OK;
   }
   const size_t smem = ((size_t)Dx * (Dx + 1) / 2 + Dx) * sizeof(double);
   VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(gn::solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   gn::solve_kernel<<<W, 256, smem, ctx->stream>>>(Dx, lambda, Sx, gx, dx, solved, cost);
+  VIML_TRY_CUDA(ctx, cudaGetLastError());
+  return VIML_OK;
+}
+
+// Reduced system + solve in one kernel (viml_gn_step when the caller does not ask for Sx / gx): returns VIML_ERR_UNSUPPORTED when
+// the system does not fit the fused kernel's shared memory, and the caller takes the two-kernel path.
+int viml_launch_gn_reduced_solve(viml_ctx* ctx, int W, int D, const DenseArgs& dn, const double* S, const double* g, double lambda,
+                                 double* dx, int32_t* solved, double* cost) {
+  const int Dx = D + dn.X, NB = (Dx + 7) / 8;
+  const size_t smem = ((size_t)NB * (NB + 1) / 2 * 64 + 3 * (size_t)NB * 8 + gn::kFusedStage) * sizeof(double);
+  if (smem > 224 * 1024 || Dx > 256 - 8 || getenv("VIML_GN_UNBLOCKED") || getenv("VIML_GN_UNFUSED")) return VIML_ERR_UNSUPPORTED;
+  LaunchScope ls(ctx, K_GN);
+  VIML_TRY_CUDA(ctx, cudaFuncSetAttribute(gn::solve_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gn::solve_tiled_kernel<true><<<W, 256, smem, ctx->stream>>>(Dx, lambda, nullptr, nullptr, dx, solved, cost, D, dn, S, g);
   VIML_TRY_CUDA(ctx, cudaGetLastError());
   return VIML_OK;
 }
