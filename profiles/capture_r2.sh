@@ -6,7 +6,7 @@ python bench.py > gpurun_out/bench_r2.json 2> gpurun_out/bench_r2.err
 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_ref_r2.json 2> gpurun_out/bench_ref_r2.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_r2.csv \
     python bench.py --steps 2 --warmup 3 --skip-cpu --skip-assoc > /dev/null 2>&1
-for k in assemble_kernel plan_kernel schur_dmma_kernel reduced_kernel solve_tiled_kernel points_kernel; do
+for k in assemble_kernel plan_kernel schur_dmma_kernel solve_tiled_kernel points_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o gpurun_out/full_${k}_r2 \
       python bench.py --steps 1 --warmup 3 --skip-cpu --skip-assoc > /dev/null 2>&1
 done
