@@ -73,6 +73,7 @@ struct viml_ctx {
   double* d_map_sorted = nullptr;   // [6][n_map]
   int32_t* d_map_orig = nullptr;    // [n_map]
   double* d_tile_sphere = nullptr;  // [n_tiles][4]
+  double* d_group_sphere = nullptr; // [ceil(n_tiles / 16)][4]: one sphere around 16 consecutive tile spheres
   int64_t n_tiles = 0;
   // FoV cache: one mask row per window slot (viml_fov_update / viml_fov_slide), sized for the current map
   uint32_t* d_fov_slots = nullptr;     // [VIML_FOV_SLOTS][fov_words]
@@ -196,6 +197,7 @@ struct AssocArgs {  // device pointers only
   const double* map_sorted;  // [6][N] Morton order
   const int32_t* map_orig;   // [N]
   const double* tile_sphere; // [n_tiles][4]
+  const double* group_sphere;// [ceil(n_tiles / 16)][4]
   int64_t n_tiles;
   const double* cull_poses;
   const double* match_poses;  // may alias cull_poses

@@ -108,6 +108,7 @@ void viml_destroy(viml_ctx* ctx) {
   if (ctx->d_map_sorted) cudaFree(ctx->d_map_sorted);
   if (ctx->d_map_orig) cudaFree(ctx->d_map_orig);
   if (ctx->d_tile_sphere) cudaFree(ctx->d_tile_sphere);
+  if (ctx->d_group_sphere) cudaFree(ctx->d_group_sphere);
   if (ctx->d_assoc_stats) cudaFree(ctx->d_assoc_stats);
   if (ctx->d_fov_slots) cudaFree(ctx->d_fov_slots);
   if (ctx->d_fov_slot_count) cudaFree(ctx->d_fov_slot_count);
@@ -207,7 +208,7 @@ int viml_set_map(viml_ctx* ctx, const double* lines, int64_t n) {
     if (ptr) cudaFree(ptr);
     ptr = nullptr;
   };
-  drop(ctx->d_map), drop(ctx->d_map_sorted), drop(ctx->d_map_orig), drop(ctx->d_tile_sphere);
+  drop(ctx->d_map), drop(ctx->d_map_sorted), drop(ctx->d_map_orig), drop(ctx->d_tile_sphere), drop(ctx->d_group_sphere);
   drop(ctx->d_fov_slots), drop(ctx->d_fov_slot_count);   // the cached FoV lists index the old map
   ctx->fov_words = 0;
   ctx->n_map = 0, ctx->n_tiles = 0;
@@ -290,6 +291,27 @@ int viml_set_map(viml_ctx* ctx, const double* lines, int64_t n) {
   VIML_TRY_CUDA(ctx, cudaMemcpy(ctx->d_map_orig, order.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
   VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_tile_sphere, sph.size() * sizeof(double)));
   VIML_TRY_CUDA(ctx, cudaMemcpy(ctx->d_tile_sphere, sph.data(), sph.size() * sizeof(double), cudaMemcpyHostToDevice));
+  // second level: one sphere around every 16 consecutive tile spheres (consecutive Morton tiles are neighbours)
+  const int64_t ngrp = (nt + 15) / 16;
+  std::vector<double> gsp((size_t)std::max<int64_t>(ngrp, 1) * 4, 0.0);
+  for (int64_t gq = 0; gq < ngrp; ++gq) {
+    const int64_t ta = gq * 16, tb = std::min<int64_t>(nt, ta + 16);
+    double c[3] = {0, 0, 0}, r = 0.0;
+    bool fin = true;
+    for (int64_t t = ta; t < tb; ++t) {
+      fin &= std::isfinite(sph[4 * t + 3]) && std::isfinite(sph[4 * t]) && std::isfinite(sph[4 * t + 1]) && std::isfinite(sph[4 * t + 2]);
+      for (int k = 0; k < 3; ++k) c[k] += sph[4 * t + k] / (double)(tb - ta);
+    }
+    for (int64_t t = ta; t < tb && fin; ++t) {
+      double d2 = 0.0;
+      for (int k = 0; k < 3; ++k) d2 += (sph[4 * t + k] - c[k]) * (sph[4 * t + k] - c[k]);
+      r = std::max(r, std::sqrt(d2) * (1.0 + 1e-12) + sph[4 * t + 3]);
+    }
+    gsp[4 * gq] = fin ? c[0] : 0.0, gsp[4 * gq + 1] = fin ? c[1] : 0.0, gsp[4 * gq + 2] = fin ? c[2] : 0.0;
+    gsp[4 * gq + 3] = fin ? r * (1.0 + 1e-12) : INFINITY;   // never rejected when a member is not finite
+  }
+  VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_group_sphere, gsp.size() * sizeof(double)));
+  VIML_TRY_CUDA(ctx, cudaMemcpy(ctx->d_group_sphere, gsp.data(), gsp.size() * sizeof(double), cudaMemcpyHostToDevice));
   ctx->n_map = n;
   ctx->n_tiles = nt;
   return VIML_OK;
@@ -732,7 +754,7 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
   if (!ctx->d_assoc_stats) VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_assoc_stats, 32));
   VIML_TRY_CUDA(ctx, cudaMemsetAsync(ctx->d_assoc_stats, 0, 32, st));
   a.stats = ctx->d_assoc_stats;
-  a.map_sorted = ctx->d_map_sorted, a.map_orig = ctx->d_map_orig, a.tile_sphere = ctx->d_tile_sphere, a.n_tiles = ctx->n_tiles;
+  a.map_sorted = ctx->d_map_sorted, a.map_orig = ctx->d_map_orig, a.tile_sphere = ctx->d_tile_sphere, a.group_sphere = ctx->d_group_sphere, a.n_tiles = ctx->n_tiles;
   a.fov_capacity = out->fov_index ? out->fov_capacity : 0;
   auto pad = [](size_t b) { return DeviceArena::padded(b); };
   const size_t nq = (size_t)Pq * L;
@@ -872,7 +894,7 @@ int viml_fov_update(viml_ctx* ctx, int32_t slot, const double* pose, const doubl
   VIML_TRY_CUDA(ctx, cudaMemcpyAsync(de, ex_pose, 56, cudaMemcpyHostToDevice, st));
   AssocArgs a{};
   a.Pq = 1, a.L = 0, a.N = ctx->n_map, a.map = ctx->d_map, a.words = ctx->fov_words;
-  a.map_sorted = ctx->d_map_sorted, a.map_orig = ctx->d_map_orig, a.tile_sphere = ctx->d_tile_sphere, a.n_tiles = ctx->n_tiles;
+  a.map_sorted = ctx->d_map_sorted, a.map_orig = ctx->d_map_orig, a.tile_sphere = ctx->d_tile_sphere, a.group_sphere = ctx->d_group_sphere, a.n_tiles = ctx->n_tiles;
   if (!ctx->d_assoc_stats) VIML_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_assoc_stats, 32));
   a.stats = ctx->d_assoc_stats;
   a.cull_poses = a.match_poses = dp, a.ex_pose = a.cull_ex_pose = de;
