@@ -218,6 +218,19 @@ struct AssocArgs {  // device pointers only
 };
 // associate_kernels.cu (compiled with -fmad=false)
 int viml_launch_associate(viml_ctx* ctx, const AssocArgs& a);
+// The same in two phases, so that a host can pipeline pose chunks without a synchronisation per chunk: phase 1 (camera poses, FoV
+// cull, list offsets for ALL poses of `a`; one device->host read of the offsets), phase 2 (list fill, projection, match) for the
+// poses [p0, p1) of a view `v` of `a` whose per-pose pointers are advanced to pose p0.
+struct AssocPlan {
+  void *cull = nullptr, *match = nullptr;   // camera poses [Pq]
+  int64_t* off = nullptr;                   // device list offsets [Pq + 1]
+  std::vector<int64_t> h_off;               // the same on the host
+  int32_t* list = nullptr;
+  void *seg = nullptr, *abc = nullptr, *aux = nullptr, *dir = nullptr, *len = nullptr, *rec = nullptr, *flen = nullptr;
+  int Pq = 0;
+};
+int viml_assoc_phase1(viml_ctx* ctx, const AssocArgs& a, AssocPlan* plan);
+int viml_assoc_phase2(viml_ctx* ctx, const AssocArgs& v, const AssocPlan& plan, int p0, int p1);
 // triangulate_kernels.cu
 int viml_launch_triangulate(viml_ctx* ctx, int P, int64_t NF, const double* poses, const double* ex, const int32_t* fwin,
                             const int32_t* start, const int64_t* off, const double* pts, double init_depth, double* depth);

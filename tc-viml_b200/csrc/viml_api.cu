@@ -817,6 +817,10 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
     if (out->err) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.err, out->err, nq * 12, cudaMemcpyHostToDevice, cs));
     if (out->projected) VIML_TRY_CUDA(ctx, cudaMemcpyAsync(a.projected, out->projected, nq * 32, cudaMemcpyHostToDevice, cs));
   }
+  // phase 1 (camera poses, FoV cull, list offsets) runs once for all poses as soon as the small arrays are up — it does not need
+  // the detected lines, whose upload it overlaps — and holds the call's only synchronisation; phase 2 then runs chunk by chunk
+  VIML_TRY_CUDA(ctx, cudaEventRecord(ctx->ev_b, cs));
+  VIML_TRY_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_b, 0));
   std::vector<cudaEvent_t> ev_in(C), ev_k(C);
   auto chunk = [&](int c, int& p0, int& p1) { p0 = (int)((int64_t)Pq * c / C), p1 = (int)((int64_t)Pq * (c + 1) / C); };
   for (int c = 0; c < C; ++c) {
@@ -828,7 +832,8 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
     if (n) cudaMemcpyAsync(d_l2d + o, q->lines2d + o, n * 8, cudaMemcpyHostToDevice, cs);
     cudaEventRecord(ev_in[c], cs);
   }
-  int rc = VIML_OK;
+  AssocPlan plan;
+  int rc = viml_assoc_phase1(ctx, a, &plan);
   auto down = [&](void* host, const void* d, size_t bytes) {
     if (host && bytes) cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, ds);
   };
@@ -844,7 +849,7 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
     v.match_index = a.match_index + (size_t)p0 * L, v.err = a.err + (size_t)p0 * L * 3, v.projected = a.projected + (size_t)p0 * L * 4;
     v.fov_count = a.fov_count + p0, v.fov_index = a.fov_index ? a.fov_index + (size_t)p0 * cap : nullptr;
     v.fov_mask = a.fov_mask + (size_t)p0 * words;
-    if (v.Pq > 0) rc = viml_launch_associate(ctx, v);
+    if (v.Pq > 0) rc = viml_assoc_phase2(ctx, v, plan, p0, p1);
     cudaEventRecord(ev_k[c], st);
     cudaStreamWaitEvent(ds, ev_k[c], 0);
     const size_t np = (size_t)(p1 - p0), nqc = np * L;
