@@ -782,7 +782,8 @@ int viml_line_associate(viml_ctx* ctx, const viml_assoc_query* q, const viml_ass
   // back on the second copy stream while chunk c + 1 computes.
   VIML_TRY_CUDA(ctx, ctx->in_arena.reserve(4 * pad((size_t)Pq * 56) + pad(nq * 32) + pad((size_t)Pq * 4)));
   cudaStream_t cs = ctx->copy_stream, ds = ctx->copy_stream2;
-  const int C = Pq >= 512 ? 4 : 1;
+  int C = Pq >= 512 ? 4 : 1;   // measured on the cfg-3 sweep: 2, 4, 6, 8, 12, 16 chunks -> 2.32, 2.19, 2.30, 2.36, 2.79, 2.76 ms
+  if (const char* e = getenv("VIML_ASSOC_CHUNKS")) C = std::max(1, std::min(Pq, atoi(e)));   // tuning hook
   auto up = [&](const void* src, size_t bytes) -> void* {
     char* d = ctx->in_arena.take<char>(bytes);
     if (bytes) cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, cs);
