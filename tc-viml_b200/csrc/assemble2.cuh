@@ -387,14 +387,21 @@ __device__ __forceinline__ Dest decode(uint32_t e) {
 template <int ROUNDS>
 __device__ __forceinline__ void scatter(const double* __restrict__ patch, const Dest (&tab)[ROUNDS], double* __restrict__ Hc,
                                         int mybase, bool store_lh = false) {
+  // destinations and values of every round first (the shuffles and patch loads overlap), then the adds one after the other
+  double v[ROUNDS];
+  double* dst[ROUNDS];
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
     const int base = __shfl_sync(0xffffffffu, mybase, tab[r].kind);
+    dst[r] = Hc + base + tab[r].off;
+    const double x = patch[tab[r].src >= 0 ? tab[r].src : 0];
+    v[r] = __hiloint2double(__double2hiint(x) ^ (int)tab[r].sign, __double2loint(x));
+  }
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
     if (tab[r].src >= 0) {
-      const double x = patch[tab[r].src];
-      const double v = __hiloint2double(__double2hiint(x) ^ (int)tab[r].sign, __double2loint(x));
-      if (store_lh && tab[r].kind == K_LH) Hc[base + tab[r].off] = v;   // single writer, written once: no read-modify-write
-      else atomicAdd(&Hc[base + tab[r].off], v);
+      if (store_lh && tab[r].kind == K_LH) *dst[r] = v[r];   // single writer, written once: no read-modify-write
+      else atomicAdd(dst[r], v[r]);
     }
   }
 }
@@ -402,7 +409,14 @@ __device__ __forceinline__ void scatter(const double* __restrict__ patch, const 
 // the compare-and-swap adds; taking entries out with a 64-bit exchange + sentinel so that the rounds of a flush pipeline —
 // 0.68 ms, the per-round address/value registers spill at the 168-register cap; prefetching the next chunk's factor inputs
 // into registers — spills as well; prefetch.global.L2 of the inputs of this window and of the window that runs on the SM one CTA
-// lifetime later, issued at CTA start — 0.507 vs 0.468 ms.)
+// lifetime later, issued at CTA start — 0.507 vs 0.468 ms.
+// Later in round 2, against 0.465 ms: the accumulator in global memory (the window's own H_pp region, zeroed, red.global.add.f64
+// fire-and-forget, read back before the expansion) — 0.470 ms, correct but no faster; one CTA-wide lock per flush (lane 0, 32-bit
+// atomicCAS) with plain vector read-modify-write under it — 0.95 ms (ATOMS.CAS is far slower than the ATOMS.CAST.SPIN of the
+// compiler's own FP64 add loop); the rounds' compare-and-swaps written out with atomicCAS so that two or four are in flight —
+// 0.54 ms, same reason; the next chunk's factor inputs loaded right after the Jacobians leave the registers — 0.466 ms, no
+// change; K-step loop unrolled by four — 0.463 ms.  Kept: shuffles and patch loads of all rounds hoisted above the first add
+// (0.465 -> 0.457 ms).  profiles/assemble_knockouts_r2.md has the knock-out timings that say where the time goes.)
 
 // Per-lane selectors of kind_base: which pose (0 = lo, 1 = hi, 2 = extrinsic) is the block row / column of kind `lane`.
 //   kind      LL HH LH LE HE EE BL BH BE
@@ -482,9 +496,9 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
   const int gx = g ^ ((kk >> 1) << 2);
   const double* __restrict__ frag0 = stage + (kk >> 1) * 32 + (kk & 1);   // record 2s + (kk>>1), row kk&1
   const unsigned full = 0xffffffffu;
-  // landmark-row units of this lane: u = lane and lane + 32 (a row has 3 NB <= 39 units of 16 bytes)
+  // landmark-row units of this lane: u = lane, and 32 + (lane & 7) in the tail pass (a row has 3 NB <= 39 units of 16 bytes)
   const int upr = 3 * NB;
-  const int ru1 = lane + 32, rb0 = (lane * 11) >> 5, rb1 = (ru1 * 43) >> 7;
+  const int ru1 = 32 + (lane & 7), rb0 = (lane * 11) >> 5, rb1 = (ru1 * 43) >> 7;   // tail units: 8 lanes per feature
   const int rp0 = lane - 3 * rb0, rp1 = ru1 - 3 * rb1;
 
   for (;;) {
@@ -636,17 +650,26 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
         const int an = m ? (int)(info >> 28) : -1;
         double2* __restrict__ dst = reinterpret_cast<double2*>(Hlp + (size_t)l * D);
         const double2* __restrict__ la = reinterpret_cast<const double2*>(lacc + f * LACC_W);
-        {
-          const bool ia = rb0 == an, ie = rb0 == P;
-          double2 v = la[ia ? rp0 : 3 + rp0];
-          if (!(ia || ie)) v = make_double2(0.0, 0.0);
-          if ((ia || ie || !((m >> rb0) & 1u)) && lane < upr) dst[lane] = v;
-        }
-        {
+        const bool ia = rb0 == an, ie = rb0 == P;
+        double2 v = la[ia ? rp0 : 3 + rp0];
+        if (!(ia || ie)) v = make_double2(0.0, 0.0);
+        if ((ia || ie || !((m >> rb0) & 1u)) && lane < upr) dst[lane] = v;
+      }
+      // units 32 .. upr-1 (at most 7): four features per step, eight lanes each
+      if (upr > 32) {
+        const int fs = lane >> 3;
+        for (int f0 = 0; f0 < n_feats; f0 += 4) {
+          const int f = f0 + fs;
+          const uint32_t info = __shfl_sync(full, fi, f & 31);
+          const int l = info & 0xffff;
+          const uint32_t m = (info >> 16) & 0xfffu;
+          const int an = m ? (int)(info >> 28) : -1;
           const bool ia = rb1 == an, ie = rb1 == P;
-          double2 v = la[ia ? rp1 : 3 + rp1];
-          if (!(ia || ie)) v = make_double2(0.0, 0.0);
-          if ((ia || ie || !((m >> rb1) & 1u)) && ru1 < upr) dst[ru1] = v;
+          if (f < n_feats && ru1 < upr) {
+            double2 v = reinterpret_cast<const double2*>(lacc + f * LACC_W)[ia ? rp1 : 3 + rp1];
+            if (!(ia || ie)) v = make_double2(0.0, 0.0);
+            if (ia || ie || !((m >> rb1) & 1u)) reinterpret_cast<double2*>(Hlp + (size_t)l * D)[ru1] = v;
+          }
         }
       }
       if (lane < n_feats) {
@@ -728,28 +751,24 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
       Hpp[e] = Hc[blk(lo, hi, NB) * 36 + (tr ? cc * 6 + rr : rr * 6 + cc)];
     }
   } else {
-    // two neighbouring columns per step (D is even, a pair never straddles a 6x6 block): one 16-byte store, and one 16-byte load
-    // where the pair comes from an upper block as it is
-    const int Dh = D / 2;
-    int r = tid / Dh, cp = tid - r * Dh;
-    const int dr = NT / Dh, dc = NT - dr * Dh;
+    // block by block: the 18 column pairs of an upper block go out as they are, and — for an off-diagonal block — once more
+    // transposed into the mirrored block (D is even, a pair never straddles a 6x6 block); a diagonal block is symmetrised
     double2* __restrict__ Hf2 = reinterpret_cast<double2*>(Hf);
-    for (int e = tid; e < D * Dh; e += NT) {
-      const int c = 2 * cp;
-      const int br = (r * 43) >> 8, bc = (c * 43) >> 8, rr = r - 6 * br, cc = c - 6 * bc;
-      double2 v;
-      if (br < bc) {
-        v = *reinterpret_cast<const double2*>(&Hc[blk(br, bc, NB) * 36 + rr * 6 + cc]);
-      } else if (br > bc) {
-        const double* __restrict__ sb = &Hc[blk(bc, br, NB) * 36 + cc * 6 + rr];
-        v = make_double2(sb[0], sb[6]);
+    const int Dh = D / 2;
+    int br = 0, row0 = 0, rown = NB;   // block row br holds the blocks row0 .. row0 + rown - 1 of the block-upper layout
+    for (int e = tid; e < nblk * 18; e += NT) {
+      const int q = (e * 3641) >> 16, k = e - 18 * q;   // e < 18 * 91
+      const int rr = (k * 11) >> 5, cp = k - 3 * rr, cc = 2 * cp;
+      while (q >= row0 + rown) row0 += rown, --rown, ++br;
+      const int bc = br + (q - row0);
+      const double* __restrict__ sb = Hc + q * 36;
+      if (br != bc) {
+        Hf2[(6 * br + rr) * Dh + 3 * bc + cp] = *reinterpret_cast<const double2*>(sb + rr * 6 + cc);
+        Hf2[(6 * bc + rr) * Dh + 3 * br + cp] = make_double2(sb[cc * 6 + rr], sb[cc * 6 + 6 + rr]);
       } else {
-        const double* __restrict__ sb = &Hc[blk(br, br, NB) * 36];
-        v = make_double2(rr <= cc ? sb[rr * 6 + cc] : sb[cc * 6 + rr], rr <= cc + 1 ? sb[rr * 6 + cc + 1] : sb[(cc + 1) * 6 + rr]);
+        Hf2[(6 * br + rr) * Dh + 3 * bc + cp] =
+            make_double2(rr <= cc ? sb[rr * 6 + cc] : sb[cc * 6 + rr], rr <= cc + 1 ? sb[rr * 6 + cc + 1] : sb[(cc + 1) * 6 + rr]);
       }
-      Hf2[e] = v;
-      cp += dc, r += dr;
-      if (cp >= Dh) cp -= Dh, ++r;
     }
   }
   if (staged) {
