@@ -260,8 +260,9 @@ __global__ void __launch_bounds__(PT_MAX) plan_kernel(LinearizeArgs A, PlanPtrs 
 enum Kind { K_LL = 0, K_HH, K_LH, K_LE, K_HE, K_EE, K_BL, K_BH, K_BE, K_NKIND };
 
 struct Tables {
-  uint32_t seg[128];   // per segment: hi-role blocks and the (lo,hi) block (99 entries)
-  uint32_t lo[96];     // per anchor change: lo-role and extrinsic blocks (90 entries)
+  uint32_t seg[128];   // per segment: hi-role blocks (63 entries) and the (lo,hi) block (33: its symmetric 3x3 as upper triangle) = 3 rounds
+  uint32_t lo[64];     // per anchor change: lo-role blocks (i,i), (i,ex), b_i (63 entries = two rounds)
+  uint32_t ee[32];     // once per warp: (ex,ex) and b_ex (27 entries), summed in registers over all of the warp's tasks
   uint32_t line[32];   // line factors of one frame: (p,p) upper + b_p (27 entries)
 };
 
@@ -279,10 +280,11 @@ constexpr int col_sub(int c) { return c < 3 ? c : (c < 6 ? c - 3 : (c < 9 ? c - 
 
 constexpr Tables make_tables() {
   Tables T{};
-  int ns = 0, nlo = 0, nli = 0;
+  int ns = 0, nlo = 0, nli = 0, nee = 0;
   // every (kind, off) in destination order; for each, the (R, C, sign) that feeds it
-  // per-segment table: the blocks that always need the atomic add first (HH, HE, BH = 63 entries = two full rounds), the
-  // (lo, hi) block last (36 entries = rounds 2 and 3, plain stores for an exclusive task)
+  // per-segment table: the blocks that always need the atomic add first (HH, HE, BH = 63 entries), the (lo, hi) block last
+  // (33 entries — the three sub-diagonal entries of its symmetric top-left 3x3 are restored by the expansion — plain stores
+  // for an exclusive task): 96 entries = three full rounds
   constexpr int kind_order[K_NKIND] = {K_LL, K_LE, K_BL, K_EE, K_BE, K_HH, K_HE, K_BH, K_LH};
   for (int ko = 0; ko < K_NKIND; ++ko)
     for (int off = 0; off < 36; ++off) {
@@ -297,7 +299,7 @@ constexpr Tables make_tables() {
           bool hit = false, neg = false;
           if (tr == 0 && tc == 0) {            // (A_r, A_c), r <= c
             if (kind == K_LL || kind == K_HH) hit = dr == r && dc == c;
-            if (kind == K_LH) hit = (dr == r && dc == c) || (dr == c && dc == r), neg = true;
+            if (kind == K_LH) hit = dr == r && dc == c, neg = true;   // -A^T A is symmetric: upper triangle only (expansion mirrors it)
           } else if (tr == 0 && tc == 1) {     // (A_r, X_c)
             if (kind == K_LL) hit = dr == r && dc == 3 + c;
             if (kind == K_LH) hit = dr == 3 + c && dc == r, neg = true;
@@ -332,8 +334,9 @@ constexpr Tables make_tables() {
           if (!hit) continue;
           const bool per_segment = kind == K_HH || kind == K_LH || kind == K_HE || kind == K_BH;
           if (per_segment) {
-            if (kind == K_LH && ns < 64) ns = 64;   // the (lo, hi) block starts a round of its own
             T.seg[ns++] = tab_entry(R, C, kind, off, neg);
+          } else if (kind == K_EE || kind == K_BE) {
+            T.ee[nee++] = tab_entry(R, C, kind, off, neg);
           } else {
             T.lo[nlo++] = tab_entry(R, C, kind, off, neg);
           }
@@ -347,9 +350,9 @@ constexpr Tables make_tables() {
 }
 // read once per CTA with lane-indexed (coalesced) loads: global memory, not __constant__ (divergent constant reads replay)
 __device__ const Tables g_tables = make_tables();
-static_assert(make_tables().seg[62] != 0u && make_tables().seg[63] == 0u && make_tables().seg[99] != 0u && make_tables().seg[100] == 0u,
-              "63 atomic + 36 (lo, hi) per-segment destinations");
-static_assert(make_tables().lo[89] != 0u && make_tables().lo[90] == 0u, "90 per-anchor destinations");
+static_assert(make_tables().seg[95] != 0u && make_tables().seg[96] == 0u, "63 hi-role + 33 (lo, hi) per-segment destinations = three full rounds");
+static_assert(make_tables().lo[62] != 0u && make_tables().lo[63] == 0u, "63 per-anchor destinations");
+static_assert(make_tables().ee[26] != 0u && make_tables().ee[27] == 0u, "27 extrinsic destinations");
 static_assert(make_tables().line[26] != 0u && make_tables().line[27] == 0u, "27 line destinations");
 
 
@@ -385,7 +388,7 @@ __device__ __forceinline__ Dest decode(uint32_t e) {
   return d;
 }
 template <int ROUNDS>
-__device__ __forceinline__ void scatter(const double* __restrict__ patch, const Dest (&tab)[ROUNDS], double* __restrict__ Hc,
+__device__ __forceinline__ void scatter(const double* __restrict__ patch, const Dest* tab, double* __restrict__ Hc,
                                         int mybase, bool store_lh = false) {
   // destinations and values of every round first (the shuffles and patch loads overlap), then the adds one after the other
   double v[ROUNDS];
@@ -416,7 +419,11 @@ __device__ __forceinline__ void scatter(const double* __restrict__ patch, const 
 // compiler's own FP64 add loop); the rounds' compare-and-swaps written out with atomicCAS so that two or four are in flight —
 // 0.54 ms, same reason; the next chunk's factor inputs loaded right after the Jacobians leave the registers — 0.466 ms, no
 // change; K-step loop unrolled by four — 0.463 ms.  Kept: shuffles and patch loads of all rounds hoisted above the first add
-// (0.465 -> 0.457 ms).  profiles/assemble_knockouts_r2.md has the knock-out timings that say where the time goes.)
+// (0.465 -> 0.457 ms); the (lo, hi) block flushed as 33 entries (its symmetric 3x3 as upper triangle) so that a segment
+// flush is three rounds instead of four (0.457 -> 0.436 ms); (ex,ex) / b_ex summed per warp in registers (lo flush two rounds;
+// no change on cfg 2).  Dropped: the (lo, hi) block of an exclusive task stored straight from the fragment registers (two rounds
+// through the patch): 0.4415 vs 0.4356 ms.  profiles/assemble_knockouts_r2.md has the knock-out timings that say where the
+// time goes.)
 
 // Per-lane selectors of kind_base: which pose (0 = lo, 1 = hi, 2 = extrinsic) is the block row / column of kind `lane`.
 //   kind      LL HH LH LE HE EE BL BH BE
@@ -477,11 +484,12 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
     for (int e = tid; e < cstride / 2; e += NT) c2[e] = gc[e];
   }
   if (tid == 0) s_next = 0;
-  Dest tab_seg[4], tab_lo[3], tab_line[1];
+  Dest tab_seg[3], tab_lo[2], tab_ee[1], tab_line[1];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) tab_seg[r] = decode(g_tables.seg[32 * r + lane]);
+  for (int r = 0; r < 3; ++r) tab_seg[r] = decode(g_tables.seg[32 * r + lane]);
 #pragma unroll
-  for (int r = 0; r < 3; ++r) tab_lo[r] = decode(g_tables.lo[32 * r + lane]);
+  for (int r = 0; r < 2; ++r) tab_lo[r] = decode(g_tables.lo[32 * r + lane]);
+  tab_ee[0] = decode(g_tables.ee[lane]);
   tab_line[0] = decode(g_tables.line[lane]);
   const int kb_rs = lane < K_NKIND ? (0x24904 >> (2 * lane)) & 3 : 0, kb_cs = lane < K_NKIND ? (0xA94 >> (2 * lane)) & 3 : 0;
   const bool kb_isb = lane >= K_BL && lane < K_NKIND;
@@ -501,6 +509,7 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
   const int ru1 = 32 + (lane & 7), rb0 = (lane * 11) >> 5, rb1 = (ru1 * 43) >> 7;   // tail units: 8 lanes per feature
   const int rp0 = lane - 3 * rb0, rp1 = ru1 - 3 * rb1;
 
+  double E[2] = {0.0, 0.0};   // tile 2 of the Gram matrix summed over every point factor this warp sees: (ex,ex) and b_ex
   for (;;) {
     int t = 0;
     if (lane == 0) t = atomicAdd(&s_next, 1);
@@ -518,7 +527,7 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
       }
       __syncwarp();
       const uint32_t* __restrict__ sl = sl_w + tk.x;
-      double G[6] = {0, 0, 0, 0, 0, 0}, R[6] = {0, 0, 0, 0, 0, 0};
+      double G[6] = {0, 0, 0, 0, 0, 0}, R[4] = {0, 0, 0, 0};
       uint32_t nsw = lane < n_slots ? sl[lane] : 0xffffu;
       for (int c0 = 0; c0 < n_slots; c0 += 32) {
         const uint32_t sw_ = nsw;
@@ -624,17 +633,21 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
             const int mybase = kind_base(kb_rs, kb_cs, kb_isb, lo, hi, NB, boff);
             put_patch(patch, lane, G);
             __syncwarp();
-            scatter<4>(patch, tab_seg, Hc, mybase, excl);
+            scatter<3>(patch, tab_seg, Hc, mybase, excl);
 #pragma unroll
-            for (int q = 0; q < 6; ++q) R[q] += G[q], G[q] = 0.0;
+            for (int q = 0; q < 4; ++q) R[q] += G[q], G[q] = 0.0;
+            E[0] += G[4], E[1] += G[5], G[4] = G[5] = 0.0;
             const bool lo_ends = knext == 0xffffffffu || min((int)(knext & 15), (int)((knext >> 4) & 15)) != lo;
             if (lo_ends) {
               __syncwarp();
-              put_patch(patch, lane, R);
+              {
+                const double R6[6] = {R[0], R[1], R[2], R[3], 0.0, 0.0};   // tile 2 holds no lo-role entry
+                put_patch(patch, lane, R6);
+              }
               __syncwarp();
-              scatter<3>(patch, tab_lo, Hc, mybase);
+              scatter<2>(patch, tab_lo, Hc, mybase);
 #pragma unroll
-              for (int q = 0; q < 6; ++q) R[q] = 0.0;
+              for (int q = 0; q < 4; ++q) R[q] = 0.0;
             }
             __syncwarp();
           }
@@ -733,6 +746,15 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
       }
     }
   }
+  {
+    // the extrinsic's own block and gradient, once per warp
+    const int mybase = kind_base(kb_rs, kb_cs, kb_isb, 0, 0, NB, boff);
+    const double E6[6] = {0.0, 0.0, 0.0, 0.0, E[0], E[1]};
+    __syncwarp();
+    put_patch(patch, lane, E6);
+    __syncwarp();
+    scatter<1>(patch, tab_ee, Hc, mybase);
+  }
   __syncthreads();
   // expand the block-upper accumulator to the full symmetric matrix (+ b_p behind it) in the warps' work areas
   double* __restrict__ Hf = work0;
@@ -748,7 +770,9 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
       const int br = r / 6, bc = c / 6, rr = r - 6 * br, cc = c - 6 * bc;
       const int lo = min(br, bc), hi = max(br, bc);
       const bool tr = br > bc || (br == bc && rr > cc);
-      Hpp[e] = Hc[blk(lo, hi, NB) * 36 + (tr ? cc * 6 + rr : rr * 6 + cc)];
+      int a = tr ? cc : rr, b = tr ? rr : cc;   // entry (a, b) of the upper block (lo, hi)
+      if (lo != hi && hi < NB - 1 && a < 3 && b < a) { const int t = a; a = b, b = t; }   // symmetric 3x3 of a pose-pose block
+      Hpp[e] = Hc[blk(lo, hi, NB) * 36 + a * 6 + b];
     }
   } else {
     // block by block: the 18 column pairs of an upper block go out as they are, and — for an off-diagonal block — once more
@@ -763,8 +787,11 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
       const int bc = br + (q - row0);
       const double* __restrict__ sb = Hc + q * 36;
       if (br != bc) {
-        Hf2[(6 * br + rr) * Dh + 3 * bc + cp] = *reinterpret_cast<const double2*>(sb + rr * 6 + cc);
-        Hf2[(6 * bc + rr) * Dh + 3 * br + cp] = make_double2(sb[cc * 6 + rr], sb[cc * 6 + 6 + rr]);
+        // a pose-pose block holds its symmetric top-left 3x3 (-A^T A) as the upper triangle only
+        const bool pp = bc < NB - 1;
+        auto at = [&](int a, int b) { return sb[(pp && a < 3 && b < a) ? b * 6 + a : a * 6 + b]; };
+        Hf2[(6 * br + rr) * Dh + 3 * bc + cp] = make_double2(at(rr, cc), at(rr, cc + 1));
+        Hf2[(6 * bc + rr) * Dh + 3 * br + cp] = make_double2(at(cc, rr), at(cc + 1, rr));
       } else {
         Hf2[(6 * br + rr) * Dh + 3 * bc + cp] =
             make_double2(rr <= cc ? sb[rr * 6 + cc] : sb[cc * 6 + rr], rr <= cc + 1 ? sb[rr * 6 + cc + 1] : sb[(cc + 1) * 6 + rr]);
