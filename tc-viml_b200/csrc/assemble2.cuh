@@ -235,12 +235,17 @@ __global__ void __launch_bounds__(PT_MAX) plan_kernel(LinearizeArgs A, PlanPtrs 
     uint32_t* sl = sl_w + tk.x;
     int off = 0;
     const unsigned lt = (1u << lane) - 1u;
-    for (int i = 0; i < P; ++i) {
-      if (!__any_sync(0xffffffffu, an == i)) continue;
-      for (int j = 0; j < P; ++j) {
+    // anchors present in this task (usually one), and for each the observing frames present: only those are visited
+    unsigned im = __reduce_or_sync(0xffffffffu, an < P ? 1u << an : 0u);
+    while (im) {
+      const int i = __ffs(im) - 1;
+      im &= im - 1;
+      unsigned jm = __reduce_or_sync(0xffffffffu, an == i ? m : 0u);
+      while (jm) {
+        const int j = __ffs(jm) - 1;
+        jm &= jm - 1;
         const bool mine = an == i && ((m >> j) & 1u);
         const unsigned b = __ballot_sync(0xffffffffu, mine);
-        if (!b) continue;
         const int n = __popc(b);
         const uint32_t key = ((uint32_t)i << 21) | ((uint32_t)j << 25);
         if (mine) sl[off + __popc(b & lt)] = (uint32_t)fid[l * P + j] | ((uint32_t)lane << 16) | key;
