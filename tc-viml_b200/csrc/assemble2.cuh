@@ -428,7 +428,8 @@ __device__ __forceinline__ void scatter(const double* __restrict__ patch, const 
 // flush is three rounds instead of four (0.457 -> 0.436 ms); (ex,ex) / b_ex summed per warp in registers (lo flush two rounds;
 // no change on cfg 2).  Dropped: the (lo, hi) block of an exclusive task stored straight from the fragment registers (two rounds
 // through the patch): 0.4415 vs 0.4356 ms.  profiles/assemble_knockouts_r2.md has the knock-out timings that say where the
-// time goes.)
+// time goes.  After that: every global load of the CTA prologue issued before the first use (0.4356 -> ~0.427 ms); the inverse
+// depth fetched once per task and handed to the factors by shuffle instead of a dependent load: 0.4397 vs 0.4356 ms, dropped.)
 
 // Per-lane selectors of kind_base: which pose (0 = lo, 1 = hi, 2 = extrinsic) is the block row / column of kind `lane`.
 //   kind      LL HH LH LE HE EE BL BH BE
@@ -474,6 +475,18 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
   double* __restrict__ Hll = A.out.H_ll + (size_t)w * F;
   double* __restrict__ bp = A.out.b_p + (size_t)w * D;
   double* __restrict__ bl = A.out.b_l + (size_t)w * F;
+  // every global load of the prologue is issued before the first one is needed (one exposed latency instead of three): the
+  // window's pose cache (up to three 16-byte units per thread) and the scatter tables
+  const double2* __restrict__ gc = reinterpret_cast<const double2*>(A.cache + (size_t)w * cstride);
+  double2 cpre[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) cpre[q] = tid + q * NT < cstride / 2 ? gc[tid + q * NT] : make_double2(0.0, 0.0);
+  uint32_t traw[7];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) traw[r] = g_tables.seg[32 * r + lane];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) traw[3 + r] = g_tables.lo[32 * r + lane];
+  traw[5] = g_tables.ee[lane], traw[6] = g_tables.line[lane];
   if (hdr.z) {   // irregular window: zero here, irregular_kernel adds with global atomics
     for (int e = tid; e < D * D; e += NT) Hpp[e] = 0.0;
     for (int e = tid; e < F * D; e += NT) Hlp[e] = 0.0;
@@ -484,18 +497,20 @@ __global__ void __maxnreg__(168) assemble_kernel(LinearizeArgs A, PlanPtrs PL, i
   {
     double2* z = reinterpret_cast<double2*>(Hc);
     for (int e = tid; e < hc_n / 2; e += NT) z[e] = make_double2(0.0, 0.0);
-    const double2* __restrict__ gc = reinterpret_cast<const double2*>(A.cache + (size_t)w * cstride);
     double2* c2 = reinterpret_cast<double2*>(cache);
-    for (int e = tid; e < cstride / 2; e += NT) c2[e] = gc[e];
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (tid + q * NT < cstride / 2) c2[tid + q * NT] = cpre[q];
+    for (int e = tid + 3 * NT; e < cstride / 2; e += NT) c2[e] = gc[e];   // (P <= 12: never taken)
   }
   if (tid == 0) s_next = 0;
   Dest tab_seg[3], tab_lo[2], tab_ee[1], tab_line[1];
 #pragma unroll
-  for (int r = 0; r < 3; ++r) tab_seg[r] = decode(g_tables.seg[32 * r + lane]);
+  for (int r = 0; r < 3; ++r) tab_seg[r] = decode(traw[r]);
 #pragma unroll
-  for (int r = 0; r < 2; ++r) tab_lo[r] = decode(g_tables.lo[32 * r + lane]);
-  tab_ee[0] = decode(g_tables.ee[lane]);
-  tab_line[0] = decode(g_tables.line[lane]);
+  for (int r = 0; r < 2; ++r) tab_lo[r] = decode(traw[3 + r]);
+  tab_ee[0] = decode(traw[5]);
+  tab_line[0] = decode(traw[6]);
   const int kb_rs = lane < K_NKIND ? (0x24904 >> (2 * lane)) & 3 : 0, kb_cs = lane < K_NKIND ? (0xA94 >> (2 * lane)) & 3 : 0;
   const bool kb_isb = lane >= K_BL && lane < K_NKIND;
   __syncthreads();
