@@ -40,7 +40,7 @@ constexpr int PMAX = 12;       // poses per window on the fused path (4-bit i/j,
 constexpr int FMAXP = 4096;    // features per window the plan kernel's shared tables are sized for
 constexpr int PT = 64;         // plan_kernel threads (warp 0 orders the features, warp 1 the line factors)
 constexpr int PT_MAX = 512;    // ... for windows with many features: more warps write the tasks' slots
-constexpr int TASK_T = 110;    // point factors per task at most (+ one feature's worth): an EuRoC anchor group fits
+constexpr int TASK_T = 180;    // point factors per task at most (+ one feature's worth): an EuRoC anchor group fits whole (88 / 110 / 140 / 180: 0.446 / 0.426 / 0.415 / 0.414 ms)
 constexpr int TASK_F = 24;     // features per task
 constexpr int LTASK = 32;      // line slots per line task
 constexpr int AW = 4;          // warps per assemble CTA (3 CTAs x 4 warps per SM = 3 warps per scheduler at <= 168 registers)
