@@ -6,7 +6,7 @@
 // leave the SM and there is no CTA-wide phase structure: a window is cut into TASKS that warps execute on their own.
 //
 //   plan_kernel (indices only)   features are ordered by anchor pose; a task is a run of consecutive features
-//       (<= 24 features, <= ~110 factors, cut at anchor boundaries); inside a task the factors are ordered by (anchor i, observing frame j) and
+//       (<= 24 features, <= ~180 factors, cut at anchor boundaries); inside a task the factors are ordered by (anchor i, observing frame j) and
 //       every (i, j) SEGMENT is padded to an even length.  The plan is a list of 32-bit slots
 //       (factor id | feature slot | i | j) plus one record per task.
 //   assemble_kernel, one CTA (4 warps) per window, three CTAs per SM.  A warp takes a task and streams its slots
@@ -22,8 +22,10 @@
 //        b_i, b_j, b_ex — is a signed sub-block of that Gram matrix.
 //     4. at the end of a segment the j-role entries and the (i,j) block are added to the window's block-upper
 //        accumulator in shared memory (shared-memory FP64 add = compare-and-swap loop; balanced over the
-//        lanes through a 192-double patch and a compile-time destination table); the i-role and extrinsic entries
-//        keep accumulating in registers until the anchor changes.
+//        lanes through a 192-double patch and a compile-time destination table: 63 j-role + 33 (i,j) entries = three
+//        rounds, the (i,j) block's symmetric top-left 3x3 travelling as its upper triangle); the i-role entries keep
+//        accumulating in registers until the anchor changes, the extrinsic's own block and gradient until the warp
+//        has no task left.
 //   When the window's tasks are done the CTA expands the block-upper accumulator to the full symmetric D x D
 //   matrix in the (now dead) warp work areas and writes it with ONE cp.async.bulk shared->global (TMA bulk store).
 //
